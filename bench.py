@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py — geodesic steps/s on BASELINE.json's headline workload (config 3: Kerr a*=0.999, 3840x2160, 512
+fixed steps, f64 + Planckian redshift LUT), one process per GPU.
+
+  python bench.py [--gpus N --steps K --warmup W]            own arm (sm_100a kernels through the C ABI)
+  python bench.py --impl reference [...]                      the reference's CPU path on the host cores
+
+A "step" of the bench = one 4K frame traced (the hot path over one batch of synthetic input: the SURVEY §8(d)
+camera). `value` = geodesic steps/s with the frame resident in HBM (no read-back in the timed region), budget
+accounting (every pixel executes exactly 512 step computations => 3840*2160*512 steps per frame); `e2e` = the
+same metric through the public render(camera, physics) call with HOST buffers: camera/physics uniforms go H2D and
+the finished RGBA32F frame comes back D2H into pinned memory inside the timed region, every frame.
+Timing: CUDA events on the library's launch stream (first op -> last op of each frame), summed over the K timed
+frames, max over ranks; wall-clock is reported beside it as a cross-check.
+
+The reference is Rust (gravitas-core) and cannot be built in this image (no cargo/rustc/wasm-pack/node), so the
+reference arm and `cpu_baseline` time oracle/ — the C++ restatement of gravitas-core's integrate() — kind "port".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "blackhole-simulation_b200"))
+
+W, H, STEPS, SPIN, MASS = 3840, 2160, 512, 0.999, 1.0
+SPEC_W, SPEC_H, TMAX = 256, 32, 1e7          # 128 KB RGBA32F spectral LUT: shared-memory resident
+# Algorithmic flop per geodesic step, SURVEY.md §8(d) (CSE'd count; add=mul=div=sqrt=1, FMA=2, sincos/pow = 0):
+FLOP_PER_STEP = {"symplectic": 330.0, "rk4": 440.0, "rkf45": 900.0}
+METRIC = "geodesic steps/s at 3840x2160x512, a=0.999; % of FP32 roofline"
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "config 3: Kerr a*=0.999 (Kerr-Schild), 3840x2160, 512 fixed implicit-midpoint steps/pixel "
+                    "(step rule compute.wgsl.ts:213), f64, thin-disk g-factor + Planckian redshift LUT 256x32, "
+                    "camera r0=30 polar 97deg azimuth pi fov 60deg; budget accounting (W*H*512 steps/frame)",
+        "width": W, "height": H, "steps_per_pixel": STEPS, "spin": SPIN, "integrator": "implicit-midpoint",
+        "precision": "f64", "shard": f"row-block x{n_gpus} + 1 ncclAllGather" if n_gpus > 1 else "single GPU",
+        "l2": "inputs are ~131 KB (LUT + camera block), compute-bound and L2-insensitive; each frame writes a "
+              "132.7 MB RGBA32F frame (> 126 MB L2), so no explicit L2 flush between iterations",
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_  # plumbing only: rendezvous, id broadcast, barrier, max-over-ranks
+        dist_.init_process_group("gloo")
+        dist = dist_
+    return rank, world, local, dist
+
+
+def barrier(dist):
+    if dist is not None:
+        dist.barrier()
+
+
+def allreduce_max(dist, x):
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def allreduce_sum(dist, x):
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t[0])
+
+
+def cpu_sample(target_seconds=15.0, threads=None):
+    """Time the oracle (C++ restatement of gravitas-core integrate(), all host threads) on a strided lattice of
+    the SAME 4K frame, sized to ~target_seconds of CPU work."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    from gravitas_b200 import camera
+    if threads:
+        O.lib().orc_set_num_threads(threads)
+    cores = O.lib().orc_num_threads()
+    spec = O.spectrum_lut(SPEC_W, SPEC_H, TMAX)
+    td = O.disk_lut(MASS, SPIN)
+    opts = O.Options.default(method=O.METHOD_SYMPLECTIC, step_rule=1, max_steps=STEPS)
+    rp, keep = O.make_render_params(W, H, MASS, SPIN, opts, spectrum=spec, spec_w=SPEC_W, spec_h=SPEC_H, tdisk=td)
+    cam, _ = camera.default_camera(W, H)
+    probe = O.render(cam, rp, x0=5, xs=32, y0=3, ys=32, want=())            # 1/1024 of the frame
+    rate = probe["total_steps"] / max(probe["seconds"], 1e-9)
+    frac = min(1.0, target_seconds * rate / (W * H * STEPS * 0.96))
+    stride = max(1, int(round((1.0 / frac) ** 0.5)))
+    res = O.render(cam, rp, x0=stride // 2, xs=stride, y0=stride // 2, ys=stride, want=())
+    return {"value": res["total_steps"] / res["seconds"], "unit": "steps/s", "cores": cores, "kind": "port",
+            "sample": f"every {stride}th pixel in x and y of the same 3840x2160x512 frame ({res['n']} rays, "
+                      f"{res['total_steps']} accepted steps, {res['seconds']:.2f} s); natural termination",
+            "seconds": res["seconds"], "steps": res["total_steps"]}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # K "steps", each a bounded sample of the frame; W warm-up samples
+    per = max(2.0, min(15.0, 120.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_sample(per)
+    tot_steps, tot_s, last = 0, 0.0, None
+    for _ in range(args.steps):
+        last = cpu_sample(per)
+        tot_steps += last["steps"]; tot_s += last["seconds"]
+    v = tot_steps / tot_s
+    cb = {"value": v, "unit": "steps/s", "cores": last["cores"], "kind": "port", "sample": last["sample"]}
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": cb, "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference = Rust gravitas-core; not buildable here (no cargo/rustc), so this arm times oracle/ "
+                "(C++ restatement of geodesic::integrate + the composite shading), all host threads",
+    }))
+
+
+def timed_frames(r, cam, phys, n, dist, readback, out=None):
+    """n frames; returns (sum of event-timed ms [max over ranks], wall ms, per-frame stats list)."""
+    barrier(dist)
+    t0 = time.perf_counter()
+    ev_ms, stats = 0.0, []
+    for _ in range(n):
+        r.render(cam, phys, out=out, readback=readback)
+        ev_ms += r.last_stats.total_ms
+        stats.append(r.last_stats)
+    wall = (time.perf_counter() - t0) * 1e3
+    barrier(dist)
+    return allreduce_max(dist, ev_ms), allreduce_max(dist, wall), stats
+
+
+def run_own(args):
+    import gravitas_b200 as g
+    from gravitas_b200 import _lib, camera, renderer as R
+
+    rank, world, local, dist = dist_setup(args.gpus)
+    nccl_id = None
+    if world > 1:
+        objs = [g.KerrRenderer.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(objs, src=0)
+        nccl_id = objs[0]
+    r = g.KerrRenderer(device=local, rank=rank, world_size=world, nccl_id=nccl_id)
+    r.init()   # raises GravitasError if no sm_100 device / library missing: there is no fallback
+    r.init_pipelines(max_steps=STEPS, mass=MASS, spin=SPIN, spec_w=SPEC_W, spec_h=SPEC_H, max_temp=TMAX)
+    cam, _ = camera.default_camera(W, H)
+    phys = R.pack_physics(MASS, SPIN, W, H)
+    pinned = r.pinned_frame(W, H)
+    info = r.device_info()
+
+    def params(**kw):
+        r.params = R.RenderParams(method=_lib.METHOD_SYMPLECTIC, precision=_lib.PRECISION_F64, max_steps=STEPS,
+                                  step_rule=_lib.STEP_WGSL, **kw)
+
+    # roofline denominators (MEASURED_PEAKS.json carries HBM and bf16 only): in-run DFMA / FFMA micro-benchmarks
+    peak64, _ = r.measure_fma_peak(_lib.PRECISION_F64)
+    peak32, _ = r.measure_fma_peak(_lib.PRECISION_F32)
+
+    sampler = ClockSampler(local)
+    params(flags=_lib.FLAG_BUDGET)
+    for _ in range(args.warmup):
+        r.render(cam, phys, readback=False)
+    if rank == 0:
+        sampler.start()
+    # ---- value: frame resident in HBM, budget accounting ----
+    ev_ms, wall_ms, stats = timed_frames(r, cam, phys, args.steps, dist, readback=False)
+    total_steps = allreduce_sum(dist, float(sum(s.steps_executed for s in stats)))
+    launches = sum(s.kernel_launches for s in stats)
+    trace_ms = sum(s.trace_ms for s in stats) / len(stats)
+    gather_ms = sum(s.gather_ms for s in stats) / len(stats)
+    value = total_steps / (ev_ms * 1e-3)
+    # ---- e2e: host buffers every frame ----
+    e_ms, e_wall, e_stats = timed_frames(r, cam, phys, args.steps, dist, readback=True, out=pinned)
+    e_steps = allreduce_sum(dist, float(sum(s.steps_executed for s in e_stats)))
+    e2e = {"value": e_steps / (e_ms * 1e-3), "unit": "steps/s", "h2d_bytes_per_step": int(e_stats[0].h2d_bytes),
+           "d2h_bytes_per_step": int(e_stats[0].d2h_bytes), "ms_per_step": e_ms / args.steps,
+           "wall_ms_per_step": e_wall / args.steps}
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- beside the headline: natural termination, and the f32 instantiation (config-2 arithmetic) ----
+    params(flags=0)
+    n_ms, _, n_stats = timed_frames(r, cam, phys, max(2, args.steps // 3), dist, readback=False)
+    n_steps = allreduce_sum(dist, float(sum(s.steps_committed for s in n_stats)))
+    s0 = n_stats[0]
+    r.params = R.RenderParams(method=_lib.METHOD_SYMPLECTIC, precision=_lib.PRECISION_F32, max_steps=STEPS,
+                              step_rule=_lib.STEP_WGSL, flags=_lib.FLAG_BUDGET)
+    r.render(cam, phys, readback=False)
+    f_ms, _, f_stats = timed_frames(r, cam, phys, max(2, args.steps // 3), dist, readback=False)
+    f_steps = allreduce_sum(dist, float(sum(s.steps_executed for s in f_stats)))
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_sample(15.0)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        fl = FLOP_PER_STEP["symplectic"]
+        # roofline of the dominant kernel (k_trace_tile): per-launch algorithmic flops / per-launch event time.
+        # At N>1 each rank's launch covers its own row block.
+        steps_per_launch = stats[0].steps_executed
+        ach = steps_per_launch * fl / (trace_ms * 1e-3) * 1e-12
+        out = {
+            "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ev_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(world), "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {
+                "bound": "fp64", "kernel": "k_trace_tile<double,symplectic,budget>", "achieved": ach, "peak": peak64,
+                "unit": "TFLOP/s", "frac": ach / peak64, "traffic": None,
+                "peak_source": "in-run DFMA micro-benchmark (gvt_measure_fma_peak; MEASURED_PEAKS.json has no "
+                               "FP32/FP64 entry). The path is FMA-pipe bound, not HBM or tensor: ~0 B read and 16 B "
+                               "written per pixel per 512 steps",
+                "flop_per_step": fl, "steps_per_launch": int(steps_per_launch), "kernel_ms": trace_ms,
+                "frac_of_fp32_peak": ach / peak32, "fp32_peak_tflops": peak32, "fp64_peak_tflops": peak64,
+                "hbm_bytes_per_launch": int(16 * (stats[0].rows_end - stats[0].rows_begin) * W),
+            },
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "extra": {
+                "device": info, "trace_kernel_ms": trace_ms, "all_gather_ms": gather_ms,
+                "natural_termination": {"steps_per_s": n_steps / (n_ms * 1e-3), "ms_per_frame": n_ms / len(n_stats),
+                                        "steps_per_frame_rank0": int(s0.steps_committed),
+                                        "census_rank0": {"horizon": int(s0.n_horizon), "escape": int(s0.n_escape),
+                                                         "max_steps": int(s0.n_maxsteps), "disk_opaque": int(s0.n_disk)}},
+                "f32_budget": {"steps_per_s": f_steps / (f_ms * 1e-3), "ms_per_frame": f_ms / len(f_stats),
+                               "frac_of_fp32_peak": (f_steps / (f_ms * 1e-3)) * fl * 1e-12 / peak32 / world},
+            },
+        }
+        print(json.dumps(out))
+    r.cleanup()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

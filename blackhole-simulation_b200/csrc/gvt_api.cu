@@ -1,0 +1,714 @@
+// gvt_api.cu — the C ABI of libgravitas_b200.so (include/gravitas_b200.h): PhysicsEngine seam + renderer seam.
+// Host-side orchestration only: streams, events, pinned staging, NCCL (dlopen'd), LUT upload. All per-pixel /
+// per-ray arithmetic is in gvt_kernels.cu.
+#include "../../include/gravitas_b200.h"
+#include "gvt_hostmath.h"
+#include "gvt_internal.h"
+
+#include <cuda_fp16.h>
+#include <dlfcn.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+using namespace gvt;
+
+// --------------------------------------------------------------------------------------------------
+// errors
+// --------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int32_t fail(int32_t code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess) return fail(GVT_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* gvt_last_error(void) { return g_err.c_str(); }
+extern "C" int32_t gvt_abi_version(void) { return GVT_ABI_VERSION; }
+extern "C" int32_t gvt_device_count(int32_t* out) {
+    if (!out) return fail(GVT_ERR_INVALID, "null out");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *out = 0; return fail(GVT_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    *out = n;
+    return GVT_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// NCCL through dlopen (so a single-GPU host needs no libnccl at all)
+// --------------------------------------------------------------------------------------------------
+namespace {
+struct NcclId { char internal[128]; };
+typedef struct ncclComm* ncclComm_t_;
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t_*, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t_) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t_, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (handle) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (handle) break; }
+        if (!handle) return false;
+        GetUniqueId = (int (*)(NcclId*))dlsym(handle, "ncclGetUniqueId");
+        CommInitRank = (int (*)(ncclComm_t_*, int, NcclId, int))dlsym(handle, "ncclCommInitRank");
+        CommDestroy = (int (*)(ncclComm_t_))dlsym(handle, "ncclCommDestroy");
+        AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t_, cudaStream_t))dlsym(handle, "ncclAllGather");
+        GetErrorString = (const char* (*)(int))dlsym(handle, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && CommDestroy && AllGather && GetErrorString;
+    }
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat32 = 7;  // ncclDataType_t::ncclFloat32
+}  // namespace
+
+extern "C" int32_t gvt_nccl_unique_id(uint8_t out128[128]) {
+    if (!out128) return fail(GVT_ERR_INVALID, "null out");
+    if (!g_nccl.load()) return fail(GVT_ERR_NCCL, "libnccl.so.2 not loadable: %s", dlerror());
+    NcclId id;
+    int rc = g_nccl.GetUniqueId(&id);
+    if (rc != 0) return fail(GVT_ERR_NCCL, "ncclGetUniqueId: %s", g_nccl.GetErrorString(rc));
+    memcpy(out128, id.internal, 128);
+    return GVT_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// Seam A: PhysicsEngine
+// --------------------------------------------------------------------------------------------------
+struct gvt_engine {
+    double mass, spin;
+    std::vector<float> sab;     // engine-owned 2048 f32 (lib.rs:67)
+    float* ext_sab = nullptr;   // lib.rs:74-76
+    host::CameraState camera, last_good;
+    // device scratch for integrate_rays
+    cudaStream_t stream = nullptr;
+    double* d_in = nullptr; double* d_out = nullptr; double* d_drift = nullptr;
+    uint32_t* d_term = nullptr; uint32_t* d_steps = nullptr; uint32_t* d_rhs = nullptr;
+    uint64_t cap = 0;
+    bool device_ready = false;
+};
+
+extern "C" int32_t gvt_engine_create(double mass, double spin, gvt_engine** out) {
+    if (!out) return fail(GVT_ERR_INVALID, "null out");
+    gvt_engine* e = new (std::nothrow) gvt_engine();
+    if (!e) return fail(GVT_ERR_INVALID, "out of memory");
+    e->mass = mass; e->spin = spin;
+    e->sab.assign(GVT_SAB_INTERNAL_F32, 0.0f);
+    *out = e;
+    return GVT_OK;
+}
+static void engine_free_device(gvt_engine* e) {
+    if (e->d_in) cudaFree(e->d_in);
+    if (e->d_out) cudaFree(e->d_out);
+    if (e->d_drift) cudaFree(e->d_drift);
+    if (e->d_term) cudaFree(e->d_term);
+    if (e->d_steps) cudaFree(e->d_steps);
+    if (e->d_rhs) cudaFree(e->d_rhs);
+    e->d_in = e->d_out = e->d_drift = nullptr; e->d_term = e->d_steps = e->d_rhs = nullptr; e->cap = 0;
+}
+extern "C" int32_t gvt_engine_destroy(gvt_engine* e) {
+    if (!e) return GVT_OK;
+    engine_free_device(e);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return GVT_OK;
+}
+extern "C" int32_t gvt_engine_update_params(gvt_engine* e, double mass, double spin) {
+    if (!e) return fail(GVT_ERR_INVALID, "null engine");
+    e->mass = mass; e->spin = spin;
+    return GVT_OK;
+}
+extern "C" int32_t gvt_engine_attach_sab(gvt_engine* e, float* sab) {
+    if (!e) return fail(GVT_ERR_INVALID, "null engine");
+    e->ext_sab = sab;
+    return GVT_OK;
+}
+extern "C" int32_t gvt_engine_get_sab_ptr(gvt_engine* e, const float** out) {
+    if (!e || !out) return fail(GVT_ERR_INVALID, "null argument");
+    *out = e->sab.data();
+    return GVT_OK;
+}
+extern "C" int32_t gvt_engine_get_sab_layout(gvt_engine* e, uint32_t out5[5]) {
+    if (!e || !out5) return fail(GVT_ERR_INVALID, "null argument");
+    out5[0] = GVT_SAB_OFFSET_CONTROL; out5[1] = GVT_SAB_OFFSET_CAMERA; out5[2] = GVT_SAB_OFFSET_PHYSICS;
+    out5[3] = GVT_SAB_OFFSET_TELEMETRY; out5[4] = GVT_SAB_OFFSET_LUTS;
+    return GVT_OK;
+}
+extern "C" int32_t gvt_engine_set_camera_state(gvt_engine* e, double px, double py, double pz, double, double, double) {
+    if (!e) return fail(GVT_ERR_INVALID, "null engine");
+    e->camera.position = {px, py, pz};  // lib.rs:120-122 sets the position only
+    return GVT_OK;
+}
+extern "C" int32_t gvt_engine_set_auto_spin(gvt_engine* e, int32_t enabled) {
+    if (!e) return fail(GVT_ERR_INVALID, "null engine");
+    e->camera.auto_spin = enabled != 0;
+    return GVT_OK;
+}
+#define ENGINE_SCALAR(NAME, EXPR)                                              \
+    extern "C" int32_t NAME(gvt_engine* e, double* out) {                      \
+        if (!e || !out) return fail(GVT_ERR_INVALID, "null argument");         \
+        host::Hole bh(e->mass, e->spin);                                       \
+        *out = (EXPR);                                                         \
+        return GVT_OK;                                                         \
+    }
+ENGINE_SCALAR(gvt_engine_compute_horizon, bh.horizon())
+ENGINE_SCALAR(gvt_engine_compute_isco, bh.isco(true))
+ENGINE_SCALAR(gvt_engine_compute_photon_sphere, bh.photon_sphere())
+extern "C" int32_t gvt_engine_compute_dilation(gvt_engine* e, double r, double* out) {
+    if (!e || !out) return fail(GVT_ERR_INVALID, "null argument");
+    *out = host::Hole(e->mass, e->spin).dilation(r);
+    return GVT_OK;
+}
+extern "C" int32_t gvt_engine_compute_g_factor(gvt_engine* e, double r, double lambda, double* out) {
+    if (!e || !out) return fail(GVT_ERR_INVALID, "null argument");
+    *out = host::g_factor(r, e->mass, e->spin, lambda);  // lib.rs:203-205 passes the raw (unclamped) spin
+    return GVT_OK;
+}
+extern "C" int32_t gvt_engine_generate_disk_lut(gvt_engine* e, float* out512) {
+    if (!e || !out512) return fail(GVT_ERR_INVALID, "null argument");
+    host::disk_lut(host::Hole(e->mass, e->spin), 512, out512);  // lut_width 512 (lib.rs:65)
+    return GVT_OK;
+}
+extern "C" int32_t gvt_engine_generate_spectrum_lut(gvt_engine* e, uint32_t w, uint32_t h, double max_temp, float* out) {
+    if (!e || !out || w == 0 || h == 0) return fail(GVT_ERR_INVALID, "bad argument");
+    host::spectrum_lut(w, h, max_temp, out);
+    return GVT_OK;
+}
+
+// lib.rs:308-409
+extern "C" int32_t gvt_engine_tick_sab(gvt_engine* e, double dt_override) {
+    if (!e) return fail(GVT_ERR_INVALID, "null engine");
+    float* sab = e->ext_sab ? e->ext_sab : e->sab.data();
+    const double mouse_dx = (double)sab[GVT_SAB_OFFSET_CONTROL + 1];
+    const double mouse_dy = (double)sab[GVT_SAB_OFFSET_CONTROL + 2];
+    const double zoom_delta = (double)sab[GVT_SAB_OFFSET_CONTROL + 3];
+    const double dt = dt_override > 0.0 ? dt_override : (double)sab[GVT_SAB_OFFSET_CONTROL + 4];
+    sab[GVT_SAB_OFFSET_CONTROL + 1] = 0.0f;
+    sab[GVT_SAB_OFFSET_CONTROL + 2] = 0.0f;
+    sab[GVT_SAB_OFFSET_CONTROL + 3] = 0.0f;
+
+    host::update_camera(mouse_dx, mouse_dy, zoom_delta, dt, e->camera);
+    if (!e->camera.valid()) e->camera = e->last_good; else e->last_good = e->camera;
+
+    float* cam = sab + GVT_SAB_OFFSET_CAMERA;
+    cam[0] = (float)e->camera.position.x; cam[1] = (float)e->camera.position.y; cam[2] = (float)e->camera.position.z;
+    cam[4] = (float)e->camera.velocity.x; cam[5] = (float)e->camera.velocity.y; cam[6] = (float)e->camera.velocity.z;
+    cam[8] = (float)e->camera.quat[0]; cam[9] = (float)e->camera.quat[1];
+    cam[10] = (float)e->camera.quat[2]; cam[11] = (float)e->camera.quat[3];
+
+    host::Hole bh(e->mass, e->spin);
+    float* phys = sab + GVT_SAB_OFFSET_PHYSICS;
+    phys[0] = (float)bh.horizon();
+    phys[1] = (float)bh.isco(true);
+    phys[2] = (float)e->mass;
+    phys[3] = (float)e->spin;
+    const host::Vec3 p = e->camera.position;
+    const double r_cam = std::sqrt(p.x * p.x + p.y * p.y + p.z * p.z);
+    if (r_cam > 0.0) {
+        const double theta_obs = std::acos(p.y / r_cam);
+        const auto curve = host::bardeen_shadow(bh, theta_obs, 32);
+        for (int i = 0; i < 128; i++) phys[16 + i] = 0.0f;
+        const size_t np = std::min<size_t>(curve.size(), 64);
+        phys[15] = (float)np;
+        for (size_t i = 0; i < np; i++) { phys[16 + 2 * i] = (float)curve[i].first; phys[16 + 2 * i + 1] = (float)curve[i].second; }
+        double min_a = 0.0, max_a = 0.0;
+        if (!curve.empty()) {
+            min_a = max_a = curve[0].first;
+            for (const auto& c : curve) { if (c.first < min_a) min_a = c.first; if (c.first > max_a) max_a = c.first; }
+        }
+        phys[4] = (float)min_a; phys[5] = (float)max_a;
+    }
+    sab[GVT_SAB_OFFSET_TELEMETRY] += 1.0f;  // lib.rs:407: an f32 increment on the engine's buffer
+    return GVT_OK;
+}
+
+static int32_t engine_ensure_device(gvt_engine* e, uint64_t n) {
+    if (!e->device_ready) {
+        int nd = 0;
+        if (cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0)
+            return fail(GVT_ERR_NO_DEVICE, "no CUDA device: geodesic integration has no CPU path");
+        CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+        e->device_ready = true;
+    }
+    if (n > e->cap) {
+        engine_free_device(e);
+        CK(cudaMalloc(&e->d_in, n * 8 * sizeof(double)));
+        CK(cudaMalloc(&e->d_out, n * 8 * sizeof(double)));
+        CK(cudaMalloc(&e->d_drift, n * sizeof(double)));
+        CK(cudaMalloc(&e->d_term, n * sizeof(uint32_t)));
+        CK(cudaMalloc(&e->d_steps, n * sizeof(uint32_t)));
+        CK(cudaMalloc(&e->d_rhs, n * sizeof(uint32_t)));
+        e->cap = n;
+    }
+    return GVT_OK;
+}
+
+extern "C" int32_t gvt_engine_integrate_rays(gvt_engine* e, const GvtRenderParams* o, uint64_t n, const double* in_xp,
+                                             double* out_xp, uint32_t* term, uint32_t* steps_taken, double* max_drift,
+                                             uint32_t* rhs_evals) {
+    if (!e || !o || !in_xp || !out_xp) return fail(GVT_ERR_INVALID, "null argument");
+    if (n == 0) return GVT_OK;
+    if (o->renormalize_interval == 0) return fail(GVT_ERR_INVALID, "renormalize_interval must be > 0");
+    int32_t rc = engine_ensure_device(e, n);
+    if (rc != GVT_OK) return rc;
+    host::Hole bh(e->mass, e->spin);
+    RayBatchParams p{};
+    p.M = bh.mass; p.a = bh.a(); p.rh = bh.horizon(); p.r_term = p.rh * 1.001; p.escape_r = o->escape_radius;
+    p.tol = o->tolerance; p.h0 = o->initial_step;
+    p.max_steps = o->max_steps; p.renorm_interval = o->renormalize_interval; p.step_rule = o->step_rule;
+    p.method = o->method; p.coords = o->coords; p.n = n;
+    p.in_xp = e->d_in; p.out_xp = e->d_out; p.term = e->d_term; p.steps = e->d_steps; p.drift = e->d_drift; p.rhs = e->d_rhs;
+    CK(cudaMemcpyAsync(e->d_in, in_xp, n * 8 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CK(launch_integrate_rays(p, e->stream));
+    CK(cudaMemcpyAsync(out_xp, e->d_out, n * 8 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (term) CK(cudaMemcpyAsync(term, e->d_term, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    if (steps_taken) CK(cudaMemcpyAsync(steps_taken, e->d_steps, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    if (max_drift) CK(cudaMemcpyAsync(max_drift, e->d_drift, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (rhs_evals) CK(cudaMemcpyAsync(rhs_evals, e->d_rhs, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return GVT_OK;
+}
+
+// lib.rs:422-464
+extern "C" int32_t gvt_engine_integrate_ray(gvt_engine* e, const double in8[8], uint64_t steps, double tolerance,
+                                            int32_t use_ks, double out8[8], uint32_t* term, uint64_t* steps_taken,
+                                            double* max_drift) {
+    if (!e || !in8 || !out8) return fail(GVT_ERR_INVALID, "null argument");
+    GvtRenderParams o{};
+    o.struct_size = sizeof(o);
+    o.method = GVT_METHOD_RKF45; o.precision = GVT_PRECISION_F64;
+    o.coords = use_ks ? GVT_COORDS_KERR_SCHILD : GVT_COORDS_BOYER_LINDQUIST;
+    o.step_rule = GVT_STEP_CONSTANT;
+    o.max_steps = steps > 0xffffffffull ? 0xffffffffu : (uint32_t)steps;
+    o.renormalize_interval = 10; o.tolerance = tolerance; o.initial_step = 0.01; o.escape_radius = 1000.0;
+    uint32_t st = 0;
+    int32_t rc = gvt_engine_integrate_rays(e, &o, 1, in8, out8, term, &st, max_drift, nullptr);
+    if (steps_taken) *steps_taken = st;
+    return rc;
+}
+
+// --------------------------------------------------------------------------------------------------
+// Seam B: renderer
+// --------------------------------------------------------------------------------------------------
+struct gvt_renderer {
+    int device = 0, rank = 0, world = 1, sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint32_t width = 0, height = 0, padded_height = 0, rows_per_rank = 0;
+    float4* cur = nullptr;      // trace output
+    float4* frame = nullptr;    // finished frame of the last call (TAA-resolved and all-gathered)
+    float4* hist = nullptr;     // previous finished frame (TAA history)
+    void* half_frame = nullptr; // RGBA16F staging
+    bool history_valid = false;
+    FrameBlock* d_block = nullptr; FrameBlock* h_block = nullptr;   // device / pinned host
+    Counters* d_counters = nullptr; Counters* h_counters = nullptr;
+    float4* d_spectrum = nullptr; uint32_t spec_w = 0, spec_h = 0;
+    std::vector<float> tdisk; double tdisk_rin = 0.0, tdisk_rout = 0.0;
+    double lut_mass = 0.0, lut_spin = 0.0; bool luts_ready = false;
+    ncclComm_t_ comm = nullptr;
+    float* d_sink = nullptr;
+    // debug buffers for gvt_trace_states
+    double* d_xp = nullptr; double* d_drift = nullptr; double* d_rgba = nullptr; uint32_t* d_term = nullptr; uint32_t* d_steps = nullptr;
+    size_t dbg_cap = 0;
+};
+
+extern "C" int32_t gvt_render_params_default(GvtRenderParams* p) {
+    if (!p) return fail(GVT_ERR_INVALID, "null params");
+    memset(p, 0, sizeof(*p));
+    p->struct_size = sizeof(*p);
+    p->method = GVT_METHOD_SYMPLECTIC; p->precision = GVT_PRECISION_F64; p->coords = GVT_COORDS_KERR_SCHILD;
+    p->step_rule = GVT_STEP_WGSL; p->max_steps = 512; p->renormalize_interval = 10; p->flags = 0;
+    p->output_format = GVT_FORMAT_RGBA32F;
+    p->tolerance = 1e-8; p->initial_step = 0.01; p->escape_radius = 1000.0; p->disk_r_out = 50.0;
+    return GVT_OK;
+}
+
+extern "C" int32_t gvt_render_create(const GvtDeviceConfig* cfg, gvt_renderer** out) {
+    if (!cfg || !out) return fail(GVT_ERR_INVALID, "null argument");
+    int nd = 0;
+    if (cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0)
+        return fail(GVT_ERR_NO_DEVICE, "no CUDA device: the renderer has no CPU path");
+    if (cfg->device < 0 || cfg->device >= nd) return fail(GVT_ERR_INVALID, "device %d out of range (%d devices)", cfg->device, nd);
+    if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) return fail(GVT_ERR_INVALID, "bad rank/world_size");
+    CK(cudaSetDevice(cfg->device));
+    gvt_renderer* r = new (std::nothrow) gvt_renderer();
+    if (!r) return fail(GVT_ERR_INVALID, "out of memory");
+    r->device = cfg->device; r->rank = cfg->rank; r->world = cfg->world_size;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    r->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        delete r;
+        return fail(GVT_ERR_UNSUPPORTED, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+    }
+    CK(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+    for (auto& e : r->ev) CK(cudaEventCreate(&e));
+    CK(cudaMalloc(&r->d_block, sizeof(FrameBlock)));
+    CK(cudaMallocHost(&r->h_block, sizeof(FrameBlock)));
+    CK(cudaMalloc(&r->d_counters, sizeof(Counters)));
+    CK(cudaMallocHost(&r->h_counters, sizeof(Counters)));
+    CK(cudaMalloc(&r->d_sink, 256));
+    if (r->world > 1) {
+        if (!g_nccl.load()) { return fail(GVT_ERR_NCCL, "libnccl.so.2 not loadable: %s", dlerror()); }
+        NcclId id;
+        memcpy(id.internal, cfg->nccl_id, 128);
+        int rc = g_nccl.CommInitRank(&r->comm, r->world, id, r->rank);
+        if (rc != 0) return fail(GVT_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(rc));
+    }
+    *out = r;
+    return GVT_OK;
+}
+
+static void free_frames(gvt_renderer* r) {
+    if (r->cur) cudaFree(r->cur);
+    if (r->frame) cudaFree(r->frame);
+    if (r->hist) cudaFree(r->hist);
+    if (r->half_frame) cudaFree(r->half_frame);
+    r->cur = r->frame = r->hist = nullptr; r->half_frame = nullptr;
+}
+
+extern "C" int32_t gvt_render_destroy(gvt_renderer* r) {
+    if (!r) return GVT_OK;
+    cudaSetDevice(r->device);
+    if (r->stream) cudaStreamSynchronize(r->stream);
+    if (r->comm) g_nccl.CommDestroy(r->comm);
+    free_frames(r);
+    if (r->d_block) cudaFree(r->d_block);
+    if (r->h_block) cudaFreeHost(r->h_block);
+    if (r->d_counters) cudaFree(r->d_counters);
+    if (r->h_counters) cudaFreeHost(r->h_counters);
+    if (r->d_spectrum) cudaFree(r->d_spectrum);
+    if (r->d_sink) cudaFree(r->d_sink);
+    if (r->d_xp) cudaFree(r->d_xp);
+    if (r->d_drift) cudaFree(r->d_drift);
+    if (r->d_rgba) cudaFree(r->d_rgba);
+    if (r->d_term) cudaFree(r->d_term);
+    if (r->d_steps) cudaFree(r->d_steps);
+    for (auto& e : r->ev) if (e) cudaEventDestroy(e);
+    if (r->stream) cudaStreamDestroy(r->stream);
+    delete r;
+    return GVT_OK;
+}
+
+extern "C" int32_t gvt_render_set_luts(gvt_renderer* r, const float* spectrum, uint32_t w, uint32_t h, const float* tdisk,
+                                       uint32_t n, double rin, double rout) {
+    if (!r || !spectrum || !tdisk || w == 0 || h == 0) return fail(GVT_ERR_INVALID, "bad argument");
+    if (n != 512) return fail(GVT_ERR_INVALID, "disk LUT must have 512 entries (lib.rs:65), got %u", n);
+    CK(cudaSetDevice(r->device));
+    if (r->d_spectrum) { CK(cudaFree(r->d_spectrum)); r->d_spectrum = nullptr; }
+    CK(cudaMalloc(&r->d_spectrum, (size_t)w * h * sizeof(float4)));
+    CK(cudaMemcpy(r->d_spectrum, spectrum, (size_t)w * h * sizeof(float4), cudaMemcpyHostToDevice));
+    r->spec_w = w; r->spec_h = h;
+    r->tdisk.assign(tdisk, tdisk + n);
+    r->tdisk_rin = rin; r->tdisk_rout = rout;
+    r->luts_ready = true;
+    return GVT_OK;
+}
+
+extern "C" int32_t gvt_render_init_luts(gvt_renderer* r, double mass, double spin, uint32_t w, uint32_t h, double max_temp) {
+    if (!r || w == 0 || h == 0) return fail(GVT_ERR_INVALID, "bad argument");
+    std::vector<float> spec((size_t)w * h * 4), td(512);
+    host::spectrum_lut(w, h, max_temp, spec.data());
+    host::Hole bh(mass, spin);
+    host::disk_lut(bh, 512, td.data());
+    int32_t rc = gvt_render_set_luts(r, spec.data(), w, h, td.data(), 512, bh.isco(true), 50.0 * bh.mass);
+    if (rc == GVT_OK) { r->lut_mass = mass; r->lut_spin = spin; }
+    return rc;
+}
+
+extern "C" int32_t gvt_render_resize(gvt_renderer* r, uint32_t width, uint32_t height) {
+    if (!r || width == 0 || height == 0) return fail(GVT_ERR_INVALID, "bad argument");
+    if (r->width == width && r->height == height && r->cur) return GVT_OK;
+    CK(cudaSetDevice(r->device));
+    CK(cudaStreamSynchronize(r->stream));
+    free_frames(r);
+    r->width = width; r->height = height;
+    r->rows_per_rank = (height + r->world - 1) / r->world;
+    r->padded_height = r->rows_per_rank * r->world;  // all-gather needs equal blocks
+    const size_t bytes = (size_t)width * r->padded_height * sizeof(float4);
+    CK(cudaMalloc(&r->cur, bytes));
+    CK(cudaMalloc(&r->frame, bytes));
+    CK(cudaMalloc(&r->hist, bytes));
+    CK(cudaMemsetAsync(r->cur, 0, bytes, r->stream));
+    CK(cudaMemsetAsync(r->frame, 0, bytes, r->stream));
+    CK(cudaMemsetAsync(r->hist, 0, bytes, r->stream));  // WebGPU textures start zeroed: so does the history
+    r->history_valid = false;
+    return GVT_OK;
+}
+
+extern "C" int32_t gvt_render_reset_history(gvt_renderer* r) {
+    if (!r) return fail(GVT_ERR_INVALID, "null renderer");
+    if (r->hist) CK(cudaMemsetAsync(r->hist, 0, (size_t)r->width * r->padded_height * sizeof(float4), r->stream));
+    r->history_valid = false;
+    return GVT_OK;
+}
+
+// compute.wgsl.ts:135-145
+static double halton(uint32_t index, uint32_t base) {
+    double result = 0.0, f = 1.0 / (double)base;
+    for (uint32_t i = index; i > 0u; i /= base) { result += f * (double)(i % base); f = f / (double)base; }
+    return result;
+}
+
+// Fill the TMA-staged block and the kernel parameters from the reference-layout uniforms.
+static int32_t build_frame(gvt_renderer* r, const GvtCamera* cam, const GvtPhysicsParams* phys, const GvtRenderParams* rp,
+                           FrameParams& P) {
+    if (!r->luts_ready) return fail(GVT_ERR_INVALID, "LUTs not initialised: call gvt_render_init_luts / gvt_render_set_luts first");
+    if (rp->coords != GVT_COORDS_KERR_SCHILD)
+        return fail(GVT_ERR_UNSUPPORTED, "the render path traces in Kerr-Schild coordinates (lib.rs:64,454); use gvt_engine_integrate_rays for Boyer-Lindquist");
+    if (rp->method > GVT_METHOD_SYMPLECTIC || rp->precision > GVT_PRECISION_F32) return fail(GVT_ERR_INVALID, "bad method/precision");
+    if (rp->renormalize_interval == 0) return fail(GVT_ERR_INVALID, "renormalize_interval must be > 0");
+    const uint32_t W = (uint32_t)phys->resolution[0], H = (uint32_t)phys->resolution[1];
+    if (W == 0 || H == 0) return fail(GVT_ERR_INVALID, "zero resolution");
+    host::Hole bh((double)phys->mass, (double)phys->spin);
+    FrameBlock* b = r->h_block;
+    for (int i = 0; i < 16; i++) { b->inv_proj[i] = (double)cam->inv_proj[i]; b->inv_view[i] = (double)cam->inv_view[i]; }
+    const double cx = (double)cam->position[0], cy = (double)cam->position[1], cz = (double)cam->position[2];
+    b->r0 = std::sqrt(cx * cx + cy * cy + cz * cz);
+    if (!(b->r0 > 0.0)) return fail(GVT_ERR_INVALID, "camera at the origin");
+    b->theta0 = std::acos(std::min(1.0, std::max(-1.0, cy / b->r0)));
+    b->phi0 = std::atan2(cz, cx);
+    b->st = std::sin(b->theta0); b->ct = std::cos(b->theta0); b->sp = std::sin(b->phi0); b->cp = std::cos(b->phi0);
+    b->safe_st = std::max(b->st, 1e-4);
+    b->inv_width = 1.0 / (double)W; b->inv_height = 1.0 / (double)H;
+    b->jx = b->jy = 0.0;
+    if (rp->flags & GVT_FLAG_JITTER) {
+        b->jx = (halton((phys->frame_index % 8u) + 1u, 2u) - 0.5) / (double)W;
+        b->jy = (halton((phys->frame_index % 8u) + 1u, 3u) - 0.5) / (double)H;
+    }
+    memcpy(b->tdisk, r->tdisk.data(), 512 * sizeof(float));
+
+    memset(&P, 0, sizeof(P));
+    P.M = bh.mass; P.a = bh.a(); P.spin = bh.spin; P.rh = bh.horizon(); P.r_term = P.rh * 1.001;
+    P.escape_r = rp->escape_radius; P.r_in = bh.isco(true); P.r_out = rp->disk_r_out;
+    P.tol = rp->tolerance; P.h0 = rp->initial_step;
+    P.tdisk_rin = r->tdisk_rin; P.tdisk_scale = 511.0 / (r->tdisk_rout - r->tdisk_rin);
+    P.width = W; P.height = H;
+    P.max_steps = rp->max_steps; P.renorm_interval = rp->renormalize_interval; P.step_rule = rp->step_rule;
+    P.tdisk_n = 512; P.spec_w = r->spec_w; P.spec_h = r->spec_h;
+    P.lut_in_smem = ((size_t)r->spec_w * r->spec_h * sizeof(float4) <= kMaxSmemLutBytes) ? 1u : 0u;
+    P.block = r->d_block; P.spectrum = r->d_spectrum; P.counters = r->d_counters;
+    return GVT_OK;
+}
+
+static void fill_taa(const GvtCamera* cam, uint32_t W, uint32_t H, TaaParams& T) {
+    memcpy(T.inv_proj, cam->inv_proj, 64); memcpy(T.inv_view, cam->inv_view, 64);
+    memcpy(T.prev_view_proj, cam->prev_view_proj, 64); memcpy(T.cam_pos, cam->position, 16);
+    T.width = W; T.height = H; T.row0 = 0; T.row1 = H;
+}
+
+extern "C" int32_t gvt_render_read_frame(gvt_renderer* r, uint32_t format, void* host_rgba) {
+    if (!r || !host_rgba || !r->frame) return fail(GVT_ERR_INVALID, "bad argument / no frame");
+    CK(cudaSetDevice(r->device));
+    const size_t n_px = (size_t)r->width * r->height;
+    if (format == GVT_FORMAT_RGBA16F) {
+        if (!r->half_frame) CK(cudaMalloc(&r->half_frame, n_px * 8));
+        CK(launch_f32_to_f16(r->frame, r->half_frame, n_px, r->stream));
+        CK(cudaMemcpyAsync(host_rgba, r->half_frame, n_px * 8, cudaMemcpyDeviceToHost, r->stream));
+    } else {
+        CK(cudaMemcpyAsync(host_rgba, r->frame, n_px * sizeof(float4), cudaMemcpyDeviceToHost, r->stream));
+    }
+    CK(cudaStreamSynchronize(r->stream));
+    return GVT_OK;
+}
+
+// webgpu/renderer.ts:280-411 render(camera, physics)
+extern "C" int32_t gvt_render_frame(gvt_renderer* r, const GvtCamera* cam, const GvtPhysicsParams* phys,
+                                    const GvtRenderParams* rp, void* host_rgba, GvtFrameStats* stats) {
+    if (!r || !cam || !phys || !rp) return fail(GVT_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(r->device));
+    const uint32_t W = (uint32_t)phys->resolution[0], H = (uint32_t)phys->resolution[1];
+    if (W != r->width || H != r->height || !r->cur) {  // renderer.ts:281-284
+        int32_t rc = gvt_render_resize(r, W, H);
+        if (rc != GVT_OK) return rc;
+    }
+    FrameParams P;
+    int32_t rc = build_frame(r, cam, phys, rp, P);
+    if (rc != GVT_OK) return rc;
+    const bool taa = (rp->flags & GVT_FLAG_TAA) != 0;
+    const bool budget = (rp->flags & GVT_FLAG_BUDGET) != 0 && rp->method != GVT_METHOD_RKF45;
+    const uint32_t row0 = std::min(H, (uint32_t)r->rank * r->rows_per_rank);
+    const uint32_t row1 = std::min(H, row0 + r->rows_per_rank);
+    // TAA needs a one-pixel halo of the current frame: trace one redundant row above and below the block
+    const uint32_t ty0 = (taa && row0 > 0) ? row0 - 1 : row0, ty1 = (taa && row1 < H) ? row1 + 1 : row1;
+    P.x0 = 0; P.xs = 1; P.y0 = ty0; P.y1 = ty1; P.ys = 1; P.nx = W; P.ny = ty1 - ty0;
+    if (taa && r->history_valid) std::swap(r->frame, r->hist);  // last finished frame becomes the history
+    float4* trace_out = taa ? r->cur : r->frame;
+    P.frame = trace_out;
+    uint32_t launches = 0;
+    uint64_t h2d = 0, d2h = 0;
+
+    CK(cudaEventRecord(r->ev[0], r->stream));
+    CK(cudaMemcpyAsync(r->d_block, r->h_block, sizeof(FrameBlock), cudaMemcpyHostToDevice, r->stream));
+    h2d += sizeof(FrameBlock);
+    CK(cudaMemsetAsync(r->d_counters, 0, sizeof(Counters), r->stream));
+    CK(cudaEventRecord(r->ev[1], r->stream));
+    if (P.ny > 0) { CK(launch_trace(P, rp->method, rp->precision, budget, false, r->sm_count, r->stream)); launches++; }
+    CK(cudaEventRecord(r->ev[2], r->stream));
+    if (taa && row1 > row0) {
+        TaaParams T;
+        fill_taa(cam, W, H, T);
+        T.cur = r->cur; T.hist = r->hist; T.out = r->frame;
+        T.row0 = row0; T.row1 = row1;
+        CK(launch_taa(T, r->stream));
+        launches++;
+    }
+    CK(cudaEventRecord(r->ev[3], r->stream));
+    if (r->world > 1 && !(rp->flags & GVT_FLAG_NO_GATHER)) {
+        const size_t count = (size_t)r->rows_per_rank * W * 4;  // floats per rank block
+        int nrc = g_nccl.AllGather(reinterpret_cast<const float*>(r->frame) + (size_t)r->rank * count, r->frame, count,
+                                   kNcclFloat32, r->comm, r->stream);
+        if (nrc != 0) return fail(GVT_ERR_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString(nrc));
+    }
+    CK(cudaEventRecord(r->ev[4], r->stream));
+    CK(cudaMemcpyAsync(r->h_counters, r->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, r->stream));
+    d2h += sizeof(Counters);
+    if (host_rgba) {
+        const size_t n_px = (size_t)W * H;
+        if (rp->output_format == GVT_FORMAT_RGBA16F) {
+            if (!r->half_frame) CK(cudaMalloc(&r->half_frame, n_px * 8));
+            CK(launch_f32_to_f16(r->frame, r->half_frame, n_px, r->stream));
+            launches++;
+            CK(cudaMemcpyAsync(host_rgba, r->half_frame, n_px * 8, cudaMemcpyDeviceToHost, r->stream));
+            d2h += n_px * 8;
+        } else {
+            CK(cudaMemcpyAsync(host_rgba, r->frame, n_px * sizeof(float4), cudaMemcpyDeviceToHost, r->stream));
+            d2h += n_px * sizeof(float4);
+        }
+    }
+    CK(cudaEventRecord(r->ev[5], r->stream));
+    CK(cudaStreamSynchronize(r->stream));
+    if (taa) r->history_valid = true;
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r->ev[1], r->ev[2]); stats->trace_ms = ms;
+        cudaEventElapsedTime(&ms, r->ev[2], r->ev[3]); stats->taa_ms = taa ? ms : 0.0;
+        cudaEventElapsedTime(&ms, r->ev[3], r->ev[4]); stats->gather_ms = (r->world > 1) ? ms : 0.0;
+        cudaEventElapsedTime(&ms, r->ev[0], r->ev[5]); stats->total_ms = ms;
+        const Counters& c = *r->h_counters;
+        stats->steps_committed = c.steps_committed; stats->steps_executed = c.steps_executed; stats->rhs_evals = c.rhs_evals;
+        stats->n_horizon = c.n_horizon; stats->n_escape = c.n_escape; stats->n_maxsteps = c.n_maxsteps; stats->n_disk = c.n_disk;
+        stats->h2d_bytes = h2d; stats->d2h_bytes = d2h; stats->kernel_launches = launches;
+        stats->rows_begin = row0; stats->rows_end = row1;
+    }
+    return GVT_OK;
+}
+
+static int32_t ensure_dbg(gvt_renderer* r, size_t n) {
+    if (n <= r->dbg_cap) return GVT_OK;
+    if (r->d_xp) cudaFree(r->d_xp);
+    if (r->d_drift) cudaFree(r->d_drift);
+    if (r->d_rgba) cudaFree(r->d_rgba);
+    if (r->d_term) cudaFree(r->d_term);
+    if (r->d_steps) cudaFree(r->d_steps);
+    r->d_xp = r->d_drift = r->d_rgba = nullptr; r->d_term = r->d_steps = nullptr; r->dbg_cap = 0;
+    CK(cudaMalloc(&r->d_xp, n * 8 * sizeof(double)));
+    CK(cudaMalloc(&r->d_drift, n * sizeof(double)));
+    CK(cudaMalloc(&r->d_rgba, n * 4 * sizeof(double)));
+    CK(cudaMalloc(&r->d_term, n * sizeof(uint32_t)));
+    CK(cudaMalloc(&r->d_steps, n * sizeof(uint32_t)));
+    r->dbg_cap = n;
+    return GVT_OK;
+}
+
+extern "C" int32_t gvt_trace_states(gvt_renderer* r, const GvtCamera* cam, const GvtPhysicsParams* phys,
+                                    const GvtRenderParams* rp, uint32_t x0, uint32_t xs, uint32_t y0, uint32_t y1,
+                                    uint32_t ys, double* out_xp8, uint32_t* term, uint32_t* steps, double* max_drift,
+                                    double* rgba64) {
+    if (!r || !cam || !phys || !rp) return fail(GVT_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(r->device));
+    FrameParams P;
+    int32_t rc = build_frame(r, cam, phys, rp, P);
+    if (rc != GVT_OK) return rc;
+    if (xs == 0 || ys == 0 || x0 >= P.width || y1 > P.height || y0 >= y1) return fail(GVT_ERR_INVALID, "bad pixel lattice");
+    P.x0 = x0; P.xs = xs; P.y0 = y0; P.y1 = y1; P.ys = ys;
+    P.nx = (P.width - x0 + xs - 1) / xs; P.ny = (y1 - y0 + ys - 1) / ys;
+    const size_t n = (size_t)P.nx * P.ny;
+    rc = ensure_dbg(r, n);
+    if (rc != GVT_OK) return rc;
+    P.frame = nullptr;
+    P.dbg_xp = r->d_xp; P.dbg_term = r->d_term; P.dbg_steps = r->d_steps; P.dbg_drift = r->d_drift; P.dbg_rgba = r->d_rgba;
+    const bool budget = (rp->flags & GVT_FLAG_BUDGET) != 0 && rp->method != GVT_METHOD_RKF45;
+    CK(cudaMemcpyAsync(r->d_block, r->h_block, sizeof(FrameBlock), cudaMemcpyHostToDevice, r->stream));
+    CK(cudaMemsetAsync(r->d_counters, 0, sizeof(Counters), r->stream));
+    CK(launch_trace(P, rp->method, rp->precision, budget, true, r->sm_count, r->stream));
+    if (out_xp8) CK(cudaMemcpyAsync(out_xp8, r->d_xp, n * 8 * sizeof(double), cudaMemcpyDeviceToHost, r->stream));
+    if (term) CK(cudaMemcpyAsync(term, r->d_term, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, r->stream));
+    if (steps) CK(cudaMemcpyAsync(steps, r->d_steps, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, r->stream));
+    if (max_drift) CK(cudaMemcpyAsync(max_drift, r->d_drift, n * sizeof(double), cudaMemcpyDeviceToHost, r->stream));
+    if (rgba64) CK(cudaMemcpyAsync(rgba64, r->d_rgba, n * 4 * sizeof(double), cudaMemcpyDeviceToHost, r->stream));
+    CK(cudaStreamSynchronize(r->stream));
+    return GVT_OK;
+}
+
+extern "C" int32_t gvt_taa_resolve(gvt_renderer* r, const GvtCamera* cam, uint32_t width, uint32_t height, const float* cur,
+                                   const float* hist, float* out) {
+    if (!r || !cam || !cur || !hist || !out || width == 0 || height == 0) return fail(GVT_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(r->device));
+    const size_t bytes = (size_t)width * height * sizeof(float4);
+    float4 *d_cur = nullptr, *d_hist = nullptr, *d_out = nullptr;
+    CK(cudaMalloc(&d_cur, bytes)); CK(cudaMalloc(&d_hist, bytes)); CK(cudaMalloc(&d_out, bytes));
+    CK(cudaMemcpyAsync(d_cur, cur, bytes, cudaMemcpyHostToDevice, r->stream));
+    CK(cudaMemcpyAsync(d_hist, hist, bytes, cudaMemcpyHostToDevice, r->stream));
+    TaaParams T;
+    fill_taa(cam, width, height, T);
+    T.cur = d_cur; T.hist = d_hist; T.out = d_out;
+    CK(launch_taa(T, r->stream));
+    CK(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, r->stream));
+    CK(cudaStreamSynchronize(r->stream));
+    cudaFree(d_cur); cudaFree(d_hist); cudaFree(d_out);
+    return GVT_OK;
+}
+
+extern "C" int32_t gvt_host_alloc(size_t bytes, void** out) {
+    if (!out || bytes == 0) return fail(GVT_ERR_INVALID, "bad argument");
+    CK(cudaMallocHost(out, bytes));
+    return GVT_OK;
+}
+extern "C" int32_t gvt_host_free(void* p) {
+    if (p) CK(cudaFreeHost(p));
+    return GVT_OK;
+}
+
+extern "C" int32_t gvt_measure_fma_peak(gvt_renderer* r, int32_t precision, double* out_tflops, double* out_ms) {
+    if (!r || !out_tflops) return fail(GVT_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(r->device));
+    double flops = 0.0;
+    // warm-up, then a launch long enough (tens of ms) for the clocks to settle
+    CK(launch_fma_peak(precision, r->sm_count, 2000, r->d_sink, r->stream, &flops));
+    const unsigned long long iters = precision == GVT_PRECISION_F32 ? 400000ull : 200000ull;
+    CK(cudaEventRecord(r->ev[0], r->stream));
+    CK(launch_fma_peak(precision, r->sm_count, iters, r->d_sink, r->stream, &flops));
+    CK(cudaEventRecord(r->ev[1], r->stream));
+    CK(cudaStreamSynchronize(r->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, r->ev[0], r->ev[1]));
+    *out_tflops = flops / ((double)ms * 1e-3) * 1e-12;
+    if (out_ms) *out_ms = ms;
+    return GVT_OK;
+}
+
+extern "C" int32_t gvt_device_info(gvt_renderer* r, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, char name[256]) {
+    if (!r) return fail(GVT_ERR_INVALID, "null renderer");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, r->device));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (name) { strncpy(name, prop.name, 255); name[255] = 0; }
+    return GVT_OK;
+}

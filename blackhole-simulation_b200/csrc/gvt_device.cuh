@@ -1,0 +1,382 @@
+// gvt_device.cuh — device-side Kerr geodesic mathematics for sm_100a, templated on the scalar type.
+//
+// This is NOT a transcription of the reference's Rust: the Hamiltonian is refactored so that one RHS
+// evaluation costs two reciprocals, one sincos and ~50 FMA-shaped flops instead of the 16 divisions / 3 trig
+// calls / 129 flops of the as-written form (metric/kerr.rs:412-499 + geodesic/hamiltonian.rs:13-35):
+//
+//   Kerr-Schild form used by the reference:   H = -pt^2/2 + N / (2 Sigma)
+//       N = 2Mr (2 pt pr - pt^2) + Delta pr^2 + pth^2 + pph^2 / sin^2 + 2 a pr pph
+//       dH/dr  = (N_r/2 - r N/Sigma) / Sigma,          N_r/2  = M (2 pt pr - pt^2) + (r - M) pr^2
+//       dH/dth = (N_th/2 + a^2 s c N/Sigma) / Sigma,   N_th/2 = - s c pph^2 / sin^4
+//   with p_t and p_phi constants of the motion (dp_t = dp_phi = 0, hamiltonian.rs:30-33), so everything
+//   built from them is hoisted out of the step loop.
+//
+// Results agree with the reference's formulas to rounding; parity against the f64 oracle is tested to 1e-6
+// relative per RGBA component (tests/test_gpu_parity.py).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gvt {
+
+// --------------------------------------------------------------------------------------------------
+// scalar traits
+// --------------------------------------------------------------------------------------------------
+template <class R> struct Num;
+template <> struct Num<double> {
+    static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+    static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+    static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
+    static __device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
+    static __device__ __forceinline__ double min_(double a, double b) { return fmin(a, b); }
+    static __device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
+    static __device__ __forceinline__ void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
+    static __device__ __forceinline__ double pow_(double a, double b) { return pow(a, b); }
+    static __device__ __forceinline__ double floor_(double a) { return floor(a); }
+};
+template <> struct Num<float> {
+    static __device__ __forceinline__ float rcp(float x) { return 1.0f / x; }
+    static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
+    static __device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
+    static __device__ __forceinline__ float min_(float a, float b) { return fminf(a, b); }
+    static __device__ __forceinline__ float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+    static __device__ __forceinline__ void sincos_(float x, float* s, float* c) { sincosf(x, s, c); }
+    static __device__ __forceinline__ float pow_(float a, float b) { return powf(a, b); }
+    static __device__ __forceinline__ float floor_(float a) { return floorf(a); }
+};
+
+template <class R> __device__ __forceinline__ R clampR(R x, R lo, R hi) {
+    return Num<R>::min_(Num<R>::max_(x, lo), hi);
+}
+
+// --------------------------------------------------------------------------------------------------
+// Per-ray state. t (x[0]) is carried only when WITH_T (the parity hook); p_t and p_phi are constants.
+// --------------------------------------------------------------------------------------------------
+template <class R>
+struct Ray {
+    R t, r, th, ph;  // x^mu
+    R pr, pth;       // the two evolving momenta
+};
+template <class R>
+struct Deriv {
+    R dt, dr, dth, dph, dpr, dpth;
+};
+
+// Constants of the hole + of the ray (p_t, p_phi and products), hoisted out of the loop.
+template <class R>
+struct HoleRay {
+    R M, a, a2, twoM;
+    R pt, pph;
+    R pt2, pph2, two_pt, two_a_pph, a_pph;
+    __device__ __forceinline__ void set_hole(R M_, R a_) { M = M_; a = a_; a2 = a_ * a_; twoM = R(2) * M_; }
+    __device__ __forceinline__ void set_ray(R pt_, R pph_) {
+        pt = pt_; pph = pph_; pt2 = pt_ * pt_; pph2 = pph_ * pph_; two_pt = R(2) * pt_;
+        a_pph = a * pph_; two_a_pph = R(2) * a_pph;
+    }
+};
+
+// One Hamiltonian RHS in the reference's Kerr-Schild form (kerr.rs:412-499, hamiltonian.rs:13-35).
+// sin^2 is clamped at 1e-12 (kerr.rs:417,448); dH/dtheta is zeroed when |sin| < 1e-10 (kerr.rs:494-496).
+template <class R, bool WITH_T>
+__device__ __forceinline__ Deriv<R> rhs_ks(const HoleRay<R>& c, R r, R s, R cth, R pr, R pth) {
+    using N = Num<R>;
+    const R sin2 = N::max_(s * s, R(1e-12));
+    const R w = N::rcp(sin2);                       // 1/sin^2
+    const R cos2 = R(1) - sin2;
+    const R r2 = r * r;
+    const R sigma = N::fma_(c.a2, cos2, r2);
+    const R delta = N::fma_(-c.twoM, r, r2 + c.a2);
+    const R isig = N::rcp(sigma);
+    const R twoMr = c.twoM * r;
+    const R A1 = c.pph2 * w;                        // pph^2 / sin^2
+    const R K = N::fma_(c.two_pt, pr, -c.pt2);      // 2 pt pr - pt^2
+    const R pr2 = pr * pr;
+    // N = 2Mr K + Delta pr^2 + pth^2 + A1 + 2 a pph pr
+    R Nn = N::fma_(twoMr, K, A1);
+    Nn = N::fma_(delta, pr2, Nn);
+    Nn = N::fma_(pth, pth, Nn);
+    Nn = N::fma_(c.two_a_pph, pr, Nn);
+    const R q = Nn * isig;
+    const R halfNr = N::fma_(r - c.M, pr2, c.M * K);
+    const R dHdr = N::fma_(-r, q, halfNr) * isig;
+    const R sc = s * cth;
+    const R halfNth = -(sc * A1) * w;
+    R dHdth = N::fma_(c.a2 * sc, q, halfNth) * isig;
+    if (N::abs_(s) < R(1e-10)) dHdth = R(0);
+    Deriv<R> d;
+    d.dr = N::fma_(delta, pr, N::fma_(twoMr, c.pt, c.a_pph)) * isig;
+    d.dth = pth * isig;
+    d.dph = N::fma_(c.pph, w, c.a * pr) * isig;
+    d.dpr = -dHdr;
+    d.dpth = -dHdth;
+    if (WITH_T) d.dt = N::fma_(twoMr * isig, pr - c.pt, -c.pt); else d.dt = R(0);
+    return d;
+}
+
+// Boyer-Lindquist form (kerr.rs:266-372): H = (P/D + Q/Sigma)/2 with D = Delta Sigma,
+//   P = -U pt^2 - 4 M r a pt pph - a^2 pph^2,  U = Sigma (r^2+a^2) + 2 M r a^2 sin^2,
+//   Q = Delta pr^2 + pth^2 + pph^2/sin^2.   g^phph is gated to 0 when sin^2 < 1e-9 (kerr.rs:282-286).
+template <class R, bool WITH_T>
+__device__ __forceinline__ Deriv<R> rhs_bl(const HoleRay<R>& c, R r, R s, R cth, R pr, R pth) {
+    using N = Num<R>;
+    const R sin2 = s * s;
+    const R cos2 = cth * cth;
+    const R r2 = r * r;
+    const R sigma = N::fma_(c.a2, cos2, r2);
+    const R delta = N::fma_(-c.twoM, r, r2 + c.a2);
+    const R ra2 = r2 + c.a2;
+    const R D = delta * sigma;
+    const R iD = N::rcp(D);
+    const R isig = N::rcp(sigma);
+    const R w = N::rcp(sin2);
+    const R twoMr = c.twoM * r;
+    const R U = N::fma_(twoMr * c.a2, sin2, sigma * ra2);
+    const R cross = R(2) * twoMr * c.a * c.pt * c.pph;   // 4 M r a pt pph
+    const R P = -(U * c.pt2) - cross - c.a2 * c.pph2;
+    const R pr2 = pr * pr;
+    const R A1 = c.pph2 * w;
+    const R Q = N::fma_(delta, pr2, N::fma_(pth, pth, A1));
+    const R sc = s * cth;
+    // radial derivatives
+    const R dDelta = R(2) * r - c.twoM;
+    const R Ur = R(2) * r * ra2 + sigma * (R(2) * r) + c.twoM * c.a2 * sin2;
+    const R Dr = dDelta * sigma + delta * (R(2) * r);
+    const R Pr = -(Ur * c.pt2) - R(2) * c.twoM * c.a * c.pt * c.pph;
+    const R Qr = dDelta * pr2;
+    const R dHdr = R(0.5) * ((Pr * D - P * Dr) * (iD * iD) + (Qr * sigma - Q * (R(2) * r)) * (isig * isig));
+    // polar derivatives
+    const R Sth = R(-2) * c.a2 * sc;
+    const R Uth = Sth * ra2 + twoMr * c.a2 * (R(2) * sc);
+    const R Dth = delta * Sth;
+    const R Pth = -(Uth * c.pt2);
+    const R Qth = R(-2) * sc * A1 * w;
+    const R dHdth = R(0.5) * ((Pth * D - P * Dth) * (iD * iD) + (Qth * sigma - Q * Sth) * (isig * isig));
+    const R g_tph = -(twoMr * c.a) * iD;
+    const R g_phph = (sin2 < R(1e-9)) ? R(0) : (delta - c.a2 * sin2) * iD * w;
+    Deriv<R> d;
+    d.dr = delta * isig * pr;
+    d.dth = pth * isig;
+    d.dph = g_tph * c.pt + g_phph * c.pph;
+    d.dpr = -dHdr;
+    d.dpth = -dHdth;
+    if (WITH_T) d.dt = -(U * iD) * c.pt + g_tph * c.pph; else d.dt = R(0);
+    return d;
+}
+
+template <class R, int COORDS, bool WITH_T>
+__device__ __forceinline__ Deriv<R> rhs_at(const HoleRay<R>& c, R r, R th, R pr, R pth) {
+    R s, cth;
+    Num<R>::sincos_(th, &s, &cth);
+    if (COORDS == 1) return rhs_ks<R, WITH_T>(c, r, s, cth, pr, pth);
+    return rhs_bl<R, WITH_T>(c, r, s, cth, pr, pth);
+}
+
+// The quadratic of invariants/renormalization.rs:13-45 and H of invariants/mod.rs:25-37 share the metric
+// evaluation; `want` selects what to produce.
+template <class R, int COORDS>
+__device__ __forceinline__ void null_quadratic(const HoleRay<R>& c, R r, R th, R pth, R& A, R& B, R& C) {
+    using N = Num<R>;
+    R s, cth;
+    N::sincos_(th, &s, &cth);
+    const R r2 = r * r;
+    const R delta = N::fma_(-c.twoM, r, r2 + c.a2);
+    if (COORDS == 1) {
+        const R sin2 = N::max_(s * s, R(1e-12));
+        const R cos2 = R(1) - sin2;
+        const R sigma = N::fma_(c.a2, cos2, r2);
+        const R isig = N::rcp(sigma);
+        const R twoMr = c.twoM * r;
+        A = delta * isig;                                              // g^rr
+        B = R(2) * isig * N::fma_(twoMr, c.pt, c.a_pph);                // 2 (g^tr pt + g^rph pph)
+        // g^tt pt^2 + g^thth pth^2 + g^phph pph^2
+        C = N::fma_(isig, N::fma_(-twoMr, c.pt2, N::fma_(pth, pth, c.pph2 / sin2)), -c.pt2);
+    } else {
+        const R sin2 = s * s;
+        const R cos2 = cth * cth;
+        const R sigma = N::fma_(c.a2, cos2, r2);
+        const R isig = N::rcp(sigma);
+        const R D = delta * sigma;
+        const R iD = N::rcp(D);
+        const R twoMr = c.twoM * r;
+        const R U = N::fma_(twoMr * c.a2, sin2, sigma * (r2 + c.a2));
+        const R g_tt = -(U * iD);
+        const R g_tph = -(twoMr * c.a) * iD;
+        const R g_phph = (sin2 < R(1e-9)) ? R(0) : (delta - c.a2 * sin2) * iD / sin2;
+        A = delta * isig;
+        B = R(0);                                                       // g^tr = g^rph = 0 in BL
+        C = g_tt * c.pt2 + isig * pth * pth + g_phph * c.pph2 + R(2) * g_tph * c.pt * c.pph;
+    }
+}
+
+// invariants/renormalization.rs:13-45
+template <class R, int COORDS>
+__device__ __forceinline__ R renormalize_pr(const HoleRay<R>& c, R r, R th, R pr, R pth) {
+    using N = Num<R>;
+    R A, B, C;
+    null_quadratic<R, COORDS>(c, r, th, pth, A, B, C);
+    if (N::abs_(A) > R(1e-12)) {
+        const R disc = N::fma_(B, B, R(-4) * A * C);
+        if (disc >= R(0)) {
+            const R sq = N::sqrt_(disc);
+            const R inv2a = N::rcp(R(2) * A);
+            const R sol1 = (-B + sq) * inv2a;
+            const R sol2 = (-B - sq) * inv2a;
+            return (N::abs_(sol1 - pr) < N::abs_(sol2 - pr)) ? sol1 : sol2;
+        }
+    }
+    return pr;
+}
+
+// invariants/mod.rs:25-37:  H = (A pr^2 + B pr + C)/2
+template <class R, int COORDS>
+__device__ __forceinline__ R hamiltonian_of(const HoleRay<R>& c, R r, R th, R pr, R pth) {
+    R A, B, C;
+    null_quadratic<R, COORDS>(c, r, th, pth, A, B, C);
+    return R(0.5) * Num<R>::fma_(Num<R>::fma_(A, pr, B), pr, C);
+}
+
+// --------------------------------------------------------------------------------------------------
+// Steppers
+// --------------------------------------------------------------------------------------------------
+// geodesic/integrator.rs:209-226 implicit midpoint: 2 fixed-point iterations + final evaluation.
+template <class R, int COORDS, bool WITH_T>
+__device__ __forceinline__ void step_symplectic(const HoleRay<R>& c, Ray<R>& y, R h) {
+    using N = Num<R>;
+    const R hh = R(0.5) * h;
+    Deriv<R> d = rhs_at<R, COORDS, false>(c, y.r, y.th, y.pr, y.pth);
+    // s_mid = 0.5 (s + (s + d h)) = s + d h/2
+    R mr = N::fma_(d.dr, hh, y.r), mth = N::fma_(d.dth, hh, y.th);
+    R mpr = N::fma_(d.dpr, hh, y.pr), mpth = N::fma_(d.dpth, hh, y.pth);
+    d = rhs_at<R, COORDS, false>(c, mr, mth, mpr, mpth);
+    mr = N::fma_(d.dr, hh, y.r); mth = N::fma_(d.dth, hh, y.th);
+    mpr = N::fma_(d.dpr, hh, y.pr); mpth = N::fma_(d.dpth, hh, y.pth);
+    d = rhs_at<R, COORDS, WITH_T>(c, mr, mth, mpr, mpth);
+    y.r = N::fma_(d.dr, h, y.r);
+    y.th = N::fma_(d.dth, h, y.th);
+    y.ph = N::fma_(d.dph, h, y.ph);
+    y.pr = N::fma_(d.dpr, h, y.pr);
+    y.pth = N::fma_(d.dpth, h, y.pth);
+    if (WITH_T) y.t = N::fma_(d.dt, h, y.t);
+}
+
+// geodesic/integrator.rs:193-203 classic RK4
+template <class R, int COORDS, bool WITH_T>
+__device__ __forceinline__ void step_rk4(const HoleRay<R>& c, Ray<R>& y, R h) {
+    using N = Num<R>;
+    const R hh = R(0.5) * h;
+    Deriv<R> k1 = rhs_at<R, COORDS, WITH_T>(c, y.r, y.th, y.pr, y.pth);
+    Deriv<R> k2 = rhs_at<R, COORDS, WITH_T>(c, N::fma_(k1.dr, hh, y.r), N::fma_(k1.dth, hh, y.th),
+                                            N::fma_(k1.dpr, hh, y.pr), N::fma_(k1.dpth, hh, y.pth));
+    Deriv<R> k3 = rhs_at<R, COORDS, WITH_T>(c, N::fma_(k2.dr, hh, y.r), N::fma_(k2.dth, hh, y.th),
+                                            N::fma_(k2.dpr, hh, y.pr), N::fma_(k2.dpth, hh, y.pth));
+    Deriv<R> k4 = rhs_at<R, COORDS, WITH_T>(c, N::fma_(k3.dr, h, y.r), N::fma_(k3.dth, h, y.th),
+                                            N::fma_(k3.dpr, h, y.pr), N::fma_(k3.dpth, h, y.pth));
+    const R h6 = h / R(6);
+    y.r += h6 * (k1.dr + R(2) * k2.dr + R(2) * k3.dr + k4.dr);
+    y.th += h6 * (k1.dth + R(2) * k2.dth + R(2) * k3.dth + k4.dth);
+    y.ph += h6 * (k1.dph + R(2) * k2.dph + R(2) * k3.dph + k4.dph);
+    y.pr += h6 * (k1.dpr + R(2) * k2.dpr + R(2) * k3.dpr + k4.dpr);
+    y.pth += h6 * (k1.dpth + R(2) * k2.dpth + R(2) * k3.dpth + k4.dpth);
+    if (WITH_T) y.t += h6 * (k1.dt + R(2) * k2.dt + R(2) * k3.dt + k4.dt);
+}
+
+// geodesic/integrator.rs:113-190 Fehlberg 4(5) attempt: returns the 5th-order state in `out` and the error
+// estimate = max over the POSITION components (t, r, theta, phi) of |h * sum (b5-b4)_j k_j|.
+// The t-row of the error needs dt at every stage, so dt is always evaluated here (it is 3 flops).
+template <class R, int COORDS>
+__device__ __forceinline__ R rkf45_attempt(const HoleRay<R>& c, const Ray<R>& y, R h, Ray<R>& out) {
+    using N = Num<R>;
+#define GVT_STAGE(K, EXPR_R, EXPR_TH, EXPR_PR, EXPR_PTH) \
+    const Deriv<R> K = rhs_at<R, COORDS, true>(c, y.r + h * (EXPR_R), y.th + h * (EXPR_TH), y.pr + h * (EXPR_PR), y.pth + h * (EXPR_PTH))
+    const Deriv<R> k1 = rhs_at<R, COORDS, true>(c, y.r, y.th, y.pr, y.pth);
+    const R a21 = R(1.0 / 4.0);
+    GVT_STAGE(k2, a21 * k1.dr, a21 * k1.dth, a21 * k1.dpr, a21 * k1.dpth);
+    const R a31 = R(3.0 / 32.0), a32 = R(9.0 / 32.0);
+    GVT_STAGE(k3, a31 * k1.dr + a32 * k2.dr, a31 * k1.dth + a32 * k2.dth, a31 * k1.dpr + a32 * k2.dpr,
+              a31 * k1.dpth + a32 * k2.dpth);
+    const R a41 = R(1932.0 / 2197.0), a42 = R(-7200.0 / 2197.0), a43 = R(7296.0 / 2197.0);
+    GVT_STAGE(k4, a41 * k1.dr + a42 * k2.dr + a43 * k3.dr, a41 * k1.dth + a42 * k2.dth + a43 * k3.dth,
+              a41 * k1.dpr + a42 * k2.dpr + a43 * k3.dpr, a41 * k1.dpth + a42 * k2.dpth + a43 * k3.dpth);
+    const R a51 = R(439.0 / 216.0), a52 = R(-8.0), a53 = R(3680.0 / 513.0), a54 = R(-845.0 / 4104.0);
+    GVT_STAGE(k5, a51 * k1.dr + a52 * k2.dr + a53 * k3.dr + a54 * k4.dr,
+              a51 * k1.dth + a52 * k2.dth + a53 * k3.dth + a54 * k4.dth,
+              a51 * k1.dpr + a52 * k2.dpr + a53 * k3.dpr + a54 * k4.dpr,
+              a51 * k1.dpth + a52 * k2.dpth + a53 * k3.dpth + a54 * k4.dpth);
+    const R a61 = R(-8.0 / 27.0), a62 = R(2.0), a63 = R(-3544.0 / 2565.0), a64 = R(1859.0 / 4104.0),
+            a65 = R(-11.0 / 40.0);
+    GVT_STAGE(k6, a61 * k1.dr + a62 * k2.dr + a63 * k3.dr + a64 * k4.dr + a65 * k5.dr,
+              a61 * k1.dth + a62 * k2.dth + a63 * k3.dth + a64 * k4.dth + a65 * k5.dth,
+              a61 * k1.dpr + a62 * k2.dpr + a63 * k3.dpr + a64 * k4.dpr + a65 * k5.dpr,
+              a61 * k1.dpth + a62 * k2.dpth + a63 * k3.dpth + a64 * k4.dpth + a65 * k5.dpth);
+#undef GVT_STAGE
+    const R b1 = R(16.0 / 135.0), b3 = R(6656.0 / 12825.0), b4 = R(28561.0 / 56430.0), b5 = R(-9.0 / 50.0),
+            b6 = R(2.0 / 55.0);
+#define GVT_B5(F) (b1 * k1.F + b3 * k3.F + b4 * k4.F + b5 * k5.F + b6 * k6.F)
+    out.t = y.t + h * GVT_B5(dt);
+    out.r = y.r + h * GVT_B5(dr);
+    out.th = y.th + h * GVT_B5(dth);
+    out.ph = y.ph + h * GVT_B5(dph);
+    out.pr = y.pr + h * GVT_B5(dpr);
+    out.pth = y.pth + h * GVT_B5(dpth);
+#undef GVT_B5
+    const R e1 = R(16.0 / 135.0 - 25.0 / 216.0), e3 = R(6656.0 / 12825.0 - 1408.0 / 2565.0),
+            e4 = R(28561.0 / 56430.0 - 2197.0 / 4104.0), e5 = R(-9.0 / 50.0 + 1.0 / 5.0), e6 = R(2.0 / 55.0);
+#define GVT_E(F) N::abs_(h * (e1 * k1.F + e3 * k3.F + e4 * k4.F + e5 * k5.F + e6 * k6.F))
+    R err = N::max_(N::max_(GVT_E(dt), GVT_E(dr)), N::max_(GVT_E(dth), GVT_E(dph)));
+#undef GVT_E
+    return err;
+}
+
+// geodesic/integrator.rs:53-108 AdaptiveStepper::step (safety 0.9, min 1e-5, max 10). Updates y, returns the
+// next step; *evals counts RHS evaluations (6 per attempt).
+template <class R, int COORDS>
+__device__ __forceinline__ R adaptive_step(const HoleRay<R>& c, Ray<R>& y, R h_try, R tol, uint32_t& evals) {
+    using N = Num<R>;
+    const R max_step = R(10), min_step = R(1e-5), safety = R(0.9);
+    R h = clampR<R>(h_try, -max_step, max_step);
+    for (;;) {
+        Ray<R> ny;
+        const R err = rkf45_attempt<R, COORDS>(c, y, h, ny);
+        evals += 6;
+        const R ratio = (err == R(0)) ? R(0) : err / tol;
+        if (ratio <= R(1)) {
+            y = ny;
+            const R growth = (ratio < R(1e-4)) ? R(5) : safety * N::pow_(ratio, R(-0.2));
+            return clampR<R>(h * N::min_(growth, R(5)), -max_step, max_step);
+        }
+        const R shrink = safety * N::pow_(ratio, R(-0.25));
+        h *= N::max_(shrink, R(0.1));
+        if (N::abs_(h) < min_step) {
+            const R hs = (h < R(0)) ? -min_step : min_step;
+            (void)rkf45_attempt<R, COORDS>(c, y, hs, ny);
+            evals += 6;
+            y = ny;
+            return hs;
+        }
+        // A NaN step size would make the reference loop forever (|NaN| < min is false); a kernel must not.
+        if (!(h == h)) { y = ny; return min_step; }
+    }
+}
+
+// physics/redshift.rs:65-95 kerr_g_factor
+template <class R>
+__device__ __forceinline__ R g_factor(R r, R mass, R spin, R lambda) {
+    using N = Num<R>;
+    const R a = spin * mass;
+    const R r2 = r * r;
+    const R sm = N::sqrt_(mass);
+    const R omega = sm / (r * N::sqrt_(r) + a * sm);   // r^1.5 = r sqrt(r)
+    const R twoM_r = R(2) * mass / r;               // 2 M r / Sigma at the equator (Sigma = r^2)
+    const R g_tt = -(R(1) - twoM_r);
+    const R g_tphi = -(twoM_r * a);
+    const R g_phiphi = r2 + a * a + twoM_r * a * a;
+    const R ut_denom = -g_tt - R(2) * omega * g_tphi - omega * omega * g_phiphi;
+    if (ut_denom <= R(0)) return R(0);
+    const R factor = R(1) - lambda * omega;
+    if (N::abs_(factor) < R(1e-30)) return R(0);
+    // 1 / (ut * factor), ut = 1/sqrt(ut_denom)
+    return N::sqrt_(ut_denom) / factor;
+}
+
+}  // namespace gvt

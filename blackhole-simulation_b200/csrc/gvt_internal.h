@@ -1,0 +1,71 @@
+// gvt_internal.h — host<->kernel contract inside libgravitas_b200.so (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gvt {
+
+// Staged by TMA (cp.async.bulk) from global into shared memory once per CTA: the camera block (the f32
+// uniforms of src/types/webgpu.ts:67-116 promoted to f64, plus the per-frame constants of
+// compute.wgsl.ts:174-187 evaluated once on the host) and the 1-D disk temperature LUT (physics/disk.rs:175-201).
+struct alignas(16) FrameBlock {
+    double inv_proj[16];   // column-major
+    double inv_view[16];   // column-major
+    double r0, theta0, phi0, st, ct, sp, cp, safe_st;
+    double inv_width, inv_height, jx, jy;   // 1/W, 1/H, jitter / resolution (compute.wgsl.ts:153-157)
+    float tdisk[512];
+};
+static_assert(sizeof(FrameBlock) % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
+
+constexpr uint32_t kMaxSmemLutBytes = 192 * 1024;  // spectral LUT is smem-resident up to this size
+
+struct Counters {  // device-side accumulators, one set per frame
+    unsigned long long steps_committed, steps_executed, rhs_evals;
+    unsigned long long n_horizon, n_escape, n_maxsteps, n_disk;
+    unsigned int tile_counter;  // dynamic warp-tile queue head
+    unsigned int _pad;
+};
+
+// Kernel parameters (constant bank): the scalars of the step loop are direct c[][] operands.
+struct FrameParams {
+    double M, a, spin, rh, r_term, escape_r, r_in, r_out;   // r_term = 1.001 * r+ (geodesic/mod.rs:257)
+    double tol, h0;
+    double tdisk_rin, tdisk_scale;                            // (n-1)/(rout-rin)
+    uint32_t width, height;                                   // full frame
+    uint32_t x0, xs, y0, y1, ys;                              // pixel lattice traced by this launch
+    uint32_t nx, ny;                                          // lattice extent
+    uint32_t max_steps, renorm_interval, step_rule;
+    uint32_t tdisk_n, spec_w, spec_h, lut_in_smem;
+    const FrameBlock* block;                                  // global copy of the TMA-staged block
+    const float4* spectrum;                                   // global spectral LUT (W*H float4)
+    float4* frame;                                            // full-frame RGBA32F (may be null for debug launches)
+    Counters* counters;
+    // parity-hook outputs (DEBUG instantiations only), dense over the lattice
+    double* dbg_xp; uint32_t* dbg_term; uint32_t* dbg_steps; double* dbg_drift; double* dbg_rgba;
+};
+
+struct RayBatchParams {  // gvt_engine_integrate_rays
+    double M, a, rh, r_term, escape_r, tol, h0;
+    uint32_t max_steps, renorm_interval, step_rule, method, coords;
+    uint64_t n;
+    const double* in_xp; double* out_xp; uint32_t* term; uint32_t* steps; double* drift; uint32_t* rhs;
+};
+
+struct TaaParams {
+    // ataa.wgsl.ts:54-69: reprojection of a point at depth 12 along the pixel's world ray through prev_view_proj
+    float inv_proj[16], inv_view[16], prev_view_proj[16], cam_pos[4];
+    uint32_t width, height;
+    uint32_t row0, row1;   // rows resolved by this launch (a rank's block); neighbours outside are still read
+    const float4* cur; const float4* hist; float4* out;
+};
+
+// launchers (gvt_kernels.cu)
+cudaError_t launch_trace(const FrameParams& p, int method, int precision, bool budget, bool debug, int sm_count,
+                         cudaStream_t stream);
+cudaError_t launch_integrate_rays(const RayBatchParams& p, cudaStream_t stream);
+cudaError_t launch_taa(const TaaParams& p, cudaStream_t stream);
+cudaError_t launch_f32_to_f16(const float4* src, void* dst, size_t n_px, cudaStream_t stream);
+cudaError_t launch_fma_peak(int precision, int sm_count, unsigned long long iters, float* sink, cudaStream_t stream,
+                            double* flops_out);
+
+}  // namespace gvt

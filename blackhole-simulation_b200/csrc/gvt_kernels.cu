@@ -1,0 +1,522 @@
+// gvt_kernels.cu — hand-written sm_100a kernels of the Kerr geodesic hot path.
+//
+//   k_trace_tile      fused per-pixel kernel: camera -> (x,p) (compute.wgsl.ts:159-187), null renormalisation,
+//                     march (geodesic/mod.rs:180-253 with step_symplectic / RK4 / adaptive RKF45), thin-disk
+//                     crossing shade through the GR g-factor + Planckian redshift LUT, float4 RGBA store.
+//                     Persistent CTAs; each warp pulls 8x4-pixel tiles from an atomic queue; the camera block +
+//                     disk LUT and the spectral LUT are staged into shared memory by TMA bulk copies
+//                     (cp.async.bulk + mbarrier); the ray state lives in registers; the LUT barrier is only
+//                     waited on at the first disk crossing, so the copy is hidden behind the march.
+//   k_integrate_rays  geodesic::integrate over a batch of explicit initial states (the PhysicsEngine seam).
+//   k_taa_resolve     YCoCg variance-clip TAA resolve (ataa.wgsl.ts:28-83), 3x3 moments by warp shuffles.
+//   k_fma_peak        FFMA / DFMA micro-benchmark: the FP32 / FP64 roofline denominators.
+#include "gvt_device.cuh"
+#include "gvt_internal.h"
+#include <cuda_fp16.h>
+
+namespace gvt {
+
+// --------------------------------------------------------------------------------------------------
+// TMA bulk copy + mbarrier (PTX, sm_90+/sm_100a). SASS: UBLKCP + SYNCS.
+// --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// --------------------------------------------------------------------------------------------------
+// LUT sampling (the two joints the reference never wired in f64; the sampling rule is specified in DESIGN.md)
+// --------------------------------------------------------------------------------------------------
+template <class R>
+__device__ __forceinline__ R sample_tdisk(const float* tdisk, uint32_t n, R rin, R scale, R r) {
+    using N = Num<R>;
+    R t = clampR<R>((r - rin) * scale, R(0), R((double)(n - 1)));
+    const R fl = N::floor_(t);
+    const uint32_t i0 = (uint32_t)fl;
+    const uint32_t i1 = min(i0 + 1u, n - 1u);
+    const R f = t - fl;
+    const R a = R(tdisk[i0]), b = R(tdisk[i1]);
+    return N::fma_(b - a, f, a);
+}
+
+// bilinear, clamp-to-edge, texel-centre (GL LINEAR): x = u W - 0.5 (rendering/spectral.ts:52-54)
+template <class R>
+__device__ __forceinline__ void sample_spectrum(const float4* lut, uint32_t W, uint32_t H, R u, R v, R rgb[3]) {
+    using N = Num<R>;
+    R x = clampR<R>(N::fma_(u, R((double)W), R(-0.5)), R(0), R((double)(W - 1)));
+    R y = clampR<R>(N::fma_(v, R((double)H), R(-0.5)), R(0), R((double)(H - 1)));
+    const R xf = N::floor_(x), yf = N::floor_(y);
+    const uint32_t x0 = (uint32_t)xf, y0 = (uint32_t)yf;
+    const uint32_t x1 = min(x0 + 1u, W - 1u), y1 = min(y0 + 1u, H - 1u);
+    const R fx = x - xf, fy = y - yf;
+    const float4 t00 = lut[(size_t)y0 * W + x0], t10 = lut[(size_t)y0 * W + x1];
+    const float4 t01 = lut[(size_t)y1 * W + x0], t11 = lut[(size_t)y1 * W + x1];
+    const float a00[3] = {t00.x, t00.y, t00.z}, a10[3] = {t10.x, t10.y, t10.z};
+    const float a01[3] = {t01.x, t01.y, t01.z}, a11[3] = {t11.x, t11.y, t11.z};
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const R top = N::fma_(R(a10[c]) - R(a00[c]), fx, R(a00[c]));
+        const R bot = N::fma_(R(a11[c]) - R(a01[c]), fx, R(a01[c]));
+        rgb[c] = N::fma_(bot - top, fy, top);
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// The fused trace kernel
+// --------------------------------------------------------------------------------------------------
+constexpr int TILE_W = 8, TILE_H = 4;  // one warp = one 8x4 pixel tile (compute.wgsl.ts:147 uses 8x8 groups)
+
+template <class R, int METHOD, bool BUDGET, bool DEBUG, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ FrameParams P) {
+    using N = Num<R>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bars[2];
+    FrameBlock* fb = reinterpret_cast<FrameBlock*>(smem_raw);
+    float4* lut_s = reinterpret_cast<float4*>(smem_raw + ((sizeof(FrameBlock) + 127) / 128) * 128);
+    const uint32_t lut_bytes = P.spec_w * P.spec_h * (uint32_t)sizeof(float4);
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bars[0], (uint32_t)sizeof(FrameBlock));
+        tma_bulk_g2s(fb, P.block, (uint32_t)sizeof(FrameBlock), &bars[0]);
+        if (P.lut_in_smem) {
+            mbar_expect_tx(&bars[1], lut_bytes);
+            // one bulk copy per <=64 KB chunk keeps each request well inside the tx-count range
+            for (uint32_t off = 0; off < lut_bytes; off += 65536u) {
+                const uint32_t n = min(65536u, lut_bytes - off);
+                tma_bulk_g2s(reinterpret_cast<unsigned char*>(lut_s) + off,
+                             reinterpret_cast<const unsigned char*>(P.spectrum) + off, n, &bars[1]);
+            }
+        }
+    }
+    mbar_wait(&bars[0], 0);  // camera block + disk LUT are needed for ray generation
+    bool lut_ready = !P.lut_in_smem;
+    const float4* lut = P.lut_in_smem ? lut_s : P.spectrum;
+
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lx = lane & (TILE_W - 1), ly = lane / TILE_W;
+    const uint32_t tiles_x = (P.nx + TILE_W - 1) / TILE_W, tiles_y = (P.ny + TILE_H - 1) / TILE_H;
+    const uint32_t n_tiles = tiles_x * tiles_y;
+
+    HoleRay<R> hc;
+    hc.set_hole(R(P.M), R(P.a));
+    const R r_term = R(P.r_term), escape_r = R(P.escape_r), rh = R(P.rh);
+    const R half_pi = R(1.5707963267948966);
+
+    unsigned long long acc_commit = 0, acc_exec = 0, acc_rhs = 0;
+    uint32_t acc_term[4] = {0, 0, 0, 0};
+
+    for (;;) {
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(&P.counters->tile_counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= n_tiles) break;
+        const uint32_t ti = tile % tiles_x, tj = tile / tiles_x;
+        const uint32_t li = ti * TILE_W + lx, lj = tj * TILE_H + ly;  // lattice coordinates
+        const bool valid = (li < P.nx) && (lj < P.ny);
+        const uint32_t px = P.x0 + min(li, P.nx - 1) * P.xs, py = P.y0 + min(lj, P.ny - 1) * P.ys;
+
+        // ---- camera -> (x, p): compute.wgsl.ts:159-187 ----
+        Ray<R> y;
+        {
+            const R ndcx = N::fma_(N::fma_(R((double)px), R(fb->inv_width), R(fb->jx)), R(2), R(-1));
+            const R ndcy = N::fma_(N::fma_(R((double)py), R(fb->inv_height), R(fb->jy)), R(2), R(-1));
+            const R cx = ndcx, cy = -ndcy;  // clip = (ndc.x, -ndc.y, 1, 1)
+            R vt[4];
+#pragma unroll
+            for (int row = 0; row < 4; row++)
+                vt[row] = R(fb->inv_proj[row]) * cx + R(fb->inv_proj[4 + row]) * cy + R(fb->inv_proj[8 + row]) +
+                          R(fb->inv_proj[12 + row]);
+            const R iw = N::rcp(vt[3]);
+            R vx = vt[0] * iw, vy = vt[1] * iw, vz = vt[2] * iw;
+            const R ivn = N::rcp(N::sqrt_(vx * vx + vy * vy + vz * vz));
+            vx *= ivn; vy *= ivn; vz *= ivn;
+            R w[3];
+#pragma unroll
+            for (int row = 0; row < 3; row++)
+                w[row] = R(fb->inv_view[row]) * vx + R(fb->inv_view[4 + row]) * vy + R(fb->inv_view[8 + row]) * vz;
+            const R iwn = N::rcp(N::sqrt_(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]));
+            const R dx = w[0] * iwn, dy = w[1] * iwn, dz = w[2] * iwn;
+            const R st = R(fb->st), ct = R(fb->ct), sp = R(fb->sp), cp = R(fb->cp), r0 = R(fb->r0);
+            const R pr_far = dx * (st * cp) + dy * ct + dz * (st * sp);
+            const R pth_far = (dx * (ct * cp) - dy * st + dz * (ct * sp)) / r0;
+            const R pph_far = (dz * cp - dx * sp) / (r0 * R(fb->safe_st));
+            y.t = R(0); y.r = r0; y.th = R(fb->theta0); y.ph = R(fb->phi0);
+            y.pr = pr_far;
+            y.pth = pth_far * r0 * r0;
+            hc.set_ray(R(-1), pph_far * r0 * r0 * st * st);
+        }
+
+        // ---- march: geodesic/mod.rs:180-253 ----
+        y.pr = renormalize_pr<R, 1>(hc, y.r, y.th, y.pr, y.pth);  // mod.rs:200
+        R col[3] = {R(0), R(0), R(0)};
+        R alpha = R(0), max_drift = R(0), h = R(P.h0);
+        uint32_t steps = 0, term = 3u, rhs_evals = 0;
+        bool done = false;
+        for (uint32_t it = 0; it < P.max_steps; it++) {
+            if (!done) {  // mod.rs:204,255-265
+                if (y.r < r_term) { term = 1u; done = true; }
+                else if (y.r > escape_r) { term = 2u; done = true; }
+            }
+            if (!BUDGET) { if (__all_sync(0xffffffffu, done)) break; }   // warp-uniform: all 32 lanes stay in the loop
+            if (BUDGET || !done) {
+                Ray<R> ny = y;
+                R hn = h;
+                if (METHOD == 0) {
+                    hn = adaptive_step<R, 1>(hc, ny, h, R(P.tol), rhs_evals);
+                } else {
+                    const R hs = (P.step_rule == 1u) ? clampR<R>((y.r - rh) * R(0.15), R(0.05), R(1.0)) : R(P.h0);
+                    if (METHOD == 1) { step_rk4<R, 1, DEBUG>(hc, ny, hs); rhs_evals += 4; }
+                    else { step_symplectic<R, 1, DEBUG>(hc, ny, hs); rhs_evals += 3; }
+                }
+                if (steps % P.renorm_interval == 0u) ny.pr = renormalize_pr<R, 1>(hc, ny.r, ny.th, ny.pr, ny.pth);
+                if (!done) {   // budget mode: terminated rays executed the step above but do not commit it
+                    const R th0 = y.th, r_prev = y.r;
+                    y = ny; h = hn; steps++;
+                    if (DEBUG) max_drift = N::max_(max_drift, N::abs_(hamiltonian_of<R, 1>(hc, y.r, y.th, y.pr, y.pth)));
+                    // ---- thin-disk crossing (compute.wgsl.ts:216-254 with a18 + a19 + a20) ----
+                    const R d0 = th0 - half_pi, d1 = y.th - half_pi;
+                    if (d0 * d1 <= R(0)) {
+                        const R dth = y.th - th0;
+                        const R f = (dth == R(0)) ? R(0) : (half_pi - th0) / dth;
+                        const R r_c = N::fma_(f, y.r - r_prev, r_prev);
+                        if (r_c > R(P.r_in) && r_c < R(P.r_out)) {
+                            if (!lut_ready) { mbar_wait(&bars[1], 0); lut_ready = true; }
+                            const R lambda = hc.pph / (-hc.pt);
+                            const R g = g_factor<R>(r_c, R(P.M), R(P.spin), lambda);
+                            const R tn = sample_tdisk<R>(fb->tdisk, P.tdisk_n, R(P.tdisk_rin), R(P.tdisk_scale), r_c);
+                            const R u = N::pow_(tn, R(0.4));
+                            const R v = (g - R(0.05)) / R(4.95);
+                            R rgb[3];
+                            sample_spectrum<R>(lut, P.spec_w, P.spec_h, u, v, rgb);
+                            const R opacity = R(0.6) * tn * g;
+                            const R wgt = (R(1) - alpha) * opacity;
+                            col[0] = N::fma_(rgb[0], wgt, col[0]);
+                            col[1] = N::fma_(rgb[1], wgt, col[1]);
+                            col[2] = N::fma_(rgb[2], wgt, col[2]);
+                            alpha += opacity;
+                        }
+                    }
+                    if (alpha > R(0.99)) { term = 4u; done = true; }
+                }
+            }
+        }
+        if (!done) term = 3u;
+
+        // ---- epilogue: coalesced float4 store + census ----
+        if (valid) {
+            if (P.frame) P.frame[(size_t)py * P.width + px] = make_float4((float)col[0], (float)col[1], (float)col[2], 1.0f);
+            if (DEBUG) {
+                const size_t k = (size_t)lj * P.nx + li;
+                if (P.dbg_xp) {
+                    double* o = P.dbg_xp + 8 * k;
+                    o[0] = (double)y.t; o[1] = (double)y.r; o[2] = (double)y.th; o[3] = (double)y.ph;
+                    o[4] = (double)hc.pt; o[5] = (double)y.pr; o[6] = (double)y.pth; o[7] = (double)hc.pph;
+                }
+                if (P.dbg_term) P.dbg_term[k] = term;
+                if (P.dbg_steps) P.dbg_steps[k] = steps;
+                if (P.dbg_drift) P.dbg_drift[k] = (double)max_drift;
+                if (P.dbg_rgba) {
+                    double* o = P.dbg_rgba + 4 * k;
+                    o[0] = (double)col[0]; o[1] = (double)col[1]; o[2] = (double)col[2]; o[3] = 1.0;
+                }
+            }
+        }
+        const uint32_t vsteps = valid ? steps : 0u, vrhs = valid ? rhs_evals : 0u;
+        acc_commit += __reduce_add_sync(0xffffffffu, vsteps);
+        acc_rhs += __reduce_add_sync(0xffffffffu, vrhs);
+        acc_exec += BUDGET ? (unsigned long long)__popc(__ballot_sync(0xffffffffu, valid)) * P.max_steps
+                           : (unsigned long long)__reduce_add_sync(0xffffffffu, vsteps);
+#pragma unroll
+        for (uint32_t c = 0; c < 4; c++) acc_term[c] += __popc(__ballot_sync(0xffffffffu, valid && term == c + 1u));
+    }
+    // a CTA must not exit while its bulk copy is still in flight
+    if (P.lut_in_smem && !lut_ready) mbar_wait(&bars[1], 0);
+    if (lane == 0) {
+        atomicAdd(&P.counters->steps_committed, acc_commit);
+        atomicAdd(&P.counters->steps_executed, acc_exec);
+        atomicAdd(&P.counters->rhs_evals, acc_rhs);
+        if (acc_term[0]) atomicAdd(&P.counters->n_horizon, (unsigned long long)acc_term[0]);
+        if (acc_term[1]) atomicAdd(&P.counters->n_escape, (unsigned long long)acc_term[1]);
+        if (acc_term[2]) atomicAdd(&P.counters->n_maxsteps, (unsigned long long)acc_term[2]);
+        if (acc_term[3]) atomicAdd(&P.counters->n_disk, (unsigned long long)acc_term[3]);
+    }
+}
+
+template <class R, int METHOD, bool BUDGET, bool DEBUG, int MAXT>
+static cudaError_t launch_trace_t(const FrameParams& p, int sm_count, cudaStream_t stream) {
+    auto kern = k_trace_tile<R, METHOD, BUDGET, DEBUG, MAXT>;
+    size_t smem = ((sizeof(FrameBlock) + 127) / 128) * 128;
+    if (p.lut_in_smem) smem += (size_t)p.spec_w * p.spec_h * sizeof(float4);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const uint32_t tiles = ((p.nx + TILE_W - 1) / TILE_W) * ((p.ny + TILE_H - 1) / TILE_H);
+    const uint32_t warps_per_cta = MAXT / 32;
+    uint32_t ctas = (tiles + warps_per_cta - 1) / warps_per_cta;
+    if (ctas > (uint32_t)sm_count) ctas = (uint32_t)sm_count;  // persistent: one CTA per SM
+    if (ctas == 0) ctas = 1;
+    kern<<<ctas, MAXT, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_trace(const FrameParams& p, int method, int precision, bool budget, bool debug, int sm_count,
+                         cudaStream_t stream) {
+#define GVT_DISPATCH(RT, MT)                                                                                   \
+    do {                                                                                                         \
+        if (method == 0) return debug ? launch_trace_t<RT, 0, false, true, 256>(p, sm_count, stream)             \
+                                      : launch_trace_t<RT, 0, false, false, 256>(p, sm_count, stream);           \
+        if (method == 1) return debug ? launch_trace_t<RT, 1, false, true, MT>(p, sm_count, stream)              \
+                                      : launch_trace_t<RT, 1, false, false, MT>(p, sm_count, stream);            \
+        if (budget) return debug ? launch_trace_t<RT, 2, true, true, MT>(p, sm_count, stream)                    \
+                                 : launch_trace_t<RT, 2, true, false, MT>(p, sm_count, stream);                  \
+        return debug ? launch_trace_t<RT, 2, false, true, MT>(p, sm_count, stream)                               \
+                     : launch_trace_t<RT, 2, false, false, MT>(p, sm_count, stream);                             \
+    } while (0)
+    if (precision == 1) GVT_DISPATCH(float, 512);
+    GVT_DISPATCH(double, 512);
+#undef GVT_DISPATCH
+}
+
+// --------------------------------------------------------------------------------------------------
+// geodesic::integrate over explicit initial states (gravitas-wasm/src/lib.rs:422-464), f64.
+// --------------------------------------------------------------------------------------------------
+template <int COORDS, int METHOD>
+__global__ void __launch_bounds__(128) k_integrate_rays(const __grid_constant__ RayBatchParams P) {
+    using R = double;
+    using N = Num<R>;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    const double* in = P.in_xp + 8 * i;
+    HoleRay<R> hc;
+    hc.set_hole(P.M, P.a);
+    hc.set_ray(in[4], in[7]);
+    Ray<R> y;
+    y.t = in[0]; y.r = in[1]; y.th = in[2]; y.ph = in[3]; y.pr = in[5]; y.pth = in[6];
+    y.pr = renormalize_pr<R, COORDS>(hc, y.r, y.th, y.pr, y.pth);
+    R h = P.h0, max_drift = 0.0;
+    uint32_t steps = 0, term = 3u, evals = 0;
+    for (uint32_t it = 0; it < P.max_steps; it++) {
+        if (y.r < P.r_term) { term = 1u; break; }
+        if (y.r > P.escape_r) { term = 2u; break; }
+        if (METHOD == 0) {
+            h = adaptive_step<R, COORDS>(hc, y, h, P.tol, evals);
+        } else {
+            const R hs = (P.step_rule == 1u) ? clampR<R>((y.r - P.rh) * 0.15, 0.05, 1.0) : P.h0;
+            if (METHOD == 1) { step_rk4<R, COORDS, true>(hc, y, hs); evals += 4; }
+            else { step_symplectic<R, COORDS, true>(hc, y, hs); evals += 3; }
+        }
+        if (steps % P.renorm_interval == 0u) y.pr = renormalize_pr<R, COORDS>(hc, y.r, y.th, y.pr, y.pth);
+        max_drift = N::max_(max_drift, N::abs_(hamiltonian_of<R, COORDS>(hc, y.r, y.th, y.pr, y.pth)));
+        steps++;
+    }
+    double* o = P.out_xp + 8 * i;
+    o[0] = y.t; o[1] = y.r; o[2] = y.th; o[3] = y.ph; o[4] = hc.pt; o[5] = y.pr; o[6] = y.pth; o[7] = hc.pph;
+    if (P.term) P.term[i] = term;
+    if (P.steps) P.steps[i] = steps;
+    if (P.drift) P.drift[i] = max_drift;
+    if (P.rhs) P.rhs[i] = evals;
+}
+
+cudaError_t launch_integrate_rays(const RayBatchParams& p, cudaStream_t stream) {
+    if (p.n == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((p.n + 127) / 128);
+#define GVT_RB(C, M) k_integrate_rays<C, M><<<blocks, 128, 0, stream>>>(p)
+    if (p.coords == 1) { if (p.method == 0) GVT_RB(1, 0); else if (p.method == 1) GVT_RB(1, 1); else GVT_RB(1, 2); }
+    else { if (p.method == 0) GVT_RB(0, 0); else if (p.method == 1) GVT_RB(0, 1); else GVT_RB(0, 2); }
+#undef GVT_RB
+    return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------------------
+// TAA resolve (ataa.wgsl.ts:28-83). One warp owns a 30-pixel-wide column strip and walks down it with a
+// rolling 3-row window: every lane loads ONE pixel per row (lanes 0 and 31 are the horizontal halo), the
+// vertical 3-row sums live in registers and the horizontal 3-tap sums come from warp shuffles.
+// --------------------------------------------------------------------------------------------------
+constexpr int TAA_STRIP_W = 30, TAA_ROWS = 32;
+
+struct YCC { float y, co, cg; };
+__device__ __forceinline__ YCC rgb_to_ycocg(float r, float g, float b) {  // ataa.wgsl.ts:11-16
+    YCC o;
+    o.y = 0.25f * r + 0.5f * g + 0.25f * b;
+    o.co = 0.5f * r - 0.5f * b;
+    o.cg = -0.25f * r + 0.5f * g - 0.25f * b;
+    return o;
+}
+__device__ __forceinline__ float sum3(float v) {
+    return __shfl_up_sync(0xffffffffu, v, 1) + v + __shfl_down_sync(0xffffffffu, v, 1);
+}
+__device__ __forceinline__ float4 ldg_px(const float4* img, int W, int H, int x, int y) {
+    x = max(0, min(x, W - 1)); y = max(0, min(y, H - 1));   // clamp(pos + d, 0, size-1), ataa.wgsl.ts:43
+    return __ldg(img + (size_t)y * W + x);
+}
+
+__global__ void __launch_bounds__(256) k_taa_resolve(const __grid_constant__ TaaParams P) {
+    const int W = (int)P.width, H = (int)P.height;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int strips_x = (W + TAA_STRIP_W - 1) / TAA_STRIP_W;
+    const int gw = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int rows = (int)P.row1 - (int)P.row0;
+    const int n_work = strips_x * ((rows + TAA_ROWS - 1) / TAA_ROWS);
+    if (gw >= n_work) return;
+    const int sx = gw % strips_x, sy = gw / strips_x;
+    const int x = sx * TAA_STRIP_W + lane - 1;  // lane 0 / 31 = halo columns
+    const int y_begin = (int)P.row0 + sy * TAA_ROWS, y_end = min(y_begin + TAA_ROWS, (int)P.row1);
+
+    // rolling window of per-pixel first/second moments for rows y-1, y, y+1
+    YCC a, b, c;
+    float4 pb;
+    {
+        const float4 pa = ldg_px(P.cur, W, H, x, y_begin - 1);
+        pb = ldg_px(P.cur, W, H, x, y_begin);
+        a = rgb_to_ycocg(pa.x, pa.y, pa.z);
+        b = rgb_to_ycocg(pb.x, pb.y, pb.z);
+    }
+    for (int y = y_begin; y < y_end; y++) {
+        const float4 pc = ldg_px(P.cur, W, H, x, y + 1);
+        c = rgb_to_ycocg(pc.x, pc.y, pc.z);
+        // vertical sums (this lane's column), then horizontal 3-tap by shuffles
+        const float m1y = sum3(a.y + b.y + c.y), m1o = sum3(a.co + b.co + c.co), m1g = sum3(a.cg + b.cg + c.cg);
+        const float m2y = sum3(a.y * a.y + b.y * b.y + c.y * c.y);
+        const float m2o = sum3(a.co * a.co + b.co * b.co + c.co * c.co);
+        const float m2g = sum3(a.cg * a.cg + b.cg * b.cg + c.cg * c.cg);
+        if (lane >= 1 && lane <= TAA_STRIP_W && x < W) {
+            const float k = 1.0f / 9.0f;
+            const float mean[3] = {m1y * k, m1o * k, m1g * k};
+            const float m2[3] = {m2y * k, m2o * k, m2g * k};
+            float lo[3], hi[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const float sd = sqrtf(fmaxf(m2[i] - mean[i] * mean[i], 0.0f));
+                lo[i] = mean[i] - 2.0f * sd; hi[i] = mean[i] + 2.0f * sd;
+            }
+            // reprojection at depth 12 through prev_view_proj (ataa.wgsl.ts:54-69)
+            const float u = ((float)x + 0.5f) / (float)W, v = ((float)y + 0.5f) / (float)H;
+            const float cx = u * 2.0f - 1.0f, cy = -(v * 2.0f - 1.0f);
+            float vt[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                vt[r] = P.inv_proj[r] * cx + P.inv_proj[4 + r] * cy + P.inv_proj[8 + r] + P.inv_proj[12 + r];
+            float vx = vt[0] / vt[3], vy = vt[1] / vt[3], vz = vt[2] / vt[3];
+            const float inv_n = 1.0f / sqrtf(vx * vx + vy * vy + vz * vz);
+            vx *= inv_n; vy *= inv_n; vz *= inv_n;
+            float wp[3];
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+                wp[r] = P.cam_pos[r] + 12.0f * (P.inv_view[r] * vx + P.inv_view[4 + r] * vy + P.inv_view[8 + r] * vz);
+            float pc4[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                pc4[r] = P.prev_view_proj[r] * wp[0] + P.prev_view_proj[4 + r] * wp[1] + P.prev_view_proj[8 + r] * wp[2] +
+                         P.prev_view_proj[12 + r];
+            const float pu = (pc4[0] / pc4[3]) * 0.5f + 0.5f, pv = (pc4[1] / pc4[3]) * -0.5f + 0.5f;
+            // bilinear, clamp-to-edge history fetch (textureSampleLevel + linear sampler, ataa.wgsl.ts:72)
+            const float hx = fminf(fmaxf(pu * (float)W - 0.5f, 0.0f), (float)(W - 1));
+            const float hy = fminf(fmaxf(pv * (float)H - 0.5f, 0.0f), (float)(H - 1));
+            const float hxf = floorf(hx), hyf = floorf(hy);
+            const int x0 = (int)hxf, y0 = (int)hyf;
+            const float fx = hx - hxf, fy = hy - hyf;
+            const float4 h00 = ldg_px(P.hist, W, H, x0, y0), h10 = ldg_px(P.hist, W, H, x0 + 1, y0);
+            const float4 h01 = ldg_px(P.hist, W, H, x0, y0 + 1), h11 = ldg_px(P.hist, W, H, x0 + 1, y0 + 1);
+            const float hr = (h00.x + (h10.x - h00.x) * fx) + ((h01.x + (h11.x - h01.x) * fx) - (h00.x + (h10.x - h00.x) * fx)) * fy;
+            const float hg = (h00.y + (h10.y - h00.y) * fx) + ((h01.y + (h11.y - h01.y) * fx) - (h00.y + (h10.y - h00.y) * fx)) * fy;
+            const float hb = (h00.z + (h10.z - h00.z) * fx) + ((h01.z + (h11.z - h01.z) * fx) - (h00.z + (h10.z - h00.z) * fx)) * fy;
+            YCC hs = rgb_to_ycocg(hr, hg, hb);
+            hs.y = fminf(fmaxf(hs.y, lo[0]), hi[0]);
+            hs.co = fminf(fmaxf(hs.co, lo[1]), hi[1]);
+            hs.cg = fminf(fmaxf(hs.cg, lo[2]), hi[2]);
+            const float fb_ = 0.92f;  // ataa.wgsl.ts:77
+            const float ry = b.y + (hs.y - b.y) * fb_, ro = b.co + (hs.co - b.co) * fb_, rg = b.cg + (hs.cg - b.cg) * fb_;
+            // YCoCgToRGB, ataa.wgsl.ts:18-26
+            P.out[(size_t)y * W + x] = make_float4(ry + ro - rg, ry + rg, ry - ro - rg, 1.0f);
+        }
+        a = b; b = c;
+    }
+}
+
+cudaError_t launch_taa(const TaaParams& p, cudaStream_t stream) {
+    const int strips_x = ((int)p.width + TAA_STRIP_W - 1) / TAA_STRIP_W;
+    const int rows = (int)p.row1 - (int)p.row0;
+    if (rows <= 0) return cudaSuccess;
+    const int n_work = strips_x * ((rows + TAA_ROWS - 1) / TAA_ROWS);
+    const int wpb = 8;
+    k_taa_resolve<<<(n_work + wpb - 1) / wpb, wpb * 32, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// RGBA32F -> RGBA16F (reprojection.ts:120-140 / webgpu/renderer.ts:161-180 texture format)
+__global__ void k_f32_to_f16(const float4* __restrict__ src, uint2* __restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = src[i];
+        const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&lo);
+        o.y = *reinterpret_cast<const uint32_t*>(&hi);
+        dst[i] = o;
+    }
+}
+cudaError_t launch_f32_to_f16(const float4* src, void* dst, size_t n_px, cudaStream_t stream) {
+    k_f32_to_f16<<<148 * 8, 256, 0, stream>>>(src, reinterpret_cast<uint2*>(dst), n_px);
+    return cudaGetLastError();
+}
+
+// --------------------------------------------------------------------------------------------------
+// FMA-pipe peak micro-benchmark: 8 independent dependent chains per thread.
+// --------------------------------------------------------------------------------------------------
+template <class R>
+__global__ void __launch_bounds__(256) k_fma_peak(float* sink, unsigned long long iters) {
+    R a0 = R(threadIdx.x) * R(1e-3), a1 = a0 + R(1), a2 = a0 + R(2), a3 = a0 + R(3), a4 = a0 + R(4), a5 = a0 + R(5),
+      a6 = a0 + R(6), a7 = a0 + R(7);
+    const R x = R(0.999999), yv = R(1e-6);
+    for (unsigned long long i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            a0 = Num<R>::fma_(a0, x, yv); a1 = Num<R>::fma_(a1, x, yv); a2 = Num<R>::fma_(a2, x, yv);
+            a3 = Num<R>::fma_(a3, x, yv); a4 = Num<R>::fma_(a4, x, yv); a5 = Num<R>::fma_(a5, x, yv);
+            a6 = Num<R>::fma_(a6, x, yv); a7 = Num<R>::fma_(a7, x, yv);
+        }
+    }
+    const R s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == R(-12345.678)) sink[0] = (float)s;  // never true; keeps the chains live
+}
+
+cudaError_t launch_fma_peak(int precision, int sm_count, unsigned long long iters, float* sink, cudaStream_t stream,
+                            double* flops_out) {
+    const int blocks = sm_count * 8, threads = 256;
+    if (precision == 1) k_fma_peak<float><<<blocks, threads, 0, stream>>>(sink, iters);
+    else k_fma_peak<double><<<blocks, threads, 0, stream>>>(sink, iters);
+    *flops_out = (double)blocks * threads * (double)iters * 64.0 * 2.0;
+    return cudaGetLastError();
+}
+
+}  // namespace gvt

@@ -1,0 +1,131 @@
+"""ctypes binding of include/gravitas_b200.h. Fails loudly if the CUDA library has not been built."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libgravitas_b200.so")
+_LIB = None
+
+# SAB v2 offsets, f32 element indices (physics-bridge.ts:5-11; lib.rs:36-40)
+OFFSETS = {"CONTROL": 0, "CAMERA": 64, "PHYSICS": 128, "TELEMETRY": 256, "LUTS": 2048}
+
+GVT_OK, GVT_ERR_INVALID, GVT_ERR_NO_DEVICE, GVT_ERR_CUDA, GVT_ERR_NCCL, GVT_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+TERM_NONE, TERM_HORIZON, TERM_ESCAPE, TERM_MAXSTEPS, TERM_DISK = 0, 1, 2, 3, 4
+COORDS_BL, COORDS_KS = 0, 1
+METHOD_RKF45, METHOD_RK4, METHOD_SYMPLECTIC = 0, 1, 2
+PRECISION_F64, PRECISION_F32 = 0, 1
+FORMAT_RGBA32F, FORMAT_RGBA16F = 0, 1
+STEP_CONSTANT, STEP_WGSL = 0, 1
+FLAG_JITTER, FLAG_BUDGET, FLAG_TRACK_DRIFT, FLAG_TAA, FLAG_NO_GATHER = 1, 2, 4, 8, 16
+
+
+class GravitasError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"gravitas_b200 error {code}: {msg}")
+        self.code = code
+
+
+class GvtCamera(C.Structure):  # 352 bytes, types/webgpu.ts:67-116
+    _fields_ = [("view", C.c_float * 16), ("proj", C.c_float * 16), ("inv_view", C.c_float * 16),
+                ("inv_proj", C.c_float * 16), ("prev_view_proj", C.c_float * 16), ("position", C.c_float * 4),
+                ("direction", C.c_float * 4)]
+
+
+class GvtPhysicsParams(C.Structure):  # 32 bytes, types/webgpu.ts:42-64
+    _fields_ = [("mass", C.c_float), ("spin", C.c_float), ("resolution", C.c_float * 2), ("time", C.c_float),
+                ("dt", C.c_float), ("frame_index", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class GvtRenderParams(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("method", C.c_uint32), ("precision", C.c_uint32), ("coords", C.c_uint32),
+                ("step_rule", C.c_uint32), ("max_steps", C.c_uint32), ("renormalize_interval", C.c_uint32),
+                ("flags", C.c_uint32), ("output_format", C.c_uint32), ("_pad", C.c_uint32), ("tolerance", C.c_double),
+                ("initial_step", C.c_double), ("escape_radius", C.c_double), ("disk_r_out", C.c_double)]
+
+
+class GvtDeviceConfig(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("rank", C.c_int32), ("world_size", C.c_int32),
+                ("nccl_id", C.c_uint8 * 128)]
+
+
+class GvtFrameStats(C.Structure):
+    _fields_ = [("trace_ms", C.c_double), ("taa_ms", C.c_double), ("gather_ms", C.c_double), ("total_ms", C.c_double),
+                ("steps_committed", C.c_uint64), ("steps_executed", C.c_uint64), ("rhs_evals", C.c_uint64),
+                ("n_horizon", C.c_uint64), ("n_escape", C.c_uint64), ("n_maxsteps", C.c_uint64), ("n_disk", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint32),
+                ("rows_begin", C.c_uint32), ("rows_end", C.c_uint32)]
+
+
+assert C.sizeof(GvtCamera) == 352 and C.sizeof(GvtPhysicsParams) == 32
+
+_d, _i32, _u32, _u64, _vp = C.c_double, C.c_int32, C.c_uint32, C.c_uint64, C.c_void_p
+_pd, _pf, _pu32, _pu64 = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+
+# every symbol include/gravitas_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "gvt_last_error": (C.c_char_p, []),
+    "gvt_abi_version": (_i32, []),
+    "gvt_device_count": (_i32, [C.POINTER(_i32)]),
+    "gvt_engine_create": (_i32, [_d, _d, C.POINTER(_vp)]),
+    "gvt_engine_destroy": (_i32, [_vp]),
+    "gvt_engine_update_params": (_i32, [_vp, _d, _d]),
+    "gvt_engine_attach_sab": (_i32, [_vp, _pf]),
+    "gvt_engine_get_sab_ptr": (_i32, [_vp, C.POINTER(_pf)]),
+    "gvt_engine_get_sab_layout": (_i32, [_vp, _pu32]),
+    "gvt_engine_tick_sab": (_i32, [_vp, _d]),
+    "gvt_engine_set_camera_state": (_i32, [_vp, _d, _d, _d, _d, _d, _d]),
+    "gvt_engine_set_auto_spin": (_i32, [_vp, _i32]),
+    "gvt_engine_compute_horizon": (_i32, [_vp, _pd]),
+    "gvt_engine_compute_isco": (_i32, [_vp, _pd]),
+    "gvt_engine_compute_photon_sphere": (_i32, [_vp, _pd]),
+    "gvt_engine_compute_dilation": (_i32, [_vp, _d, _pd]),
+    "gvt_engine_compute_g_factor": (_i32, [_vp, _d, _d, _pd]),
+    "gvt_engine_generate_disk_lut": (_i32, [_vp, _pf]),
+    "gvt_engine_generate_spectrum_lut": (_i32, [_vp, _u32, _u32, _d, _pf]),
+    "gvt_engine_integrate_ray": (_i32, [_vp, _pd, _u64, _d, _i32, _pd, _pu32, _pu64, _pd]),
+    "gvt_engine_integrate_rays": (_i32, [_vp, C.POINTER(GvtRenderParams), _u64, _pd, _pd, _pu32, _pu32, _pd, _pu32]),
+    "gvt_nccl_unique_id": (_i32, [C.POINTER(C.c_uint8)]),
+    "gvt_render_params_default": (_i32, [C.POINTER(GvtRenderParams)]),
+    "gvt_render_create": (_i32, [C.POINTER(GvtDeviceConfig), C.POINTER(_vp)]),
+    "gvt_render_destroy": (_i32, [_vp]),
+    "gvt_render_init_luts": (_i32, [_vp, _d, _d, _u32, _u32, _d]),
+    "gvt_render_set_luts": (_i32, [_vp, _pf, _u32, _u32, _pf, _u32, _d, _d]),
+    "gvt_render_resize": (_i32, [_vp, _u32, _u32]),
+    "gvt_render_frame": (_i32, [_vp, C.POINTER(GvtCamera), C.POINTER(GvtPhysicsParams), C.POINTER(GvtRenderParams), _vp,
+                                C.POINTER(GvtFrameStats)]),
+    "gvt_render_read_frame": (_i32, [_vp, _u32, _vp]),
+    "gvt_trace_states": (_i32, [_vp, C.POINTER(GvtCamera), C.POINTER(GvtPhysicsParams), C.POINTER(GvtRenderParams), _u32,
+                                _u32, _u32, _u32, _u32, _pd, _pu32, _pu32, _pd, _pd]),
+    "gvt_taa_resolve": (_i32, [_vp, C.POINTER(GvtCamera), _u32, _u32, _pf, _pf, _pf]),
+    "gvt_render_reset_history": (_i32, [_vp]),
+    "gvt_host_alloc": (_i32, [C.c_size_t, C.POINTER(_vp)]),
+    "gvt_host_free": (_i32, [_vp]),
+    "gvt_measure_fma_peak": (_i32, [_vp, _i32, _pd, _pd]),
+    "gvt_device_info": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.c_char_p]),
+}
+
+
+def lib_path():
+    return _SO
+
+
+def lib():
+    """Load libgravitas_b200.so. There is no fallback implementation: a missing library is an error."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(_SO):
+            raise GravitasError(GVT_ERR_NO_DEVICE,
+                                f"{_SO} not built — run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                "(nvcc, sm_100a). This package has no CPU or PyTorch fallback.")
+        L = C.CDLL(_SO)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError here = header/library mismatch
+            fn.restype, fn.argtypes = res, args
+        _LIB = L
+    return _LIB
+
+
+def check(rc):
+    if rc != GVT_OK:
+        msg = lib().gvt_last_error()
+        raise GravitasError(rc, msg.decode() if msg else "unknown")

@@ -1,0 +1,202 @@
+"""KerrRenderer — the src/rendering renderer / frame-buffer API over gvt_render_* (Seam B).
+
+Mirrors WebGPURenderer (rendering/webgpu/renderer.ts:82-411): ``init`` -> ``init_pipelines(max_steps)`` ->
+``resize(w, h)`` -> ``render(camera, physics)``; ``render`` returns the finished frame buffer instead of presenting
+to a canvas."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (GvtCamera, GvtDeviceConfig, GvtFrameStats, GvtPhysicsParams, GvtRenderParams, check, lib)
+
+
+class RenderParams:
+    """Integration options of the trace (IntegrationOptions, geodesic/integrator.rs:24-47 + WGSL overrides)."""
+
+    def __init__(self, **kw):
+        self.c = GvtRenderParams()
+        check(lib().gvt_render_params_default(C.byref(self.c)))
+        for k, v in kw.items():
+            if not hasattr(self.c, k):
+                raise AttributeError(k)
+            setattr(self.c, k, v)
+
+    def __getattr__(self, k):
+        return getattr(self.__dict__["c"], k)
+
+
+class FrameStats(dict):
+    __getattr__ = dict.__getitem__
+
+
+def _stats(s):
+    return FrameStats({f[0]: getattr(s, f[0]) for f in GvtFrameStats._fields_})
+
+
+def pack_camera(cam88):
+    cam88 = np.ascontiguousarray(cam88, dtype=np.float32)
+    if cam88.size != 88:
+        raise ValueError("CameraUniforms is 88 floats (352 bytes, types/webgpu.ts:25)")
+    c = GvtCamera()
+    C.memmove(C.byref(c), cam88.ctypes.data, 352)
+    return c
+
+
+def pack_physics(mass, spin, width, height, time=0.0, dt=0.016, frame_index=0):
+    p = GvtPhysicsParams()
+    p.mass, p.spin = mass, spin
+    p.resolution[0], p.resolution[1] = float(width), float(height)
+    p.time, p.dt, p.frame_index = time, dt, frame_index
+    return p
+
+
+class PinnedBuffer:
+    """Page-locked host frame buffer (what an N-API external ArrayBuffer would wrap)."""
+
+    def __init__(self, nbytes):
+        self.ptr = C.c_void_p()
+        self.nbytes = nbytes
+        check(lib().gvt_host_alloc(nbytes, C.byref(self.ptr)))
+
+    def array(self, dtype, shape):
+        buf = (C.c_uint8 * self.nbytes).from_address(self.ptr.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            lib().gvt_host_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+    __del__ = free
+
+
+class KerrRenderer:
+    def __init__(self, device=0, rank=0, world_size=1, nccl_id=None):
+        self._h = C.c_void_p()
+        self.device, self.rank, self.world_size = device, rank, world_size
+        self._nccl_id = nccl_id
+        self.params = RenderParams()
+        self.width = self.height = 0
+        self.last_stats = None
+        self._pinned = None
+
+    # WebGPURenderer.init (renderer.ts:82-136): acquire the device
+    def init(self):
+        cfg = GvtDeviceConfig()
+        cfg.struct_size = C.sizeof(cfg)
+        cfg.device, cfg.rank, cfg.world_size = self.device, self.rank, self.world_size
+        if self.world_size > 1:
+            if self._nccl_id is None or len(self._nccl_id) != 128:
+                raise ValueError("world_size > 1 needs the 128-byte ncclUniqueId from nccl_unique_id() on rank 0")
+            C.memmove(cfg.nccl_id, bytes(self._nccl_id), 128)
+        check(lib().gvt_render_create(C.byref(cfg), C.byref(self._h)))
+        return True
+
+    @staticmethod
+    def nccl_unique_id():
+        out = (C.c_uint8 * 128)()
+        check(lib().gvt_nccl_unique_id(out))
+        return bytes(out)
+
+    # initPipelines(format, maxSteps) (renderer.ts:186-254) + SpectralManager.initialize (spectral.ts:21-61)
+    def init_pipelines(self, max_steps=None, mass=1.0, spin=0.999, spec_w=256, spec_h=32, max_temp=1e7):
+        if max_steps is not None:
+            self.params.c.max_steps = int(max_steps)
+        check(lib().gvt_render_init_luts(self._h, mass, spin, spec_w, spec_h, max_temp))
+
+    def set_luts(self, spectrum, spec_w, spec_h, tdisk, rin, rout):
+        spectrum = np.ascontiguousarray(spectrum, np.float32)
+        tdisk = np.ascontiguousarray(tdisk, np.float32)
+        pf = C.POINTER(C.c_float)
+        check(lib().gvt_render_set_luts(self._h, spectrum.ctypes.data_as(pf), spec_w, spec_h, tdisk.ctypes.data_as(pf),
+                                        tdisk.size, rin, rout))
+
+    def update_settings(self, max_steps):  # renderer.ts:256-263
+        self.params.c.max_steps = int(max_steps)
+
+    def resize(self, width, height):  # renderer.ts:269-278
+        check(lib().gvt_render_resize(self._h, int(width), int(height)))
+        self.width, self.height = int(width), int(height)
+
+    def pinned_frame(self, width, height, fmt=_lib.FORMAT_RGBA32F):
+        nbytes = width * height * (16 if fmt == _lib.FORMAT_RGBA32F else 8)
+        if self._pinned is None or self._pinned.nbytes != nbytes:
+            self._pinned = PinnedBuffer(nbytes)
+        return self._pinned
+
+    def render(self, camera, physics, out=None, readback=True):
+        """render(camera: CameraUniforms[88 f32], physics: PhysicsParams) (renderer.ts:280).
+
+        Returns the frame (H, W, 4) float32 (or float16 for RGBA16F) when ``readback``; with ``readback=False`` the
+        frame stays in device memory (use ``read_frame``). ``out`` may be a PinnedBuffer to receive the frame."""
+        cam = camera if isinstance(camera, GvtCamera) else pack_camera(camera)
+        W, H = int(physics.resolution[0]), int(physics.resolution[1])
+        st = GvtFrameStats()
+        host = None
+        if readback:
+            buf = out if out is not None else self.pinned_frame(W, H, self.params.c.output_format)
+            host = buf.ptr
+        check(lib().gvt_render_frame(self._h, C.byref(cam), C.byref(physics), C.byref(self.params.c), host, C.byref(st)))
+        self.width, self.height = W, H
+        self.last_stats = _stats(st)
+        if not readback:
+            return None
+        dt = np.float32 if self.params.c.output_format == _lib.FORMAT_RGBA32F else np.float16
+        return buf.array(dt, (H, W, 4))
+
+    def read_frame(self, fmt=_lib.FORMAT_RGBA32F):
+        dt = np.float32 if fmt == _lib.FORMAT_RGBA32F else np.float16
+        out = np.zeros((self.height, self.width, 4), dt)
+        check(lib().gvt_render_read_frame(self._h, fmt, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def trace_states(self, camera, physics, x0=0, xs=1, y0=0, y1=None, ys=1):
+        """Parity hook: per-pixel final (x,p), termination, steps, max|H|, f64 RGBA over a pixel lattice."""
+        cam = camera if isinstance(camera, GvtCamera) else pack_camera(camera)
+        W, H = int(physics.resolution[0]), int(physics.resolution[1])
+        if y1 is None:
+            y1 = H
+        nx, ny = (W - x0 + xs - 1) // xs, (y1 - y0 + ys - 1) // ys
+        xp = np.zeros((ny, nx, 8))
+        term = np.zeros((ny, nx), np.uint32)
+        steps = np.zeros((ny, nx), np.uint32)
+        drift = np.zeros((ny, nx))
+        rgba = np.zeros((ny, nx, 4))
+        pd, pu = C.POINTER(C.c_double), C.POINTER(C.c_uint32)
+        check(lib().gvt_trace_states(self._h, C.byref(cam), C.byref(physics), C.byref(self.params.c), x0, xs, y0, y1, ys,
+                                     xp.ctypes.data_as(pd), term.ctypes.data_as(pu), steps.ctypes.data_as(pu),
+                                     drift.ctypes.data_as(pd), rgba.ctypes.data_as(pd)))
+        return dict(xp=xp, term=term, steps=steps, drift=drift, rgba=rgba)
+
+    def taa_resolve(self, camera, cur, hist):
+        cam = camera if isinstance(camera, GvtCamera) else pack_camera(camera)
+        cur = np.ascontiguousarray(cur, np.float32)
+        hist = np.ascontiguousarray(hist, np.float32)
+        H, W = cur.shape[:2]
+        out = np.zeros_like(cur)
+        pf = C.POINTER(C.c_float)
+        check(lib().gvt_taa_resolve(self._h, C.byref(cam), W, H, cur.ctypes.data_as(pf), hist.ctypes.data_as(pf),
+                                    out.ctypes.data_as(pf)))
+        return out
+
+    def reset_history(self):
+        check(lib().gvt_render_reset_history(self._h))
+
+    def measure_fma_peak(self, precision):
+        t, ms = C.c_double(), C.c_double()
+        check(lib().gvt_measure_fma_peak(self._h, precision, C.byref(t), C.byref(ms)))
+        return t.value, ms.value
+
+    def device_info(self):
+        sm, ma, mi = C.c_int32(), C.c_int32(), C.c_int32()
+        name = C.create_string_buffer(256)
+        check(lib().gvt_device_info(self._h, C.byref(sm), C.byref(ma), C.byref(mi), name))
+        return dict(sm_count=sm.value, cc=(ma.value, mi.value), name=name.value.decode())
+
+    def cleanup(self):  # WebGLRenderer.cleanup (webgl/renderer.ts:471)
+        if self._h:
+            lib().gvt_render_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = cleanup

@@ -1,0 +1,206 @@
+/* gravitas_b200.h — C ABI of libgravitas_b200.so: the B200-native replacement for the reference's
+ * per-pixel Kerr geodesic hot path, behind the reference's own two seams.
+ *
+ *   Seam A  `PhysicsEngine` (wasm-bindgen class, physics-engine/gravitas-wasm/src/lib.rs:42-465) and the
+ *           SharedArrayBuffer f32-offset protocol (lib.rs:36-40, sab.rs:18-22, src/engine/physics-bridge.ts:5-11).
+ *   Seam B  the src/rendering renderer / frame-buffer API (src/rendering/webgpu/renderer.ts:280 `render(camera,
+ *           physics)`; uniform layouts src/types/webgpu.ts:25,42,67-116 and src/shaders/types.wgsl.ts:6-29).
+ *
+ * Conventions: every entry point returns an int32 status (GVT_OK = 0, negative = error; the reference has no
+ * error returns — Rust panics go to console_error_panic_hook, lib.rs:30-33 — so hosts may ignore it exactly as
+ * they do today, or read gvt_last_error()). No exceptions cross the boundary. Handles are opaque. The caller
+ * owns every buffer it passes. Thread-compatible, not thread-safe: one handle per thread (the worker model of
+ * src/workers/physics.worker.ts). All arithmetic on this path runs in hand-written sm_100a CUDA kernels; there
+ * is no CPU fallback — creation fails with GVT_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef GRAVITAS_B200_H
+#define GRAVITAS_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GVT_ABI_VERSION 1
+
+/* status codes */
+enum {
+    GVT_OK = 0,
+    GVT_ERR_INVALID = -1,     /* null pointer / bad argument */
+    GVT_ERR_NO_DEVICE = -2,   /* no usable CUDA device (the product has no CPU path) */
+    GVT_ERR_CUDA = -3,        /* CUDA runtime error, see gvt_last_error() */
+    GVT_ERR_NCCL = -4,        /* NCCL error / libnccl not loadable for world_size > 1 */
+    GVT_ERR_UNSUPPORTED = -5
+};
+
+/* SAB v2 layout: f32 ELEMENT indices (lib.rs:36-40; sab.rs:18-22; physics-bridge.ts:5-11) */
+#define GVT_SAB_OFFSET_CONTROL 0
+#define GVT_SAB_OFFSET_CAMERA 64
+#define GVT_SAB_OFFSET_PHYSICS 128
+#define GVT_SAB_OFFSET_TELEMETRY 256
+#define GVT_SAB_OFFSET_LUTS 2048
+#define GVT_SAB_INTERNAL_F32 2048 /* engine-owned buffer when no SAB is attached (lib.rs:67) */
+
+/* geodesic/termination.rs:4-17 (#[repr(C)]) */
+enum { GVT_TERM_NONE = 0, GVT_TERM_HORIZON = 1, GVT_TERM_ESCAPE = 2, GVT_TERM_MAXSTEPS = 3, GVT_TERM_DISK = 4 };
+/* metric/kerr.rs:16-22 */
+enum { GVT_COORDS_BOYER_LINDQUIST = 0, GVT_COORDS_KERR_SCHILD = 1 };
+/* geodesic/integrator.rs:14-21 */
+enum { GVT_METHOD_RKF45 = 0, GVT_METHOD_RK4 = 1, GVT_METHOD_SYMPLECTIC = 2 };
+enum { GVT_PRECISION_F64 = 0, GVT_PRECISION_F32 = 1 };
+enum { GVT_FORMAT_RGBA32F = 0, GVT_FORMAT_RGBA16F = 1 }; /* RGBA16F = reprojection.ts:120-140 texture format */
+/* step rule for the fixed-step methods: constant `initial_step` (geodesic/mod.rs:218-223) or the per-step rule
+ * h = clamp(0.15 (r - r+), 0.05, 1.0) of src/shaders/compute.wgsl.ts:213 */
+enum { GVT_STEP_CONSTANT = 0, GVT_STEP_WGSL = 1 };
+
+enum {
+    GVT_FLAG_JITTER = 1u << 0,      /* Halton(2,3) sub-pixel jitter on frame_index (compute.wgsl.ts:153-157) */
+    GVT_FLAG_BUDGET = 1u << 1,      /* budget accounting: every pixel executes exactly max_steps step computations;
+                                       terminated rays keep stepping with commits masked */
+    GVT_FLAG_TRACK_DRIFT = 1u << 2, /* max |H| per ray, as geodesic/mod.rs:233-237 */
+    GVT_FLAG_TAA = 1u << 3,         /* run the TAA resolve (ataa.wgsl.ts:28-83) after the trace */
+    GVT_FLAG_NO_GATHER = 1u << 4    /* multi-GPU: skip the all-gather (each rank keeps only its row block) */
+};
+
+/* src/types/webgpu.ts:67-116 / src/shaders/types.wgsl.ts:6-16 — 352 bytes, column-major mat4 as gl-matrix */
+typedef struct GvtCamera {
+    float view[16];
+    float proj[16];
+    float inv_view[16];
+    float inv_proj[16];
+    float prev_view_proj[16];
+    float position[4];  /* xyz + pad */
+    float direction[4]; /* xyz + pad */
+} GvtCamera;
+
+/* src/types/webgpu.ts:42-64 / types.wgsl.ts:19-29 — 32 bytes */
+typedef struct GvtPhysicsParams {
+    float mass;
+    float spin; /* dimensionless a*, clamped to [-1,1] like Kerr::new (kerr.rs:49-55) */
+    float resolution[2];
+    float time;
+    float dt;
+    uint32_t frame_index;
+    uint32_t _pad;
+} GvtPhysicsParams;
+
+/* What the WGSL bakes in as constants / overrides (compute.wgsl.ts:11-15) plus IntegrationOptions
+ * (geodesic/integrator.rs:24-47; values used by the wasm seam: lib.rs:444-452). */
+typedef struct GvtRenderParams {
+    uint32_t struct_size;          /* sizeof(GvtRenderParams), for forward compatibility */
+    uint32_t method;               /* GVT_METHOD_* */
+    uint32_t precision;            /* GVT_PRECISION_* */
+    uint32_t coords;               /* GVT_COORDS_* (render path: Kerr-Schild, lib.rs:64,454-455) */
+    uint32_t step_rule;            /* GVT_STEP_* */
+    uint32_t max_steps;            /* MAX_STEPS override (compute.wgsl.ts:13) / IntegrationOptions.max_steps */
+    uint32_t renormalize_interval; /* integrator.rs:44 (10) */
+    uint32_t flags;                /* GVT_FLAG_* */
+    uint32_t output_format;        /* GVT_FORMAT_* of the host frame buffer */
+    uint32_t _pad;
+    double tolerance;              /* RKF45 local error tolerance (1e-8) */
+    double initial_step;           /* h0 (0.01) or the constant step */
+    double escape_radius;          /* 1000 (lib.rs:449) */
+    double disk_r_out;             /* thin-disk outer edge, 50 M (physics/disk.rs:177); inner = ISCO prograde */
+} GvtRenderParams;
+
+typedef struct GvtDeviceConfig {
+    uint32_t struct_size;
+    int32_t device;        /* CUDA device ordinal */
+    int32_t rank;          /* row-block shard index, 0..world_size-1 */
+    int32_t world_size;    /* 1 = single GPU */
+    uint8_t nccl_id[128];  /* ncclUniqueId from gvt_nccl_unique_id() on rank 0, broadcast by the host */
+} GvtDeviceConfig;
+
+typedef struct GvtFrameStats {
+    double trace_ms;          /* device time of the fused trace kernel (CUDA events on the launch stream) */
+    double taa_ms;            /* device time of the TAA resolve (0 when off) */
+    double gather_ms;         /* device time of the all-gather (0 at world_size 1) */
+    double total_ms;          /* first launch -> last device op of the frame, incl. copies when host buffers are used */
+    uint64_t steps_committed; /* accepted geodesic steps summed over this rank's pixels (device-counted) */
+    uint64_t steps_executed;  /* step computations executed (= pixels*max_steps in budget mode) */
+    uint64_t rhs_evals;       /* Hamiltonian RHS evaluations */
+    uint64_t n_horizon, n_escape, n_maxsteps, n_disk; /* termination census */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint32_t kernel_launches; /* kernels of this library launched for the frame */
+    uint32_t rows_begin, rows_end; /* this rank's row block */
+} GvtFrameStats;
+
+const char* gvt_last_error(void);
+int32_t gvt_abi_version(void);
+int32_t gvt_device_count(int32_t* out);
+
+/* ---- Seam A: PhysicsEngine (gravitas-wasm/src/lib.rs) -------------------------------------------------- */
+typedef struct gvt_engine gvt_engine;
+
+int32_t gvt_engine_create(double mass, double spin, gvt_engine** out);            /* lib.rs:59-72 `new` */
+int32_t gvt_engine_destroy(gvt_engine* e);                                          /* wasm-bindgen `.free()` */
+int32_t gvt_engine_update_params(gvt_engine* e, double mass, double spin);         /* lib.rs:78-83 */
+int32_t gvt_engine_attach_sab(gvt_engine* e, float* sab);                           /* lib.rs:74-76 */
+int32_t gvt_engine_get_sab_ptr(gvt_engine* e, const float** out);                   /* lib.rs:116-118 */
+int32_t gvt_engine_get_sab_layout(gvt_engine* e, uint32_t out5[5]);                 /* lib.rs:411-419 */
+int32_t gvt_engine_tick_sab(gvt_engine* e, double dt_override);                     /* lib.rs:308-409 */
+int32_t gvt_engine_set_camera_state(gvt_engine* e, double px, double py, double pz,
+                                    double lx, double ly, double lz);               /* lib.rs:120-122 */
+int32_t gvt_engine_set_auto_spin(gvt_engine* e, int32_t enabled);                   /* lib.rs:124-126 */
+int32_t gvt_engine_compute_horizon(gvt_engine* e, double* out);                     /* lib.rs:85-87 */
+int32_t gvt_engine_compute_isco(gvt_engine* e, double* out);                        /* lib.rs:89-91 */
+int32_t gvt_engine_compute_photon_sphere(gvt_engine* e, double* out);               /* lib.rs:93-95 */
+int32_t gvt_engine_compute_dilation(gvt_engine* e, double r, double* out);          /* lib.rs:97-105 */
+int32_t gvt_engine_compute_g_factor(gvt_engine* e, double r, double lambda, double* out); /* redshift.rs:65-95 */
+int32_t gvt_engine_generate_disk_lut(gvt_engine* e, float* out512);                 /* lib.rs:107-110 */
+int32_t gvt_engine_generate_spectrum_lut(gvt_engine* e, uint32_t width, uint32_t height, double max_temp,
+                                         float* out_rgba);                          /* lib.rs:128-136 */
+/* lib.rs:422-464 integrate_ray_relativistic: RKF45, h0 0.01, escape 1000, renorm 10. Runs on the GPU.
+ * term / steps_taken / max_drift may be NULL. */
+int32_t gvt_engine_integrate_ray(gvt_engine* e, const double in8[8], uint64_t steps, double tolerance,
+                                 int32_t use_kerr_schild, double out8[8], uint32_t* term, uint64_t* steps_taken,
+                                 double* max_drift);
+/* Batched form of the same call (n rays, xp[n][8]); geodesic::integrate (geodesic/mod.rs:180-253) with full
+ * IntegrationOptions. Output arrays other than out_xp may be NULL. */
+int32_t gvt_engine_integrate_rays(gvt_engine* e, const GvtRenderParams* opts, uint64_t n, const double* in_xp,
+                                  double* out_xp, uint32_t* term, uint32_t* steps_taken, double* max_drift,
+                                  uint32_t* rhs_evals);
+
+/* ---- Seam B: renderer / frame buffer ------------------------------------------------------------------- */
+typedef struct gvt_renderer gvt_renderer;
+
+int32_t gvt_nccl_unique_id(uint8_t out128[128]);
+int32_t gvt_render_params_default(GvtRenderParams* p); /* config-3 defaults: symplectic, f64, KS, WGSL rule, 512 */
+int32_t gvt_render_create(const GvtDeviceConfig* cfg, gvt_renderer** out);          /* WebGPURenderer.init */
+int32_t gvt_render_destroy(gvt_renderer* r);
+/* (Re)build the spectral LUT (physics/spectrum.rs:76-102) and disk temperature LUT (physics/disk.rs:175-201)
+ * for (mass, spin) on the host and upload them. Mirrors SpectralManager.initialize (rendering/spectral.ts:21-61). */
+int32_t gvt_render_init_luts(gvt_renderer* r, double mass, double spin, uint32_t spec_w, uint32_t spec_h,
+                             double max_temp);
+/* Upload caller-provided LUTs instead (spectrum: w*h*4 f32; tdisk: n f32 over [rin, rout]). */
+int32_t gvt_render_set_luts(gvt_renderer* r, const float* spectrum, uint32_t spec_w, uint32_t spec_h,
+                            const float* tdisk, uint32_t tdisk_n, double tdisk_rin, double tdisk_rout);
+int32_t gvt_render_resize(gvt_renderer* r, uint32_t width, uint32_t height);        /* renderer.ts:269-278 */
+/* renderer.ts:280 `render(camera, physics)`: trace (+TAA) (+all-gather); the finished frame is copied into
+ * host_rgba (width*height*4 f32 or f16) when it is non-NULL, else it stays in device memory. */
+int32_t gvt_render_frame(gvt_renderer* r, const GvtCamera* cam, const GvtPhysicsParams* phys,
+                         const GvtRenderParams* params, void* host_rgba, GvtFrameStats* stats);
+int32_t gvt_render_read_frame(gvt_renderer* r, uint32_t format, void* host_rgba);
+/* Parity hook: per-pixel final state (x,p)[8] f64, termination, accepted steps, max|H|, f64 RGBA over the pixel
+ * lattice x = x0 + i*xs, y = y0 + j*ys (y < y1). Any output may be NULL. */
+int32_t gvt_trace_states(gvt_renderer* r, const GvtCamera* cam, const GvtPhysicsParams* phys,
+                         const GvtRenderParams* params, uint32_t x0, uint32_t xs, uint32_t y0, uint32_t y1,
+                         uint32_t ys, double* out_xp8, uint32_t* term, uint32_t* steps, double* max_drift,
+                         double* rgba64);
+/* TAA resolve on caller-provided frames (ataa.wgsl.ts:28-83): cur, hist, out are width*height*4 f32 host buffers. */
+int32_t gvt_taa_resolve(gvt_renderer* r, const GvtCamera* cam, uint32_t width, uint32_t height, const float* cur,
+                        const float* hist, float* out);
+int32_t gvt_render_reset_history(gvt_renderer* r);
+/* Pinned host memory for frame buffers (what an N-API external ArrayBuffer would wrap). */
+int32_t gvt_host_alloc(size_t bytes, void** out);
+int32_t gvt_host_free(void* p);
+/* In-run FMA-pipe micro-benchmarks (dependent-chain FFMA / DFMA, all SMs): the FP32/FP64 roofline denominators
+ * MEASURED_PEAKS.json does not carry. Returns TFLOP/s (2 flop per FMA). */
+int32_t gvt_measure_fma_peak(gvt_renderer* r, int32_t precision, double* out_tflops, double* out_ms);
+int32_t gvt_device_info(gvt_renderer* r, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, char name[256]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAVITAS_B200_H */

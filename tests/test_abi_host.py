@@ -1,0 +1,143 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports every symbol include/gravitas_b200.h
+declares; host-side (once-per-tick) functions agree with the oracle bit-for-bit; compute entry points fail loudly
+without a GPU. No compute kernels run here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "gravitas_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gvt_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    from gravitas_b200 import _lib
+    L = C.CDLL(built.lib_path())
+    syms = header_symbols()
+    assert len(syms) >= 35
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/gravitas_b200.h but not exported"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes signature in gravitas_b200/_lib.py"
+    assert built.lib().gvt_abi_version() == 1
+
+
+def test_struct_layouts_match_reference_uniforms(built):
+    from gravitas_b200 import _lib
+    assert C.sizeof(_lib.GvtCamera) == 352          # types/webgpu.ts:25 CAMERA_UNIFORM_SIZE
+    assert C.sizeof(_lib.GvtPhysicsParams) == 32    # types/webgpu.ts:42 PHYSICS_PARAM_SIZE
+    assert _lib.GvtCamera.inv_view.offset == 128 and _lib.GvtCamera.inv_proj.offset == 192
+    assert _lib.GvtCamera.prev_view_proj.offset == 256 and _lib.GvtCamera.position.offset == 320
+    assert _lib.GvtPhysicsParams.frame_index.offset == 24
+    assert built.OFFSETS == {"CONTROL": 0, "CAMERA": 64, "PHYSICS": 128, "TELEMETRY": 256, "LUTS": 2048}
+
+
+def test_engine_scalars_match_oracle_bitwise(built, oracle):
+    L = oracle.lib()
+    for m, a in [(1.0, 0.0), (1.0, 0.5), (1.0, 0.9), (1.0, 0.999), (2.5, -0.7), (1.0, 1.0)]:
+        e = built.PhysicsEngine(m, a)
+        assert e.compute_horizon() == L.orc_event_horizon(m, a, 0)
+        assert e.compute_isco() == L.orc_isco(m, a, 1)
+        assert e.compute_photon_sphere() == L.orc_photon_sphere(m, a)
+        for r in (1.2, 2.0, 3.0, 10.0):
+            td = L.orc_time_dilation(m, a, r, np.pi / 2)
+            assert e.compute_dilation(r) == (100.0 if td <= 0 else 1.0 / td)   # lib.rs:97-105
+            assert e.compute_g_factor(r + 5, 1.3) == L.orc_g_factor(r + 5, m, a, 1.3)
+        assert e.get_sab_layout() == [0, 64, 128, 256, 2048]
+
+
+def test_luts_match_oracle_bitwise(built, oracle):
+    e = built.PhysicsEngine(1.0, 0.999)
+    assert np.array_equal(e.generate_disk_lut(), oracle.disk_lut(1.0, 0.999))
+    assert np.array_equal(e.generate_spectrum_lut(48, 12, 1e7), oracle.spectrum_lut(48, 12, 1e7, serial=True))
+    e2 = built.PhysicsEngine(1.0, 0.0)
+    assert np.array_equal(e2.generate_disk_lut(), oracle.disk_lut(1.0, 0.0))
+    lut = e.generate_disk_lut()
+    assert lut.shape == (512,) and lut[0] == 0.0 and lut.max() == 1.0
+
+
+def test_tick_sab_protocol(built):
+    e = built.PhysicsEngine(1.0, 0.9)
+    sab = e.get_sab_ptr()
+    assert sab.shape == (2048,) and not sab.any()
+    sab[1], sab[2], sab[3], sab[4] = 0.25, -0.5, 0.1, 0.016     # CONTROL: mouse_dx, mouse_dy, zoom, dt
+    e.tick_sab(0.0)                                             # dt <= 0 -> read control[4] (lib.rs:319-323)
+    assert sab[1] == 0 and sab[2] == 0 and sab[3] == 0 and sab[4] == np.float32(0.016)   # inputs consumed
+    cam = sab[64:76]
+    yaw = -0.25 * 2.0 * float(np.float32(0.016))
+    zf = 1.0 + float(np.float32(0.1)) * float(np.float32(0.016))
+    np.testing.assert_allclose(cam[0:3], [20 * np.sin(yaw) * zf, 0.0, 20 * np.cos(yaw) * zf], rtol=1e-6, atol=1e-7)
+    assert list(cam[8:12]) == [0.0, 1.0, 0.0, 0.0]              # orientation xyzw (camera.rs:31)
+    phys = sab[128:256]
+    assert phys[0] == np.float32(e.compute_horizon()) and phys[1] == np.float32(e.compute_isco())
+    assert phys[2] == 1.0 and phys[3] == np.float32(0.9) and phys[15] == 64.0
+    assert phys[4] < 0 < phys[5]                                # shadow extents min/max alpha
+    # The reference writes 64 (alpha,beta) pairs from PHYSICS+16, i.e. f32 indices 144..271: the last 16 floats
+    # spill into the TELEMETRY block and the "sequence" increment lands on curve[56].alpha (lib.rs:381-407). Kept.
+    curve_tail = sab[256:272].copy()
+    assert np.any(curve_tail != 0)
+    # external SAB (attach_sab, lib.rs:74-76) receives the same writes
+    ext = np.zeros(4096, np.float32)
+    e2 = built.PhysicsEngine(1.0, 0.9)
+    e2.attach_sab(ext)
+    ext[1], ext[2], ext[3], ext[4] = 0.25, -0.5, 0.1, 0.016
+    e2.tick_sab(0.0)
+    assert np.array_equal(ext[:2048], sab)
+    # NaN guard: camera falls back to last-good (lib.rs:339-343)
+    e2.set_camera_state(float("nan"), 0.0, 0.0)
+    e2.tick_sab(0.016)
+    assert np.all(np.isfinite(ext[64:76]))
+    # auto spin rotates about Y at 0.15 rad/s (camera.rs:60-65)
+    e3 = built.PhysicsEngine(1.0, 0.0)
+    e3.set_auto_spin(True)
+    e3.tick_sab(1.0)
+    s3 = e3.get_sab_ptr()
+    np.testing.assert_allclose(s3[64:67], [20 * np.sin(0.15), 0, 20 * np.cos(0.15)], rtol=1e-6, atol=1e-6)
+    assert s3[143] == 32.0                                      # a = 0 -> 32-point circle (shadow.rs:90-99)
+    np.testing.assert_allclose(np.hypot(s3[144:208:2], s3[145:208:2]), 3 * np.sqrt(3), rtol=1e-6)
+
+
+def test_camera_uniforms_are_consistent(built):
+    from gravitas_b200 import camera
+    cam, vp = camera.default_camera(1920, 1080)
+    V, P = cam[0:16].reshape(4, 4).T.astype(np.float64), cam[16:32].reshape(4, 4).T.astype(np.float64)
+    IV, IP = cam[32:48].reshape(4, 4).T.astype(np.float64), cam[48:64].reshape(4, 4).T.astype(np.float64)
+    np.testing.assert_allclose(V @ IV, np.eye(4), atol=1e-5)
+    np.testing.assert_allclose(P @ IP, np.eye(4), atol=1e-4)
+    np.testing.assert_allclose(np.linalg.norm(cam[80:83]), 30.0, rtol=1e-6)
+    assert abs(np.degrees(np.arccos(cam[81] / 30.0)) - 97.0) < 1e-4
+    np.testing.assert_allclose(vp.reshape(4, 4).T, P @ V, rtol=1e-5, atol=1e-5)
+    assert cam[83] == 0 and cam[87] == 0
+
+
+def test_compute_fails_loudly_without_gpu(built):
+    n = C.c_int32(-1)
+    rc = built.lib().gvt_device_count(C.byref(n))
+    if rc == 0 and n.value > 0:
+        pytest.skip("a GPU is present; the no-device path is exercised on CPU-only hosts")
+    e = built.PhysicsEngine(1.0, 0.9)
+    with pytest.raises(built.GravitasError) as ei:
+        e.integrate_ray_relativistic([0, 20, 1.57, 0, -1, -1, 0, 3.5], 100, 1e-8, True)
+    assert ei.value.code == -2
+    assert list(e.integrate_ray_relativistic([1, 2, 3], 100, 1e-8, True)) == [1, 2, 3]   # lib.rs:429-431
+    r = built.KerrRenderer()
+    with pytest.raises(built.GravitasError) as ei:
+        r.init()
+    assert ei.value.code == -2
+
+
+def test_product_does_not_reference_the_oracle():
+    pkg = os.path.join(ROOT, "blackhole-simulation_b200")
+    for dp, _, fns in os.walk(pkg):
+        if os.path.basename(dp) in ("build", "__pycache__"):
+            continue
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
+                txt = open(os.path.join(dp, fn), errors="ignore").read()
+                assert "liboracle" not in txt and "gravitas_oracle" not in txt and "import oracle" not in txt, fn

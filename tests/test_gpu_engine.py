@@ -1,0 +1,70 @@
+"""PhysicsEngine.integrate_ray_relativistic and the batched integrate on the GPU vs the oracle / known answers."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+KAT = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kat.json")))["survey"]
+
+
+def test_integrate_ray_relativistic_doctest_ray(built, oracle):
+    e = built.PhysicsEngine(1.0, 0.9)
+    ray = [0, 20, math.pi / 2, 0, -1, -1, 0, 3.5]
+    for use_ks, key in ((False, "doctest_ray_bl"), (True, "doctest_ray_ks")):
+        out = e.integrate_ray_relativistic(ray, 10000, 1e-8, use_ks)
+        np.testing.assert_allclose(out[:4], KAT[key]["x"], rtol=1e-9)
+        ref = oracle.integrate(1, 0.9, 1 if use_ks else 0, oracle.Options.default(), ray)["xp"][0]
+        np.testing.assert_allclose(out, ref, rtol=1e-9, atol=1e-13)
+    assert list(e.integrate_ray_relativistic([1.0, 2.0], 10, 1e-8, True)) == [1.0, 2.0]
+
+
+@pytest.mark.parametrize("coords", [0, 1])
+@pytest.mark.parametrize("method", [0, 1, 2])
+def test_batched_integrate_vs_oracle(built, oracle, coords, method):
+    from gravitas_b200 import renderer as R
+    rng = np.random.default_rng(1234 + 10 * coords + method)
+    n = 512
+    xp = np.zeros((n, 8))
+    xp[:, 1] = rng.uniform(6.0, 40.0, n)
+    xp[:, 2] = rng.uniform(0.3, math.pi - 0.3, n)
+    xp[:, 3] = rng.uniform(0, 2 * math.pi, n)
+    xp[:, 4] = -1.0
+    xp[:, 5] = rng.uniform(-1.0, 1.0, n)
+    xp[:, 6] = rng.uniform(-3.0, 3.0, n)
+    xp[:, 7] = rng.uniform(-6.0, 6.0, n)
+    e = built.PhysicsEngine(1.0, 0.9)
+    p = R.RenderParams(method=method, coords=coords, step_rule=0, max_steps=400 if method == 0 else 300,
+                       initial_step=0.01 if method == 0 else 0.05)
+    got = e.integrate_rays(xp, p)
+    opts = oracle.Options.default(method=method, step_rule=0, max_steps=p.c.max_steps, initial_step=p.c.initial_step)
+    ref = oracle.integrate(1.0, 0.9, coords, opts, xp)
+    same = (got["term"] == ref["term"]) & (got["steps"] == ref["steps"])
+    assert same.mean() > 0.98, f"termination/steps agree on {same.mean():.3f}"
+    err = np.abs(got["xp"] - ref["xp"])[same] / np.maximum(np.abs(ref["xp"][same]), 1.0)
+    print(f"coords {coords} method {method}: agree {same.mean():.4f}, state err median {np.median(err):.2e} "
+          f"p99 {np.percentile(err, 99):.2e} max {err.max():.2e}")
+    assert np.percentile(err, 99) < 1e-7
+    d = np.abs(got["drift"] - ref["drift"])[same]
+    assert np.percentile(d / np.maximum(ref["drift"][same], 1e-12), 90) < 1e-3
+    if method == 0:
+        assert np.array_equal(got["rhs"][same], ref["rhs"][same].astype(np.uint32))
+
+
+def test_legacy_known_answers_on_gpu(built):
+    """_legacy_src/integrator.rs:352-386 (horizon crossing, KS a=0.9) through the GPU integrator: ends captured."""
+    from gravitas_b200 import renderer as R
+    e = built.PhysicsEngine(1.0, 0.9)
+    p = R.RenderParams(method=0, coords=1, step_rule=0, max_steps=1000, tolerance=1e-11)
+    got = e.integrate_rays([[0, 3, 1.57, 0, -1, -1, 0, 0]], p)
+    assert got["term"][0] == 1 and got["xp"][0, 1] < 1.4358898944 * 1.001
+    assert got["drift"][0] < 1e-4          # _legacy_src/integrator.rs:146-149 bound
+
+
+def test_empty_batch(built):
+    from gravitas_b200 import renderer as R
+    e = built.PhysicsEngine(1.0, 0.9)
+    got = e.integrate_rays(np.zeros((0, 8)), R.RenderParams())
+    assert got["xp"].shape == (0, 8)

@@ -1,0 +1,211 @@
+"""Parity tests proper: the sm_100a kernels, called through the C ABI, against the CPU oracle on identical inputs.
+
+Tolerance (north_star): <= 1e-6 relative per RGBA component. "Relative" needs a floor for components that are
+(near) zero: |gpu - ref| <= 1e-6 * max(|ref|, 1e-3 * frame_peak). Near-critical rays amplify 1-ulp differences
+(CUDA vs glibc sin/cos/pow, FMA contraction) exponentially and the disk-crossing / termination tests are
+discontinuous, so a pixel is allowed to miss only if the ORACLE ITSELF is unstable there: its result changes by
+more than the tolerance under a 1e-13 relative perturbation of the camera position (SURVEY §7 hard part 2). The
+excluded fraction is asserted to be tiny and is printed."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-6
+SPEC_W, SPEC_H, TMAX = 64, 16, 1e7
+
+
+def rel_err(gpu, ref):
+    ref = np.asarray(ref, np.float64)
+    peak = max(float(np.abs(ref[..., :3]).max()), 1e-300)
+    return np.abs(np.asarray(gpu, np.float64) - ref) / np.maximum(np.abs(ref), 1e-3 * peak)
+
+
+@pytest.fixture(scope="module")
+def luts(oracle):
+    return oracle.spectrum_lut(SPEC_W, SPEC_H, TMAX), oracle.disk_lut(1.0, 0.999)
+
+
+def setup(renderer, oracle, luts, W, H, **kw):
+    from gravitas_b200 import camera, renderer as R, _lib
+    spec, td = luts
+    spin = kw.pop("spin", 0.999)
+    if spin != 0.999:
+        td = oracle.disk_lut(1.0, spin)
+    renderer.init_pipelines(mass=1.0, spin=spin, spec_w=SPEC_W, spec_h=SPEC_H, max_temp=TMAX)
+    method = kw.pop("method", _lib.METHOD_SYMPLECTIC)
+    steps = kw.pop("max_steps", 256)
+    precision = kw.pop("precision", 0)
+    flags = kw.pop("flags", 0)
+    frame_index = kw.pop("frame_index", 0)
+    cam_kw = kw.pop("cam", {})
+    renderer.params = R.RenderParams(method=method, max_steps=steps, precision=precision, flags=flags,
+                                     step_rule=1 if method != 0 else 0, **kw)
+    cam, _ = camera.default_camera(W, H, **cam_kw)
+    phys = R.pack_physics(1.0, spin, W, H, frame_index=frame_index)
+    opts = oracle.Options.default(method=method, step_rule=1 if method != 0 else 0, max_steps=steps)
+    for k in ("tolerance", "initial_step", "escape_radius"):
+        if k in kw:
+            setattr(opts, k, kw[k])
+    rp, keep = oracle.make_render_params(W, H, 1.0, spin, opts, precision=precision, frame_index=frame_index,
+                                         jitter=1 if flags & 1 else 0, spectrum=spec, spec_w=SPEC_W, spec_h=SPEC_H,
+                                         tdisk=td)
+    return cam, phys, rp, keep
+
+
+def unstable_mask(oracle, cam, rp, ref, **lattice):
+    """Pixels where the oracle's own RGBA moves by > TOL under a 1e-13 relative nudge of the camera position."""
+    cam2 = np.array(cam, np.float32).copy()
+    out = np.zeros(ref["rgba"].shape[:2], bool)
+    # the uniforms are f32, so nudge through the f64 oracle instead: perturb mass by 1e-13 relative
+    rp2 = type(rp).from_buffer_copy(rp)
+    rp2.mass = rp.mass * (1.0 + 1e-13)
+    alt = oracle.render(cam2, rp2, want=("rgba", "term"), **lattice)
+    out |= (rel_err(alt["rgba"], ref["rgba"]) > TOL).any(-1)
+    out |= alt["term"] != ref["term"]
+    return out
+
+
+def compare(renderer, oracle, cam, phys, rp, lattice=None, allow_unstable=2e-3, check_states=True):
+    lattice = lattice or {}
+    ref = oracle.render(cam, rp, **lattice)
+    got = renderer.trace_states(cam, phys, **lattice)
+    e_rgba = rel_err(got["rgba"], ref["rgba"]).max(-1)
+    bad = e_rgba > TOL
+    term_diff = got["term"] != ref["term"]
+    n = bad.size
+    info = f"pixels {n}, lit {(ref['rgba'][..., :3].sum(-1) > 0).sum()}, max rel err {e_rgba.max():.3e}, " \
+           f"bad {bad.sum()}, term diff {term_diff.sum()}"
+    if bad.any() or term_diff.any():
+        unstable = unstable_mask(oracle, cam, rp, ref, **lattice)
+        unexplained = (bad | term_diff) & ~unstable
+        info += f", oracle-unstable {unstable.sum()}, unexplained {unexplained.sum()}"
+        print(info)
+        assert unexplained.sum() == 0, info
+        assert (bad | term_diff).sum() <= max(1, allow_unstable * n), info
+    else:
+        print(info)
+    ok = ~(bad | term_diff)
+    if check_states:
+        # final phase-space state of stable rays: tight agreement
+        np.testing.assert_array_equal(got["steps"][ok], ref["steps"][ok])
+        ex = np.abs(got["xp"] - ref["xp"])[ok] / np.maximum(np.abs(ref["xp"][ok]), 1.0)
+        assert np.percentile(ex, 99) < 1e-8, f"state p99 rel err {np.percentile(ex, 99):.3e}"
+    return ref, got
+
+
+def test_fma_contraction_level_parity_small_frame(renderer, oracle, luts):
+    """config-3 scheme (implicit midpoint + WGSL step rule, f64, LUT) on a small frame, every pixel."""
+    cam, phys, rp, keep = setup(renderer, oracle, luts, 160, 90, max_steps=512)
+    ref, got = compare(renderer, oracle, cam, phys, rp)
+    assert (ref["term"] == 1).sum() > 0 and (ref["crossings"] > 0).sum() > 100
+
+
+def test_render_frame_matches_trace_states_and_oracle(renderer, oracle, luts):
+    """The production entry point (float4 frame buffer, not the parity hook) gives the same pixels."""
+    cam, phys, rp, keep = setup(renderer, oracle, luts, 128, 72, max_steps=256)
+    frame = np.array(renderer.render(cam, phys))
+    st = renderer.last_stats
+    dbg = renderer.trace_states(cam, phys)
+    assert np.array_equal(frame, dbg["rgba"].astype(np.float32))
+    assert np.all(frame[..., 3] == 1.0)                      # compute.wgsl.ts:257 alpha = 1
+    ref = oracle.render(cam, rp, want=("rgba", "steps", "term"))
+    assert (rel_err(frame, ref["rgba"]).max(-1) > TOL).sum() <= 2
+    assert st.steps_committed == int(dbg["steps"].sum())
+    assert st.n_horizon + st.n_escape + st.n_maxsteps + st.n_disk == 128 * 72
+    assert st.n_horizon == int((dbg["term"] == 1).sum())
+    assert st.kernel_launches == 1 and st.d2h_bytes >= 128 * 72 * 16
+
+
+def test_budget_mode_same_pixels_more_work(renderer, oracle, luts):
+    from gravitas_b200 import _lib
+    cam, phys, rp, keep = setup(renderer, oracle, luts, 96, 54, max_steps=192)
+    natural = np.array(renderer.render(cam, phys))
+    st_n = renderer.last_stats
+    renderer.params.c.flags = _lib.FLAG_BUDGET
+    budget = np.array(renderer.render(cam, phys))
+    st_b = renderer.last_stats
+    assert np.array_equal(natural, budget)
+    assert st_b.steps_executed == 96 * 54 * 192
+    assert st_b.steps_committed == st_n.steps_committed < st_b.steps_executed
+    assert st_n.steps_executed == st_n.steps_committed
+
+
+def test_rkf45_adaptive_parity(renderer, oracle, luts):
+    """config-4 scheme: adaptive Fehlberg RKF45, tol 1e-8, escape 1000, natural termination."""
+    from gravitas_b200 import _lib
+    cam, phys, rp, keep = setup(renderer, oracle, luts, 96, 54, method=_lib.METHOD_RKF45, max_steps=1024)
+    ref, got = compare(renderer, oracle, cam, phys, rp)
+    assert (ref["term"] == 2).sum() > 0.8 * ref["term"].size      # most rays escape (SURVEY §8d probe: 96 %)
+    assert ref["steps"].max() < 1024
+
+
+def test_rk4_parity(renderer, oracle, luts):
+    from gravitas_b200 import _lib
+    cam, phys, rp, keep = setup(renderer, oracle, luts, 64, 36, method=_lib.METHOD_RK4, max_steps=256)
+    compare(renderer, oracle, cam, phys, rp)
+
+
+@pytest.mark.parametrize("spin,polar,azimuth", [(0.0, 97.0, math.pi), (0.5, 60.0, 0.3), (-0.9, 120.0, 2.0),
+                                                 (0.999, 90.0, math.pi), (0.999, 5.0, 1.0)])
+def test_other_spins_and_cameras(renderer, oracle, luts, spin, polar, azimuth):
+    """Schwarzschild, retrograde, exactly equatorial (every step 'crosses' the plane) and near-polar cameras."""
+    cam, phys, rp, keep = setup(renderer, oracle, luts, 64, 36, spin=spin, max_steps=256,
+                                cam=dict(polar_deg=polar, azimuth=azimuth))
+    compare(renderer, oracle, cam, phys, rp, allow_unstable=2e-2)
+
+
+def test_jitter_and_ragged_lattice(renderer, oracle, luts):
+    """Halton jitter on frame_index (compute.wgsl.ts:153-157); width/height not multiples of the 8x4 warp tile;
+    strided lattice with offsets."""
+    from gravitas_b200 import _lib
+    cam, phys, rp, keep = setup(renderer, oracle, luts, 157, 83, max_steps=200, flags=_lib.FLAG_JITTER, frame_index=5)
+    compare(renderer, oracle, cam, phys, rp, lattice=dict(x0=3, xs=7, y0=2, y1=81, ys=5))
+    compare(renderer, oracle, cam, phys, rp, lattice=dict(x0=150, xs=1, y0=80, y1=83, ys=1))   # 7x3 corner
+
+
+def test_config2_f32_against_f32_oracle_and_f64(renderer, oracle, luts):
+    """config 2: f32 instantiation. Against the f32 oracle (same algorithm on float) the bulk of pixels agrees to
+    f32 rounding amplified by the march; against the f64 oracle it is an accuracy statement, not parity."""
+    cam, phys, rp, keep = setup(renderer, oracle, luts, 96, 54, max_steps=256, precision=1)
+    ref32 = oracle.render(cam, rp, want=("rgba", "term"))
+    got = renderer.trace_states(cam, phys)
+    e = rel_err(got["rgba"], ref32["rgba"]).max(-1)
+    print(f"f32 kernel vs f32 oracle: median {np.median(e):.2e} p90 {np.percentile(e, 90):.2e} max {e.max():.2e}; "
+          f"term diff {(got['term'] != ref32['term']).sum()}")
+    assert np.percentile(e, 90) < 5e-2
+    assert (got["term"] != ref32["term"]).mean() < 0.02
+    rp.precision = 0
+    ref64 = oracle.render(cam, rp, want=("rgba",))
+    e64 = rel_err(got["rgba"], ref64["rgba"]).max(-1)
+    print(f"f32 kernel vs f64 oracle: median {np.median(e64):.2e} p90 {np.percentile(e64, 90):.2e}")
+    assert np.median(e64) < 1e-2
+
+
+def test_full_size_strided_sample_and_properties(renderer, oracle, luts):
+    """BASELINE config 3 at full size (3840x2160x512, f64 + LUT): the whole frame is rendered once; a strided
+    lattice of it is checked against the oracle, and size-independent properties are checked on all of it."""
+    from gravitas_b200 import _lib
+    W, H = 3840, 2160
+    cam, phys, rp, keep = setup(renderer, oracle, luts, W, H, max_steps=512)
+    frame = np.array(renderer.render(cam, phys))
+    st = renderer.last_stats
+    assert frame.shape == (H, W, 4) and np.isfinite(frame).all() and (frame[..., :3] >= 0).all()
+    assert np.all(frame[..., 3] == 1.0)
+    assert st.n_horizon + st.n_escape + st.n_maxsteps + st.n_disk == W * H
+    assert st.steps_committed <= W * H * 512 and st.rhs_evals == 3 * st.steps_committed
+    lat = dict(x0=11, xs=97, y0=7, y1=H, ys=61)
+    ref = oracle.render(cam, rp, want=("rgba", "term"), **lat)
+    sub = frame[lat["y0"]::lat["ys"], lat["x0"]::lat["xs"]]
+    e = rel_err(sub, ref["rgba"]).max(-1)
+    print(f"4K strided sample: {e.size} px, max rel err {e.max():.3e}, > tol: {(e > TOL).sum()}")
+    assert (e > TOL).sum() <= max(1, 2e-3 * e.size)
+    # idempotence: the same call gives the same bits (dynamic tile scheduling must not matter)
+    again = np.array(renderer.render(cam, phys))
+    assert np.array_equal(frame, again)
+    # budget accounting = W*H*512 exactly, same pixels
+    renderer.params.c.flags = _lib.FLAG_BUDGET
+    b = np.array(renderer.render(cam, phys))
+    assert np.array_equal(frame, b) and renderer.last_stats.steps_executed == W * H * 512
