@@ -27,7 +27,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "blackhole-simulation_b200"))
 
-W, H, STEPS, SPIN, MASS = 3840, 2160, 512, 0.999, 1.0
+W, H, STEPS, MASS = 3840, 2160, 512, 1.0
+SPIN = 0.9990000128746033   # 0.999 as the f32 the PhysicsParams uniform carries (types/webgpu.ts:42-64)
 SPEC_W, SPEC_H, TMAX = 256, 32, 1e7          # 128 KB RGBA32F spectral LUT: shared-memory resident
 # Algorithmic flop per geodesic step, SURVEY.md §8(d) (CSE'd count; add=mul=div=sqrt=1, FMA=2, sincos/pow = 0):
 FLOP_PER_STEP = {"symplectic": 330.0, "rk4": 440.0, "rkf45": 900.0}

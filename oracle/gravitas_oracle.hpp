@@ -66,6 +66,7 @@ inline Counted floor(Counted a) { return Counted(std::floor(a.v)); }
 inline double to_double(Counted a) { return a.v; }
 inline double to_double(double a) { return a; }
 inline double to_double(float a) { return (double)a; }
+inline double to_double(long double a) { return (double)a; }
 
 using std::sin; using std::cos; using std::acos; using std::sqrt; using std::fabs; using std::pow;
 using std::exp; using std::floor;

@@ -210,8 +210,11 @@ double orc_render(const float* cam88, const orc_render_params* p, uint32_t x0, u
         uint64_t lsteps = 0, lrhs = 0;
         for (uint32_t i = 0; i < nx; i++) {
             uint32_t px = x0 + i * xs, py = y0 + (uint32_t)j * ys;
-            PixelResult r = (p->precision == 1) ? render_pixel<float>(cam, rp, l, px, py)
-                                                : render_pixel<double>(cam, rp, l, px, py);
+            // precision 2 = x87 80-bit long double: used only to measure how sensitive a pixel of the f64
+            // algorithm is to rounding (tests' "oracle-unstable" mask), never as the reference value
+            PixelResult r = (p->precision == 1)   ? render_pixel<float>(cam, rp, l, px, py)
+                            : (p->precision == 2) ? render_pixel<long double>(cam, rp, l, px, py)
+                                                  : render_pixel<double>(cam, rp, l, px, py);
             size_t k = (size_t)j * nx + i;
             if (rgba) for (int c = 0; c < 4; c++) rgba[4 * k + c] = r.rgba[c];
             if (xp) for (int c = 0; c < 8; c++) xp[8 * k + c] = r.xp[c];
