@@ -22,9 +22,79 @@ namespace gvt {
 // --------------------------------------------------------------------------------------------------
 // scalar traits
 // --------------------------------------------------------------------------------------------------
+// ---- lean reciprocal: MUFU.RCP64H seed (~2^-20) + two Newton steps on the FP64 FMA pipe; no IEEE special-case
+// slow path (callers guarantee a normal, non-zero argument: Sigma >= r^2 > 0, sin^2 >= 1e-12). <= 1 ulp.
+__device__ __forceinline__ double rcp_nr(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+__device__ __forceinline__ float rcp_nr(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // MUFU.RCP, 1 ulp
+    return fmaf(y, fmaf(-x, y, 1.0f), y);
+}
+
+// ---- what one Kerr-Schild RHS needs from theta: a with a^2 = sin^2 and |a| = |sin|, and sc = sin cos.
+// Branch-free Cody-Waite reduction by the magic-number rint (valid for |theta| < 2^30 pi/2 -- geodesic polar
+// angles stay within a few multiples of pi), fdlibm minimax kernels on |r| <= pi/4, quadrant handled by two
+// selects and one sign flip: for odd k sin <-> cos and the product changes sign. ~19 FP64 ops, no I2F/F2I, no
+// Payne-Hanek slow path (CUDA's sincos() costs ~2x that in issue slots).
+__device__ __forceinline__ void trig_pair(double x, double& a, double& sc) {
+    const double kd_m = fma(x, 0.63661977236758138, 6755399441055744.0);   // x * 2/pi + 1.5*2^52
+    const int k = __double2loint(kd_m);
+    const double kd = kd_m - 6755399441055744.0;
+    double r = fma(-kd, 1.5707963267948966, x);
+    r = fma(-kd, 6.123233995736766e-17, r);
+    const double z = r * r;
+    double ps = 1.58969099521155010221e-10;
+    ps = fma(ps, z, -2.50507602534068634195e-08);
+    ps = fma(ps, z, 2.75573137070700676789e-06);
+    ps = fma(ps, z, -1.98412698298579493134e-04);
+    ps = fma(ps, z, 8.33333333332248946124e-03);
+    ps = fma(ps, z, -1.66666666666666324348e-01);
+    const double sr = fma(r * z, ps, r);
+    double pc = -1.13596475577881948265e-11;
+    pc = fma(pc, z, 2.08757232129817482790e-09);
+    pc = fma(pc, z, -2.75573143513906633035e-07);
+    pc = fma(pc, z, 2.48015872894767294178e-05);
+    pc = fma(pc, z, -1.38888888888741095749e-03);
+    pc = fma(pc, z, 4.16666666666666019037e-02);
+    const double cr = fma(z, fma(z, pc, -0.5), 1.0);
+    const bool odd = (k & 1) != 0;
+    a = odd ? cr : sr;
+    const double p = sr * cr;
+    sc = odd ? -p : p;
+}
+__device__ __forceinline__ void trig_pair(float x, float& a, float& sc) {
+    const float kf_m = fmaf(x, 0.636619772f, 12582912.0f);                  // 1.5*2^23
+    const int k = __float_as_int(kf_m);
+    const float kf = kf_m - 12582912.0f;
+    float r = fmaf(-kf, 1.57079601e+00f, x);
+    r = fmaf(-kf, 3.13916473e-07f, r);
+    r = fmaf(-kf, 5.39030253e-15f, r);
+    const float z = r * r;
+    float ps = -1.9515295891e-4f;
+    ps = fmaf(ps, z, 8.3321608736e-3f);
+    ps = fmaf(ps, z, -1.6666654611e-1f);
+    const float sr = fmaf(r * z, ps, r);
+    float pc = 2.443315711809948e-5f;
+    pc = fmaf(pc, z, -1.388731625493765e-3f);
+    pc = fmaf(pc, z, 4.166664568298827e-2f);
+    const float cr = fmaf(z, fmaf(z, pc, -0.5f), 1.0f);
+    const bool odd = (k & 1) != 0;
+    a = odd ? cr : sr;
+    const float p = sr * cr;
+    sc = odd ? -p : p;
+}
+
 template <class R> struct Num;
 template <> struct Num<double> {
-    static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+    static __device__ __forceinline__ double rcp(double x) { return rcp_nr(x); }
+    static __device__ __forceinline__ double rcp_ieee(double x) { return 1.0 / x; }   // may be 0/inf (BL poles, horizon)
     static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
     static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
     static __device__ __forceinline__ double max_(double a, double b) { return fmax(a, b); }
@@ -35,7 +105,8 @@ template <> struct Num<double> {
     static __device__ __forceinline__ double floor_(double a) { return floor(a); }
 };
 template <> struct Num<float> {
-    static __device__ __forceinline__ float rcp(float x) { return 1.0f / x; }
+    static __device__ __forceinline__ float rcp(float x) { return rcp_nr(x); }
+    static __device__ __forceinline__ float rcp_ieee(float x) { return 1.0f / x; }
     static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
     static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
     static __device__ __forceinline__ float max_(float a, float b) { return fmaxf(a, b); }
@@ -78,16 +149,19 @@ struct HoleRay {
 
 // One Hamiltonian RHS in the reference's Kerr-Schild form (kerr.rs:412-499, hamiltonian.rs:13-35).
 // sin^2 is clamped at 1e-12 (kerr.rs:417,448); dH/dtheta is zeroed when |sin| < 1e-10 (kerr.rs:494-496).
+// Inputs: a with a^2 = sin^2(theta), |a| = |sin(theta)|; sc = sin(theta) cos(theta)  (see trig_pair).
 template <class R, bool WITH_T>
-__device__ __forceinline__ Deriv<R> rhs_ks(const HoleRay<R>& c, R r, R s, R cth, R pr, R pth) {
+__device__ __forceinline__ Deriv<R> rhs_ks(const HoleRay<R>& c, R r, R a, R sc, R pr, R pth) {
     using N = Num<R>;
-    const R sin2 = N::max_(s * s, R(1e-12));
-    const R w = N::rcp(sin2);                       // 1/sin^2
+    const R sin2 = N::max_(a * a, R(1e-12));
     const R cos2 = R(1) - sin2;
     const R r2 = r * r;
     const R sigma = N::fma_(c.a2, cos2, r2);
     const R delta = N::fma_(-c.twoM, r, r2 + c.a2);
-    const R isig = N::rcp(sigma);
+    // one reciprocal serves both 1/Sigma and 1/sin^2 (Sigma sin^2 >= 1e-12 r^2: far from under/overflow)
+    const R t = N::rcp(sigma * sin2);
+    const R isig = t * sin2;
+    const R w = t * sigma;                          // 1/sin^2
     const R twoMr = c.twoM * r;
     const R A1 = c.pph2 * w;                        // pph^2 / sin^2
     const R K = N::fma_(c.two_pt, pr, -c.pt2);      // 2 pt pr - pt^2
@@ -100,10 +174,9 @@ __device__ __forceinline__ Deriv<R> rhs_ks(const HoleRay<R>& c, R r, R s, R cth,
     const R q = Nn * isig;
     const R halfNr = N::fma_(r - c.M, pr2, c.M * K);
     const R dHdr = N::fma_(-r, q, halfNr) * isig;
-    const R sc = s * cth;
     const R halfNth = -(sc * A1) * w;
     R dHdth = N::fma_(c.a2 * sc, q, halfNth) * isig;
-    if (N::abs_(s) < R(1e-10)) dHdth = R(0);
+    if (N::abs_(a) < R(1e-10)) dHdth = R(0);
     Deriv<R> d;
     d.dr = N::fma_(delta, pr, N::fma_(twoMr, c.pt, c.a_pph)) * isig;
     d.dth = pth * isig;
@@ -127,9 +200,9 @@ __device__ __forceinline__ Deriv<R> rhs_bl(const HoleRay<R>& c, R r, R s, R cth,
     const R delta = N::fma_(-c.twoM, r, r2 + c.a2);
     const R ra2 = r2 + c.a2;
     const R D = delta * sigma;
-    const R iD = N::rcp(D);
-    const R isig = N::rcp(sigma);
-    const R w = N::rcp(sin2);
+    const R iD = N::rcp_ieee(D);
+    const R isig = N::rcp_ieee(sigma);
+    const R w = N::rcp_ieee(sin2);
     const R twoMr = c.twoM * r;
     const R U = N::fma_(twoMr * c.a2, sin2, sigma * ra2);
     const R cross = R(2) * twoMr * c.a * c.pt * c.pph;   // 4 M r a pt pph
@@ -166,9 +239,13 @@ __device__ __forceinline__ Deriv<R> rhs_bl(const HoleRay<R>& c, R r, R s, R cth,
 
 template <class R, int COORDS, bool WITH_T>
 __device__ __forceinline__ Deriv<R> rhs_at(const HoleRay<R>& c, R r, R th, R pr, R pth) {
+    if (COORDS == 1) {
+        R a, sc;
+        trig_pair(th, a, sc);
+        return rhs_ks<R, WITH_T>(c, r, a, sc, pr, pth);
+    }
     R s, cth;
     Num<R>::sincos_(th, &s, &cth);
-    if (COORDS == 1) return rhs_ks<R, WITH_T>(c, r, s, cth, pr, pth);
     return rhs_bl<R, WITH_T>(c, r, s, cth, pr, pth);
 }
 
@@ -177,12 +254,12 @@ __device__ __forceinline__ Deriv<R> rhs_at(const HoleRay<R>& c, R r, R th, R pr,
 template <class R, int COORDS>
 __device__ __forceinline__ void null_quadratic(const HoleRay<R>& c, R r, R th, R pth, R& A, R& B, R& C) {
     using N = Num<R>;
-    R s, cth;
-    N::sincos_(th, &s, &cth);
     const R r2 = r * r;
     const R delta = N::fma_(-c.twoM, r, r2 + c.a2);
     if (COORDS == 1) {
-        const R sin2 = N::max_(s * s, R(1e-12));
+        R a, sc;
+        trig_pair(th, a, sc);
+        const R sin2 = N::max_(a * a, R(1e-12));
         const R cos2 = R(1) - sin2;
         const R sigma = N::fma_(c.a2, cos2, r2);
         const R isig = N::rcp(sigma);
@@ -190,14 +267,16 @@ __device__ __forceinline__ void null_quadratic(const HoleRay<R>& c, R r, R th, R
         A = delta * isig;                                              // g^rr
         B = R(2) * isig * N::fma_(twoMr, c.pt, c.a_pph);                // 2 (g^tr pt + g^rph pph)
         // g^tt pt^2 + g^thth pth^2 + g^phph pph^2
-        C = N::fma_(isig, N::fma_(-twoMr, c.pt2, N::fma_(pth, pth, c.pph2 / sin2)), -c.pt2);
+        C = N::fma_(isig, N::fma_(-twoMr, c.pt2, N::fma_(pth, pth, c.pph2 * N::rcp(sin2))), -c.pt2);
     } else {
+        R s, cth;
+        N::sincos_(th, &s, &cth);
         const R sin2 = s * s;
         const R cos2 = cth * cth;
         const R sigma = N::fma_(c.a2, cos2, r2);
-        const R isig = N::rcp(sigma);
+        const R isig = N::rcp_ieee(sigma);
         const R D = delta * sigma;
-        const R iD = N::rcp(D);
+        const R iD = N::rcp_ieee(D);
         const R twoMr = c.twoM * r;
         const R U = N::fma_(twoMr * c.a2, sin2, sigma * (r2 + c.a2));
         const R g_tt = -(U * iD);
@@ -219,7 +298,7 @@ __device__ __forceinline__ R renormalize_pr(const HoleRay<R>& c, R r, R th, R pr
         const R disc = N::fma_(B, B, R(-4) * A * C);
         if (disc >= R(0)) {
             const R sq = N::sqrt_(disc);
-            const R inv2a = N::rcp(R(2) * A);
+            const R inv2a = N::rcp_ieee(R(2) * A);
             const R sol1 = (-B + sq) * inv2a;
             const R sol2 = (-B - sq) * inv2a;
             return (N::abs_(sol1 - pr) < N::abs_(sol2 - pr)) ? sol1 : sol2;

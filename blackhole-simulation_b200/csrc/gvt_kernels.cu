@@ -183,7 +183,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
         R col[3] = {R(0), R(0), R(0)};
         R alpha = R(0), max_drift = R(0), h = R(P.h0);
         uint32_t steps = 0, term = 3u, rhs_evals = 0;
+        uint32_t renorm_in = 0;          // steps until the next renormalisation (steps % interval == 0, mod.rs:229)
         bool done = false;
+        bool above = y.th > half_pi, below = y.th < half_pi;   // side of the equatorial plane before the step
+#pragma unroll 1
         for (uint32_t it = 0; it < P.max_steps; it++) {
             if (!done) {  // mod.rs:204,255-265
                 if (y.r < r_term) { term = 1u; done = true; }
@@ -200,14 +203,19 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
                     if (METHOD == 1) { step_rk4<R, 1, DEBUG>(hc, ny, hs); rhs_evals += 4; }
                     else { step_symplectic<R, 1, DEBUG>(hc, ny, hs); rhs_evals += 3; }
                 }
-                if (steps % P.renorm_interval == 0u) ny.pr = renormalize_pr<R, 1>(hc, ny.r, ny.th, ny.pr, ny.pth);
+                const bool renorm_now = (renorm_in == 0u);
+                if (renorm_now) ny.pr = renormalize_pr<R, 1>(hc, ny.r, ny.th, ny.pr, ny.pth);
                 if (!done) {   // budget mode: terminated rays executed the step above but do not commit it
                     const R th0 = y.th, r_prev = y.r;
                     y = ny; h = hn; steps++;
+                    renorm_in = renorm_now ? P.renorm_interval - 1u : renorm_in - 1u;
                     if (DEBUG) max_drift = N::max_(max_drift, N::abs_(hamiltonian_of<R, 1>(hc, y.r, y.th, y.pr, y.pth)));
-                    // ---- thin-disk crossing (compute.wgsl.ts:216-254 with a18 + a19 + a20) ----
-                    const R d0 = th0 - half_pi, d1 = y.th - half_pi;
-                    if (d0 * d1 <= R(0)) {
+                    // ---- thin-disk crossing (compute.wgsl.ts:216-254 with a18 + a19 + a20):
+                    //      (th0 - pi/2)(th1 - pi/2) <= 0  <=>  not strictly on the same side before and after
+                    const bool above1 = y.th > half_pi, below1 = y.th < half_pi;
+                    const bool crossed = !((above && above1) || (below && below1));
+                    above = above1; below = below1;
+                    if (crossed) {
                         const R dth = y.th - th0;
                         const R f = (dth == R(0)) ? R(0) : (half_pi - th0) / dth;
                         const R r_c = N::fma_(f, y.r - r_prev, r_prev);
@@ -226,9 +234,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
                             col[1] = N::fma_(rgb[1], wgt, col[1]);
                             col[2] = N::fma_(rgb[2], wgt, col[2]);
                             alpha += opacity;
+                            if (alpha > R(0.99)) { term = 4u; done = true; }
                         }
                     }
-                    if (alpha > R(0.99)) { term = 4u; done = true; }
                 }
             }
         }
@@ -325,7 +333,7 @@ __global__ void __launch_bounds__(128) k_integrate_rays(const __grid_constant__ 
     y.t = in[0]; y.r = in[1]; y.th = in[2]; y.ph = in[3]; y.pr = in[5]; y.pth = in[6];
     y.pr = renormalize_pr<R, COORDS>(hc, y.r, y.th, y.pr, y.pth);
     R h = P.h0, max_drift = 0.0;
-    uint32_t steps = 0, term = 3u, evals = 0;
+    uint32_t steps = 0, term = 3u, evals = 0, renorm_in = 0;
     for (uint32_t it = 0; it < P.max_steps; it++) {
         if (y.r < P.r_term) { term = 1u; break; }
         if (y.r > P.escape_r) { term = 2u; break; }
@@ -336,7 +344,8 @@ __global__ void __launch_bounds__(128) k_integrate_rays(const __grid_constant__ 
             if (METHOD == 1) { step_rk4<R, COORDS, true>(hc, y, hs); evals += 4; }
             else { step_symplectic<R, COORDS, true>(hc, y, hs); evals += 3; }
         }
-        if (steps % P.renorm_interval == 0u) y.pr = renormalize_pr<R, COORDS>(hc, y.r, y.th, y.pr, y.pth);
+        if (renorm_in == 0u) { y.pr = renormalize_pr<R, COORDS>(hc, y.r, y.th, y.pr, y.pth); renorm_in = P.renorm_interval; }
+        renorm_in--;
         max_drift = N::max_(max_drift, N::abs_(hamiltonian_of<R, COORDS>(hc, y.r, y.th, y.pr, y.pth)));
         steps++;
     }
