@@ -43,52 +43,73 @@ __device__ __forceinline__ float rcp_nr(float x) {
 // angles stay within a few multiples of pi), fdlibm minimax kernels on |r| <= pi/4, quadrant handled by two
 // selects and one sign flip: for odd k sin <-> cos and the product changes sign. ~19 FP64 ops, no I2F/F2I, no
 // Payne-Hanek slow path (CUDA's sincos() costs ~2x that in issue slots).
-__device__ __forceinline__ void trig_pair(double x, double& a, double& sc) {
-    const double kd_m = fma(x, 0.63661977236758138, 6755399441055744.0);   // x * 2/pi + 1.5*2^52
+// minimax kernels of fdlibm's __kernel_sin / __kernel_cos. The kernels receive the table inside their
+// __grid_constant__ parameter block (constant bank 0), so the coefficients reach DFMA/FFMA through uniform
+// registers instead of per-iteration literal materialisation.
+struct TrigTable {
+    double d[16];
+    float f[16];
+};
+#define GVT_TRIG_TABLE_INIT                                                                                   \
+    {{0.63661977236758138, 6755399441055744.0, 1.5707963267948966, 6.123233995736766e-17,                     \
+      -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,                   \
+      2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,                    \
+      4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,                    \
+      -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11},                  \
+     {0.636619772f, 12582912.0f, 1.57079601e+00f, 3.13916473e-07f, 5.39030253e-15f, -1.6666654611e-1f,         \
+      8.3321608736e-3f, -1.9515295891e-4f, 4.166664568298827e-2f, -1.388731625493765e-3f,                      \
+      2.443315711809948e-5f, 0.f, 0.f, 0.f, 0.f, 0.f}}
+// d: [0] 2/pi  [1] 1.5*2^52  [2] pi/2 hi  [3] pi/2 lo  [4..9] S1..S6  [10..15] C1..C6
+// f: [0] 2/pi  [1] 1.5*2^23  [2..4] pi/2 in three parts  [5..7] S1..S3  [8..10] C1..C3
+
+__device__ __forceinline__ void trig_pair(const TrigTable& T, double x, double& a, double& sc) {
+    const double* K = T.d;
+    const double kd_m = fma(x, K[0], K[1]);
     const int k = __double2loint(kd_m);
-    const double kd = kd_m - 6755399441055744.0;
-    double r = fma(-kd, 1.5707963267948966, x);
-    r = fma(-kd, 6.123233995736766e-17, r);
+    const double kd = kd_m - K[1];
+    double r = fma(-kd, K[2], x);
+    r = fma(-kd, K[3], r);
     const double z = r * r;
-    double ps = 1.58969099521155010221e-10;
-    ps = fma(ps, z, -2.50507602534068634195e-08);
-    ps = fma(ps, z, 2.75573137070700676789e-06);
-    ps = fma(ps, z, -1.98412698298579493134e-04);
-    ps = fma(ps, z, 8.33333333332248946124e-03);
-    ps = fma(ps, z, -1.66666666666666324348e-01);
+    double ps = K[9];
+    ps = fma(ps, z, K[8]);
+    ps = fma(ps, z, K[7]);
+    ps = fma(ps, z, K[6]);
+    ps = fma(ps, z, K[5]);
+    ps = fma(ps, z, K[4]);
     const double sr = fma(r * z, ps, r);
-    double pc = -1.13596475577881948265e-11;
-    pc = fma(pc, z, 2.08757232129817482790e-09);
-    pc = fma(pc, z, -2.75573143513906633035e-07);
-    pc = fma(pc, z, 2.48015872894767294178e-05);
-    pc = fma(pc, z, -1.38888888888741095749e-03);
-    pc = fma(pc, z, 4.16666666666666019037e-02);
+    double pc = K[15];
+    pc = fma(pc, z, K[14]);
+    pc = fma(pc, z, K[13]);
+    pc = fma(pc, z, K[12]);
+    pc = fma(pc, z, K[11]);
+    pc = fma(pc, z, K[10]);
     const double cr = fma(z, fma(z, pc, -0.5), 1.0);
     const bool odd = (k & 1) != 0;
     a = odd ? cr : sr;
     const double p = sr * cr;
-    sc = odd ? -p : p;
+    // odd quadrant: sin cos changes sign -- flip the sign bit with one integer op
+    sc = __hiloint2double(__double2hiint(p) ^ (k << 31), __double2loint(p));
 }
-__device__ __forceinline__ void trig_pair(float x, float& a, float& sc) {
-    const float kf_m = fmaf(x, 0.636619772f, 12582912.0f);                  // 1.5*2^23
+__device__ __forceinline__ void trig_pair(const TrigTable& T, float x, float& a, float& sc) {
+    const float* K = T.f;
+    const float kf_m = fmaf(x, K[0], K[1]);
     const int k = __float_as_int(kf_m);
-    const float kf = kf_m - 12582912.0f;
-    float r = fmaf(-kf, 1.57079601e+00f, x);
-    r = fmaf(-kf, 3.13916473e-07f, r);
-    r = fmaf(-kf, 5.39030253e-15f, r);
+    const float kf = kf_m - K[1];
+    float r = fmaf(-kf, K[2], x);
+    r = fmaf(-kf, K[3], r);
+    r = fmaf(-kf, K[4], r);
     const float z = r * r;
-    float ps = -1.9515295891e-4f;
-    ps = fmaf(ps, z, 8.3321608736e-3f);
-    ps = fmaf(ps, z, -1.6666654611e-1f);
+    float ps = K[7];
+    ps = fmaf(ps, z, K[6]);
+    ps = fmaf(ps, z, K[5]);
     const float sr = fmaf(r * z, ps, r);
-    float pc = 2.443315711809948e-5f;
-    pc = fmaf(pc, z, -1.388731625493765e-3f);
-    pc = fmaf(pc, z, 4.166664568298827e-2f);
+    float pc = K[10];
+    pc = fmaf(pc, z, K[9]);
+    pc = fmaf(pc, z, K[8]);
     const float cr = fmaf(z, fmaf(z, pc, -0.5f), 1.0f);
     const bool odd = (k & 1) != 0;
     a = odd ? cr : sr;
-    const float p = sr * cr;
-    sc = odd ? -p : p;
+    sc = __int_as_float(__float_as_int(sr * cr) ^ (k << 31));
 }
 
 template <class R> struct Num;
@@ -117,9 +138,13 @@ template <> struct Num<float> {
     static __device__ __forceinline__ float floor_(float a) { return floorf(a); }
 };
 
+// plain compare-selects (no NaN canonicalisation like fmin/fmax): inputs here are never NaN unless the ray
+// already is, and then the result is garbage either way
 template <class R> __device__ __forceinline__ R clampR(R x, R lo, R hi) {
-    return Num<R>::min_(Num<R>::max_(x, lo), hi);
+    x = (x < lo) ? lo : x;
+    return (x > hi) ? hi : x;
 }
+template <class R> __device__ __forceinline__ R floorAt(R x, R lo) { return (x > lo) ? x : lo; }
 
 // --------------------------------------------------------------------------------------------------
 // Per-ray state. t (x[0]) is carried only when WITH_T (the parity hook); p_t and p_phi are constants.
@@ -137,6 +162,7 @@ struct Deriv {
 // Constants of the hole + of the ray (p_t, p_phi and products), hoisted out of the loop.
 template <class R>
 struct HoleRay {
+    const TrigTable* trig;
     R M, a, a2, twoM;
     R pt, pph;
     R pt2, pph2, two_pt, two_a_pph, a_pph;
@@ -153,7 +179,11 @@ struct HoleRay {
 template <class R, bool WITH_T>
 __device__ __forceinline__ Deriv<R> rhs_ks(const HoleRay<R>& c, R r, R a, R sc, R pr, R pth) {
     using N = Num<R>;
-    const R sin2 = N::max_(a * a, R(1e-12));
+    R sin2 = a * a;
+    if (__builtin_expect(sin2 < R(1e-12), 0)) {      // within 1e-6 rad of the polar axis: rare, one branch
+        sin2 = R(1e-12);                             // kerr.rs:417,448
+        if (N::abs_(a) < R(1e-10)) sc = R(0);        // kerr.rs:494-496: dH/dtheta = 0 (both its terms carry sc)
+    }
     const R cos2 = R(1) - sin2;
     const R r2 = r * r;
     const R sigma = N::fma_(c.a2, cos2, r2);
@@ -175,8 +205,7 @@ __device__ __forceinline__ Deriv<R> rhs_ks(const HoleRay<R>& c, R r, R a, R sc, 
     const R halfNr = N::fma_(r - c.M, pr2, c.M * K);
     const R dHdr = N::fma_(-r, q, halfNr) * isig;
     const R halfNth = -(sc * A1) * w;
-    R dHdth = N::fma_(c.a2 * sc, q, halfNth) * isig;
-    if (N::abs_(a) < R(1e-10)) dHdth = R(0);
+    const R dHdth = N::fma_(c.a2 * sc, q, halfNth) * isig;
     Deriv<R> d;
     d.dr = N::fma_(delta, pr, N::fma_(twoMr, c.pt, c.a_pph)) * isig;
     d.dth = pth * isig;
@@ -241,7 +270,7 @@ template <class R, int COORDS, bool WITH_T>
 __device__ __forceinline__ Deriv<R> rhs_at(const HoleRay<R>& c, R r, R th, R pr, R pth) {
     if (COORDS == 1) {
         R a, sc;
-        trig_pair(th, a, sc);
+        trig_pair(*c.trig, th, a, sc);
         return rhs_ks<R, WITH_T>(c, r, a, sc, pr, pth);
     }
     R s, cth;
@@ -258,8 +287,8 @@ __device__ __forceinline__ void null_quadratic(const HoleRay<R>& c, R r, R th, R
     const R delta = N::fma_(-c.twoM, r, r2 + c.a2);
     if (COORDS == 1) {
         R a, sc;
-        trig_pair(th, a, sc);
-        const R sin2 = N::max_(a * a, R(1e-12));
+        trig_pair(*c.trig, th, a, sc);
+        const R sin2 = floorAt<R>(a * a, R(1e-12));
         const R cos2 = R(1) - sin2;
         const R sigma = N::fma_(c.a2, cos2, r2);
         const R isig = N::rcp(sigma);

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "gvt_device.cuh"
 
 namespace gvt {
 
@@ -28,6 +29,7 @@ struct Counters {  // device-side accumulators, one set per frame
 
 // Kernel parameters (constant bank): the scalars of the step loop are direct c[][] operands.
 struct FrameParams {
+    TrigTable trig;                                           // set by the launcher (GVT_TRIG_TABLE_INIT)
     double M, a, spin, rh, r_term, escape_r, r_in, r_out;   // r_term = 1.001 * r+ (geodesic/mod.rs:257)
     double tol, h0;
     double tdisk_rin, tdisk_scale;                            // (n-1)/(rout-rin)
@@ -45,6 +47,7 @@ struct FrameParams {
 };
 
 struct RayBatchParams {  // gvt_engine_integrate_rays
+    TrigTable trig;
     double M, a, rh, r_term, escape_r, tol, h0;
     uint32_t max_steps, renorm_interval, step_rule, method, coords;
     uint64_t n;

@@ -90,6 +90,12 @@ __device__ __forceinline__ void sample_spectrum(const float4* lut, uint32_t W, u
 // --------------------------------------------------------------------------------------------------
 // The fused trace kernel
 // --------------------------------------------------------------------------------------------------
+#ifndef GVT_MAXT_F64
+#define GVT_MAXT_F64 512   // threads per persistent CTA (one CTA per SM) for the fixed-step f64 instantiations
+#endif
+#ifndef GVT_MAXT_F32
+#define GVT_MAXT_F32 512
+#endif
 constexpr int TILE_W = 8, TILE_H = 4;  // one warp = one 8x4 pixel tile (compute.wgsl.ts:147 uses 8x8 groups)
 
 template <class R, int METHOD, bool BUDGET, bool DEBUG, int MAXT>
@@ -130,6 +136,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
     const uint32_t n_tiles = tiles_x * tiles_y;
 
     HoleRay<R> hc;
+    hc.trig = &P.trig;
     hc.set_hole(R(P.M), R(P.a));
     const R r_term = R(P.r_term), escape_r = R(P.escape_r), rh = R(P.rh);
     const R half_pi = R(1.5707963267948966);
@@ -194,21 +201,21 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
             }
             if (!BUDGET) { if (__all_sync(0xffffffffu, done)) break; }   // warp-uniform: all 32 lanes stay in the loop
             if (BUDGET || !done) {
-                Ray<R> ny = y;
-                R hn = h;
+                const R th0 = y.th, r_prev = y.r;
                 if (METHOD == 0) {
-                    hn = adaptive_step<R, 1>(hc, ny, h, R(P.tol), rhs_evals);
+                    h = adaptive_step<R, 1>(hc, y, h, R(P.tol), rhs_evals);
                 } else {
-                    const R hs = (P.step_rule == 1u) ? clampR<R>((y.r - rh) * R(0.15), R(0.05), R(1.0)) : R(P.h0);
-                    if (METHOD == 1) { step_rk4<R, 1, DEBUG>(hc, ny, hs); rhs_evals += 4; }
-                    else { step_symplectic<R, 1, DEBUG>(hc, ny, hs); rhs_evals += 3; }
+                    R hs = (P.step_rule == 1u) ? clampR<R>((y.r - rh) * R(0.15), R(0.05), R(1.0)) : R(P.h0);
+                    // budget accounting: a terminated ray still executes the full step computation, on its frozen
+                    // state with h = 0, so nothing needs to be selected back afterwards
+                    if (BUDGET && done) hs = R(0);
+                    if (METHOD == 1) { step_rk4<R, 1, DEBUG>(hc, y, hs); rhs_evals += 4; }
+                    else { step_symplectic<R, 1, DEBUG>(hc, y, hs); rhs_evals += 3; }
                 }
-                const bool renorm_now = (renorm_in == 0u);
-                if (renorm_now) ny.pr = renormalize_pr<R, 1>(hc, ny.r, ny.th, ny.pr, ny.pth);
-                if (!done) {   // budget mode: terminated rays executed the step above but do not commit it
-                    const R th0 = y.th, r_prev = y.r;
-                    y = ny; h = hn; steps++;
-                    renorm_in = renorm_now ? P.renorm_interval - 1u : renorm_in - 1u;
+                if (!done) {
+                    if (renorm_in == 0u) { y.pr = renormalize_pr<R, 1>(hc, y.r, y.th, y.pr, y.pth); renorm_in = P.renorm_interval; }
+                    renorm_in--;
+                    steps++;
                     if (DEBUG) max_drift = N::max_(max_drift, N::abs_(hamiltonian_of<R, 1>(hc, y.r, y.th, y.pr, y.pth)));
                     // ---- thin-disk crossing (compute.wgsl.ts:216-254 with a18 + a19 + a20):
                     //      (th0 - pi/2)(th1 - pi/2) <= 0  <=>  not strictly on the same side before and after
@@ -298,8 +305,11 @@ static cudaError_t launch_trace_t(const FrameParams& p, int sm_count, cudaStream
     return cudaGetLastError();
 }
 
-cudaError_t launch_trace(const FrameParams& p, int method, int precision, bool budget, bool debug, int sm_count,
+cudaError_t launch_trace(const FrameParams& p_in, int method, int precision, bool budget, bool debug, int sm_count,
                          cudaStream_t stream) {
+    FrameParams p = p_in;
+    const TrigTable tt = GVT_TRIG_TABLE_INIT;
+    p.trig = tt;
 #define GVT_DISPATCH(RT, MT)                                                                                   \
     do {                                                                                                         \
         if (method == 0) return debug ? launch_trace_t<RT, 0, false, true, 256>(p, sm_count, stream)             \
@@ -311,8 +321,8 @@ cudaError_t launch_trace(const FrameParams& p, int method, int precision, bool b
         return debug ? launch_trace_t<RT, 2, false, true, MT>(p, sm_count, stream)                               \
                      : launch_trace_t<RT, 2, false, false, MT>(p, sm_count, stream);                             \
     } while (0)
-    if (precision == 1) GVT_DISPATCH(float, 512);
-    GVT_DISPATCH(double, 512);
+    if (precision == 1) GVT_DISPATCH(float, GVT_MAXT_F32);
+    GVT_DISPATCH(double, GVT_MAXT_F64);
 #undef GVT_DISPATCH
 }
 
@@ -327,6 +337,7 @@ __global__ void __launch_bounds__(128) k_integrate_rays(const __grid_constant__ 
     if (i >= P.n) return;
     const double* in = P.in_xp + 8 * i;
     HoleRay<R> hc;
+    hc.trig = &P.trig;
     hc.set_hole(P.M, P.a);
     hc.set_ray(in[4], in[7]);
     Ray<R> y;
@@ -357,8 +368,11 @@ __global__ void __launch_bounds__(128) k_integrate_rays(const __grid_constant__ 
     if (P.rhs) P.rhs[i] = evals;
 }
 
-cudaError_t launch_integrate_rays(const RayBatchParams& p, cudaStream_t stream) {
-    if (p.n == 0) return cudaSuccess;
+cudaError_t launch_integrate_rays(const RayBatchParams& p_in, cudaStream_t stream) {
+    if (p_in.n == 0) return cudaSuccess;
+    RayBatchParams p = p_in;
+    const TrigTable tt = GVT_TRIG_TABLE_INIT;
+    p.trig = tt;
     const unsigned blocks = (unsigned)((p.n + 127) / 128);
 #define GVT_RB(C, M) k_integrate_rays<C, M><<<blocks, 128, 0, stream>>>(p)
     if (p.coords == 1) { if (p.method == 0) GVT_RB(1, 0); else if (p.method == 1) GVT_RB(1, 1); else GVT_RB(1, 2); }

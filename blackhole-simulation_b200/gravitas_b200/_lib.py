@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libgravitas_b200.so")
+# GRAVITAS_B200_LIB selects another build of the SAME library (kernel tuning experiments); never a fallback.
+_SO = os.environ.get("GRAVITAS_B200_LIB") or os.path.join(_HERE, "libgravitas_b200.so")
 _LIB = None
 
 # SAB v2 offsets, f32 element indices (physics-bridge.ts:5-11; lib.rs:36-40)
