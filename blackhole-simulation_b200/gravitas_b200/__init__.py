@@ -14,4 +14,4 @@ with ``GravitasError`` when no sm_100 device is present or the shared library is
 from ._lib import GravitasError, lib, lib_path, OFFSETS  # noqa: F401
 from .engine import PhysicsEngine  # noqa: F401
 from .renderer import KerrRenderer, RenderParams, FrameStats  # noqa: F401
-from . import camera  # noqa: F401
+from . import camera, shard  # noqa: F401
