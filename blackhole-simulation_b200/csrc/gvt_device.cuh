@@ -15,6 +15,9 @@
 // relative per RGBA component (tests/test_gpu_parity.py).
 #pragma once
 #include <cuda_runtime.h>
+#ifndef GVT_POLE_MODE
+#define GVT_POLE_MODE 1   // 1: predicated rare path (best for f64); 0: plain selects
+#endif
 #include <stdint.h>
 
 namespace gvt {
@@ -173,21 +176,31 @@ struct HoleRay {
     }
 };
 
-// One Hamiltonian RHS in the reference's Kerr-Schild form (kerr.rs:412-499, hamiltonian.rs:13-35).
+// One Hamiltonian RHS in the reference's Kerr-Schild form (kerr.rs:412-499, hamiltonian.rs:13-35), returned
+// UNSCALED: the true derivatives are (dr, dth, dph, dpr, dpth) * isig, dt is already scaled. The implicit-midpoint
+// stepper folds isig into its step factor (one multiply instead of four).
 // sin^2 is clamped at 1e-12 (kerr.rs:417,448); dH/dtheta is zeroed when |sin| < 1e-10 (kerr.rs:494-496).
 // Inputs: a with a^2 = sin^2(theta), |a| = |sin(theta)|; sc = sin(theta) cos(theta)  (see trig_pair).
-template <class R, bool WITH_T>
-__device__ __forceinline__ Deriv<R> rhs_ks(const HoleRay<R>& c, R r, R a, R sc, R pr, R pth) {
+template <class R>
+struct DerivU {
+    R dr, dth, dph, dpr, dpth, dt, isig;
+};
+template <class R, bool WITH_T, bool WITH_PHI>
+__device__ __forceinline__ DerivU<R> rhs_ks_u(const HoleRay<R>& c, R r, R a, R sc, R pr, R pth) {
     using N = Num<R>;
     R sin2 = a * a;
-    if (__builtin_expect(sin2 < R(1e-12), 0)) {      // within 1e-6 rad of the polar axis: rare, one branch
-        sin2 = R(1e-12);                             // kerr.rs:417,448
-        if (N::abs_(a) < R(1e-10)) sc = R(0);        // kerr.rs:494-496: dH/dtheta = 0 (both its terms carry sc)
+#if GVT_POLE_MODE == 1
+    if (sin2 < R(1e-12)) {                           // within 1e-6 rad of the polar axis (rare)
+        sin2 = R(1e-12);
+        if (N::abs_(a) < R(1e-10)) sc = R(0);        // both terms of dH/dtheta carry sc
     }
-    const R cos2 = R(1) - sin2;
-    const R r2 = r * r;
-    const R sigma = N::fma_(c.a2, cos2, r2);
-    const R delta = N::fma_(-c.twoM, r, r2 + c.a2);
+#else
+    if (sin2 < R(1e-20)) sc = R(0);                  // |a| < 1e-10
+    sin2 = floorAt<R>(sin2, R(1e-12));
+#endif
+    const R r2a2 = N::fma_(r, r, c.a2);
+    const R sigma = N::fma_(-c.a2, sin2, r2a2);      // r^2 + a^2 cos^2, cos^2 = 1 - sin^2 (kerr.rs:418,449)
+    const R delta = N::fma_(-c.twoM, r, r2a2);
     // one reciprocal serves both 1/Sigma and 1/sin^2 (Sigma sin^2 >= 1e-12 r^2: far from under/overflow)
     const R t = N::rcp(sigma * sin2);
     const R isig = t * sin2;
@@ -203,16 +216,22 @@ __device__ __forceinline__ Deriv<R> rhs_ks(const HoleRay<R>& c, R r, R a, R sc, 
     Nn = N::fma_(c.two_a_pph, pr, Nn);
     const R q = Nn * isig;
     const R halfNr = N::fma_(r - c.M, pr2, c.M * K);
-    const R dHdr = N::fma_(-r, q, halfNr) * isig;
-    const R halfNth = -(sc * A1) * w;
-    const R dHdth = N::fma_(c.a2 * sc, q, halfNth) * isig;
+    DerivU<R> d;
+    d.isig = isig;
+    d.dr = N::fma_(delta, pr, N::fma_(twoMr, c.pt, c.a_pph));
+    d.dth = pth;
+    d.dpr = N::fma_(r, q, -halfNr);                          // -(N_r/2 - r N/Sigma)
+    d.dpth = sc * N::fma_(-c.a2, q, A1 * w);                 // -(sc (a^2 N/Sigma - pph^2/sin^4))
+    d.dph = WITH_PHI ? N::fma_(c.pph, w, c.a * pr) : R(0);
+    d.dt = WITH_T ? N::fma_(twoMr * isig, pr - c.pt, -c.pt) : R(0);
+    return d;
+}
+template <class R, bool WITH_T>
+__device__ __forceinline__ Deriv<R> rhs_ks(const HoleRay<R>& c, R r, R a, R sc, R pr, R pth) {
+    const DerivU<R> u = rhs_ks_u<R, WITH_T, true>(c, r, a, sc, pr, pth);
     Deriv<R> d;
-    d.dr = N::fma_(delta, pr, N::fma_(twoMr, c.pt, c.a_pph)) * isig;
-    d.dth = pth * isig;
-    d.dph = N::fma_(c.pph, w, c.a * pr) * isig;
-    d.dpr = -dHdr;
-    d.dpth = -dHdth;
-    if (WITH_T) d.dt = N::fma_(twoMr * isig, pr - c.pt, -c.pt); else d.dt = R(0);
+    d.dr = u.dr * u.isig; d.dth = u.dth * u.isig; d.dph = u.dph * u.isig;
+    d.dpr = u.dpr * u.isig; d.dpth = u.dpth * u.isig; d.dt = u.dt;
     return d;
 }
 
@@ -348,12 +367,34 @@ __device__ __forceinline__ R hamiltonian_of(const HoleRay<R>& c, R r, R th, R pr
 // Steppers
 // --------------------------------------------------------------------------------------------------
 // geodesic/integrator.rs:209-226 implicit midpoint: 2 fixed-point iterations + final evaluation.
+// s_mid = 0.5 (s + (s + d h)) = s + d h/2.
 template <class R, int COORDS, bool WITH_T>
 __device__ __forceinline__ void step_symplectic(const HoleRay<R>& c, Ray<R>& y, R h) {
     using N = Num<R>;
     const R hh = R(0.5) * h;
+    if (COORDS == 1) {
+        R a, sc;
+        trig_pair(*c.trig, y.th, a, sc);
+        DerivU<R> d = rhs_ks_u<R, false, false>(c, y.r, a, sc, y.pr, y.pth);
+        R f = hh * d.isig;
+        R mr = N::fma_(d.dr, f, y.r), mth = N::fma_(d.dth, f, y.th);
+        R mpr = N::fma_(d.dpr, f, y.pr), mpth = N::fma_(d.dpth, f, y.pth);
+        trig_pair(*c.trig, mth, a, sc);
+        d = rhs_ks_u<R, false, false>(c, mr, a, sc, mpr, mpth);
+        f = hh * d.isig;
+        mr = N::fma_(d.dr, f, y.r); mth = N::fma_(d.dth, f, y.th);
+        mpr = N::fma_(d.dpr, f, y.pr); mpth = N::fma_(d.dpth, f, y.pth);
+        trig_pair(*c.trig, mth, a, sc);
+        d = rhs_ks_u<R, WITH_T, WITH_T>(c, mr, a, sc, mpr, mpth);
+        f = h * d.isig;
+        y.r = N::fma_(d.dr, f, y.r);
+        y.th = N::fma_(d.dth, f, y.th);
+        y.pr = N::fma_(d.dpr, f, y.pr);
+        y.pth = N::fma_(d.dpth, f, y.pth);
+        if (WITH_T) { y.ph = N::fma_(d.dph, f, y.ph); y.t = N::fma_(d.dt, h, y.t); }
+        return;
+    }
     Deriv<R> d = rhs_at<R, COORDS, false>(c, y.r, y.th, y.pr, y.pth);
-    // s_mid = 0.5 (s + (s + d h)) = s + d h/2
     R mr = N::fma_(d.dr, hh, y.r), mth = N::fma_(d.dth, hh, y.th);
     R mpr = N::fma_(d.dpr, hh, y.pr), mpth = N::fma_(d.dpth, hh, y.pth);
     d = rhs_at<R, COORDS, false>(c, mr, mth, mpr, mpth);

@@ -96,9 +96,20 @@ __device__ __forceinline__ void sample_spectrum(const float4* lut, uint32_t W, u
 #ifndef GVT_MAXT_F32
 #define GVT_MAXT_F32 512
 #endif
-constexpr int TILE_W = 8, TILE_H = 4;  // one warp = one 8x4 pixel tile (compute.wgsl.ts:147 uses 8x8 groups)
+constexpr int TILE_W = 8, TILE_H = 4;
 
-template <class R, int METHOD, bool BUDGET, bool DEBUG, int MAXT>
+// (a)(b) <= 0 without FP64-pipe work: compare sign words, and test either operand for +-0 with integer ops.
+__device__ __forceinline__ bool sign_differs_or_zero(double a, double b) {
+    const int ah = __double2hiint(a), bh = __double2hiint(b);
+    const bool az = ((ah & 0x7fffffff) | __double2loint(a)) == 0, bz = ((bh & 0x7fffffff) | __double2loint(b)) == 0;
+    return ((ah ^ bh) < 0) || az || bz;
+}
+__device__ __forceinline__ bool sign_differs_or_zero(float a, float b) {
+    const int ai = __float_as_int(a), bi = __float_as_int(b);
+    return ((ai ^ bi) < 0) || ((ai & 0x7fffffff) == 0) || ((bi & 0x7fffffff) == 0);
+}  // one warp = one 8x4 pixel tile (compute.wgsl.ts:147 uses 8x8 groups)
+
+template <class R, int METHOD, bool BUDGET, bool DEBUG, int MAXT, bool WGSL_RULE>
 __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ FrameParams P) {
     using N = Num<R>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -191,21 +202,21 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
         R alpha = R(0), max_drift = R(0), h = R(P.h0);
         uint32_t steps = 0, term = 3u, rhs_evals = 0;
         uint32_t renorm_in = 0;          // steps until the next renormalisation (steps % interval == 0, mod.rs:229)
-        bool done = false;
-        bool above = y.th > half_pi, below = y.th < half_pi;   // side of the equatorial plane before the step
+        bool done = false, by_radius = false;
+        // side of the equatorial plane before the step, as the sign word of (theta - pi/2) and an "exactly on it" flag
+        R dprev = y.th - half_pi;
 #pragma unroll 1
         for (uint32_t it = 0; it < P.max_steps; it++) {
-            if (!done) {  // mod.rs:204,255-265
-                if (y.r < r_term) { term = 1u; done = true; }
-                else if (y.r > escape_r) { term = 2u; done = true; }
-            }
+            // mod.rs:204,255-265: alive iff 1.001 r+ <= r <= escape radius (which of the two ended it is resolved
+            // after the loop from the frozen state)
+            if (!done && !(y.r >= r_term && y.r <= escape_r)) { done = true; by_radius = true; }
             if (!BUDGET) { if (__all_sync(0xffffffffu, done)) break; }   // warp-uniform: all 32 lanes stay in the loop
             if (BUDGET || !done) {
                 const R th0 = y.th, r_prev = y.r;
                 if (METHOD == 0) {
                     h = adaptive_step<R, 1>(hc, y, h, R(P.tol), rhs_evals);
                 } else {
-                    R hs = (P.step_rule == 1u) ? clampR<R>((y.r - rh) * R(0.15), R(0.05), R(1.0)) : R(P.h0);
+                    R hs = WGSL_RULE ? clampR<R>((y.r - rh) * R(0.15), R(0.05), R(1.0)) : R(P.h0);
                     // budget accounting: a terminated ray still executes the full step computation, on its frozen
                     // state with h = 0, so nothing needs to be selected back afterwards
                     if (BUDGET && done) hs = R(0);
@@ -218,10 +229,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
                     steps++;
                     if (DEBUG) max_drift = N::max_(max_drift, N::abs_(hamiltonian_of<R, 1>(hc, y.r, y.th, y.pr, y.pth)));
                     // ---- thin-disk crossing (compute.wgsl.ts:216-254 with a18 + a19 + a20):
-                    //      (th0 - pi/2)(th1 - pi/2) <= 0  <=>  not strictly on the same side before and after
-                    const bool above1 = y.th > half_pi, below1 = y.th < half_pi;
-                    const bool crossed = !((above && above1) || (below && below1));
-                    above = above1; below = below1;
+                    //      (th0 - pi/2)(th1 - pi/2) <= 0  <=>  the signs differ or either factor is zero
+                    const R dcur = y.th - half_pi;
+                    const bool crossed = sign_differs_or_zero(dprev, dcur);
+                    dprev = dcur;
                     if (crossed) {
                         const R dth = y.th - th0;
                         const R f = (dth == R(0)) ? R(0) : (half_pi - th0) / dth;
@@ -247,7 +258,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
                 }
             }
         }
-        if (!done) term = 3u;
+        if (by_radius) term = (y.r < r_term) ? 1u : 2u;   // Horizon is tested first (mod.rs:257-263)
+        else if (!done) term = 3u;
 
         // ---- epilogue: coalesced float4 store + census ----
         if (valid) {
@@ -291,7 +303,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
 
 template <class R, int METHOD, bool BUDGET, bool DEBUG, int MAXT>
 static cudaError_t launch_trace_t(const FrameParams& p, int sm_count, cudaStream_t stream) {
-    auto kern = k_trace_tile<R, METHOD, BUDGET, DEBUG, MAXT>;
+    // the per-step rule of compute.wgsl.ts:213 is a compile-time switch for the fixed-step methods
+    auto kern = (METHOD != 0 && p.step_rule == 1u) ? k_trace_tile<R, METHOD, BUDGET, DEBUG, MAXT, true>
+                                                    : k_trace_tile<R, METHOD, BUDGET, DEBUG, MAXT, false>;
     size_t smem = ((sizeof(FrameBlock) + 127) / 128) * 128;
     if (p.lut_in_smem) smem += (size_t)p.spec_w * p.spec_h * sizeof(float4);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
