@@ -15,9 +15,7 @@
 // relative per RGBA component (tests/test_gpu_parity.py).
 #pragma once
 #include <cuda_runtime.h>
-#ifndef GVT_POLE_MODE
-#define GVT_POLE_MODE 1   // 1: predicated rare path (best for f64); 0: plain selects
-#endif
+
 #include <stdint.h>
 
 namespace gvt {
@@ -25,20 +23,19 @@ namespace gvt {
 // --------------------------------------------------------------------------------------------------
 // scalar traits
 // --------------------------------------------------------------------------------------------------
-// ---- lean reciprocal: MUFU.RCP64H seed (~2^-20) + two Newton steps on the FP64 FMA pipe; no IEEE special-case
+// ---- lean reciprocal: MUFU.RCP64H seed (~2^-21) + one cubic Newton step on the FP64 FMA pipe; no IEEE special-case
 // slow path (callers guarantee a normal, non-zero argument: Sigma >= r^2 > 0, sin^2 >= 1e-12). <= 1 ulp.
 __device__ __forceinline__ double rcp_nr(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    return fma(y, e, y);
+    // one cubically convergent step: y (1 + e + e^2), e = 1 - x y ~ 2^-21  ->  e^3 ~ 2^-63
+    const double e = fma(-x, y, 1.0);
+    return fma(y, fma(e, e, e), y);
 }
 __device__ __forceinline__ float rcp_nr(float x) {
     float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // MUFU.RCP, 1 ulp
-    return fmaf(y, fmaf(-x, y, 1.0f), y);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // MUFU.RCP: 1 ulp, no refinement needed in f32
+    return y;
 }
 
 // ---- what one Kerr-Schild RHS needs from theta: a with a^2 = sin^2 and |a| = |sin|, and sc = sin cos.
@@ -189,15 +186,17 @@ template <class R, bool WITH_T, bool WITH_PHI>
 __device__ __forceinline__ DerivU<R> rhs_ks_u(const HoleRay<R>& c, R r, R a, R sc, R pr, R pth) {
     using N = Num<R>;
     R sin2 = a * a;
-#if GVT_POLE_MODE == 1
-    if (sin2 < R(1e-12)) {                           // within 1e-6 rad of the polar axis (rare)
-        sin2 = R(1e-12);
-        if (N::abs_(a) < R(1e-10)) sc = R(0);        // both terms of dH/dtheta carry sc
+    // Within 1e-6 rad of the polar axis (rare): clamp sin^2 and zero dH/dtheta below |sin| = 1e-10 (both of its
+    // terms carry sc). f64: nested rare path (ptxas predicates it; cheapest on the FP64 pipe). f32: two plain selects.
+    if (sizeof(R) == 8) {
+        if (sin2 < R(1e-12)) {
+            sin2 = R(1e-12);
+            if (N::abs_(a) < R(1e-10)) sc = R(0);
+        }
+    } else {
+        if (sin2 < R(1e-20)) sc = R(0);
+        sin2 = floorAt<R>(sin2, R(1e-12));
     }
-#else
-    if (sin2 < R(1e-20)) sc = R(0);                  // |a| < 1e-10
-    sin2 = floorAt<R>(sin2, R(1e-12));
-#endif
     const R r2a2 = N::fma_(r, r, c.a2);
     const R sigma = N::fma_(-c.a2, sin2, r2a2);      // r^2 + a^2 cos^2, cos^2 = 1 - sin^2 (kerr.rs:418,449)
     const R delta = N::fma_(-c.twoM, r, r2a2);
