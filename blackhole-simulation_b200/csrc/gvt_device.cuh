@@ -95,9 +95,8 @@ __device__ __forceinline__ void trig_pair(const TrigTable& T, float x, float& a,
     const float kf_m = fmaf(x, K[0], K[1]);
     const int k = __float_as_int(kf_m);
     const float kf = kf_m - K[1];
-    float r = fmaf(-kf, K[2], x);
-    r = fmaf(-kf, K[3], r);
-    r = fmaf(-kf, K[4], r);
+    float r = fmaf(-kf, K[2], x);          // |k| is a handful for geodesic polar angles: two parts suffice
+    r = fmaf(-kf, K[3], r);               // (|k| * 5.4e-15 is far below f32 resolution)
     const float z = r * r;
     float ps = K[7];
     ps = fmaf(ps, z, K[6]);
