@@ -68,3 +68,24 @@ def test_empty_batch(built):
     e = built.PhysicsEngine(1.0, 0.9)
     got = e.integrate_rays(np.zeros((0, 8)), R.RenderParams())
     assert got["xp"].shape == (0, 8)
+
+
+def test_config1_schwarzschild_bl_rkf45_128(built, oracle):
+    """BASELINE config 1: Schwarzschild a=0, 256x256 camera rays, 128 adaptive-RKF45 steps in Boyer-Lindquist
+    (use_kerr_schild=false, options of lib.rs:444-452). From r0=30 with h0=0.01 every ray ends MaxSteps,
+    so parity is on the 128-step phase-space state."""
+    from gravitas_b200 import camera, renderer as R
+    W = H = 256
+    cam, _ = camera.default_camera(W, H)
+    opts = oracle.Options.default(max_steps=128)
+    rp, keep = oracle.make_render_params(W, H, 1.0, 0.0, opts, coords=0)
+    rays = np.array([oracle.camera_ray(cam, rp, x, y) for y in range(H) for x in range(W)])
+    ref = oracle.integrate(1.0, 0.0, 0, opts, rays)
+    e = built.PhysicsEngine(1.0, 0.0)
+    got = e.integrate_rays(rays, R.RenderParams(method=0, coords=0, step_rule=0, max_steps=128))
+    assert (ref["term"] == 3).all() and (ref["steps"] == 128).all()
+    assert np.array_equal(got["term"], ref["term"]) and np.array_equal(got["steps"], ref["steps"].astype(np.uint32))
+    assert np.array_equal(got["rhs"], ref["rhs"].astype(np.uint32))          # same accept/reject history on every ray
+    err = np.abs(got["xp"] - ref["xp"]) / np.maximum(np.abs(ref["xp"]), 1.0)
+    print(f"config 1: {W * H} rays, state err median {np.median(err):.2e} max {err.max():.2e}")
+    assert np.percentile(err, 99.9) < 1e-9 and err.max() < 1e-7   # rays grazing the polar axis amplify rounding
