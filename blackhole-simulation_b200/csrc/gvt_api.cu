@@ -578,15 +578,23 @@ extern "C" int32_t gvt_render_frame(gvt_renderer* r, const GvtCamera* cam, const
     d2h += sizeof(Counters);
     if (host_rgba) {
         const size_t n_px = (size_t)W * H;
+        // which pixels go back: the whole frame, or only this rank's row block at its place in the host frame
+        const bool own = (rp->flags & GVT_FLAG_D2H_OWN_ROWS) != 0 && r->world > 1;
+        const size_t px0 = own ? (size_t)row0 * W : 0, npx = own ? (size_t)(row1 - row0) * W : n_px;
         if (rp->output_format == GVT_FORMAT_RGBA16F) {
             if (!r->half_frame) CK(cudaMalloc(&r->half_frame, n_px * 8));
-            CK(launch_f32_to_f16(r->frame, r->half_frame, n_px, r->stream));
-            launches++;
-            CK(cudaMemcpyAsync(host_rgba, r->half_frame, n_px * 8, cudaMemcpyDeviceToHost, r->stream));
-            d2h += n_px * 8;
+            if (npx) {
+                CK(launch_f32_to_f16(r->frame + px0, static_cast<char*>(r->half_frame) + px0 * 8, npx, r->stream));
+                launches++;
+                CK(cudaMemcpyAsync(static_cast<char*>(host_rgba) + px0 * 8, static_cast<char*>(r->half_frame) + px0 * 8,
+                                   npx * 8, cudaMemcpyDeviceToHost, r->stream));
+            }
+            d2h += npx * 8;
         } else {
-            CK(cudaMemcpyAsync(host_rgba, r->frame, n_px * sizeof(float4), cudaMemcpyDeviceToHost, r->stream));
-            d2h += n_px * sizeof(float4);
+            if (npx)
+                CK(cudaMemcpyAsync(static_cast<char*>(host_rgba) + px0 * sizeof(float4), r->frame + px0, npx * sizeof(float4),
+                                   cudaMemcpyDeviceToHost, r->stream));
+            d2h += npx * sizeof(float4);
         }
     }
     CK(cudaEventRecord(r->ev[5], r->stream));
@@ -681,6 +689,15 @@ extern "C" int32_t gvt_host_alloc(size_t bytes, void** out) {
 }
 extern "C" int32_t gvt_host_free(void* p) {
     if (p) CK(cudaFreeHost(p));
+    return GVT_OK;
+}
+extern "C" int32_t gvt_host_register(void* p, size_t bytes) {
+    if (!p || bytes == 0) return fail(GVT_ERR_INVALID, "bad argument");
+    CK(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return GVT_OK;
+}
+extern "C" int32_t gvt_host_unregister(void* p) {
+    if (p) CK(cudaHostUnregister(p));
     return GVT_OK;
 }
 

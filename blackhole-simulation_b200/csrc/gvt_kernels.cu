@@ -104,10 +104,7 @@ __device__ __forceinline__ bool sign_differs_or_zero(double a, double b) {
     const bool az = ((ah & 0x7fffffff) | __double2loint(a)) == 0, bz = ((bh & 0x7fffffff) | __double2loint(b)) == 0;
     return ((ah ^ bh) < 0) || az || bz;
 }
-__device__ __forceinline__ bool sign_differs_or_zero(float a, float b) {
-    const int ai = __float_as_int(a), bi = __float_as_int(b);
-    return ((ai ^ bi) < 0) || ((ai & 0x7fffffff) == 0) || ((bi & 0x7fffffff) == 0);
-}  // one warp = one 8x4 pixel tile (compute.wgsl.ts:147 uses 8x8 groups)
+__device__ __forceinline__ bool sign_differs_or_zero(float a, float b) { return a * b <= 0.0f; }  // FP32 ops are cheap  // one warp = one 8x4 pixel tile (compute.wgsl.ts:147 uses 8x8 groups)
 
 template <class R, int METHOD, bool BUDGET, bool DEBUG, int MAXT, bool WGSL_RULE>
 __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ FrameParams P) {

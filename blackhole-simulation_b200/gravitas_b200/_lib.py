@@ -17,7 +17,7 @@ METHOD_RKF45, METHOD_RK4, METHOD_SYMPLECTIC = 0, 1, 2
 PRECISION_F64, PRECISION_F32 = 0, 1
 FORMAT_RGBA32F, FORMAT_RGBA16F = 0, 1
 STEP_CONSTANT, STEP_WGSL = 0, 1
-FLAG_JITTER, FLAG_BUDGET, FLAG_TRACK_DRIFT, FLAG_TAA, FLAG_NO_GATHER = 1, 2, 4, 8, 16
+FLAG_JITTER, FLAG_BUDGET, FLAG_TRACK_DRIFT, FLAG_TAA, FLAG_NO_GATHER, FLAG_D2H_OWN_ROWS = 1, 2, 4, 8, 16, 32
 
 
 class GravitasError(RuntimeError):
@@ -101,6 +101,8 @@ SIGNATURES = {
     "gvt_render_reset_history": (_i32, [_vp]),
     "gvt_host_alloc": (_i32, [C.c_size_t, C.POINTER(_vp)]),
     "gvt_host_free": (_i32, [_vp]),
+    "gvt_host_register": (_i32, [_vp, C.c_size_t]),
+    "gvt_host_unregister": (_i32, [_vp]),
     "gvt_measure_fma_peak": (_i32, [_vp, _i32, _pd, _pd]),
     "gvt_device_info": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.c_char_p]),
 }

@@ -71,6 +71,44 @@ class PinnedBuffer:
     __del__ = free
 
 
+class SharedFrame:
+    """One host frame buffer shared by all ranks of a box (POSIX shared memory, page-locked in every process): with
+    GVT_FLAG_D2H_OWN_ROWS each rank copies its row block straight into it, so the consumer (rank 0's host) gets the
+    assembled frame for one frame's worth of PCIe traffic in total."""
+
+    def __init__(self, width, height, fmt=_lib.FORMAT_RGBA32F, name=None, create=True):
+        from multiprocessing import shared_memory
+        self.nbytes = width * height * (16 if fmt == _lib.FORMAT_RGBA32F else 8)
+        self.shape, self.dtype = (height, width, 4), (np.float32 if fmt == _lib.FORMAT_RGBA32F else np.float16)
+        self.shm = shared_memory.SharedMemory(name=name, create=create, size=self.nbytes)
+        self.owner = create
+        if not create:   # only the creating rank unlinks; keep the other ranks' resource trackers out of it
+            try:
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
+        self._view = np.ndarray(self.shape, dtype=self.dtype, buffer=self.shm.buf)
+        self.ptr = C.c_void_p(self._view.ctypes.data)
+        check(lib().gvt_host_register(self.ptr, self.nbytes))
+
+    @property
+    def name(self):
+        return self.shm.name
+
+    def array(self, dtype=None, shape=None):
+        return self._view
+
+    def close(self):
+        if self.shm is not None:
+            lib().gvt_host_unregister(self.ptr)
+            self._view = None
+            self.shm.close()
+            if self.owner:
+                self.shm.unlink()
+            self.shm = None
+
+
 class KerrRenderer:
     def __init__(self, device=0, rank=0, world_size=1, nccl_id=None):
         self._h = C.c_void_p()

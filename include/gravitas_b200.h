@@ -60,7 +60,11 @@ enum {
                                        terminated rays keep stepping with commits masked */
     GVT_FLAG_TRACK_DRIFT = 1u << 2, /* max |H| per ray, as geodesic/mod.rs:233-237 */
     GVT_FLAG_TAA = 1u << 3,         /* run the TAA resolve (ataa.wgsl.ts:28-83) after the trace */
-    GVT_FLAG_NO_GATHER = 1u << 4    /* multi-GPU: skip the all-gather (each rank keeps only its row block) */
+    GVT_FLAG_NO_GATHER = 1u << 4,   /* multi-GPU: skip the all-gather (each rank keeps only its row block) */
+    GVT_FLAG_D2H_OWN_ROWS = 1u << 5 /* multi-GPU: copy only this rank's row block into host_rgba (at its place in the
+                                       full-size buffer). With one host frame shared by all ranks (POSIX shm registered
+                                       through gvt_host_register) the ranks assemble the frame in parallel, one
+                                       frame's worth of PCIe traffic in total instead of one per rank. */
 };
 
 /* src/types/webgpu.ts:67-116 / src/shaders/types.wgsl.ts:6-16 — 352 bytes, column-major mat4 as gl-matrix */
@@ -195,6 +199,9 @@ int32_t gvt_render_reset_history(gvt_renderer* r);
 /* Pinned host memory for frame buffers (what an N-API external ArrayBuffer would wrap). */
 int32_t gvt_host_alloc(size_t bytes, void** out);
 int32_t gvt_host_free(void* p);
+/* Page-lock caller-owned host memory (e.g. a shared-memory frame all ranks of a box write into). */
+int32_t gvt_host_register(void* p, size_t bytes);
+int32_t gvt_host_unregister(void* p);
 /* In-run FMA-pipe micro-benchmarks (dependent-chain FFMA / DFMA, all SMs): the FP32/FP64 roofline denominators
  * MEASURED_PEAKS.json does not carry. Returns TFLOP/s (2 flop per FMA). */
 int32_t gvt_measure_fma_peak(gvt_renderer* r, int32_t precision, double* out_tflops, double* out_ms);

@@ -46,7 +46,27 @@ for (W, H, steps) in ((256, 144, 128), (157, 83, 64)):       # divisible and rag
             if not taa:
                 assert int(t[0]) == int(single.last_stats.steps_committed)
             prev = vp
+# one shared host frame assembled by all ranks (GVT_FLAG_D2H_OWN_ROWS): equals the single-GPU frame on every rank
+W, H, steps = 256, 144, 64
+names = [None]
+if rank == 0:
+    shared = R.SharedFrame(W, H)
+    names = [shared.name]
+dist.broadcast_object_list(names, src=0)
+if rank != 0:
+    shared = R.SharedFrame(W, H, name=names[0], create=False)
+cam, _ = camera.default_camera(W, H)
+phys = R.pack_physics(1.0, spin, W, H)
+multi.params = R.RenderParams(max_steps=steps, flags=_lib.FLAG_D2H_OWN_ROWS)
+single.params = R.RenderParams(max_steps=steps)
+multi.render(cam, phys, out=shared)
+r0, r1 = shard.shard_rows(H, rank, world)
+assert multi.last_stats.d2h_bytes == (r1 - r0) * W * 16 + 64, multi.last_stats.d2h_bytes
 dist.barrier()
+b = np.array(single.render(cam, phys))
+assert np.array_equal(np.array(shared.array()), b), f"rank {rank}: shared host frame differs"
+dist.barrier()
+shared.close()
 multi.cleanup(); single.cleanup()
 dist.destroy_process_group()
 print(f"rank {rank} ok")
