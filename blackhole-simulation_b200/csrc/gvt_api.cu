@@ -507,7 +507,7 @@ static int32_t build_frame(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
 static void fill_taa(const GvtCamera* cam, uint32_t W, uint32_t H, TaaParams& T) {
     memcpy(T.inv_proj, cam->inv_proj, 64); memcpy(T.inv_view, cam->inv_view, 64);
     memcpy(T.prev_view_proj, cam->prev_view_proj, 64); memcpy(T.cam_pos, cam->position, 16);
-    T.width = W; T.height = H; T.row0 = 0; T.row1 = H;
+    T.width = W; T.height = H; T.row0 = 0; T.row1 = H; T.host_out = nullptr;
 }
 
 extern "C" int32_t gvt_render_read_frame(gvt_renderer* r, uint32_t format, void* host_rgba) {
@@ -550,6 +550,20 @@ extern "C" int32_t gvt_render_frame(gvt_renderer* r, const GvtCamera* cam, const
     P.frame = trace_out;
     uint32_t launches = 0;
     uint64_t h2d = 0, d2h = 0;
+    // Host frame delivery. If the caller's buffer is page-locked (gvt_host_alloc / gvt_host_register) and this rank
+    // produces every pixel it has to deliver (single GPU, or GVT_FLAG_D2H_OWN_ROWS), the producing kernel stores each
+    // finished pixel straight into host memory over PCIe (132.7 MB spread over the whole kernel: ~2 GB/s) and no D2H
+    // copy follows. Otherwise the finished frame is copied after the last kernel.
+    const bool own = (rp->flags & GVT_FLAG_D2H_OWN_ROWS) != 0 && r->world > 1;
+    float4* host_alias = nullptr;
+    if (host_rgba && rp->output_format == GVT_FORMAT_RGBA32F && (r->world == 1 || own)) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, host_rgba) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+            host_alias = static_cast<float4*>(at.devicePointer);
+        else
+            (void)cudaGetLastError();   // pageable memory: not an error, just the copy path
+    }
+    P.host_frame = taa ? nullptr : host_alias;
 
     CK(cudaEventRecord(r->ev[0], r->stream));
     CK(cudaMemcpyAsync(r->d_block, r->h_block, sizeof(FrameBlock), cudaMemcpyHostToDevice, r->stream));
@@ -563,6 +577,7 @@ extern "C" int32_t gvt_render_frame(gvt_renderer* r, const GvtCamera* cam, const
         fill_taa(cam, W, H, T);
         T.cur = r->cur; T.hist = r->hist; T.out = r->frame;
         T.row0 = row0; T.row1 = row1;
+        T.host_out = host_alias;
         CK(launch_taa(T, r->stream));
         launches++;
     }
@@ -576,10 +591,11 @@ extern "C" int32_t gvt_render_frame(gvt_renderer* r, const GvtCamera* cam, const
     CK(cudaEventRecord(r->ev[4], r->stream));
     CK(cudaMemcpyAsync(r->h_counters, r->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, r->stream));
     d2h += sizeof(Counters);
-    if (host_rgba) {
+    if (host_rgba && host_alias) {
+        d2h += (size_t)(row1 - row0) * W * sizeof(float4);   // delivered by the kernel's own stores
+    } else if (host_rgba) {
         const size_t n_px = (size_t)W * H;
         // which pixels go back: the whole frame, or only this rank's row block at its place in the host frame
-        const bool own = (rp->flags & GVT_FLAG_D2H_OWN_ROWS) != 0 && r->world > 1;
         const size_t px0 = own ? (size_t)row0 * W : 0, npx = own ? (size_t)(row1 - row0) * W : n_px;
         if (rp->output_format == GVT_FORMAT_RGBA16F) {
             if (!r->half_frame) CK(cudaMalloc(&r->half_frame, n_px * 8));

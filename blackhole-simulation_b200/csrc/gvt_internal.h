@@ -41,6 +41,8 @@ struct FrameParams {
     const FrameBlock* block;                                  // global copy of the TMA-staged block
     const float4* spectrum;                                   // global spectral LUT (W*H float4)
     float4* frame;                                            // full-frame RGBA32F (may be null for debug launches)
+    float4* host_frame;                                       // device alias of a page-locked HOST frame (or null): the
+                                                              // epilogue stores the pixel there too, so no D2H copy follows
     Counters* counters;
     // parity-hook outputs (DEBUG instantiations only), dense over the lattice
     double* dbg_xp; uint32_t* dbg_term; uint32_t* dbg_steps; double* dbg_drift; double* dbg_rgba;
@@ -60,6 +62,7 @@ struct TaaParams {
     uint32_t width, height;
     uint32_t row0, row1;   // rows resolved by this launch (a rank's block); neighbours outside are still read
     const float4* cur; const float4* hist; float4* out;
+    float4* host_out;      // device alias of a page-locked host frame, or null
 };
 
 // launchers (gvt_kernels.cu)

@@ -262,7 +262,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
 
         // ---- epilogue: coalesced float4 store + census ----
         if (valid) {
-            if (P.frame) P.frame[(size_t)py * P.width + px] = make_float4((float)col[0], (float)col[1], (float)col[2], 1.0f);
+            const float4 px_out = make_float4((float)col[0], (float)col[1], (float)col[2], 1.0f);
+            if (P.frame) P.frame[(size_t)py * P.width + px] = px_out;
+            if (P.host_frame) P.host_frame[(size_t)py * P.width + px] = px_out;   // posted PCIe write, off the critical path
             if (DEBUG) {
                 const size_t k = (size_t)lj * P.nx + li;
                 if (P.dbg_xp) {
@@ -494,7 +496,9 @@ __global__ void __launch_bounds__(256) k_taa_resolve(const __grid_constant__ Taa
             const float fb_ = 0.92f;  // ataa.wgsl.ts:77
             const float ry = b.y + (hs.y - b.y) * fb_, ro = b.co + (hs.co - b.co) * fb_, rg = b.cg + (hs.cg - b.cg) * fb_;
             // YCoCgToRGB, ataa.wgsl.ts:18-26
-            P.out[(size_t)y * W + x] = make_float4(ry + ro - rg, ry + rg, ry - ro - rg, 1.0f);
+            const float4 px_out = make_float4(ry + ro - rg, ry + rg, ry - ro - rg, 1.0f);
+            P.out[(size_t)y * W + x] = px_out;
+            if (P.host_out) P.host_out[(size_t)y * W + x] = px_out;
         }
         a = b; b = c;
     }
