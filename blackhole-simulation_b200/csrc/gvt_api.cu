@@ -493,6 +493,7 @@ static int32_t build_frame(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
 
     memset(&P, 0, sizeof(P));
     P.M = bh.mass; P.a = bh.a(); P.spin = bh.spin; P.rh = bh.horizon(); P.r_term = P.rh * 1.001;
+    P.sqrtM = std::sqrt(bh.mass);
     P.escape_r = rp->escape_radius; P.r_in = bh.isco(true); P.r_out = rp->disk_r_out;
     P.tol = rp->tolerance; P.h0 = rp->initial_step;
     P.tdisk_rin = r->tdisk_rin; P.tdisk_scale = 511.0 / (r->tdisk_rout - r->tdisk_rin);

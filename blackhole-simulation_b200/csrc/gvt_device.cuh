@@ -43,6 +43,37 @@ __device__ __forceinline__ float rcp_nr(float x) {
 // angles stay within a few multiples of pi), fdlibm minimax kernels on |r| <= pi/4, quadrant handled by two
 // selects and one sign flip: for odd k sin <-> cos and the product changes sign. ~19 FP64 ops, no I2F/F2I, no
 // Payne-Hanek slow path (CUDA's sincos() costs ~2x that in issue slots).
+// ---- call-free sqrt / x^0.4 for the march. CUDA's sqrt(), pow() and IEEE division compile to a fast path plus a
+// CALL to a slow-path subroutine; a CALL anywhere inside the step loop makes ptxas keep every loop-invariant FP64
+// constant in ordinary registers instead of uniform registers, and a DFMA with three distinct register operands
+// costs 3 cycles instead of 2 on B200 (register-file port limit; scripts/ubench/issue_model.cu). Arguments here are
+// finite and either zero or comfortably normal.
+__device__ __forceinline__ double sqrt_nr(double x) {
+    if (!(x > 1e-290)) return 0.0;                    // 0 (double root), or negative/NaN never reach here meaningfully
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));          // MUFU.RSQ64H seed
+    double e = fma(-(x * y), y, 1.0);                                  // 1 - x y^2
+    y = fma(y, e * fma(0.375, e, 0.5), y);                             // cubic: y (1 + e/2 + 3e^2/8)
+    e = fma(-(x * y), y, 1.0);
+    y = fma(0.5 * y, e, y);
+    const double s = x * y;                                            // sqrt estimate, then one correction step
+    return fma(0.5 * y, fma(-s, s, x), s);
+}
+__device__ __forceinline__ float sqrt_nr(float x) { return sqrtf(x); }    // MUFU.SQRT path, no call in f32
+// t^0.4 = (t^2)^(1/5): MUFU.LG2/EX2 seed in f32, then Newton on y^5 = t^2 in the working precision.
+__device__ __forceinline__ double pow04(double t) {
+    if (!(t > 1e-30)) return 0.0;          // below this the LUT coordinate clamps to texel 0 anyway
+    double y = (double)exp2f(0.4f * __log2f((float)t));
+    const double c = t * t;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const double y2 = y * y, y5 = y2 * y2 * y;
+        y = y * fma(0.2, c * rcp_nr(y5), 0.8);
+    }
+    return y;
+}
+__device__ __forceinline__ float pow04(float t) { return (t > 0.0f) ? exp2f(0.4f * log2f(t)) : 0.0f; }
+
 // minimax kernels of fdlibm's __kernel_sin / __kernel_cos. The kernels receive the table inside their
 // __grid_constant__ parameter block (constant bank 0), so the coefficients reach DFMA/FFMA through uniform
 // registers instead of per-iteration literal materialisation.
@@ -62,8 +93,13 @@ struct TrigTable {
 // d: [0] 2/pi  [1] 1.5*2^52  [2] pi/2 hi  [3] pi/2 lo  [4..9] S1..S6  [10..15] C1..C6
 // f: [0] 2/pi  [1] 1.5*2^23  [2..4] pi/2 in three parts  [5..7] S1..S3  [8..10] C1..C3
 
+__constant__ TrigTable c_trig = GVT_TRIG_TABLE_INIT;
 __device__ __forceinline__ void trig_pair(const TrigTable& T, double x, double& a, double& sc) {
+#ifdef GVT_TRIG_NAMED_CONST
+    const double* K = c_trig.d;
+#else
     const double* K = T.d;
+#endif
     const double kd_m = fma(x, K[0], K[1]);
     const int k = __double2loint(kd_m);
     const double kd = kd_m - K[1];
@@ -343,8 +379,8 @@ __device__ __forceinline__ R renormalize_pr(const HoleRay<R>& c, R r, R th, R pr
     if (N::abs_(A) > R(1e-12)) {
         const R disc = N::fma_(B, B, R(-4) * A * C);
         if (disc >= R(0)) {
-            const R sq = N::sqrt_(disc);
-            const R inv2a = N::rcp_ieee(R(2) * A);
+            const R sq = (COORDS == 1) ? sqrt_nr(disc) : N::sqrt_(disc);
+            const R inv2a = (COORDS == 1) ? N::rcp(R(2) * A) : N::rcp_ieee(R(2) * A);
             const R sol1 = (-B + sq) * inv2a;
             const R sol2 = (-B - sq) * inv2a;
             return (N::abs_(sol1 - pr) < N::abs_(sol2 - pr)) ? sol1 : sol2;
@@ -506,15 +542,14 @@ __device__ __forceinline__ R adaptive_step(const HoleRay<R>& c, Ray<R>& y, R h_t
     }
 }
 
-// physics/redshift.rs:65-95 kerr_g_factor
+// physics/redshift.rs:65-95 kerr_g_factor (sm = sqrt(mass), evaluated once on the host)
 template <class R>
-__device__ __forceinline__ R g_factor(R r, R mass, R spin, R lambda) {
+__device__ __forceinline__ R g_factor(R r, R mass, R sm, R spin, R lambda) {
     using N = Num<R>;
     const R a = spin * mass;
     const R r2 = r * r;
-    const R sm = N::sqrt_(mass);
-    const R omega = sm / (r * N::sqrt_(r) + a * sm);   // r^1.5 = r sqrt(r)
-    const R twoM_r = R(2) * mass / r;               // 2 M r / Sigma at the equator (Sigma = r^2)
+    const R omega = sm * N::rcp(N::fma_(r, sqrt_nr(r), a * sm));     // sqrt(M) / (r^1.5 + a sqrt(M))
+    const R twoM_r = R(2) * mass * N::rcp(r);                         // 2 M r / Sigma at the equator (Sigma = r^2)
     const R g_tt = -(R(1) - twoM_r);
     const R g_tphi = -(twoM_r * a);
     const R g_phiphi = r2 + a * a + twoM_r * a * a;
@@ -522,8 +557,7 @@ __device__ __forceinline__ R g_factor(R r, R mass, R spin, R lambda) {
     if (ut_denom <= R(0)) return R(0);
     const R factor = R(1) - lambda * omega;
     if (N::abs_(factor) < R(1e-30)) return R(0);
-    // 1 / (ut * factor), ut = 1/sqrt(ut_denom)
-    return N::sqrt_(ut_denom) / factor;
+    return sqrt_nr(ut_denom) * N::rcp(factor);                        // 1 / (u^t (1 - lambda Omega))
 }
 
 }  // namespace gvt

@@ -31,6 +31,7 @@ struct Counters {  // device-side accumulators, one set per frame
 struct FrameParams {
     TrigTable trig;                                           // set by the launcher (GVT_TRIG_TABLE_INIT)
     double M, a, spin, rh, r_term, escape_r, r_in, r_out;   // r_term = 1.001 * r+ (geodesic/mod.rs:257)
+    double sqrtM;                                             // sqrt(M) for the Keplerian frequency (redshift.rs:72)
     double tol, h0;
     double tdisk_rin, tdisk_scale;                            // (n-1)/(rout-rin)
     uint32_t width, height;                                   // full frame

@@ -5,8 +5,8 @@
 //                     crossing shade through the GR g-factor + Planckian redshift LUT, float4 RGBA store.
 //                     Persistent CTAs; each warp pulls 8x4-pixel tiles from an atomic queue; the camera block +
 //                     disk LUT and the spectral LUT are staged into shared memory by TMA bulk copies
-//                     (cp.async.bulk + mbarrier); the ray state lives in registers; the LUT barrier is only
-//                     waited on at the first disk crossing, so the copy is hidden behind the march.
+//                     (cp.async.bulk + mbarrier); the ray state lives in registers; the LUT barrier is waited on
+//                     after the first tile's ray generation, so the copy overlaps that set-up work.
 //   k_integrate_rays  geodesic::integrate over a batch of explicit initial states (the PhysicsEngine seam).
 //   k_taa_resolve     YCoCg variance-clip TAA resolve (ataa.wgsl.ts:28-83), 3x3 moments by warp shuffles.
 //   k_fma_peak        FFMA / DFMA micro-benchmark: the FP32 / FP64 roofline denominators.
@@ -175,24 +175,29 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
                           R(fb->inv_proj[12 + row]);
             const R iw = N::rcp(vt[3]);
             R vx = vt[0] * iw, vy = vt[1] * iw, vz = vt[2] * iw;
-            const R ivn = N::rcp(N::sqrt_(vx * vx + vy * vy + vz * vz));
+            const R ivn = N::rcp(sqrt_nr(vx * vx + vy * vy + vz * vz));
             vx *= ivn; vy *= ivn; vz *= ivn;
             R w[3];
 #pragma unroll
             for (int row = 0; row < 3; row++)
                 w[row] = R(fb->inv_view[row]) * vx + R(fb->inv_view[4 + row]) * vy + R(fb->inv_view[8 + row]) * vz;
-            const R iwn = N::rcp(N::sqrt_(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]));
+            const R iwn = N::rcp(sqrt_nr(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]));
             const R dx = w[0] * iwn, dy = w[1] * iwn, dz = w[2] * iwn;
             const R st = R(fb->st), ct = R(fb->ct), sp = R(fb->sp), cp = R(fb->cp), r0 = R(fb->r0);
             const R pr_far = dx * (st * cp) + dy * ct + dz * (st * sp);
-            const R pth_far = (dx * (ct * cp) - dy * st + dz * (ct * sp)) / r0;
-            const R pph_far = (dz * cp - dx * sp) / (r0 * R(fb->safe_st));
+            const R inv_r0 = N::rcp(r0);
+            const R pth_far = (dx * (ct * cp) - dy * st + dz * (ct * sp)) * inv_r0;
+            const R pph_far = (dz * cp - dx * sp) * N::rcp(r0 * R(fb->safe_st));
             y.t = R(0); y.r = r0; y.th = R(fb->theta0); y.ph = R(fb->phi0);
             y.pr = pr_far;
             y.pth = pth_far * r0 * r0;
             hc.set_ray(R(-1), pph_far * r0 * r0 * st * st);
         }
 
+        // The spectral-LUT copy was issued before ray generation; by now it has had a tile's worth of set-up time to
+        // land. (The wait must not sit inside the step loop: an mbarrier try_wait spin loop there stops ptxas from
+        // keeping the loop's FP64 constants in uniform registers, which costs a cycle on every three-register DFMA.)
+        if (!lut_ready) { mbar_wait(&bars[1], 0); lut_ready = true; }
         // ---- march: geodesic/mod.rs:180-253 ----
         y.pr = renormalize_pr<R, 1>(hc, y.r, y.th, y.pr, y.pth);  // mod.rs:200
         R col[3] = {R(0), R(0), R(0)};
@@ -234,15 +239,14 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
                     dprev = dcur;
                     if (crossed) {
                         const R dth = y.th - th0;
-                        const R f = (dth == R(0)) ? R(0) : (half_pi - th0) / dth;
+                        const R f = (dth == R(0)) ? R(0) : (half_pi - th0) * N::rcp(dth);
                         const R r_c = N::fma_(f, y.r - r_prev, r_prev);
                         if (r_c > R(P.r_in) && r_c < R(P.r_out)) {
-                            if (!lut_ready) { mbar_wait(&bars[1], 0); lut_ready = true; }
-                            const R lambda = hc.pph / (-hc.pt);
-                            const R g = g_factor<R>(r_c, R(P.M), R(P.spin), lambda);
+                            const R lambda = hc.pph * N::rcp(-hc.pt);
+                            const R g = g_factor<R>(r_c, R(P.M), R(P.sqrtM), R(P.spin), lambda);
                             const R tn = sample_tdisk<R>(fb->tdisk, P.tdisk_n, R(P.tdisk_rin), R(P.tdisk_scale), r_c);
-                            const R u = N::pow_(tn, R(0.4));
-                            const R v = (g - R(0.05)) / R(4.95);
+                            const R u = pow04(tn);
+                            const R v = (g - R(0.05)) * R(1.0 / 4.95);
                             R rgb[3];
                             sample_spectrum<R>(lut, P.spec_w, P.spec_h, u, v, rgb);
                             const R opacity = R(0.6) * tn * g;
