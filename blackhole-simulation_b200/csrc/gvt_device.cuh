@@ -73,6 +73,20 @@ __device__ __forceinline__ double pow04(double t) {
     return y;
 }
 __device__ __forceinline__ float pow04(float t) { return (t > 0.0f) ? exp2f(0.4f * log2f(t)) : 0.0f; }
+// x^(-1/5) for the RKF45 step controller (integrator.rs:90): division-free Newton on y^-5 = x, y <- y (6 - x y^5)/5
+__device__ __forceinline__ double pow_m02(double x) {
+    double y = (double)exp2f(-0.2f * __log2f((float)x));
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const double y2 = y * y, y5 = y2 * y2 * y;
+        y = y * fma(-0.2 * x, y5, 1.2);
+    }
+    return y;
+}
+__device__ __forceinline__ float pow_m02(float x) { return exp2f(-0.2f * log2f(x)); }
+// x^(-1/4) (integrator.rs:96) = 1 / sqrt(sqrt(x))
+__device__ __forceinline__ double pow_m025(double x) { return rcp_nr(sqrt_nr(sqrt_nr(x))); }
+__device__ __forceinline__ float pow_m025(float x) { return rsqrtf(sqrtf(x)); }
 
 // minimax kernels of fdlibm's __kernel_sin / __kernel_cos. The kernels receive the table inside their
 // __grid_constant__ parameter block (constant bank 0), so the coefficients reach DFMA/FFMA through uniform
@@ -518,17 +532,18 @@ __device__ __forceinline__ R adaptive_step(const HoleRay<R>& c, Ray<R>& y, R h_t
     using N = Num<R>;
     const R max_step = R(10), min_step = R(1e-5), safety = R(0.9);
     R h = clampR<R>(h_try, -max_step, max_step);
+    const R inv_tol = Num<R>::rcp_ieee(tol);
     for (;;) {
         Ray<R> ny;
         const R err = rkf45_attempt<R, COORDS>(c, y, h, ny);
         evals += 6;
-        const R ratio = (err == R(0)) ? R(0) : err / tol;
+        const R ratio = (err == R(0)) ? R(0) : err * inv_tol;
         if (ratio <= R(1)) {
             y = ny;
-            const R growth = (ratio < R(1e-4)) ? R(5) : safety * N::pow_(ratio, R(-0.2));
+            const R growth = (ratio < R(1e-4)) ? R(5) : safety * pow_m02(ratio);
             return clampR<R>(h * N::min_(growth, R(5)), -max_step, max_step);
         }
-        const R shrink = safety * N::pow_(ratio, R(-0.25));
+        const R shrink = safety * pow_m025(ratio);
         h *= N::max_(shrink, R(0.1));
         if (N::abs_(h) < min_step) {
             const R hs = (h < R(0)) ? -min_step : min_step;
