@@ -207,25 +207,33 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
         bool done = false, by_radius = false;
         // side of the equatorial plane before the step, as the sign word of (theta - pi/2) and an "exactly on it" flag
         R dprev = y.th - half_pi;
-        // fixed-step methods: unroll x4 to amortise the loop bookkeeping (-3.5 % at 4Kx512); the adaptive stepper's
-        // body is far too large for that (it spills when unrolled)
+        // The warp-uniform early exit (all 32 rays finished) is voted once per chunk of 8 steps, outside the inner
+        // loop: a vote.sync inside the step loop, like any warp-synchronising instruction there, stops ptxas from
+        // keeping the loop's FP64 constants in uniform registers (3-register DFMAs cost 3 cycles instead of 2).
+        // Fixed-step methods unroll the inner loop x4 to amortise its bookkeeping; the adaptive stepper's body is far
+        // too large for that (it spills when unrolled).
+        constexpr uint32_t CHUNK = 8;
+        for (uint32_t it0 = 0; it0 < P.max_steps; it0 += CHUNK) {
+        if (!BUDGET) { if (__all_sync(0xffffffffu, done)) break; }
+        const uint32_t it1 = min(it0 + CHUNK, P.max_steps);
 #pragma unroll(METHOD == 0 ? 1 : 4)
-        for (uint32_t it = 0; it < P.max_steps; it++) {
+        for (uint32_t it = it0; it < it1; it++) {
             // mod.rs:204,255-265: alive iff 1.001 r+ <= r <= escape radius (which of the two ended it is resolved
             // after the loop from the frozen state)
             if (!done && !(y.r >= r_term && y.r <= escape_r)) { done = true; by_radius = true; }
-            if (!BUDGET) { if (__all_sync(0xffffffffu, done)) break; }   // warp-uniform: all 32 lanes stay in the loop
-            if (BUDGET || !done) {
+            // Fixed-step methods run the step for every lane, finished rays with h = 0 on their frozen state (nothing to
+            // select back afterwards): in budget accounting that IS the definition; with natural termination the lanes
+            // would idle under predication anyway, and keeping the step out of a divergent region lets ptxas feed its
+            // constants from uniform registers. The adaptive stepper keeps the branch (its retry loop diverges anyway).
+            if (METHOD != 0 || !done) {
                 const R th0 = y.th, r_prev = y.r;
                 if (METHOD == 0) {
                     h = adaptive_step<R, 1>(hc, y, h, R(P.tol), rhs_evals);
                 } else {
                     R hs = WGSL_RULE ? clampR<R>((y.r - rh) * R(0.15), R(0.05), R(1.0)) : R(P.h0);
-                    // budget accounting: a terminated ray still executes the full step computation, on its frozen
-                    // state with h = 0, so nothing needs to be selected back afterwards
-                    if (BUDGET && done) hs = R(0);
-                    if (METHOD == 1) { step_rk4<R, 1, DEBUG>(hc, y, hs); rhs_evals += 4; }
-                    else { step_symplectic<R, 1, DEBUG>(hc, y, hs); rhs_evals += 3; }
+                    if (done) hs = R(0);
+                    if (METHOD == 1) { step_rk4<R, 1, DEBUG>(hc, y, hs); rhs_evals += (BUDGET || !done) ? 4u : 0u; }
+                    else { step_symplectic<R, 1, DEBUG>(hc, y, hs); rhs_evals += (BUDGET || !done) ? 3u : 0u; }
                 }
                 if (!done) {
                     if (renorm_in == 0u) { y.pr = renormalize_pr<R, 1>(hc, y.r, y.th, y.pr, y.pth); renorm_in = P.renorm_interval; }
@@ -260,6 +268,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
                     }
                 }
             }
+        }
         }
         if (by_radius) term = (y.r < r_term) ? 1u : 2u;   // Horizon is tested first (mod.rs:257-263)
         else if (!done) term = 3u;
