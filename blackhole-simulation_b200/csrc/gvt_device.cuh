@@ -557,6 +557,38 @@ __device__ __forceinline__ R adaptive_step(const HoleRay<R>& c, Ray<R>& y, R h_t
     }
 }
 
+// The same controller for a converged warp (the trace kernel): every lane executes every attempt, lanes that are
+// finished or already accepted step with h = 0 (their state does not move), and the retry loop runs while any lane
+// still has a rejected step. In SIMT a rejection on one lane costs the whole warp another pass anyway; keeping the
+// attempt out of divergent control flow lets ptxas feed the Butcher coefficients from uniform registers.
+template <class R, int COORDS>
+__device__ __forceinline__ void adaptive_step_warp(const HoleRay<R>& c, Ray<R>& y, R& h, R tol, bool active,
+                                                   uint32_t& evals) {
+    using N = Num<R>;
+    const R max_step = R(10), min_step = R(1e-5), safety = R(0.9);
+    const R inv_tol = Num<R>::rcp_ieee(tol);
+    R ht = clampR<R>(h, -max_step, max_step);
+    bool pending = active, forced = false;
+    while (__any_sync(0xffffffffu, pending)) {
+        Ray<R> ny;
+        const R err = rkf45_attempt<R, COORDS>(c, y, pending ? ht : R(0), ny);
+        if (pending) {
+            evals += 6;
+            const R ratio = (err == R(0)) ? R(0) : err * inv_tol;
+            if (forced || ratio <= R(1)) {
+                y = ny;
+                const R growth = (ratio < R(1e-4)) ? R(5) : safety * pow_m02(ratio);
+                h = forced ? ht : clampR<R>(ht * N::min_(growth, R(5)), -max_step, max_step);
+                pending = false;
+            } else {
+                ht *= N::max_(safety * pow_m025(ratio), R(0.1));
+                if (N::abs_(ht) < min_step) { ht = (ht < R(0)) ? -min_step : min_step; forced = true; }
+                else if (!(ht == ht)) { ht = min_step; forced = true; }   // NaN step: take the forced minimum step
+            }
+        }
+    }
+}
+
 // physics/redshift.rs:65-95 kerr_g_factor (sm = sqrt(mass), evaluated once on the host)
 template <class R>
 __device__ __forceinline__ R g_factor(R r, R mass, R sm, R spin, R lambda) {

@@ -224,11 +224,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
             // Fixed-step methods run the step for every lane, finished rays with h = 0 on their frozen state (nothing to
             // select back afterwards): in budget accounting that IS the definition; with natural termination the lanes
             // would idle under predication anyway, and keeping the step out of a divergent region lets ptxas feed its
-            // constants from uniform registers. The adaptive stepper keeps the branch (its retry loop diverges anyway).
-            if (METHOD != 0 || !done) {
+            // constants from uniform registers. The adaptive stepper does the same per attempt (adaptive_step_warp).
+            {
                 const R th0 = y.th, r_prev = y.r;
                 if (METHOD == 0) {
-                    h = adaptive_step<R, 1>(hc, y, h, R(P.tol), rhs_evals);
+                    adaptive_step_warp<R, 1>(hc, y, h, R(P.tol), !done, rhs_evals);
                 } else {
                     R hs = WGSL_RULE ? clampR<R>((y.r - rh) * R(0.15), R(0.05), R(1.0)) : R(P.h0);
                     if (done) hs = R(0);
