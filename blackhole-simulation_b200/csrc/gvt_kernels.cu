@@ -93,6 +93,9 @@ __device__ __forceinline__ void sample_spectrum(const float4* lut, uint32_t W, u
 #ifndef GVT_MAXT_F64
 #define GVT_MAXT_F64 512   // threads per persistent CTA (one CTA per SM) for the fixed-step f64 instantiations
 #endif
+#ifndef GVT_MAXT_RKF
+#define GVT_MAXT_RKF 512
+#endif
 #ifndef GVT_MAXT_F32
 #define GVT_MAXT_F32 512
 #endif
@@ -340,8 +343,8 @@ cudaError_t launch_trace(const FrameParams& p_in, int method, int precision, boo
     p.trig = tt;
 #define GVT_DISPATCH(RT, MT)                                                                                   \
     do {                                                                                                         \
-        if (method == 0) return debug ? launch_trace_t<RT, 0, false, true, 256>(p, sm_count, stream)             \
-                                      : launch_trace_t<RT, 0, false, false, 256>(p, sm_count, stream);           \
+        if (method == 0) return debug ? launch_trace_t<RT, 0, false, true, GVT_MAXT_RKF>(p, sm_count, stream)             \
+                                      : launch_trace_t<RT, 0, false, false, GVT_MAXT_RKF>(p, sm_count, stream);           \
         if (method == 1) return debug ? launch_trace_t<RT, 1, false, true, MT>(p, sm_count, stream)              \
                                       : launch_trace_t<RT, 1, false, false, MT>(p, sm_count, stream);            \
         if (budget) return debug ? launch_trace_t<RT, 2, true, true, MT>(p, sm_count, stream)                    \
