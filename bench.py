@@ -32,6 +32,9 @@ SPIN = 0.9990000128746033   # 0.999 as the f32 the PhysicsParams uniform carries
 SPEC_W, SPEC_H, TMAX = 256, 32, 1e7          # 128 KB RGBA32F spectral LUT: shared-memory resident
 # Algorithmic flop per geodesic step, SURVEY.md §8(d) (CSE'd count; add=mul=div=sqrt=1, FMA=2, sincos/pow = 0):
 FLOP_PER_STEP = {"symplectic": 330.0, "rk4": 440.0, "rkf45": 900.0}
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_trace_tile<double,...> launch on the full 4K x 512 frame, from
+# the committed ncu --set full capture (profiles/r01_k_trace_tile_f64_budget_4k512.txt). Reported only at N = 1.
+NCU_DRAM_BYTES_PER_LAUNCH_4K = 2654720 + 75954688   # 78.6 MB: < the 132.7 MB frame (L2 write-back in flight)
 METRIC = "geodesic steps/s at 3840x2160x512, a=0.999; % of FP32 roofline"
 
 
@@ -281,7 +284,8 @@ def run_own(args):
             "config": workload_config(world), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {
                 "bound": "fp64", "kernel": "k_trace_tile<double,symplectic,budget>", "achieved": ach, "peak": peak64,
-                "unit": "TFLOP/s", "frac": ach / peak64, "traffic": None,
+                "unit": "TFLOP/s", "frac": ach / peak64,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH_4K if world == 1 else None,
                 "peak_source": "in-run DFMA micro-benchmark (gvt_measure_fma_peak; MEASURED_PEAKS.json has no "
                                "FP32/FP64 entry). The path is FMA-pipe bound, not HBM or tensor: ~0 B read and 16 B "
                                "written per pixel per 512 steps",
