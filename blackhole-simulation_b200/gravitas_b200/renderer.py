@@ -195,7 +195,7 @@ class KerrRenderer:
         W, H = int(physics.resolution[0]), int(physics.resolution[1])
         if y1 is None:
             y1 = H
-        nx, ny = (W - x0 + xs - 1) // xs, (y1 - y0 + ys - 1) // ys
+        nx, ny = max((W - x0 + xs - 1) // xs, 0), max((y1 - y0 + ys - 1) // ys, 0)   # the library validates the lattice
         xp = np.zeros((ny, nx, 8))
         term = np.zeros((ny, nx), np.uint32)
         steps = np.zeros((ny, nx), np.uint32)
