@@ -1,0 +1,223 @@
+// addon/binding.cc — thin N-API shim over libgravitas_b200.so (C ABI in include/gravitas_b200.h).
+// Exposes the two seams of the reference to TypeScript:
+//   class PhysicsEngine  — same method names as the wasm-bindgen class (physics-engine/gravitas-wasm/src/lib.rs:42-465)
+//   class KerrRenderer   — init/resize/renderFrame for the src/rendering renderer API (rendering/webgpu/renderer.ts:82-411)
+// Build (on a machine with node): node-gyp rebuild (addon/binding.gyp). Not load-tested in the build image (no node);
+// syntax-checked against addon/stub/node_api.h by tests/test_abi_host.py.
+#include <node_api.h>
+#include <string.h>
+#include "gravitas_b200.h"
+
+#define NAPI_OK(c) do { if ((c) != napi_ok) { napi_throw_error(env, nullptr, #c); return nullptr; } } while (0)
+#define GVT(c) do { if ((c) != GVT_OK) { napi_throw_error(env, nullptr, gvt_last_error()); return nullptr; } } while (0)
+
+namespace {
+
+napi_value Undefined(napi_env env) { napi_value u; napi_get_undefined(env, &u); return u; }
+double Num(napi_env env, napi_value v) { double d = 0; napi_get_value_double(env, v, &d); return d; }
+
+template <class T> T* Self(napi_env env, napi_callback_info info, size_t* argc, napi_value* argv) {
+    napi_value self; void* p = nullptr;
+    if (napi_get_cb_info(env, info, argc, argv, &self, nullptr) != napi_ok) return nullptr;
+    napi_unwrap(env, self, &p);
+    return static_cast<T*>(p);
+}
+napi_value F32Array(napi_env env, size_t n, float** data) {
+    napi_value ab, out; void* p;
+    if (napi_create_arraybuffer(env, n * 4, &p, &ab) != napi_ok) return nullptr;
+    *data = static_cast<float*>(p);
+    napi_create_typedarray(env, napi_float32_array, n, ab, 0, &out);
+    return out;
+}
+
+// ---------------------------------------------------------------- PhysicsEngine (Seam A)
+napi_value EngineNew(napi_env env, napi_callback_info info) {                    // lib.rs:59
+    size_t argc = 2; napi_value argv[2], self;
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, &self, nullptr));
+    gvt_engine* e = nullptr;
+    GVT(gvt_engine_create(Num(env, argv[0]), Num(env, argv[1]), &e));
+    NAPI_OK(napi_wrap(env, self, e, [](napi_env, void* d, void*) { gvt_engine_destroy(static_cast<gvt_engine*>(d)); }, nullptr, nullptr));
+    return self;
+}
+napi_value UpdateParams(napi_env env, napi_callback_info info) {                 // lib.rs:78
+    size_t argc = 2; napi_value argv[2];
+    gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
+    GVT(gvt_engine_update_params(e, Num(env, argv[0]), Num(env, argv[1])));
+    return Undefined(env);
+}
+napi_value TickSab(napi_env env, napi_callback_info info) {                      // lib.rs:308
+    size_t argc = 1; napi_value argv[1];
+    gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
+    GVT(gvt_engine_tick_sab(e, Num(env, argv[0])));
+    return Undefined(env);
+}
+napi_value AttachSab(napi_env env, napi_callback_info info) {                    // lib.rs:74 (SharedArrayBuffer in)
+    size_t argc = 1; napi_value argv[1];
+    gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
+    void* data = nullptr; size_t len = 0;
+    NAPI_OK(napi_get_arraybuffer_info(env, argv[0], &data, &len));
+    if (len < GVT_SAB_INTERNAL_F32 * 4) { napi_throw_range_error(env, nullptr, "SAB smaller than 2048 f32"); return nullptr; }
+    GVT(gvt_engine_attach_sab(e, static_cast<float*>(data)));
+    return Undefined(env);
+}
+napi_value GetSab(napi_env env, napi_callback_info info) {                       // get_sab_ptr, lib.rs:116 -> a copy-free view is not
+    size_t argc = 0;                                                             // possible over N-API without an external buffer;
+    gvt_engine* e = Self<gvt_engine>(env, info, &argc, nullptr);                 // hosts should use attach_sab. This returns a snapshot.
+    const float* p = nullptr; float* out = nullptr;
+    GVT(gvt_engine_get_sab_ptr(e, &p));
+    napi_value arr = F32Array(env, GVT_SAB_INTERNAL_F32, &out);
+    if (arr) memcpy(out, p, GVT_SAB_INTERNAL_F32 * 4);
+    return arr;
+}
+napi_value SetCameraState(napi_env env, napi_callback_info info) {               // lib.rs:120
+    size_t argc = 6; napi_value argv[6];
+    gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
+    GVT(gvt_engine_set_camera_state(e, Num(env, argv[0]), Num(env, argv[1]), Num(env, argv[2]), 0, 0, 0));
+    return Undefined(env);
+}
+napi_value SetAutoSpin(napi_env env, napi_callback_info info) {                  // lib.rs:124
+    size_t argc = 1; napi_value argv[1]; bool b = false;
+    gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
+    napi_get_value_bool(env, argv[0], &b);
+    GVT(gvt_engine_set_auto_spin(e, b ? 1 : 0));
+    return Undefined(env);
+}
+#define ENGINE_GETTER(NAME, CALL)                                          \
+    napi_value NAME(napi_env env, napi_callback_info info) {                \
+        size_t argc = 2; napi_value argv[2];                                \
+        gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);           \
+        double out = 0;                                                     \
+        GVT(CALL);                                                          \
+        napi_value v; napi_create_double(env, out, &v); return v;           \
+    }
+ENGINE_GETTER(ComputeHorizon, gvt_engine_compute_horizon(e, &out))               // lib.rs:85
+ENGINE_GETTER(ComputeIsco, gvt_engine_compute_isco(e, &out))                     // lib.rs:89
+ENGINE_GETTER(ComputePhotonSphere, gvt_engine_compute_photon_sphere(e, &out))    // lib.rs:93
+ENGINE_GETTER(ComputeDilation, gvt_engine_compute_dilation(e, Num(env, argv[0]), &out))             // lib.rs:97
+ENGINE_GETTER(ComputeGFactor, gvt_engine_compute_g_factor(e, Num(env, argv[0]), Num(env, argv[1]), &out))   // lib.rs:203
+napi_value DiskLut(napi_env env, napi_callback_info info) {                      // lib.rs:107
+    size_t argc = 0;
+    gvt_engine* e = Self<gvt_engine>(env, info, &argc, nullptr);
+    float* out = nullptr;
+    napi_value arr = F32Array(env, 512, &out);
+    if (arr) GVT(gvt_engine_generate_disk_lut(e, out));
+    return arr;
+}
+napi_value SpectrumLut(napi_env env, napi_callback_info info) {                  // lib.rs:128
+    size_t argc = 3; napi_value argv[3];
+    gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
+    const uint32_t w = (uint32_t)Num(env, argv[0]), h = (uint32_t)Num(env, argv[1]);
+    float* out = nullptr;
+    napi_value arr = F32Array(env, (size_t)w * h * 4, &out);
+    if (arr) GVT(gvt_engine_generate_spectrum_lut(e, w, h, Num(env, argv[2]), out));
+    return arr;
+}
+napi_value IntegrateRay(napi_env env, napi_callback_info info) {                 // lib.rs:422
+    size_t argc = 4; napi_value argv[4];
+    gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
+    uint32_t n = 0; napi_get_array_length(env, argv[0], &n);
+    if (n < 8) return argv[0];                                                   // lib.rs:429-431: returned unchanged
+    double in8[8], out8[8]; bool ks = false;
+    for (uint32_t i = 0; i < 8; i++) { napi_value v; napi_get_element(env, argv[0], i, &v); in8[i] = Num(env, v); }
+    napi_get_value_bool(env, argv[3], &ks);
+    GVT(gvt_engine_integrate_ray(e, in8, (uint64_t)Num(env, argv[1]), Num(env, argv[2]), ks ? 1 : 0, out8, nullptr, nullptr, nullptr));
+    void* data; napi_value ab, out;
+    NAPI_OK(napi_create_arraybuffer(env, 64, &data, &ab));
+    memcpy(data, out8, 64);
+    NAPI_OK(napi_create_typedarray(env, napi_float64_array, 8, ab, 0, &out));
+    return out;
+}
+napi_value SabLayout(napi_env env, napi_callback_info info) {                    // lib.rs:411
+    size_t argc = 0;
+    gvt_engine* e = Self<gvt_engine>(env, info, &argc, nullptr);
+    uint32_t l[5];
+    GVT(gvt_engine_get_sab_layout(e, l));
+    void* data; napi_value ab, out;
+    NAPI_OK(napi_create_arraybuffer(env, 20, &data, &ab));
+    memcpy(data, l, 20);
+    NAPI_OK(napi_create_typedarray(env, napi_uint32_array, 5, ab, 0, &out));
+    return out;
+}
+
+// ---------------------------------------------------------------- KerrRenderer (Seam B)
+napi_value RendererNew(napi_env env, napi_callback_info info) {                  // new KerrRenderer(device = 0)
+    size_t argc = 1; napi_value argv[1], self;
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, &self, nullptr));
+    GvtDeviceConfig cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.struct_size = sizeof(cfg); cfg.device = argc > 0 ? (int32_t)Num(env, argv[0]) : 0; cfg.rank = 0; cfg.world_size = 1;
+    gvt_renderer* r = nullptr;
+    GVT(gvt_render_create(&cfg, &r));
+    NAPI_OK(napi_wrap(env, self, r, [](napi_env, void* d, void*) { gvt_render_destroy(static_cast<gvt_renderer*>(d)); }, nullptr, nullptr));
+    return self;
+}
+napi_value InitLuts(napi_env env, napi_callback_info info) {                     // (mass, spin, w, h, maxTemp)  spectral.ts:21-61
+    size_t argc = 5; napi_value argv[5];
+    gvt_renderer* r = Self<gvt_renderer>(env, info, &argc, argv);
+    GVT(gvt_render_init_luts(r, Num(env, argv[0]), Num(env, argv[1]), (uint32_t)Num(env, argv[2]), (uint32_t)Num(env, argv[3]), Num(env, argv[4])));
+    return Undefined(env);
+}
+napi_value Resize(napi_env env, napi_callback_info info) {                       // renderer.ts:269
+    size_t argc = 2; napi_value argv[2];
+    gvt_renderer* r = Self<gvt_renderer>(env, info, &argc, argv);
+    GVT(gvt_render_resize(r, (uint32_t)Num(env, argv[0]), (uint32_t)Num(env, argv[1])));
+    return Undefined(env);
+}
+uint32_t OptU32(napi_env env, napi_value obj, const char* key, uint32_t dflt) {
+    bool has = false; napi_value v;
+    if (napi_has_named_property(env, obj, key, &has) != napi_ok || !has) return dflt;
+    napi_get_named_property(env, obj, key, &v);
+    return (uint32_t)Num(env, v);
+}
+// renderFrame(cameraF32x88, physF32x8, {maxSteps, method, precision, taa, jitter, f16}, outArrayBuffer) -> stats   renderer.ts:280
+napi_value RenderFrame(napi_env env, napi_callback_info info) {
+    size_t argc = 4; napi_value argv[4];
+    gvt_renderer* r = Self<gvt_renderer>(env, info, &argc, argv);
+    napi_typedarray_type t; size_t n; void *cam, *phys, *out; napi_value ab; size_t off, outlen;
+    NAPI_OK(napi_get_typedarray_info(env, argv[0], &t, &n, &cam, &ab, &off));
+    if (t != napi_float32_array || n < 88) { napi_throw_range_error(env, nullptr, "camera: Float32Array(88) expected"); return nullptr; }
+    NAPI_OK(napi_get_typedarray_info(env, argv[1], &t, &n, &phys, &ab, &off));
+    if (n < 8) { napi_throw_range_error(env, nullptr, "physics: 32 bytes expected"); return nullptr; }
+    NAPI_OK(napi_get_arraybuffer_info(env, argv[3], &out, &outlen));
+    GvtRenderParams p; gvt_render_params_default(&p);
+    p.max_steps = OptU32(env, argv[2], "maxSteps", p.max_steps);
+    p.method = OptU32(env, argv[2], "method", p.method);
+    p.precision = OptU32(env, argv[2], "precision", p.precision);
+    if (OptU32(env, argv[2], "taa", 0)) p.flags |= GVT_FLAG_TAA;
+    if (OptU32(env, argv[2], "jitter", 0)) p.flags |= GVT_FLAG_JITTER;
+    if (OptU32(env, argv[2], "f16", 0)) p.output_format = GVT_FORMAT_RGBA16F;
+    const GvtPhysicsParams* ph = static_cast<const GvtPhysicsParams*>(phys);
+    const size_t need = (size_t)ph->resolution[0] * (size_t)ph->resolution[1] * (p.output_format == GVT_FORMAT_RGBA16F ? 8 : 16);
+    if (outlen < need) { napi_throw_range_error(env, nullptr, "output buffer too small"); return nullptr; }
+    GvtFrameStats st;
+    GVT(gvt_render_frame(r, static_cast<const GvtCamera*>(cam), ph, &p, out, &st));
+    napi_value o, v;
+    NAPI_OK(napi_create_object(env, &o));
+    napi_create_double(env, st.total_ms, &v); napi_set_named_property(env, o, "totalMs", v);
+    napi_create_double(env, st.trace_ms, &v); napi_set_named_property(env, o, "traceMs", v);
+    napi_create_double(env, (double)st.steps_committed, &v); napi_set_named_property(env, o, "steps", v);
+    return o;
+}
+
+}  // namespace
+
+NAPI_MODULE_INIT() {
+    const napi_property_descriptor engine[] = {
+        {"update_params", 0, UpdateParams, 0, 0, 0, napi_default, 0}, {"tick_sab", 0, TickSab, 0, 0, 0, napi_default, 0},
+        {"attach_sab", 0, AttachSab, 0, 0, 0, napi_default, 0}, {"get_sab", 0, GetSab, 0, 0, 0, napi_default, 0},
+        {"get_sab_layout", 0, SabLayout, 0, 0, 0, napi_default, 0},
+        {"set_camera_state", 0, SetCameraState, 0, 0, 0, napi_default, 0}, {"set_auto_spin", 0, SetAutoSpin, 0, 0, 0, napi_default, 0},
+        {"compute_horizon", 0, ComputeHorizon, 0, 0, 0, napi_default, 0}, {"compute_isco", 0, ComputeIsco, 0, 0, 0, napi_default, 0},
+        {"compute_photon_sphere", 0, ComputePhotonSphere, 0, 0, 0, napi_default, 0},
+        {"compute_dilation", 0, ComputeDilation, 0, 0, 0, napi_default, 0}, {"compute_g_factor", 0, ComputeGFactor, 0, 0, 0, napi_default, 0},
+        {"generate_disk_lut", 0, DiskLut, 0, 0, 0, napi_default, 0}, {"generate_spectrum_lut", 0, SpectrumLut, 0, 0, 0, napi_default, 0},
+        {"integrate_ray_relativistic", 0, IntegrateRay, 0, 0, 0, napi_default, 0}};
+    const napi_property_descriptor renderer[] = {
+        {"initLuts", 0, InitLuts, 0, 0, 0, napi_default, 0}, {"resize", 0, Resize, 0, 0, 0, napi_default, 0},
+        {"renderFrame", 0, RenderFrame, 0, 0, 0, napi_default, 0}};
+    napi_value cls;
+    NAPI_OK(napi_define_class(env, "PhysicsEngine", NAPI_AUTO_LENGTH, EngineNew, nullptr, sizeof(engine) / sizeof(engine[0]), engine, &cls));
+    NAPI_OK(napi_set_named_property(env, exports, "PhysicsEngine", cls));
+    NAPI_OK(napi_define_class(env, "KerrRenderer", NAPI_AUTO_LENGTH, RendererNew, nullptr, sizeof(renderer) / sizeof(renderer[0]), renderer, &cls));
+    NAPI_OK(napi_set_named_property(env, exports, "KerrRenderer", cls));
+    return exports;
+}

@@ -141,3 +141,22 @@ def test_product_does_not_reference_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
                 txt = open(os.path.join(dp, fn), errors="ignore").read()
                 assert "liboracle" not in txt and "gravitas_oracle" not in txt and "import oracle" not in txt, fn
+
+
+def test_napi_shim_compiles_against_the_header():
+    """addon/binding.cc (the N-API shim of INTEGRATION.md) is syntax-checked against include/gravitas_b200.h and a
+    minimal declaration-only node_api.h (node itself is not in this image, so it cannot be load-tested here)."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    p = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "addon", "stub"),
+                        "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "addon", "binding.cc")],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-3000:]
+    src = open(os.path.join(ROOT, "addon", "binding.cc")).read()
+    for name in ("tick_sab", "attach_sab", "update_params", "set_camera_state", "set_auto_spin", "compute_horizon",
+                 "compute_isco", "compute_photon_sphere", "compute_dilation", "generate_disk_lut",
+                 "generate_spectrum_lut", "integrate_ray_relativistic", "get_sab_layout"):
+        assert f'"{name}"' in src, f"PhysicsEngine.{name} (gravitas-wasm/src/lib.rs) missing from the shim"
