@@ -38,13 +38,14 @@ NCU_DRAM_BYTES_PER_LAUNCH_4K = 2654720 + 75954688   # 78.6 MB: < the 132.7 MB fr
 METRIC = "geodesic steps/s at 3840x2160x512, a=0.999; % of FP32 roofline"
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, peer_store=False):
     return {
         "workload": "config 3: Kerr a*=0.999 (Kerr-Schild), 3840x2160, 512 fixed implicit-midpoint steps/pixel "
                     "(step rule compute.wgsl.ts:213), f64, thin-disk g-factor + Planckian redshift LUT 256x32, "
                     "camera r0=30 polar 97deg azimuth pi fov 60deg; budget accounting (W*H*512 steps/frame)",
         "width": W, "height": H, "steps_per_pixel": STEPS, "spin": SPIN, "integrator": "implicit-midpoint",
-        "precision": "f64", "shard": f"row-block x{n_gpus} + 1 ncclAllGather" if n_gpus > 1 else "single GPU",
+        "precision": "f64", "shard": (f"row-block x{n_gpus} + " + ("NVLink peer stores fused into the trace kernel"
+                                                         if peer_store else "1 ncclAllGather")) if n_gpus > 1 else "single GPU",
         "l2": "inputs are ~131 KB (LUT + camera block), compute-bound and L2-insensitive; each frame writes a "
               "132.7 MB RGBA32F frame (> 126 MB L2), so no explicit L2 flush between iterations",
     }
@@ -222,9 +223,14 @@ def run_own(args):
         pinned = r.pinned_frame(W, H)
     info = r.device_info()
 
-    def params(**kw):
+    peer = _lib.FLAG_PEER_STORE if (world > 1 and args.peer_store) else 0
+    if peer:
+        r.resize(W, H)
+        r.connect_peers(dist)
+
+    def params(flags=0, **kw):
         r.params = R.RenderParams(method=_lib.METHOD_SYMPLECTIC, precision=_lib.PRECISION_F64, max_steps=STEPS,
-                                  step_rule=_lib.STEP_WGSL, **kw)
+                                  step_rule=_lib.STEP_WGSL, flags=flags | peer, **kw)
 
     # roofline denominators (MEASURED_PEAKS.json carries HBM and bf16 only): in-run DFMA / FFMA micro-benchmarks
     peak64, _ = r.measure_fma_peak(_lib.PRECISION_F64)
@@ -261,7 +267,7 @@ def run_own(args):
     n_steps = allreduce_sum(dist, float(sum(s.steps_committed for s in n_stats)))
     s0 = n_stats[0]
     r.params = R.RenderParams(method=_lib.METHOD_SYMPLECTIC, precision=_lib.PRECISION_F32, max_steps=STEPS,
-                              step_rule=_lib.STEP_WGSL, flags=_lib.FLAG_BUDGET)
+                              step_rule=_lib.STEP_WGSL, flags=_lib.FLAG_BUDGET | peer)
     r.render(cam, phys, readback=False)
     f_ms, _, f_stats = timed_frames(r, cam, phys, max(2, args.steps // 3), dist, readback=False)
     f_steps = allreduce_sum(dist, float(sum(s.steps_executed for s in f_stats)))
@@ -281,7 +287,7 @@ def run_own(args):
             "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ev_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world), "e2e": e2e, "gpu_launches": int(launches),
+            "config": workload_config(world, bool(peer)), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {
                 "bound": "fp64", "kernel": "k_trace_tile<double,symplectic,budget>", "achieved": ach, "peak": peak64,
                 "unit": "TFLOP/s", "frac": ach / peak64,
@@ -381,6 +387,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--peer-store", action="store_true",
+                    help="N > 1: fuse the gather into the trace kernel (NVLink peer stores + 4-byte all-reduce barrier) "
+                         "instead of the ncclAllGather")
     ap.add_argument("--workload", default="config3", choices=["config3", "config4", "config5"],
                     help="config3 = the headline (default). config4 / config5 print an 'extra_workload' JSON line for "
                          "BASELINE configs[3] (8K, 1024 adaptive RKF45) / configs[4] (orbit, 4K x frames, TAA)")

@@ -57,6 +57,7 @@ struct NcclApi {
     int (*CommInitRank)(ncclComm_t_*, int, NcclId, int) = nullptr;
     int (*CommDestroy)(ncclComm_t_) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, ncclComm_t_, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t_, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     bool load() {
         if (handle) return true;
@@ -67,12 +68,14 @@ struct NcclApi {
         CommInitRank = (int (*)(ncclComm_t_*, int, NcclId, int))dlsym(handle, "ncclCommInitRank");
         CommDestroy = (int (*)(ncclComm_t_))dlsym(handle, "ncclCommDestroy");
         AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t_, cudaStream_t))dlsym(handle, "ncclAllGather");
+        AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t_, cudaStream_t))dlsym(handle, "ncclAllReduce");
         GetErrorString = (const char* (*)(int))dlsym(handle, "ncclGetErrorString");
-        return GetUniqueId && CommInitRank && CommDestroy && AllGather && GetErrorString;
+        return GetUniqueId && CommInitRank && CommDestroy && AllGather && AllReduce && GetErrorString;
     }
 };
 NcclApi g_nccl;
 constexpr int kNcclFloat32 = 7;  // ncclDataType_t::ncclFloat32
+constexpr int kNcclSum = 0;      // ncclRedOp_t::ncclSum
 }  // namespace
 
 extern "C" int32_t gvt_nccl_unique_id(uint8_t out128[128]) {
@@ -311,6 +314,9 @@ struct gvt_renderer {
     float4* cur = nullptr;      // trace output
     float4* frame = nullptr;    // finished frame of the last call (TAA-resolved and all-gathered)
     float4* hist = nullptr;     // previous finished frame (TAA history)
+    float4* buf[2] = {nullptr, nullptr};            // the two allocations frame/hist alternate between
+    float4* peer[GVT_MAX_PEERS][2] = {};            // peer ranks' buf[0], buf[1] (CUDA IPC), GVT_FLAG_PEER_STORE
+    bool peer_open[GVT_MAX_PEERS] = {};
     void* half_frame = nullptr; // RGBA16F staging
     bool history_valid = false;
     FrameBlock* d_block = nullptr; FrameBlock* h_block = nullptr;   // device / pinned host
@@ -372,7 +378,14 @@ extern "C" int32_t gvt_render_create(const GvtDeviceConfig* cfg, gvt_renderer** 
     return GVT_OK;
 }
 
+static void close_peers(gvt_renderer* r) {
+    for (int p = 0; p < GVT_MAX_PEERS; p++) {
+        if (r->peer_open[p]) { cudaIpcCloseMemHandle(r->peer[p][0]); cudaIpcCloseMemHandle(r->peer[p][1]); }
+        r->peer_open[p] = false; r->peer[p][0] = r->peer[p][1] = nullptr;
+    }
+}
 static void free_frames(gvt_renderer* r) {
+    close_peers(r);
     if (r->cur) cudaFree(r->cur);
     if (r->frame) cudaFree(r->frame);
     if (r->hist) cudaFree(r->hist);
@@ -442,6 +455,7 @@ extern "C" int32_t gvt_render_resize(gvt_renderer* r, uint32_t width, uint32_t h
     CK(cudaMalloc(&r->cur, bytes));
     CK(cudaMalloc(&r->frame, bytes));
     CK(cudaMalloc(&r->hist, bytes));
+    r->buf[0] = r->frame; r->buf[1] = r->hist;
     CK(cudaMemsetAsync(r->cur, 0, bytes, r->stream));
     CK(cudaMemsetAsync(r->frame, 0, bytes, r->stream));
     CK(cudaMemsetAsync(r->hist, 0, bytes, r->stream));  // WebGPU textures start zeroed: so does the history
@@ -508,7 +522,7 @@ static int32_t build_frame(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
 static void fill_taa(const GvtCamera* cam, uint32_t W, uint32_t H, TaaParams& T) {
     memcpy(T.inv_proj, cam->inv_proj, 64); memcpy(T.inv_view, cam->inv_view, 64);
     memcpy(T.prev_view_proj, cam->prev_view_proj, 64); memcpy(T.cam_pos, cam->position, 16);
-    T.width = W; T.height = H; T.row0 = 0; T.row1 = H; T.host_out = nullptr;
+    T.width = W; T.height = H; T.row0 = 0; T.row1 = H; T.host_out = nullptr; T.n_peer = 0;
 }
 
 extern "C" int32_t gvt_render_read_frame(gvt_renderer* r, uint32_t format, void* host_rgba) {
@@ -565,11 +579,30 @@ extern "C" int32_t gvt_render_frame(gvt_renderer* r, const GvtCamera* cam, const
             (void)cudaGetLastError();   // pageable memory: not an error, just the copy path
     }
     P.host_frame = taa ? nullptr : host_alias;
+    // Fused gather: the producing kernel writes each finished pixel into the same frame on every peer.
+    const bool peer_store = (rp->flags & GVT_FLAG_PEER_STORE) != 0 && r->world > 1 && !(rp->flags & GVT_FLAG_NO_GATHER);
+    float4* peer_targets[GVT_MAX_PEERS];
+    uint32_t n_peer = 0;
+    if (peer_store) {
+        const int idx = (r->frame == r->buf[0]) ? 0 : 1;
+        for (int p = 0; p < r->world; p++) {
+            if (p == r->rank) continue;
+            if (p >= GVT_MAX_PEERS || !r->peer_open[p]) return fail(GVT_ERR_INVALID, "GVT_FLAG_PEER_STORE: frames of rank %d not imported (gvt_render_import_peer_frames)", p);
+            peer_targets[n_peer++] = r->peer[p][idx];
+        }
+        if (!taa) { for (uint32_t q = 0; q < n_peer; q++) P.peer_frame[q] = peer_targets[q]; P.n_peer = n_peer; }
+    }
 
     CK(cudaEventRecord(r->ev[0], r->stream));
     CK(cudaMemcpyAsync(r->d_block, r->h_block, sizeof(FrameBlock), cudaMemcpyHostToDevice, r->stream));
     h2d += sizeof(FrameBlock);
     CK(cudaMemsetAsync(r->d_counters, 0, sizeof(Counters), r->stream));
+    if (peer_store) {
+        // peers are about to write into this rank's frame: everything this rank still had queued on the previous
+        // frame (TAA history reads, D2H copy) is ahead of this barrier in stream order on every rank
+        int nrc = g_nccl.AllReduce(r->d_sink, r->d_sink, 1, kNcclFloat32, kNcclSum, r->comm, r->stream);
+        if (nrc != 0) return fail(GVT_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(nrc));
+    }
     CK(cudaEventRecord(r->ev[1], r->stream));
     if (P.ny > 0) { CK(launch_trace(P, rp->method, rp->precision, budget, false, r->sm_count, r->stream)); launches++; }
     CK(cudaEventRecord(r->ev[2], r->stream));
@@ -579,11 +612,17 @@ extern "C" int32_t gvt_render_frame(gvt_renderer* r, const GvtCamera* cam, const
         T.cur = r->cur; T.hist = r->hist; T.out = r->frame;
         T.row0 = row0; T.row1 = row1;
         T.host_out = host_alias;
+        if (peer_store) { for (uint32_t q = 0; q < n_peer; q++) T.peer_out[q] = peer_targets[q]; T.n_peer = n_peer; }
         CK(launch_taa(T, r->stream));
         launches++;
     }
     CK(cudaEventRecord(r->ev[3], r->stream));
-    if (r->world > 1 && !(rp->flags & GVT_FLAG_NO_GATHER)) {
+    if (peer_store) {
+        // all ranks' stores must have landed before anyone reads its frame: a 1-element all-reduce is the barrier
+        if (!r->d_sink) return fail(GVT_ERR_INVALID, "no barrier buffer");
+        int nrc = g_nccl.AllReduce(r->d_sink, r->d_sink, 1, kNcclFloat32, kNcclSum, r->comm, r->stream);
+        if (nrc != 0) return fail(GVT_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(nrc));
+    } else if (r->world > 1 && !(rp->flags & GVT_FLAG_NO_GATHER)) {
         const size_t count = (size_t)r->rows_per_rank * W * 4;  // floats per rank block
         int nrc = g_nccl.AllGather(reinterpret_cast<const float*>(r->frame) + (size_t)r->rank * count, r->frame, count,
                                    kNcclFloat32, r->comm, r->stream);
@@ -744,5 +783,36 @@ extern "C" int32_t gvt_device_info(gvt_renderer* r, int32_t* sm_count, int32_t* 
     if (cc_major) *cc_major = prop.major;
     if (cc_minor) *cc_minor = prop.minor;
     if (name) { strncpy(name, prop.name, 255); name[255] = 0; }
+    return GVT_OK;
+}
+
+extern "C" int32_t gvt_render_export_frames(gvt_renderer* r, uint8_t handles[2][64]) {
+    if (!r || !handles || !r->buf[0]) return fail(GVT_ERR_INVALID, "bad argument / no frame buffers (call gvt_render_resize first)");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    CK(cudaSetDevice(r->device));
+    for (int i = 0; i < 2; i++) {
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, r->buf[i]));
+        memcpy(handles[i], &h, 64);
+    }
+    return GVT_OK;
+}
+
+extern "C" int32_t gvt_render_import_peer_frames(gvt_renderer* r, int32_t peer_rank, const uint8_t handles[2][64]) {
+    if (!r || !handles || peer_rank < 0 || peer_rank >= GVT_MAX_PEERS || peer_rank >= r->world || peer_rank == r->rank)
+        return fail(GVT_ERR_INVALID, "bad peer rank");
+    CK(cudaSetDevice(r->device));
+    if (r->peer_open[peer_rank]) {
+        cudaIpcCloseMemHandle(r->peer[peer_rank][0]); cudaIpcCloseMemHandle(r->peer[peer_rank][1]);
+        r->peer_open[peer_rank] = false;
+    }
+    for (int i = 0; i < 2; i++) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles[i], 64);
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        r->peer[peer_rank][i] = static_cast<float4*>(p);
+    }
+    r->peer_open[peer_rank] = true;
     return GVT_OK;
 }

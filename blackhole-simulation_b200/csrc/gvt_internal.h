@@ -44,6 +44,8 @@ struct FrameParams {
     float4* frame;                                            // full-frame RGBA32F (may be null for debug launches)
     float4* host_frame;                                       // device alias of a page-locked HOST frame (or null): the
                                                               // epilogue stores the pixel there too, so no D2H copy follows
+    float4* peer_frame[8];                                    // GVT_FLAG_PEER_STORE: the same frame on every other rank
+    uint32_t n_peer, _pad_peer;
     Counters* counters;
     // parity-hook outputs (DEBUG instantiations only), dense over the lattice
     double* dbg_xp; uint32_t* dbg_term; uint32_t* dbg_steps; double* dbg_drift; double* dbg_rgba;
@@ -64,6 +66,8 @@ struct TaaParams {
     uint32_t row0, row1;   // rows resolved by this launch (a rank's block); neighbours outside are still read
     const float4* cur; const float4* hist; float4* out;
     float4* host_out;      // device alias of a page-locked host frame, or null
+    float4* peer_out[8];   // GVT_FLAG_PEER_STORE targets
+    uint32_t n_peer, _pad_peer;
 };
 
 // launchers (gvt_kernels.cu)

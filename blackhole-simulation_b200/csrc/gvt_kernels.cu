@@ -281,6 +281,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
             const float4 px_out = make_float4((float)col[0], (float)col[1], (float)col[2], 1.0f);
             if (P.frame) P.frame[(size_t)py * P.width + px] = px_out;
             if (P.host_frame) P.host_frame[(size_t)py * P.width + px] = px_out;   // posted PCIe write, off the critical path
+            for (uint32_t q = 0; q < P.n_peer; q++)                               // fused gather: NVLink peer stores
+                P.peer_frame[q][(size_t)py * P.width + px] = px_out;
             if (DEBUG) {
                 const size_t k = (size_t)lj * P.nx + li;
                 if (P.dbg_xp) {
@@ -515,6 +517,7 @@ __global__ void __launch_bounds__(256) k_taa_resolve(const __grid_constant__ Taa
             const float4 px_out = make_float4(ry + ro - rg, ry + rg, ry - ro - rg, 1.0f);
             P.out[(size_t)y * W + x] = px_out;
             if (P.host_out) P.host_out[(size_t)y * W + x] = px_out;
+            for (uint32_t q = 0; q < P.n_peer; q++) P.peer_out[q][(size_t)y * W + x] = px_out;
         }
         a = b; b = c;
     }

@@ -17,7 +17,7 @@ METHOD_RKF45, METHOD_RK4, METHOD_SYMPLECTIC = 0, 1, 2
 PRECISION_F64, PRECISION_F32 = 0, 1
 FORMAT_RGBA32F, FORMAT_RGBA16F = 0, 1
 STEP_CONSTANT, STEP_WGSL = 0, 1
-FLAG_JITTER, FLAG_BUDGET, FLAG_TRACK_DRIFT, FLAG_TAA, FLAG_NO_GATHER, FLAG_D2H_OWN_ROWS = 1, 2, 4, 8, 16, 32
+FLAG_JITTER, FLAG_BUDGET, FLAG_TRACK_DRIFT, FLAG_TAA, FLAG_NO_GATHER, FLAG_D2H_OWN_ROWS, FLAG_PEER_STORE = 1, 2, 4, 8, 16, 32, 64
 
 
 class GravitasError(RuntimeError):
@@ -99,6 +99,8 @@ SIGNATURES = {
                                 _u32, _u32, _u32, _u32, _pd, _pu32, _pu32, _pd, _pd]),
     "gvt_taa_resolve": (_i32, [_vp, C.POINTER(GvtCamera), _u32, _u32, _pf, _pf, _pf]),
     "gvt_render_reset_history": (_i32, [_vp]),
+    "gvt_render_export_frames": (_i32, [_vp, C.POINTER(C.c_uint8)]),
+    "gvt_render_import_peer_frames": (_i32, [_vp, _i32, C.POINTER(C.c_uint8)]),
     "gvt_host_alloc": (_i32, [C.c_size_t, C.POINTER(_vp)]),
     "gvt_host_free": (_i32, [_vp]),
     "gvt_host_register": (_i32, [_vp, C.c_size_t]),

@@ -157,6 +157,19 @@ class KerrRenderer:
         check(lib().gvt_render_resize(self._h, int(width), int(height)))
         self.width, self.height = int(width), int(height)
 
+    def connect_peers(self, dist):
+        """GVT_FLAG_PEER_STORE set-up: exchange the CUDA IPC handles of the two frame buffers between all ranks (through
+        the host's process group — plumbing only) and map every peer's pair. Call after resize()."""
+        mine = (C.c_uint8 * 128)()
+        check(lib().gvt_render_export_frames(self._h, mine))
+        allh = [None] * self.world_size
+        dist.all_gather_object(allh, bytes(mine))
+        for p, hb in enumerate(allh):
+            if p != self.rank:
+                buf = (C.c_uint8 * 128).from_buffer_copy(hb)
+                check(lib().gvt_render_import_peer_frames(self._h, p, buf))
+        dist.barrier()
+
     def pinned_frame(self, width, height, fmt=_lib.FORMAT_RGBA32F):
         nbytes = width * height * (16 if fmt == _lib.FORMAT_RGBA32F else 8)
         if self._pinned is None or self._pinned.nbytes != nbytes:

@@ -61,6 +61,10 @@ enum {
     GVT_FLAG_TRACK_DRIFT = 1u << 2, /* max |H| per ray, as geodesic/mod.rs:233-237 */
     GVT_FLAG_TAA = 1u << 3,         /* run the TAA resolve (ataa.wgsl.ts:28-83) after the trace */
     GVT_FLAG_NO_GATHER = 1u << 4,   /* multi-GPU: skip the all-gather (each rank keeps only its row block) */
+    GVT_FLAG_PEER_STORE = 1u << 6,  /* multi-GPU: fuse the gather into the producing kernel — every finished pixel is stored
+                                       into every peer's frame over NVLink (peer frames imported with
+                                       gvt_render_import_peer_frames) and a 4-byte ncclAllReduce closes the frame as the
+                                       cross-GPU barrier; replaces the ncclAllGather */
     GVT_FLAG_D2H_OWN_ROWS = 1u << 5 /* multi-GPU: copy only this rank's row block into host_rgba (at its place in the
                                        full-size buffer). With one host frame shared by all ranks (POSIX shm registered
                                        through gvt_host_register) the ranks assemble the frame in parallel, one
@@ -196,6 +200,12 @@ int32_t gvt_trace_states(gvt_renderer* r, const GvtCamera* cam, const GvtPhysics
 int32_t gvt_taa_resolve(gvt_renderer* r, const GvtCamera* cam, uint32_t width, uint32_t height, const float* cur,
                         const float* hist, float* out);
 int32_t gvt_render_reset_history(gvt_renderer* r);
+/* Peer-store gather (GVT_FLAG_PEER_STORE): each rank exports CUDA IPC handles of its two frame buffers; the host
+ * exchanges them (any transport) and every rank imports every peer's pair. Call again after gvt_render_resize. All
+ * ranks must issue the same sequence of gvt_render_frame calls (the buffers ping-pong in lockstep under TAA). */
+#define GVT_MAX_PEERS 8
+int32_t gvt_render_export_frames(gvt_renderer* r, uint8_t handles[2][64]);
+int32_t gvt_render_import_peer_frames(gvt_renderer* r, int32_t peer_rank, const uint8_t handles[2][64]);
 /* Pinned host memory for frame buffers (what an N-API external ArrayBuffer would wrap). */
 int32_t gvt_host_alloc(size_t bytes, void** out);
 int32_t gvt_host_free(void* p);

@@ -46,6 +46,26 @@ for (W, H, steps) in ((256, 144, 128), (157, 83, 64)):       # divisible and rag
             if not taa:
                 assert int(t[0]) == int(single.last_stats.steps_committed)
             prev = vp
+# fused gather (GVT_FLAG_PEER_STORE): NVLink peer stores from the producing kernel + a 4-byte all-reduce barrier give
+# the same frames as the ncclAllGather, with and without TAA
+for (W, H, steps) in ((256, 144, 96), (157, 83, 48)):
+    for taa in (False, True):
+        flags = _lib.FLAG_PEER_STORE | ((_lib.FLAG_TAA | _lib.FLAG_JITTER) if taa else 0)
+        multi.resize(W, H); multi.reset_history(); single.resize(W, H); single.reset_history()
+        multi.connect_peers(dist)
+        prev = None
+        for k in range(3):
+            cam, vp = camera.default_camera(W, H, azimuth=math.pi + 0.005 * k, prev_view_proj=prev)
+            phys = R.pack_physics(1.0, spin, W, H, frame_index=k)
+            multi.params = R.RenderParams(max_steps=steps, flags=flags)
+            single.params = R.RenderParams(max_steps=steps, flags=flags & ~_lib.FLAG_PEER_STORE)
+            a = np.array(multi.render(cam, phys))
+            assert multi.last_stats.gather_ms >= 0
+            b = np.array(single.render(cam, phys))
+            assert np.array_equal(a, b), f"rank {rank}: peer-store frame differs (W={W} H={H} taa={taa} k={k})"
+            prev = vp
+dist.barrier()
+
 # one shared host frame assembled by all ranks (GVT_FLAG_D2H_OWN_ROWS): equals the single-GPU frame on every rank
 W, H, steps = 256, 144, 64
 names = [None]
