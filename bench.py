@@ -223,10 +223,19 @@ def run_own(args):
         pinned = r.pinned_frame(W, H)
     info = r.device_info()
 
-    peer = _lib.FLAG_PEER_STORE if (world > 1 and args.peer_store) else 0
-    if peer:
+    peer = 0
+    if world > 1 and not args.no_peer_store:
+        # both gathers are GPU paths of the library; if CUDA IPC is not permitted on this box every rank falls back to
+        # the ncclAllGather together (the choice is all-reduced so that no rank is left in the other protocol)
         r.resize(W, H)
-        r.connect_peers(dist)
+        ok = 1.0
+        try:
+            r.connect_peers(dist)
+        except g.GravitasError as ex:
+            ok = 0.0
+            print(f"[bench] rank {rank}: peer-store unavailable ({ex}); using ncclAllGather", file=sys.stderr)
+        if allreduce_sum(dist, ok) == world:
+            peer = _lib.FLAG_PEER_STORE
 
     def params(flags=0, **kw):
         r.params = R.RenderParams(method=_lib.METHOD_SYMPLECTIC, precision=_lib.PRECISION_F64, max_steps=STEPS,
@@ -387,9 +396,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--peer-store", action="store_true",
-                    help="N > 1: fuse the gather into the trace kernel (NVLink peer stores + 4-byte all-reduce barrier) "
-                         "instead of the ncclAllGather")
+    ap.add_argument("--no-peer-store", action="store_true",
+                    help="N > 1: use the ncclAllGather after the trace kernel instead of the default fused gather (NVLink "
+                         "peer stores from the trace kernel + 4-byte all-reduce barriers)")
     ap.add_argument("--workload", default="config3", choices=["config3", "config4", "config5"],
                     help="config3 = the headline (default). config4 / config5 print an 'extra_workload' JSON line for "
                          "BASELINE configs[3] (8K, 1024 adaptive RKF45) / configs[4] (orbit, 4K x frames, TAA)")

@@ -161,14 +161,24 @@ class KerrRenderer:
         """GVT_FLAG_PEER_STORE set-up: exchange the CUDA IPC handles of the two frame buffers between all ranks (through
         the host's process group — plumbing only) and map every peer's pair. Call after resize()."""
         mine = (C.c_uint8 * 128)()
-        check(lib().gvt_render_export_frames(self._h, mine))
+        rc = lib().gvt_render_export_frames(self._h, mine)
         allh = [None] * self.world_size
-        dist.all_gather_object(allh, bytes(mine))
+        dist.all_gather_object(allh, bytes(mine) if rc == 0 else None)   # every rank takes part in the exchange even on error
+        check(rc)
+        err = None
         for p, hb in enumerate(allh):
-            if p != self.rank:
+            if p != self.rank and err is None:
+                if hb is None:
+                    err = _lib.GravitasError(_lib.GVT_ERR_CUDA, f"rank {p} could not export its frames")
+                    break
                 buf = (C.c_uint8 * 128).from_buffer_copy(hb)
-                check(lib().gvt_render_import_peer_frames(self._h, p, buf))
+                rc = lib().gvt_render_import_peer_frames(self._h, p, buf)
+                if rc != 0:
+                    msg = lib().gvt_last_error()
+                    err = _lib.GravitasError(rc, msg.decode() if msg else "import failed")
         dist.barrier()
+        if err is not None:
+            raise err
 
     def pinned_frame(self, width, height, fmt=_lib.FORMAT_RGBA32F):
         nbytes = width * height * (16 if fmt == _lib.FORMAT_RGBA32F else 8)
