@@ -344,7 +344,59 @@ def run_extra(args):
     r = g.KerrRenderer(device=local, rank=rank, world_size=world, nccl_id=nccl_id)
     r.init()
     r.init_pipelines(mass=MASS, spin=SPIN, spec_w=SPEC_W, spec_h=SPEC_H, max_temp=TMAX)
-    if args.workload == "config4":
+    if args.workload == "config1":
+        # BASELINE configs[0]: Schwarzschild a=0, 256x256 camera rays, 128 RKF45 steps, Boyer-Lindquist, through the
+        # PhysicsEngine seam (batched integrate_ray_relativistic on the GPU) and, beside it, the CPU port
+        import time as _t
+        import numpy as np
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle as O
+        Wx = Hx = 256
+        cam, _ = camera.default_camera(Wx, Hx)
+        opts = O.Options.default(max_steps=128)
+        rp_o, keep = O.make_render_params(Wx, Hx, 1.0, 0.0, opts, coords=0)
+        rays = np.array([O.camera_ray(cam, rp_o, x, y) for y in range(Hx) for x in range(Wx)])
+        eng = g.PhysicsEngine(1.0, 0.0)
+        prm = R.RenderParams(method=_lib.METHOD_RKF45, coords=_lib.COORDS_BL, step_rule=_lib.STEP_CONSTANT, max_steps=128)
+        for _ in range(args.warmup):
+            eng.integrate_rays(rays, prm)
+        t0 = _t.perf_counter()
+        for _ in range(args.steps):
+            got = eng.integrate_rays(rays, prm)
+        gpu_s = (_t.perf_counter() - t0) / args.steps
+        t0 = _t.perf_counter()
+        ref = O.integrate(1.0, 0.0, 0, opts, rays)
+        cpu_s = _t.perf_counter() - t0
+        steps = float(ref["steps"].sum())
+        err = np.abs(got["xp"] - ref["xp"]) / np.maximum(np.abs(ref["xp"]), 1.0)
+        if rank == 0:
+            print(json.dumps({"extra_workload": "config 1: Schwarzschild a=0, 256x256 rays, 128 adaptive RKF45 steps, Boyer-Lindquist "
+                              "(every ray ends MaxSteps; parity is on the 128-step state)", "n_gpus": 1,
+                              "gpu_e2e_ms_host_arrays_in_out": gpu_s * 1e3, "gpu_steps_per_s_e2e": steps / gpu_s,
+                              "cpu_port_ms": cpu_s * 1e3, "cpu_port_steps_per_s": steps / cpu_s,
+                              "cpu_threads": O.lib().orc_num_threads(), "state_rel_err_median": float(np.median(err)),
+                              "state_rel_err_max": float(err.max())}))
+    elif args.workload == "config2":
+        # BASELINE configs[1]: Kerr a*=0.999, 1920x1080, 256 fixed steps, f32
+        Wx, Hx = 1920, 1080
+        r.params = R.RenderParams(method=_lib.METHOD_SYMPLECTIC, precision=_lib.PRECISION_F32, max_steps=256,
+                                  step_rule=_lib.STEP_WGSL, flags=_lib.FLAG_BUDGET)
+        cam, _ = camera.default_camera(Wx, Hx)
+        phys = R.pack_physics(MASS, SPIN, Wx, Hx)
+        for _ in range(args.warmup):
+            r.render(cam, phys, readback=False)
+        ev_ms, wall_ms, stats = timed_frames(r, cam, phys, args.steps, dist, readback=False)
+        steps = allreduce_sum(dist, float(sum(s.steps_executed for s in stats)))
+        e_ms, _, _ = timed_frames(r, cam, phys, args.steps, dist, readback=True, out=r.pinned_frame(Wx, Hx))
+        peak32, _ = r.measure_fma_peak(_lib.PRECISION_F32)
+        if rank == 0:
+            sps = steps / (ev_ms * 1e-3)
+            print(json.dumps({"extra_workload": "config 2: Kerr a*=0.999, 1920x1080, 256 fixed implicit-midpoint steps, f32, budget "
+                              "accounting", "n_gpus": world, "frames": args.steps, "ms_per_frame": ev_ms / args.steps,
+                              "e2e_ms_per_frame": e_ms / args.steps, "steps_per_s": sps,
+                              "frac_of_fp32_peak": sps * FLOP_PER_STEP["symplectic"] * 1e-12 / peak32 / world,
+                              "fp32_peak_tflops": peak32, "fps": 1e3 * args.steps / ev_ms}))
+    elif args.workload == "config4":
         Wx, Hx = 7680, 4320
         r.params = R.RenderParams(method=_lib.METHOD_RKF45, max_steps=1024, step_rule=_lib.STEP_CONSTANT)
         cam, _ = camera.default_camera(Wx, Hx)
@@ -399,9 +451,10 @@ def main():
     ap.add_argument("--no-peer-store", action="store_true",
                     help="N > 1: use the ncclAllGather after the trace kernel instead of the default fused gather (NVLink "
                          "peer stores from the trace kernel + 4-byte all-reduce barriers)")
-    ap.add_argument("--workload", default="config3", choices=["config3", "config4", "config5"],
-                    help="config3 = the headline (default). config4 / config5 print an 'extra_workload' JSON line for "
-                         "BASELINE configs[3] (8K, 1024 adaptive RKF45) / configs[4] (orbit, 4K x frames, TAA)")
+    ap.add_argument("--workload", default="config3", choices=["config1", "config2", "config3", "config4", "config5"],
+                    help="config3 = the headline (default). The others print an 'extra_workload' JSON line for BASELINE "
+                         "configs[0] (Schwarzschild 256x256x128 RKF45: GPU batch integrate + the CPU port), configs[1] "
+                         "(1080p, 256 steps, f32), configs[3] (8K, 1024 adaptive RKF45), configs[4] (orbit, 4K, TAA)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
     if args.impl == "reference":
