@@ -214,3 +214,27 @@ def test_full_size_strided_sample_and_properties(renderer, oracle, luts):
     renderer.params.c.flags = _lib.FLAG_BUDGET
     b = np.array(renderer.render(cam, phys))
     assert np.array_equal(frame, b) and renderer.last_stats.steps_executed == W * H * 512
+
+
+def test_full_size_rkf45_strided_sample(renderer, oracle, luts):
+    """BASELINE config 4's scheme (adaptive RKF45, tol 1e-8, <= 1024 steps, natural termination) on a full 4K frame
+    (one GPU's share of the 8K frame): strided sample against the oracle + census properties."""
+    from gravitas_b200 import _lib
+    W, H = 3840, 2160
+    cam, phys, rp, keep = setup(renderer, oracle, luts, W, H, method=_lib.METHOD_RKF45, max_steps=1024)
+    frame = np.array(renderer.render(cam, phys))
+    st = renderer.last_stats
+    assert np.isfinite(frame).all() and (frame[..., :3] >= 0).all() and np.all(frame[..., 3] == 1.0)
+    assert st.n_horizon + st.n_escape + st.n_maxsteps + st.n_disk == W * H
+    assert st.n_escape > 0.8 * W * H and st.rhs_evals >= 6 * st.steps_committed
+    mean_steps = st.steps_committed / (W * H)
+    assert 150 < mean_steps < 220                       # SURVEY §8d probe: mean 182 accepted steps per ray
+    lat = dict(x0=13, xs=101, y0=5, y1=H, ys=67)
+    ref = oracle.render(cam, rp, want=("rgba", "term", "steps"), **lat)
+    sub = frame[lat["y0"]::lat["ys"], lat["x0"]::lat["xs"]]
+    e = rel_err(sub, ref["rgba"]).max(-1)
+    print(f"4K RKF45 strided sample: {e.size} px, max rel err {e.max():.3e}, > tol: {(e > TOL).sum()}, "
+          f"mean accepted steps/ray {mean_steps:.1f}")
+    assert (e > TOL).sum() <= max(1, 2e-3 * e.size)
+    again = np.array(renderer.render(cam, phys))
+    assert np.array_equal(frame, again)
