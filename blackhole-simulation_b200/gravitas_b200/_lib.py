@@ -17,7 +17,7 @@ METHOD_RKF45, METHOD_RK4, METHOD_SYMPLECTIC = 0, 1, 2
 PRECISION_F64, PRECISION_F32 = 0, 1
 FORMAT_RGBA32F, FORMAT_RGBA16F = 0, 1
 STEP_CONSTANT, STEP_WGSL = 0, 1
-FLAG_JITTER, FLAG_BUDGET, FLAG_TRACK_DRIFT, FLAG_TAA, FLAG_NO_GATHER, FLAG_D2H_OWN_ROWS, FLAG_PEER_STORE = 1, 2, 4, 8, 16, 32, 64
+FLAG_JITTER, FLAG_BUDGET, FLAG_TAA, FLAG_NO_GATHER, FLAG_D2H_OWN_ROWS, FLAG_PEER_STORE = 1, 2, 8, 16, 32, 64
 
 
 class GravitasError(RuntimeError):

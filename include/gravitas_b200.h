@@ -58,7 +58,8 @@ enum {
     GVT_FLAG_JITTER = 1u << 0,      /* Halton(2,3) sub-pixel jitter on frame_index (compute.wgsl.ts:153-157) */
     GVT_FLAG_BUDGET = 1u << 1,      /* budget accounting: every pixel executes exactly max_steps step computations;
                                        terminated rays keep stepping with commits masked */
-    GVT_FLAG_TRACK_DRIFT = 1u << 2, /* max |H| per ray, as geodesic/mod.rs:233-237 */
+    /* bit 2 reserved (per-ray max |H| of geodesic/mod.rs:233-237 is reported by gvt_trace_states and
+       gvt_engine_integrate_rays, not by the frame path) */
     GVT_FLAG_TAA = 1u << 3,         /* run the TAA resolve (ataa.wgsl.ts:28-83) after the trace */
     GVT_FLAG_NO_GATHER = 1u << 4,   /* multi-GPU: skip the all-gather (each rank keeps only its row block) */
     GVT_FLAG_PEER_STORE = 1u << 6,  /* multi-GPU: fuse the gather into the producing kernel — every finished pixel is stored
