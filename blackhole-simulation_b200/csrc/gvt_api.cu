@@ -8,6 +8,7 @@
 #include <cuda_fp16.h>
 #include <dlfcn.h>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -339,6 +340,7 @@ extern "C" int32_t gvt_render_params_default(GvtRenderParams* p) {
     p->step_rule = GVT_STEP_WGSL; p->max_steps = 512; p->renormalize_interval = 10; p->flags = 0;
     p->output_format = GVT_FORMAT_RGBA32F;
     p->tolerance = 1e-8; p->initial_step = 0.01; p->escape_radius = 1000.0; p->disk_r_out = 50.0;
+    p->taa_blend = 0.75f; p->taa_camera_moving = 0;   // webgl/renderer.ts:380-385
     return GVT_OK;
 }
 
@@ -523,6 +525,7 @@ static void fill_taa(const GvtCamera* cam, uint32_t W, uint32_t H, TaaParams& T)
     memcpy(T.inv_proj, cam->inv_proj, 64); memcpy(T.inv_view, cam->inv_view, 64);
     memcpy(T.prev_view_proj, cam->prev_view_proj, 64); memcpy(T.cam_pos, cam->position, 16);
     T.width = W; T.height = H; T.row0 = 0; T.row1 = H; T.host_out = nullptr; T.n_peer = 0;
+    T.mode = 0; T.blend = 0.75f; T.moving = 0;
 }
 
 extern "C" int32_t gvt_render_read_frame(gvt_renderer* r, uint32_t format, void* host_rgba) {
@@ -611,6 +614,10 @@ extern "C" int32_t gvt_render_frame(gvt_renderer* r, const GvtCamera* cam, const
         fill_taa(cam, W, H, T);
         T.cur = r->cur; T.hist = r->hist; T.out = r->frame;
         T.row0 = row0; T.row1 = row1;
+        if (rp->flags & GVT_FLAG_TAA_WEBGL) {
+            const bool has = rp->struct_size >= offsetof(GvtRenderParams, taa_camera_moving) + sizeof(uint32_t);
+            T.mode = 1; T.blend = has ? rp->taa_blend : 0.75f; T.moving = has ? rp->taa_camera_moving : 0u;
+        }
         T.host_out = host_alias;
         if (peer_store) { for (uint32_t q = 0; q < n_peer; q++) T.peer_out[q] = peer_targets[q]; T.n_peer = n_peer; }
         CK(launch_taa(T, r->stream));
@@ -730,6 +737,27 @@ extern "C" int32_t gvt_taa_resolve(gvt_renderer* r, const GvtCamera* cam, uint32
     CK(cudaMemcpyAsync(d_hist, hist, bytes, cudaMemcpyHostToDevice, r->stream));
     TaaParams T;
     fill_taa(cam, width, height, T);
+    T.cur = d_cur; T.hist = d_hist; T.out = d_out;
+    CK(launch_taa(T, r->stream));
+    CK(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, r->stream));
+    CK(cudaStreamSynchronize(r->stream));
+    cudaFree(d_cur); cudaFree(d_hist); cudaFree(d_out);
+    return GVT_OK;
+}
+
+extern "C" int32_t gvt_taa_resolve_webgl(gvt_renderer* r, uint32_t width, uint32_t height, const float* cur, const float* hist,
+                                         float blend, int32_t camera_moving, float* out) {
+    if (!r || !cur || !hist || !out || width == 0 || height == 0) return fail(GVT_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(r->device));
+    const size_t bytes = (size_t)width * height * sizeof(float4);
+    float4 *d_cur = nullptr, *d_hist = nullptr, *d_out = nullptr;
+    CK(cudaMalloc(&d_cur, bytes)); CK(cudaMalloc(&d_hist, bytes)); CK(cudaMalloc(&d_out, bytes));
+    CK(cudaMemcpyAsync(d_cur, cur, bytes, cudaMemcpyHostToDevice, r->stream));
+    CK(cudaMemcpyAsync(d_hist, hist, bytes, cudaMemcpyHostToDevice, r->stream));
+    TaaParams T;
+    memset(&T, 0, sizeof(T));
+    T.width = width; T.height = height; T.row0 = 0; T.row1 = height;
+    T.mode = 1; T.blend = blend; T.moving = camera_moving ? 1u : 0u;
     T.cur = d_cur; T.hist = d_hist; T.out = d_out;
     CK(launch_taa(T, r->stream));
     CK(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, r->stream));

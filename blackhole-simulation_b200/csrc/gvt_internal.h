@@ -63,6 +63,9 @@ struct TaaParams {
     // ataa.wgsl.ts:54-69: reprojection of a point at depth 12 along the pixel's world ray through prev_view_proj
     float inv_proj[16], inv_view[16], prev_view_proj[16], cam_pos[4];
     uint32_t width, height;
+    uint32_t mode;         // 0: ataa.wgsl.ts (WebGPU); 1: reprojection.glsl.ts (WebGL2)
+    float blend;           // mode 1: u_blendFactor
+    uint32_t moving, _pad_taa;   // mode 1: u_cameraMoving
     uint32_t row0, row1;   // rows resolved by this launch (a rank's block); neighbours outside are still read
     const float4* cur; const float4* hist; float4* out;
     float4* host_out;      // device alias of a page-locked host frame, or null

@@ -470,12 +470,21 @@ __global__ void __launch_bounds__(256) k_taa_resolve(const __grid_constant__ Taa
             const float k = 1.0f / 9.0f;
             const float mean[3] = {m1y * k, m1o * k, m1g * k};
             const float m2[3] = {m2y * k, m2o * k, m2g * k};
-            float lo[3], hi[3];
+            float lo[3], hi[3], sd_y = 0.0f;
+            const float nsig = (P.mode == 1u) ? 1.5f : 2.0f;             // reprojection.glsl.ts:90-91 / ataa.wgsl.ts:51-52
 #pragma unroll
             for (int i = 0; i < 3; i++) {
                 const float sd = sqrtf(fmaxf(m2[i] - mean[i] * mean[i], 0.0f));
-                lo[i] = mean[i] - 2.0f * sd; hi[i] = mean[i] + 2.0f * sd;
+                if (i == 0) sd_y = sd;
+                lo[i] = mean[i] - nsig * sd; hi[i] = mean[i] + nsig * sd;
             }
+            float hr, hg, hb, fb_;
+            if (P.mode == 1u) {
+                // WebGL2 resolve: history at the same texel, variance-guided weight (reprojection.glsl.ts:93-110)
+                const float4 h0 = ldg_px(P.hist, W, H, x, y);
+                hr = h0.x; hg = h0.y; hb = h0.z;
+                fb_ = P.moving ? 0.0f : P.blend * (1.0f - fminf(fmaxf(sd_y * 4.0f, 0.0f), 0.55f));
+            } else {
             // reprojection at depth 12 through prev_view_proj (ataa.wgsl.ts:54-69)
             const float u = ((float)x + 0.5f) / (float)W, v = ((float)y + 0.5f) / (float)H;
             const float cx = u * 2.0f - 1.0f, cy = -(v * 2.0f - 1.0f);
@@ -504,14 +513,15 @@ __global__ void __launch_bounds__(256) k_taa_resolve(const __grid_constant__ Taa
             const float fx = hx - hxf, fy = hy - hyf;
             const float4 h00 = ldg_px(P.hist, W, H, x0, y0), h10 = ldg_px(P.hist, W, H, x0 + 1, y0);
             const float4 h01 = ldg_px(P.hist, W, H, x0, y0 + 1), h11 = ldg_px(P.hist, W, H, x0 + 1, y0 + 1);
-            const float hr = (h00.x + (h10.x - h00.x) * fx) + ((h01.x + (h11.x - h01.x) * fx) - (h00.x + (h10.x - h00.x) * fx)) * fy;
-            const float hg = (h00.y + (h10.y - h00.y) * fx) + ((h01.y + (h11.y - h01.y) * fx) - (h00.y + (h10.y - h00.y) * fx)) * fy;
-            const float hb = (h00.z + (h10.z - h00.z) * fx) + ((h01.z + (h11.z - h01.z) * fx) - (h00.z + (h10.z - h00.z) * fx)) * fy;
+            hr = (h00.x + (h10.x - h00.x) * fx) + ((h01.x + (h11.x - h01.x) * fx) - (h00.x + (h10.x - h00.x) * fx)) * fy;
+            hg = (h00.y + (h10.y - h00.y) * fx) + ((h01.y + (h11.y - h01.y) * fx) - (h00.y + (h10.y - h00.y) * fx)) * fy;
+            hb = (h00.z + (h10.z - h00.z) * fx) + ((h01.z + (h11.z - h01.z) * fx) - (h00.z + (h10.z - h00.z) * fx)) * fy;
+            fb_ = 0.92f;  // ataa.wgsl.ts:77
+            }
             YCC hs = rgb_to_ycocg(hr, hg, hb);
             hs.y = fminf(fmaxf(hs.y, lo[0]), hi[0]);
             hs.co = fminf(fmaxf(hs.co, lo[1]), hi[1]);
             hs.cg = fminf(fmaxf(hs.cg, lo[2]), hi[2]);
-            const float fb_ = 0.92f;  // ataa.wgsl.ts:77
             const float ry = b.y + (hs.y - b.y) * fb_, ro = b.co + (hs.co - b.co) * fb_, rg = b.cg + (hs.cg - b.cg) * fb_;
             // YCoCgToRGB, ataa.wgsl.ts:18-26
             const float4 px_out = make_float4(ry + ro - rg, ry + rg, ry - ro - rg, 1.0f);

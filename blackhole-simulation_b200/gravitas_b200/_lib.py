@@ -17,7 +17,7 @@ METHOD_RKF45, METHOD_RK4, METHOD_SYMPLECTIC = 0, 1, 2
 PRECISION_F64, PRECISION_F32 = 0, 1
 FORMAT_RGBA32F, FORMAT_RGBA16F = 0, 1
 STEP_CONSTANT, STEP_WGSL = 0, 1
-FLAG_JITTER, FLAG_BUDGET, FLAG_TAA, FLAG_NO_GATHER, FLAG_D2H_OWN_ROWS, FLAG_PEER_STORE = 1, 2, 8, 16, 32, 64
+FLAG_JITTER, FLAG_BUDGET, FLAG_TAA, FLAG_NO_GATHER, FLAG_D2H_OWN_ROWS, FLAG_PEER_STORE, FLAG_TAA_WEBGL = 1, 2, 8, 16, 32, 64, 128
 
 
 class GravitasError(RuntimeError):
@@ -41,7 +41,8 @@ class GvtRenderParams(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("method", C.c_uint32), ("precision", C.c_uint32), ("coords", C.c_uint32),
                 ("step_rule", C.c_uint32), ("max_steps", C.c_uint32), ("renormalize_interval", C.c_uint32),
                 ("flags", C.c_uint32), ("output_format", C.c_uint32), ("_pad", C.c_uint32), ("tolerance", C.c_double),
-                ("initial_step", C.c_double), ("escape_radius", C.c_double), ("disk_r_out", C.c_double)]
+                ("initial_step", C.c_double), ("escape_radius", C.c_double), ("disk_r_out", C.c_double),
+                ("taa_blend", C.c_float), ("taa_camera_moving", C.c_uint32)]
 
 
 class GvtDeviceConfig(C.Structure):
@@ -98,6 +99,7 @@ SIGNATURES = {
     "gvt_trace_states": (_i32, [_vp, C.POINTER(GvtCamera), C.POINTER(GvtPhysicsParams), C.POINTER(GvtRenderParams), _u32,
                                 _u32, _u32, _u32, _u32, _pd, _pu32, _pu32, _pd, _pd]),
     "gvt_taa_resolve": (_i32, [_vp, C.POINTER(GvtCamera), _u32, _u32, _pf, _pf, _pf]),
+    "gvt_taa_resolve_webgl": (_i32, [_vp, _u32, _u32, _pf, _pf, C.c_float, _i32, _pf]),
     "gvt_render_reset_history": (_i32, [_vp]),
     "gvt_render_export_frames": (_i32, [_vp, C.POINTER(C.c_uint8)]),
     "gvt_render_import_peer_frames": (_i32, [_vp, _i32, C.POINTER(C.c_uint8)]),

@@ -241,6 +241,17 @@ class KerrRenderer:
                                     out.ctypes.data_as(pf)))
         return out
 
+    def taa_resolve_webgl(self, cur, hist, blend=0.75, camera_moving=False):
+        """ReprojectionManager.resolve (rendering/reprojection.ts:195-272) semantics on host frames."""
+        cur = np.ascontiguousarray(cur, np.float32)
+        hist = np.ascontiguousarray(hist, np.float32)
+        H, W = cur.shape[:2]
+        out = np.zeros_like(cur)
+        pf = C.POINTER(C.c_float)
+        check(lib().gvt_taa_resolve_webgl(self._h, W, H, cur.ctypes.data_as(pf), hist.ctypes.data_as(pf), float(blend),
+                                          1 if camera_moving else 0, out.ctypes.data_as(pf)))
+        return out
+
     def reset_history(self):
         check(lib().gvt_render_reset_history(self._h))
 

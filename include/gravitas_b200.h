@@ -62,6 +62,9 @@ enum {
        gvt_engine_integrate_rays, not by the frame path) */
     GVT_FLAG_TAA = 1u << 3,         /* run the TAA resolve (ataa.wgsl.ts:28-83) after the trace */
     GVT_FLAG_NO_GATHER = 1u << 4,   /* multi-GPU: skip the all-gather (each rank keeps only its row block) */
+    GVT_FLAG_TAA_WEBGL = 1u << 7,   /* with GVT_FLAG_TAA: the WebGL2 resolve of src/shaders/postprocess/reprojection.glsl.ts:70-115
+                                       (mu +- 1.5 sigma clip, no reprojection, alpha = moving ? 0 : blend (1 - clamp(4 sigma_Y,
+                                       0, 0.55))) instead of the WebGPU one (ataa.wgsl.ts:28-83) */
     GVT_FLAG_PEER_STORE = 1u << 6,  /* multi-GPU: fuse the gather into the producing kernel — every finished pixel is stored
                                        into every peer's frame over NVLink (peer frames imported with
                                        gvt_render_import_peer_frames) and a 4-byte ncclAllReduce closes the frame as the
@@ -111,6 +114,8 @@ typedef struct GvtRenderParams {
     double initial_step;           /* h0 (0.01) or the constant step */
     double escape_radius;          /* 1000 (lib.rs:449) */
     double disk_r_out;             /* thin-disk outer edge, 50 M (physics/disk.rs:177); inner = ISCO prograde */
+    float taa_blend;               /* GVT_FLAG_TAA_WEBGL: u_blendFactor (0.75 in webgl/renderer.ts:380-385) */
+    uint32_t taa_camera_moving;    /* GVT_FLAG_TAA_WEBGL: u_cameraMoving */
 } GvtRenderParams;
 
 typedef struct GvtDeviceConfig {
@@ -200,6 +205,9 @@ int32_t gvt_trace_states(gvt_renderer* r, const GvtCamera* cam, const GvtPhysics
 /* TAA resolve on caller-provided frames (ataa.wgsl.ts:28-83): cur, hist, out are width*height*4 f32 host buffers. */
 int32_t gvt_taa_resolve(gvt_renderer* r, const GvtCamera* cam, uint32_t width, uint32_t height, const float* cur,
                         const float* hist, float* out);
+/* The WebGL2 variant (reprojection.glsl.ts:70-115) on caller-provided frames. */
+int32_t gvt_taa_resolve_webgl(gvt_renderer* r, uint32_t width, uint32_t height, const float* cur, const float* hist,
+                              float blend, int32_t camera_moving, float* out);
 int32_t gvt_render_reset_history(gvt_renderer* r);
 /* Peer-store gather (GVT_FLAG_PEER_STORE): each rank exports CUDA IPC handles of its two frame buffers; the host
  * exchanges them (any transport) and every rank imports every peer's pair. Call again after gvt_render_resize. All

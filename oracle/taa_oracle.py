@@ -68,3 +68,27 @@ def taa_resolve(cam88, cur, hist):
     out = np.ones((H, W, 4), F)
     out[..., :3] = ycocg_to_rgb(res)
     return out
+
+
+def taa_resolve_webgl(cur, hist, blend=0.75, camera_moving=False):
+    """numpy f32 restatement of src/shaders/postprocess/reprojection.glsl.ts:70-115 at render scale 1 (texel-centre
+    fetches with CLAMP_TO_EDGE): mu +- 1.5 sigma clip of the same-texel history, variance-guided blend weight."""
+    cur = np.asarray(cur, F); hist = np.asarray(hist, F)
+    H, W = cur.shape[:2]
+    ycc = rgb_to_ycocg(cur[..., :3])
+    m1 = np.zeros_like(ycc); m2 = np.zeros_like(ycc)
+    ys, xs = np.arange(H), np.arange(W)
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            s = ycc[np.clip(ys + dy, 0, H - 1)][:, np.clip(xs + dx, 0, W - 1)]
+            m1 += s; m2 += s * s
+    mean = m1 / F(9.0)
+    std = np.sqrt(np.maximum(m2 / F(9.0) - mean * mean, F(0)))
+    lo, hi = mean - F(1.5) * std, mean + F(1.5) * std
+    h = np.minimum(np.maximum(rgb_to_ycocg(hist[..., :3]), lo), hi)
+    wv = F(1.0) - np.clip(std[..., 0] * F(4.0), F(0), F(0.55))
+    alpha = (np.zeros_like(wv) if camera_moving else F(blend) * wv)[..., None]
+    res = ycc * (F(1.0) - alpha) + h * alpha
+    out = np.ones((H, W, 4), F)
+    out[..., :3] = ycocg_to_rgb(res)
+    return out

@@ -89,3 +89,46 @@ def test_render_with_taa_flag_equals_trace_then_resolve(renderer, oracle):
         hist = got
         prev_vp = vp
     plain.cleanup()
+
+
+@pytest.mark.parametrize("W,H,moving", [(64, 40, False), (157, 83, False), (31, 33, True), (1, 1, False)])
+def test_webgl_reprojection_variant(renderer, W, H, moving):
+    """reprojection.glsl.ts:70-115 (the WebGL2 pipeline's resolve): +-1.5 sigma, same-texel history, variance-guided alpha."""
+    import taa_oracle
+    rng = np.random.default_rng(5)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    cur = np.stack([1 + 0.5 * np.sin(xx / 9.0) * np.cos(yy / 7.0), 0.8 + 0.3 * np.cos(xx / 5.0), 0.6 + 0.2 * np.sin(yy / 11.0),
+                    np.ones_like(xx)], -1).astype(np.float32) + rng.random((H, W, 4), dtype=np.float32) * 0.05
+    cur[..., 3] = 1.0
+    hist = (cur * np.float32(1.2) + np.float32(0.1)).astype(np.float32)
+    got = renderer.taa_resolve_webgl(cur, hist, blend=0.75, camera_moving=moving)
+    ref = taa_oracle.taa_resolve_webgl(cur, hist, 0.75, moving)
+    np.testing.assert_allclose(got, ref, rtol=1e-3, atol=1e-3)
+    if moving:
+        np.testing.assert_allclose(got[..., :3], cur[..., :3], rtol=1e-5, atol=1e-6)    # alpha = 0: current frame only
+
+
+def test_render_with_webgl_taa_flag(renderer):
+    import taa_oracle
+    import gravitas_b200 as g
+    from gravitas_b200 import camera, renderer as R, _lib
+    W, H, steps = 96, 54, 64
+    spin = float(np.float32(0.999))
+    renderer.init_pipelines(mass=1.0, spin=spin, spec_w=64, spec_h=16, max_temp=1e7)
+    renderer.resize(W, H); renderer.reset_history()
+    plain = g.KerrRenderer(device=0); plain.init()
+    plain.init_pipelines(mass=1.0, spin=spin, spec_w=64, spec_h=16, max_temp=1e7)
+    hist = np.zeros((H, W, 4), np.float32)
+    cam, _ = camera.default_camera(W, H)
+    for k in range(3):
+        phys = R.pack_physics(1.0, spin, W, H, frame_index=k)
+        plain.params = R.RenderParams(max_steps=steps, flags=_lib.FLAG_JITTER)
+        cur = np.array(plain.render(cam, phys))
+        renderer.params = R.RenderParams(max_steps=steps, flags=_lib.FLAG_JITTER | _lib.FLAG_TAA | _lib.FLAG_TAA_WEBGL,
+                                         taa_blend=0.75, taa_camera_moving=0)
+        got = np.array(renderer.render(cam, phys))
+        ref = taa_oracle.taa_resolve_webgl(cur, hist, 0.75, False)
+        scale = float(np.abs(ref[..., :3]).max())
+        np.testing.assert_allclose(got, ref, rtol=1e-3, atol=1e-3 * scale)
+        hist = got
+    plain.cleanup()
