@@ -396,6 +396,25 @@ def run_extra(args):
                               "e2e_ms_per_frame": e_ms / args.steps, "steps_per_s": sps,
                               "frac_of_fp32_peak": sps * FLOP_PER_STEP["symplectic"] * 1e-12 / peak32 / world,
                               "fp32_peak_tflops": peak32, "fps": 1e3 * args.steps / ev_ms}))
+    elif args.workload == "glsl":
+        # the production WebGL2 shader's march: Cartesian Velocity-Verlet, f32, "ultra" budget of 256
+        # steps (simulation.config.ts:205-211), MAX_DIST 10000 (physics.config.ts:60), at 1080p and at 4K
+        res = {}
+        for (Wx, Hx) in ((1920, 1080), (3840, 2160)):
+            r.params = R.RenderParams(method=_lib.METHOD_VERLET_GLSL, precision=_lib.PRECISION_F32, max_steps=256,
+                                      step_rule=_lib.STEP_CONSTANT, escape_radius=10000.0)
+            cam, _ = camera.default_camera(Wx, Hx)
+            phys = R.pack_physics(MASS, SPIN, Wx, Hx)
+            for _ in range(args.warmup):
+                r.render(cam, phys, readback=False)
+            ev_ms, wall_ms, stats = timed_frames(r, cam, phys, args.steps, dist, readback=False)
+            steps = allreduce_sum(dist, float(sum(s.steps_committed for s in stats)))
+            res[f"{Wx}x{Hx}"] = {"ms_per_frame": ev_ms / args.steps, "fps": 1e3 * args.steps / ev_ms,
+                                 "verlet_steps_per_s": steps / (ev_ms * 1e-3), "mean_steps_per_pixel": steps / args.steps / (Wx * Hx)}
+        if rank == 0:
+            print(json.dumps({"extra_workload": "GLSL-semantics path: Cartesian Velocity-Verlet on the shader's pseudo-Kerr acceleration "
+                              "(fragment.glsl.ts:129-221), f32, 256-step budget, natural termination, thin-disk LUT shading",
+                              "n_gpus": world, "frames": args.steps, **res}))
     elif args.workload == "config4":
         Wx, Hx = 7680, 4320
         r.params = R.RenderParams(method=_lib.METHOD_RKF45, max_steps=1024, step_rule=_lib.STEP_CONSTANT)
@@ -451,7 +470,7 @@ def main():
     ap.add_argument("--no-peer-store", action="store_true",
                     help="N > 1: use the ncclAllGather after the trace kernel instead of the default fused gather (NVLink "
                          "peer stores from the trace kernel + 4-byte all-reduce barriers)")
-    ap.add_argument("--workload", default="config3", choices=["config1", "config2", "config3", "config4", "config5"],
+    ap.add_argument("--workload", default="config3", choices=["config1", "config2", "config3", "config4", "config5", "glsl"],
                     help="config3 = the headline (default). The others print an 'extra_workload' JSON line for BASELINE "
                          "configs[0] (Schwarzschild 256x256x128 RKF45: GPU batch integrate + the CPU port), configs[1] "
                          "(1080p, 256 steps, f32), configs[3] (8K, 1024 adaptive RKF45), configs[4] (orbit, 4K, TAA)")

@@ -485,7 +485,7 @@ static int32_t build_frame(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
     if (!r->luts_ready) return fail(GVT_ERR_INVALID, "LUTs not initialised: call gvt_render_init_luts / gvt_render_set_luts first");
     if (rp->coords != GVT_COORDS_KERR_SCHILD)
         return fail(GVT_ERR_UNSUPPORTED, "the render path traces in Kerr-Schild coordinates (lib.rs:64,454); use gvt_engine_integrate_rays for Boyer-Lindquist");
-    if (rp->method > GVT_METHOD_SYMPLECTIC || rp->precision > GVT_PRECISION_F32) return fail(GVT_ERR_INVALID, "bad method/precision");
+    if (rp->method > GVT_METHOD_VERLET_GLSL || rp->precision > GVT_PRECISION_F32) return fail(GVT_ERR_INVALID, "bad method/precision");
     if (rp->renormalize_interval == 0) return fail(GVT_ERR_INVALID, "renormalize_interval must be > 0");
     const uint32_t W = (uint32_t)phys->resolution[0], H = (uint32_t)phys->resolution[1];
     if (W == 0 || H == 0) return fail(GVT_ERR_INVALID, "zero resolution");
@@ -504,6 +504,11 @@ static int32_t build_frame(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
     if (rp->flags & GVT_FLAG_JITTER) {
         b->jx = (halton((phys->frame_index % 8u) + 1u, 2u) - 0.5) / (double)W;
         b->jy = (halton((phys->frame_index % 8u) + 1u, 3u) - 0.5) / (double)H;
+    }
+    b->cam_pos[0] = cx; b->cam_pos[1] = cy; b->cam_pos[2] = cz;
+    {   // kerr_photon_sphere, chunks/metric.ts:32-37
+        const double as = std::min(0.9999, std::max(-0.9999, bh.a() / bh.mass));
+        b->rph = 2.0 * bh.mass * (1.0 + std::cos((2.0 / 3.0) * std::acos(std::min(1.0, std::max(-1.0, -as)))));
     }
     memcpy(b->tdisk, r->tdisk.data(), 512 * sizeof(float));
 
@@ -557,7 +562,7 @@ extern "C" int32_t gvt_render_frame(gvt_renderer* r, const GvtCamera* cam, const
     int32_t rc = build_frame(r, cam, phys, rp, P);
     if (rc != GVT_OK) return rc;
     const bool taa = (rp->flags & GVT_FLAG_TAA) != 0;
-    const bool budget = (rp->flags & GVT_FLAG_BUDGET) != 0 && rp->method != GVT_METHOD_RKF45;
+    const bool budget = (rp->flags & GVT_FLAG_BUDGET) != 0 && (rp->method == GVT_METHOD_RK4 || rp->method == GVT_METHOD_SYMPLECTIC);
     const uint32_t row0 = std::min(H, (uint32_t)r->rank * r->rows_per_rank);
     const uint32_t row1 = std::min(H, row0 + r->rows_per_rank);
     // TAA needs a one-pixel halo of the current frame: trace one redundant row above and below the block
@@ -713,7 +718,7 @@ extern "C" int32_t gvt_trace_states(gvt_renderer* r, const GvtCamera* cam, const
     if (rc != GVT_OK) return rc;
     P.frame = nullptr;
     P.dbg_xp = r->d_xp; P.dbg_term = r->d_term; P.dbg_steps = r->d_steps; P.dbg_drift = r->d_drift; P.dbg_rgba = r->d_rgba;
-    const bool budget = (rp->flags & GVT_FLAG_BUDGET) != 0 && rp->method != GVT_METHOD_RKF45;
+    const bool budget = (rp->flags & GVT_FLAG_BUDGET) != 0 && (rp->method == GVT_METHOD_RK4 || rp->method == GVT_METHOD_SYMPLECTIC);
     CK(cudaMemcpyAsync(r->d_block, r->h_block, sizeof(FrameBlock), cudaMemcpyHostToDevice, r->stream));
     CK(cudaMemsetAsync(r->d_counters, 0, sizeof(Counters), r->stream));
     CK(launch_trace(P, rp->method, rp->precision, budget, true, r->sm_count, r->stream));

@@ -607,4 +607,64 @@ __device__ __forceinline__ R g_factor(R r, R mass, R sm, R spin, R lambda) {
     return sqrt_nr(ut_denom) * N::rcp(factor);                        // 1 / (u^t (1 - lambda Omega))
 }
 
+// --------------------------------------------------------------------------------------------------
+// GLSL-semantics path: Cartesian Velocity-Verlet on the production fragment shader's pseudo-Kerr
+// acceleration field (src/shaders/blackhole/chunks/metric.ts:96-149, fragment.glsl.ts:129-221).
+// --------------------------------------------------------------------------------------------------
+template <class R>
+struct Vec3 {
+    R x, y, z;
+};
+template <class R> __device__ __forceinline__ R dot3(const Vec3<R>& a, const Vec3<R>& b) {
+    return Num<R>::fma_(a.x, b.x, Num<R>::fma_(a.y, b.y, a.z * b.z));
+}
+
+// kerr_geodesic_accel: Darwin-type radial pull scaled by r^2/Sigma with the spin-coupled L_eff^2, plus the
+// gravito-magnetic term (0,1,0) x v. Returns the acceleration and the ZAMO angular velocity.
+template <class R>
+__device__ __forceinline__ void glsl_accel(const Vec3<R>& p, const Vec3<R>& v, R M, R a, Vec3<R>& acc, R& omega) {
+    using N = Num<R>;
+    const R a2 = a * a;
+    const R rho2 = dot3(p, p);
+    const R diff = rho2 - a2;
+    const R disc = N::fma_(diff, diff, R(4) * a2 * p.y * p.y);
+    const R r2 = R(0.5) * (diff + sqrt_nr(N::max_(R(0), disc)));
+    const R r2c = N::max_(R(1e-8), r2);
+    const R r_k = sqrt_nr(r2c);
+    const R sigma = N::fma_(a2, p.y * p.y * N::rcp(r2c), r2);
+    const R Lx = p.y * v.z - p.z * v.y, Ly = p.z * v.x - p.x * v.z, Lz = p.x * v.y - p.y * v.x;
+    const R Ly_eff = Ly - a;
+    const R L2_eff = N::fma_(Ly_eff, Ly_eff, N::fma_(Lx, Lx, Lz * Lz));          // Ly_eff^2 + (L.L - Ly^2)
+    const R r2_inv = N::rcp(r_k * r_k);
+    const R sigma_ratio = r2 * N::rcp(N::max_(R(1e-8), sigma));
+    const R f = M * r2_inv * sigma_ratio * N::fma_(R(3) * N::max_(R(0), L2_eff), r2_inv, R(1));
+    const R k = -f * N::rcp(sqrt_nr(rho2));                                       // r_hat = -p/|p|
+    omega = R(2) * M * a * N::rcp(N::max_(R(1e-8), r_k * (r2 + a2)));
+    acc.x = N::fma_(p.x, k, v.z * omega);
+    acc.y = p.y * k;
+    acc.z = N::fma_(p.z, k, -v.x * omega);
+}
+
+template <class R> __device__ __forceinline__ R smoothstep_glsl(R e0, R e1, R x) {
+    const R t = clampR<R>((x - e0) * Num<R>::rcp_ieee(e1 - e0), R(0), R(1));
+    return t * t * (R(3) - R(2) * t);
+}
+
+// One iteration's step size (fragment.glsl.ts:141-162).
+template <class R>
+__device__ __forceinline__ R glsl_step_size(R r, R py_abs, R rh, R rph) {
+    using N = Num<R>;
+    const R MIN_STEP = R(0.01), MAX_STEP = R(1.2);
+    const R distFactor = N::fma_(r, R(0.05), R(1));
+    R dt = clampR<R>((r - rh) * R(0.1) * distFactor, MIN_STEP, MAX_STEP * distFactor);
+    if (r > R(30)) {
+        dt = N::max_(dt, N::fma_(r - R(30), R(0.08), MIN_STEP));
+        dt = N::min_(dt, MAX_STEP * R(2.5));
+    }
+    dt = N::min_(dt, N::fma_(N::abs_(r - rph), R(0.15), MIN_STEP));
+    const R t = clampR<R>((py_abs - R(0.2)) * R(-5), R(0), R(1));                 // smoothstep(0.2, 0.0, |y|)
+    const R hRef = t * t * (R(3) - R(2) * t);
+    return dt * N::fma_(hRef, R(-0.7), R(1));
+}
+
 }  // namespace gvt

@@ -14,6 +14,7 @@ struct alignas(16) FrameBlock {
     double inv_view[16];   // column-major
     double r0, theta0, phi0, st, ct, sp, cp, safe_st;
     double inv_width, inv_height, jx, jy;   // 1/W, 1/H, jitter / resolution (compute.wgsl.ts:153-157)
+    double cam_pos[3], rph;                 // camera position; prograde photon sphere as the GLSL computes it
     float tdisk[512];
 };
 static_assert(sizeof(FrameBlock) % 16 == 0, "TMA bulk copies move multiples of 16 bytes");

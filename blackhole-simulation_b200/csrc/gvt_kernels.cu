@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
 
         // ---- camera -> (x, p): compute.wgsl.ts:159-187 ----
         Ray<R> y;
+        Vec3<R> wdir;          // world-space ray direction (the Cartesian march of METHOD 3 starts from it)
         {
             const R ndcx = N::fma_(N::fma_(R((double)px), R(fb->inv_width), R(fb->jx)), R(2), R(-1));
             const R ndcy = N::fma_(N::fma_(R((double)py), R(fb->inv_height), R(fb->jy)), R(2), R(-1));
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
                 w[row] = R(fb->inv_view[row]) * vx + R(fb->inv_view[4 + row]) * vy + R(fb->inv_view[8 + row]) * vz;
             const R iwn = N::rcp(sqrt_nr(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]));
             const R dx = w[0] * iwn, dy = w[1] * iwn, dz = w[2] * iwn;
+            wdir.x = dx; wdir.y = dy; wdir.z = dz;
             const R st = R(fb->st), ct = R(fb->ct), sp = R(fb->sp), cp = R(fb->cp), r0 = R(fb->r0);
             const R pr_far = dx * (st * cp) + dy * ct + dz * (st * sp);
             const R inv_r0 = N::rcp(r0);
@@ -201,11 +203,89 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
         // land. (The wait must not sit inside the step loop: an mbarrier try_wait spin loop there stops ptxas from
         // keeping the loop's FP64 constants in uniform registers, which costs a cycle on every three-register DFMA.)
         if (!lut_ready) { mbar_wait(&bars[1], 0); lut_ready = true; }
-        // ---- march: geodesic/mod.rs:180-253 ----
-        y.pr = renormalize_pr<R, 1>(hc, y.r, y.th, y.pr, y.pth);  // mod.rs:200
         R col[3] = {R(0), R(0), R(0)};
         R alpha = R(0), max_drift = R(0), h = R(P.h0);
         uint32_t steps = 0, term = 3u, rhs_evals = 0;
+        Vec3<R> gp = {R(0), R(0), R(0)}, gv = {R(0), R(0), R(0)};   // METHOD 3 state (for the parity hook)
+        uint32_t photon = 0;
+        bool hit = false;
+        if (METHOD == 3) {
+            // ---- GLSL-semantics march: fragment.glsl.ts:89-221 (deterministic subset) ----
+            const R Mh = R(P.M), ah = R(P.a), rph = R(fb->rph), max_dist = R(P.escape_r);
+            Vec3<R> ro = {R(fb->cam_pos[0]), R(fb->cam_pos[1]), R(fb->cam_pos[2])};
+            const R ron = N::sqrt_(dot3(ro, ro));
+            if (ron < rh * R(1.5)) { const R k = rh * R(1.5) / ron; ro.x *= k; ro.y *= k; ro.z *= k; }   // :94-97
+            gp = ro; gv = wdir;
+            {
+                const R cx = ro.y * wdir.z - ro.z * wdir.y, cy = ro.z * wdir.x - ro.x * wdir.z, cz = ro.x * wdir.y - ro.y * wdir.x;
+                hit = N::sqrt_(cx * cx + cy * cy + cz * cz) < rh * R(0.9);                                 // :124-126
+            }
+            R prevY = gp.y;
+            const uint32_t nmax = min(P.max_steps, 500u);                                                   // :115
+            bool done = false;
+            for (uint32_t it0 = 0; it0 < nmax; it0 += 8u) {
+                if (__all_sync(0xffffffffu, done)) break;
+                const uint32_t it1 = min(it0 + 8u, nmax);
+                for (uint32_t it = it0; it < it1; it++) {
+                    const R r = N::sqrt_(dot3(gp, gp));
+                    if (!done) {
+                        if (r < rh * R(1.15)) { hit = true; term = 1u; done = true; }                       // :135-138
+                        else if (r > max_dist) { term = 2u; done = true; }
+                    }
+                    if (!done) {
+                        const Vec3<R> pp = gp;
+                        const R cdt = glsl_step_size<R>(r, N::abs_(gp.y), rh, rph);
+                        Vec3<R> acc; R omega;
+                        glsl_accel<R>(gp, gv, Mh, ah, acc, omega);
+                        {   // v.xz *= rot(omega dt), rot(t) = mat2(c, -s, s, c)  (chunks/common.ts:46-49)
+                            R sn, cs;
+                            N::sincos_(omega * cdt, &sn, &cs);
+                            const R nx = gv.x * cs - gv.z * sn, nz = gv.x * sn + gv.z * cs;
+                            gv.x = nx; gv.z = nz;
+                        }
+                        const R hdt2 = R(0.5) * cdt * cdt;
+                        gp.x = N::fma_(acc.x, hdt2, N::fma_(gv.x, cdt, gp.x));
+                        gp.y = N::fma_(acc.y, hdt2, N::fma_(gv.y, cdt, gp.y));
+                        gp.z = N::fma_(acc.z, hdt2, N::fma_(gv.z, cdt, gp.z));
+                        const R r_new = N::sqrt_(dot3(gp, gp));
+                        if (alpha < R(0.95)) {
+                            Vec3<R> acc2; R om2;
+                            glsl_accel<R>(gp, gv, Mh, ah, acc2, om2);
+                            const R hdt = R(0.5) * cdt;
+                            gv.x = N::fma_(acc.x + acc2.x, hdt, gv.x);
+                            gv.y = N::fma_(acc.y + acc2.y, hdt, gv.y);
+                            gv.z = N::fma_(acc.z + acc2.z, hdt, gv.z);
+                        }
+                        const R ivn = N::rcp_ieee(N::sqrt_(dot3(gv, gv)));
+                        gv.x *= ivn; gv.y *= ivn; gv.z *= ivn;
+                        if (prevY * gp.y < R(0) && r_new < rph * R(2) && r_new > rh) photon = min(photon + 1u, 3u);
+                        prevY = gp.y;
+                        steps++; rhs_evals += 2;
+                        if (pp.y * gp.y < R(0)) {                                                            // chunks/disk.ts:22-30
+                            const R t = N::abs_(pp.y) / N::max_(R(0.0001), N::abs_(pp.y) + N::abs_(gp.y));
+                            const Vec3<R> sp = {N::fma_(gp.x - pp.x, t, pp.x), N::fma_(gp.y - pp.y, t, pp.y), N::fma_(gp.z - pp.z, t, pp.z)};
+                            const R r_c = N::sqrt_(dot3(sp, sp));
+                            if (r_c > R(P.r_in) && r_c < R(P.r_out)) {
+                                const R lambda = gp.z * gv.x - gp.x * gv.z;                                  // L_photon, chunks/disk.ts:92
+                                const R g = g_factor<R>(r_c, R(P.M), R(P.sqrtM), R(P.spin), lambda);
+                                const R tn = sample_tdisk<R>(fb->tdisk, P.tdisk_n, R(P.tdisk_rin), R(P.tdisk_scale), r_c);
+                                R rgb[3];
+                                sample_spectrum<R>(lut, P.spec_w, P.spec_h, pow04(tn), (g - R(0.05)) * R(1.0 / 4.95), rgb);
+                                const R opacity = R(0.6) * tn * g;
+                                const R wgt = (R(1) - alpha) * opacity;
+                                col[0] = N::fma_(rgb[0], wgt, col[0]);
+                                col[1] = N::fma_(rgb[1], wgt, col[1]);
+                                col[2] = N::fma_(rgb[2], wgt, col[2]);
+                                alpha += opacity;
+                            }
+                        }
+                        if (alpha > R(0.99)) { term = 4u; done = true; }
+                    }
+                }
+            }
+        } else {
+        // ---- march: geodesic/mod.rs:180-253 ----
+        y.pr = renormalize_pr<R, 1>(hc, y.r, y.th, y.pr, y.pth);  // mod.rs:200
         uint32_t renorm_in = 0;          // steps until the next renormalisation (steps % interval == 0, mod.rs:229)
         bool done = false, by_radius = false;
         // side of the equatorial plane before the step, as the sign word of (theta - pi/2) and an "exactly on it" flag
@@ -275,6 +355,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
         }
         if (by_radius) term = (y.r < r_term) ? 1u : 2u;   // Horizon is tested first (mod.rs:257-263)
         else if (!done) term = 3u;
+        }   // METHOD != 3
 
         // ---- epilogue: coalesced float4 store + census ----
         if (valid) {
@@ -285,7 +366,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
                 P.peer_frame[q][(size_t)py * P.width + px] = px_out;
             if (DEBUG) {
                 const size_t k = (size_t)lj * P.nx + li;
-                if (P.dbg_xp) {
+                if (P.dbg_xp && METHOD == 3) {
+                    double* o = P.dbg_xp + 8 * k;
+                    o[0] = (double)gp.x; o[1] = (double)gp.y; o[2] = (double)gp.z; o[3] = (double)gv.x; o[4] = (double)gv.y;
+                    o[5] = (double)gv.z; o[6] = (double)photon; o[7] = hit ? 1.0 : 0.0;
+                } else if (P.dbg_xp) {
                     double* o = P.dbg_xp + 8 * k;
                     o[0] = (double)y.t; o[1] = (double)y.r; o[2] = (double)y.th; o[3] = (double)y.ph;
                     o[4] = (double)hc.pt; o[5] = (double)y.pr; o[6] = (double)y.pth; o[7] = (double)hc.pph;
@@ -347,6 +432,8 @@ cudaError_t launch_trace(const FrameParams& p_in, int method, int precision, boo
     do {                                                                                                         \
         if (method == 0) return debug ? launch_trace_t<RT, 0, false, true, GVT_MAXT_RKF>(p, sm_count, stream)             \
                                       : launch_trace_t<RT, 0, false, false, GVT_MAXT_RKF>(p, sm_count, stream);           \
+        if (method == 3) return debug ? launch_trace_t<RT, 3, false, true, MT>(p, sm_count, stream)              \
+                                      : launch_trace_t<RT, 3, false, false, MT>(p, sm_count, stream);            \
         if (method == 1) return debug ? launch_trace_t<RT, 1, false, true, MT>(p, sm_count, stream)              \
                                       : launch_trace_t<RT, 1, false, false, MT>(p, sm_count, stream);            \
         if (budget) return debug ? launch_trace_t<RT, 2, true, true, MT>(p, sm_count, stream)                    \

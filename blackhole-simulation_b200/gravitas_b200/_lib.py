@@ -13,7 +13,7 @@ OFFSETS = {"CONTROL": 0, "CAMERA": 64, "PHYSICS": 128, "TELEMETRY": 256, "LUTS":
 GVT_OK, GVT_ERR_INVALID, GVT_ERR_NO_DEVICE, GVT_ERR_CUDA, GVT_ERR_NCCL, GVT_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 TERM_NONE, TERM_HORIZON, TERM_ESCAPE, TERM_MAXSTEPS, TERM_DISK = 0, 1, 2, 3, 4
 COORDS_BL, COORDS_KS = 0, 1
-METHOD_RKF45, METHOD_RK4, METHOD_SYMPLECTIC = 0, 1, 2
+METHOD_RKF45, METHOD_RK4, METHOD_SYMPLECTIC, METHOD_VERLET_GLSL = 0, 1, 2, 3
 PRECISION_F64, PRECISION_F32 = 0, 1
 FORMAT_RGBA32F, FORMAT_RGBA16F = 0, 1
 STEP_CONSTANT, STEP_WGSL = 0, 1

@@ -47,7 +47,11 @@ enum { GVT_TERM_NONE = 0, GVT_TERM_HORIZON = 1, GVT_TERM_ESCAPE = 2, GVT_TERM_MA
 /* metric/kerr.rs:16-22 */
 enum { GVT_COORDS_BOYER_LINDQUIST = 0, GVT_COORDS_KERR_SCHILD = 1 };
 /* geodesic/integrator.rs:14-21 */
-enum { GVT_METHOD_RKF45 = 0, GVT_METHOD_RK4 = 1, GVT_METHOD_SYMPLECTIC = 2 };
+enum { GVT_METHOD_RKF45 = 0, GVT_METHOD_RK4 = 1, GVT_METHOD_SYMPLECTIC = 2,
+       /* render path only: the production WebGL2 shader's Cartesian Velocity-Verlet march on its pseudo-Kerr acceleration
+          (fragment.glsl.ts:129-221, chunks/metric.ts:96-149); max_steps is capped at 500 as there (:115); escape_radius
+          plays MAX_DIST. Thin-disk light comes from the same LUT composite as the Hamiltonian path. */
+       GVT_METHOD_VERLET_GLSL = 3 };
 enum { GVT_PRECISION_F64 = 0, GVT_PRECISION_F32 = 1 };
 enum { GVT_FORMAT_RGBA32F = 0, GVT_FORMAT_RGBA16F = 1 }; /* RGBA16F = reprojection.ts:120-140 texture format */
 /* step rule for the fixed-step methods: constant `initial_step` (geodesic/mod.rs:218-223) or the per-step rule

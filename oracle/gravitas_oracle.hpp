@@ -80,7 +80,7 @@ template <class R> inline R rsignum(R x) { return (x < R(0.0)) ? R(-1.0) : R(1.0
 enum Coords : int { BOYER_LINDQUIST = 0, KERR_SCHILD = 1 };
 // geodesic/termination.rs:4-17 (#[repr(C)] enum)
 enum Termination : uint32_t { TERM_NONE = 0, TERM_HORIZON = 1, TERM_ESCAPE = 2, TERM_MAXSTEPS = 3, TERM_DISK = 4 };
-enum Method : int { METHOD_RKF45 = 0, METHOD_RK4 = 1, METHOD_SYMPLECTIC = 2 };
+enum Method : int { METHOD_RKF45 = 0, METHOD_RK4 = 1, METHOD_SYMPLECTIC = 2, METHOD_VERLET_GLSL = 3 };
 
 // ---------------------------------------------------------------------------------------------
 // metric/kerr.rs — Kerr metric (mass, clamped spin, coordinate system)
@@ -883,6 +883,50 @@ struct DiskHook {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// GLSL-semantics path: the production WebGL2 fragment shader's Cartesian Velocity-Verlet march on
+// its pseudo-Kerr acceleration field. src/shaders/blackhole/chunks/metric.ts:96-149 (kerr_geodesic_accel),
+// fragment.glsl.ts:129-221 (loop, step-size heuristics, ZAMO rotation), chunks/common.ts:40-49 (constants, rot()).
+// Deterministic subset: blue-noise dither = 0, lensing strength 1, no volumetric disk / jets / stars (they sample
+// Math.random noise textures); disk light comes from the same thin-disk crossing composite as the Hamiltonian path,
+// evaluated at the equatorial crossing point the shader itself computes (chunks/disk.ts:22-30).
+// ---------------------------------------------------------------------------------------------
+template <class R> struct V3 { R x, y, z; };
+template <class R> inline R dot3(V3<R> a, V3<R> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <class R> inline V3<R> cross3(V3<R> a, V3<R> b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+
+template <class R>
+inline void glsl_kerr_accel(V3<R> p, V3<R> v, R M, R a, V3<R>& accel, R& omega) {   // metric.ts:96-149
+    R a2 = a * a;
+    R rho2 = dot3(p, p);
+    R diff = rho2 - a2;
+    R disc = diff * diff + R(4.0) * a2 * p.y * p.y;
+    R r2 = R(0.5) * (diff + sqrt(rmax<R>(R(0.0), disc)));
+    R r_k = sqrt(rmax<R>(R(1e-8), r2));
+    R sigma = r2 + a2 * (p.y * p.y / rmax<R>(R(1e-8), r2));
+    V3<R> L = cross3(p, v);
+    R Ly = L.y;
+    R Ly_eff = Ly - a;
+    R L2_eff = Ly_eff * Ly_eff + (dot3(L, L) - Ly * Ly);
+    R r_inv = R(1.0) / r_k;
+    R r2_inv = r_inv * r_inv;
+    R r4_inv = r2_inv * r2_inv;
+    R sigma_ratio = r2 / rmax<R>(R(1e-8), sigma);
+    R pn = sqrt(dot3(p, p));
+    V3<R> r_hat = {-(p.x / pn), -(p.y / pn), -(p.z / pn)};
+    R f = M * r2_inv * sigma_ratio + R(3.0) * M * rmax<R>(R(0.0), L2_eff) * r4_inv * sigma_ratio;
+    accel = {r_hat.x * f, r_hat.y * f, r_hat.z * f};
+    R r3_p_a2r = r_k * r2 + a2 * r_k;
+    R drag = R(2.0) * M * a / rmax<R>(R(1e-8), r3_p_a2r);
+    accel.x += v.z * drag;          // cross((0,1,0), v) = (v.z, 0, -v.x)
+    accel.z += -v.x * drag;
+    omega = R(2.0) * M * a / rmax<R>(R(1e-8), r3_p_a2r);
+}
+template <class R> inline R glsl_smoothstep(R e0, R e1, R x) {
+    R t = rclamp<R>((x - e0) / (e1 - e0), R(0.0), R(1.0));
+    return t * t * (R(3.0) - R(2.0) * t);
+}
+
 struct PixelResult {
     double rgba[4];
     double xp[8];
@@ -914,6 +958,125 @@ inline PixelResult render_pixel(const CameraUniforms& cam, const RenderParams& r
     out.max_drift = to_double(t.max_hamiltonian_drift);
     out.crossings = hook.crossings;
     out.attempts = t.attempts; out.rhs_evals = t.rhs_evals;
+    return out;
+}
+
+// world-space ray of a pixel: the direction part of camera_ray() (compute.wgsl.ts:159-171)
+template <class R>
+inline void camera_dir(const CameraUniforms& cam, const RenderParams& rp, uint32_t px, uint32_t py, V3<R>& ro, V3<R>& rd) {
+    const float* inv_view = cam.f + 32;
+    const float* inv_proj = cam.f + 48;
+    R width = R((double)rp.width), height = R((double)rp.height);
+    R jx(0.0), jy(0.0);
+    if (rp.jitter) {
+        jx = (R(halton((rp.frame_index % 8u) + 1u, 2u)) - R(0.5)) / width;
+        jy = (R(halton((rp.frame_index % 8u) + 1u, 3u)) - R(0.5)) / height;
+    }
+    R ndcx = (R((double)px) / width + jx) * R(2.0) - R(1.0);
+    R ndcy = (R((double)py) / height + jy) * R(2.0) - R(1.0);
+    R clip[4] = {ndcx, -ndcy, R(1.0), R(1.0)};
+    R vt[4];
+    for (int row = 0; row < 4; row++)
+        vt[row] = R((double)inv_proj[row]) * clip[0] + R((double)inv_proj[4 + row]) * clip[1] +
+                  R((double)inv_proj[8 + row]) * clip[2] + R((double)inv_proj[12 + row]) * clip[3];
+    R vx = vt[0] / vt[3], vy = vt[1] / vt[3], vz = vt[2] / vt[3];
+    R vn = sqrt(vx * vx + vy * vy + vz * vz);
+    vx = vx / vn; vy = vy / vn; vz = vz / vn;
+    R w[3];
+    for (int row = 0; row < 3; row++)
+        w[row] = R((double)inv_view[row]) * vx + R((double)inv_view[4 + row]) * vy + R((double)inv_view[8 + row]) * vz;
+    R wn = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    rd = {w[0] / wn, w[1] / wn, w[2] / wn};
+    ro = {R((double)cam.f[80]), R((double)cam.f[81]), R((double)cam.f[82])};
+}
+
+// fragment.glsl.ts:89-221 with the deterministic subset described above. xp = (p, v, photonCrossings, 0).
+template <class R>
+inline PixelResult render_pixel_verlet(const CameraUniforms& cam, const RenderParams& rp, const Luts& luts, uint32_t px,
+                                       uint32_t py) {
+    const R M = R(rp.mass);
+    Kerr<R> metric(M, R(rp.spin), KERR_SCHILD);
+    const R a = metric.spin * M;
+    const R rh = M + sqrt(rmax<R>(R(0.0), M * M - a * a));                       // kerr_horizon, metric.ts:13-15
+    R a_star = rclamp<R>(a / M, R(-0.9999), R(0.9999));                           // kerr_photon_sphere, metric.ts:32-37
+    const R rph = R(2.0) * M * (R(1.0) + cos(R(2.0 / 3.0) * acos(rclamp<R>(-a_star, R(-1.0), R(1.0)))));
+    const R r_in = metric.isco(true), r_out = R(rp.disk_r_out);
+    const R MIN_STEP(0.01), MAX_STEP(1.2), max_dist = R(rp.opts.escape_radius);   // common.ts:41-43
+    V3<R> ro, rd;
+    camera_dir<R>(cam, rp, px, py, ro, rd);
+    R ron = sqrt(dot3(ro, ro));
+    if (ron < rh * R(1.5)) { R k = rh * R(1.5) / ron; ro = {ro.x * k, ro.y * k, ro.z * k}; }   // fragment.glsl.ts:94-97
+    V3<R> p = ro, v = rd;
+    R col[3] = {R(0.0), R(0.0), R(0.0)}, alpha(0.0);
+    uint32_t term = TERM_MAXSTEPS, steps = 0, crossings = 0, photon = 0;
+    R prevY = p.y;
+    V3<R> c0 = cross3(ro, rd);
+    bool hit = sqrt(dot3(c0, c0)) < rh * R(0.9);                                  // fragment.glsl.ts:124-126
+    const uint64_t max_steps = rp.opts.max_steps < 500 ? rp.opts.max_steps : 500;  // :115
+    for (uint64_t i = 0; i < max_steps; i++) {
+        V3<R> p_prev = p;
+        R r = sqrt(dot3(p, p));
+        if (r < rh * R(1.15)) { hit = true; term = TERM_HORIZON; break; }          // :135-138 (horizonThreshold 1.15)
+        if (r > max_dist) { term = TERM_ESCAPE; break; }
+        R distFactor = R(1.0) + r * R(0.05);
+        R dt = rclamp<R>((r - rh) * R(0.1) * distFactor, MIN_STEP, MAX_STEP * distFactor);
+        if (r > R(30.0)) {
+            R farBoost = (r - R(30.0)) * R(0.08);
+            dt = rmax<R>(dt, MIN_STEP + farBoost);
+            dt = rmin<R>(dt, MAX_STEP * R(2.5));
+        }
+        R sphereProx = fabs(r - rph);
+        dt = rmin<R>(dt, MIN_STEP + sphereProx * R(0.15));
+        R hRef = glsl_smoothstep<R>(R(0.2), R(0.0), fabs(p.y));
+        R cdt = dt * (R(1.0) - hRef * R(0.7));
+        V3<R> acc; R omega;
+        glsl_kerr_accel<R>(p, v, M, a, acc, omega);
+        {   // v.xz *= rot(omega * cdt), rot(t) = mat2(c, -s, s, c)  (common.ts:46-49)
+            R ang = omega * cdt, sn = sin(ang), cs = cos(ang);
+            R nx = v.x * cs - v.z * sn, nz = v.x * sn + v.z * cs;
+            v.x = nx; v.z = nz;
+        }
+        p = {p.x + v.x * cdt + R(0.5) * acc.x * cdt * cdt, p.y + v.y * cdt + R(0.5) * acc.y * cdt * cdt,
+             p.z + v.z * cdt + R(0.5) * acc.z * cdt * cdt};
+        R r_new = sqrt(dot3(p, p));
+        if (alpha < R(0.95)) {
+            V3<R> acc2; R om2;
+            glsl_kerr_accel<R>(p, v, M, a, acc2, om2);
+            v = {v.x + R(0.5) * (acc.x + acc2.x) * cdt, v.y + R(0.5) * (acc.y + acc2.y) * cdt,
+                 v.z + R(0.5) * (acc.z + acc2.z) * cdt};
+        }
+        R vn = sqrt(dot3(v, v));
+        v = {v.x / vn, v.y / vn, v.z / vn};
+        if (prevY * p.y < R(0.0) && r_new < rph * R(2.0) && r_new > rh) photon = photon + 1 < 3 ? photon + 1 : 3;
+        prevY = p.y;
+        steps++;
+        if (p_prev.y * p.y < R(0.0)) {                                            // chunks/disk.ts:22-30
+            R t = fabs(p_prev.y) / rmax<R>(R(0.0001), fabs(p_prev.y) + fabs(p.y));
+            V3<R> sp = {p_prev.x + (p.x - p_prev.x) * t, p_prev.y + (p.y - p_prev.y) * t, p_prev.z + (p.z - p_prev.z) * t};
+            R r_c = sqrt(dot3(sp, sp));
+            if (r_c > r_in && r_c < r_out) {
+                crossings++;
+                R lambda = p.z * v.x - p.x * v.z;                                  // L_photon, chunks/disk.ts:92
+                R g = kerr_g_factor<R>(r_c, M, metric.spin, lambda);
+                R tn = sample_tdisk<R>(luts, r_c);
+                R rgb[3];
+                sample_spectrum<R>(luts, pow(tn, R(0.4)), (g - R(0.05)) / R(4.95), rgb);
+                R opacity = R(0.6) * tn * g;
+                R w = (R(1.0) - alpha) * opacity;
+                for (int c = 0; c < 3; c++) col[c] += rgb[c] * w;
+                alpha += opacity;
+            }
+        }
+        if (alpha > R(0.99)) { term = TERM_DISK; break; }
+    }
+    PixelResult out;
+    for (int c = 0; c < 3; c++) out.rgba[c] = to_double(col[c]);
+    out.rgba[3] = 1.0;
+    out.xp[0] = to_double(p.x); out.xp[1] = to_double(p.y); out.xp[2] = to_double(p.z);
+    out.xp[3] = to_double(v.x); out.xp[4] = to_double(v.y); out.xp[5] = to_double(v.z);
+    out.xp[6] = (double)photon; out.xp[7] = hit ? 1.0 : 0.0;
+    out.termination = term; out.steps = steps; out.max_drift = 0.0; out.crossings = crossings;
+    out.attempts = steps; out.rhs_evals = 2ull * steps;
     return out;
 }
 

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 BOYER_LINDQUIST, KERR_SCHILD = 0, 1
-METHOD_RKF45, METHOD_RK4, METHOD_SYMPLECTIC = 0, 1, 2
+METHOD_RKF45, METHOD_RK4, METHOD_SYMPLECTIC, METHOD_VERLET_GLSL = 0, 1, 2, 3
 TERM_NONE, TERM_HORIZON, TERM_ESCAPE, TERM_MAXSTEPS, TERM_DISK = 0, 1, 2, 3, 4
 
 

@@ -212,7 +212,10 @@ double orc_render(const float* cam88, const orc_render_params* p, uint32_t x0, u
             uint32_t px = x0 + i * xs, py = y0 + (uint32_t)j * ys;
             // precision 2 = x87 80-bit long double: used only to measure how sensitive a pixel of the f64
             // algorithm is to rounding (tests' "oracle-unstable" mask), never as the reference value
-            PixelResult r = (p->precision == 1)   ? render_pixel<float>(cam, rp, l, px, py)
+            PixelResult r = (rp.opts.method == METHOD_VERLET_GLSL)
+                                ? ((p->precision == 1) ? render_pixel_verlet<float>(cam, rp, l, px, py)
+                                                       : render_pixel_verlet<double>(cam, rp, l, px, py))
+                            : (p->precision == 1)   ? render_pixel<float>(cam, rp, l, px, py)
                             : (p->precision == 2) ? render_pixel<long double>(cam, rp, l, px, py)
                                                   : render_pixel<double>(cam, rp, l, px, py);
             size_t k = (size_t)j * nx + i;

@@ -238,3 +238,31 @@ def test_full_size_rkf45_strided_sample(renderer, oracle, luts):
     assert (e > TOL).sum() <= max(1, 2e-3 * e.size)
     again = np.array(renderer.render(cam, phys))
     assert np.array_equal(frame, again)
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_glsl_verlet_path(renderer, oracle, luts, precision):
+    """the production WebGL2 shader's Cartesian Velocity-Verlet march (fragment.glsl.ts:129-221 on the
+    acceleration field of chunks/metric.ts:96-149), deterministic subset, against its own oracle. f64: 1e-6 RGBA
+    parity like the Hamiltonian path; f32 (what the shader runs in): agreement of the bulk, as for config 2."""
+    from gravitas_b200 import _lib
+    W, H = 160, 90
+    cam, phys, rp, keep = setup(renderer, oracle, luts, W, H, method=_lib.METHOD_VERLET_GLSL, max_steps=500,
+                                precision=precision, escape_radius=100.0)
+    rp.opts.step_rule = 0
+    ref = oracle.render(cam, rp)
+    got = renderer.trace_states(cam, phys)
+    frame = np.array(renderer.render(cam, phys))
+    assert np.array_equal(frame, got["rgba"].astype(np.float32))
+    e = rel_err(got["rgba"], ref["rgba"]).max(-1)
+    same = (got["term"] == ref["term"]) & (got["steps"] == ref["steps"])
+    print(f"GLSL Verlet precision {precision}: term/steps agree {same.mean():.4f}, rgba err median {np.median(e):.2e} "
+          f"p99 {np.percentile(e, 99):.2e} max {e.max():.2e}; horizon {int((ref['term'] == 1).sum())} disk {int((ref['term'] == 4).sum())}")
+    assert (ref["term"] == 1).sum() > 100 and (ref["rgba"][..., :3].sum(-1) > 0).sum() > 1000
+    if precision == 0:
+        assert same.mean() > 0.999 and (e > TOL).sum() <= max(1, 2e-3 * e.size)
+        ex = np.abs(got["xp"][..., :6] - ref["xp"][..., :6])[same] / np.maximum(np.abs(ref["xp"][..., :6][same]), 1.0)
+        assert np.percentile(ex, 99) < 1e-9
+        assert np.array_equal(got["xp"][..., 6][same], ref["xp"][..., 6][same])       # photon-ring crossing counter
+    else:
+        assert same.mean() > 0.97 and np.percentile(e, 90) < 5e-2
