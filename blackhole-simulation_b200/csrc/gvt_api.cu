@@ -46,6 +46,16 @@ extern "C" int32_t gvt_device_count(int32_t* out) {
     return GVT_OK;
 }
 
+namespace {
+// scoped device allocation for the one-shot helpers (no leak on an early error return)
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes); }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+}  // namespace
+
 // --------------------------------------------------------------------------------------------------
 // NCCL through dlopen (so a single-GPU host needs no libnccl at all)
 // --------------------------------------------------------------------------------------------------
@@ -354,12 +364,15 @@ extern "C" int32_t gvt_render_create(const GvtDeviceConfig* cfg, gvt_renderer** 
     CK(cudaSetDevice(cfg->device));
     gvt_renderer* r = new (std::nothrow) gvt_renderer();
     if (!r) return fail(GVT_ERR_INVALID, "out of memory");
+    struct Guard {   // a failing step below must not leak the half-built renderer
+        gvt_renderer* r;
+        ~Guard() { if (r) { const std::string keep = g_err; gvt_render_destroy(r); g_err = keep; } }
+    } guard{r};
     r->device = cfg->device; r->rank = cfg->rank; r->world = cfg->world_size;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, cfg->device));
     r->sm_count = prop.multiProcessorCount;
     if (prop.major < 10) {
-        delete r;
         return fail(GVT_ERR_UNSUPPORTED, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
     }
     CK(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
@@ -376,6 +389,7 @@ extern "C" int32_t gvt_render_create(const GvtDeviceConfig* cfg, gvt_renderer** 
         int rc = g_nccl.CommInitRank(&r->comm, r->world, id, r->rank);
         if (rc != 0) return fail(GVT_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(rc));
     }
+    guard.r = nullptr;
     *out = r;
     return GVT_OK;
 }
@@ -482,6 +496,8 @@ static double halton(uint32_t index, uint32_t base) {
 // Fill the TMA-staged block and the kernel parameters from the reference-layout uniforms.
 static int32_t build_frame(gvt_renderer* r, const GvtCamera* cam, const GvtPhysicsParams* phys, const GvtRenderParams* rp,
                            FrameParams& P) {
+    if (rp->struct_size < offsetof(GvtRenderParams, disk_r_out) + sizeof(double))
+        return fail(GVT_ERR_INVALID, "GvtRenderParams.struct_size = %u: fill the struct with gvt_render_params_default first", rp->struct_size);
     if (!r->luts_ready) return fail(GVT_ERR_INVALID, "LUTs not initialised: call gvt_render_init_luts / gvt_render_set_luts first");
     if (rp->coords != GVT_COORDS_KERR_SCHILD)
         return fail(GVT_ERR_UNSUPPORTED, "the render path traces in Kerr-Schild coordinates (lib.rs:64,454); use gvt_engine_integrate_rays for Boyer-Lindquist");
@@ -736,8 +752,9 @@ extern "C" int32_t gvt_taa_resolve(gvt_renderer* r, const GvtCamera* cam, uint32
     if (!r || !cam || !cur || !hist || !out || width == 0 || height == 0) return fail(GVT_ERR_INVALID, "bad argument");
     CK(cudaSetDevice(r->device));
     const size_t bytes = (size_t)width * height * sizeof(float4);
-    float4 *d_cur = nullptr, *d_hist = nullptr, *d_out = nullptr;
-    CK(cudaMalloc(&d_cur, bytes)); CK(cudaMalloc(&d_hist, bytes)); CK(cudaMalloc(&d_out, bytes));
+    DevBuf b_cur, b_hist, b_out;
+    CK(b_cur.alloc(bytes)); CK(b_hist.alloc(bytes)); CK(b_out.alloc(bytes));
+    float4 *d_cur = b_cur.as<float4>(), *d_hist = b_hist.as<float4>(), *d_out = b_out.as<float4>();
     CK(cudaMemcpyAsync(d_cur, cur, bytes, cudaMemcpyHostToDevice, r->stream));
     CK(cudaMemcpyAsync(d_hist, hist, bytes, cudaMemcpyHostToDevice, r->stream));
     TaaParams T;
@@ -746,7 +763,6 @@ extern "C" int32_t gvt_taa_resolve(gvt_renderer* r, const GvtCamera* cam, uint32
     CK(launch_taa(T, r->stream));
     CK(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, r->stream));
     CK(cudaStreamSynchronize(r->stream));
-    cudaFree(d_cur); cudaFree(d_hist); cudaFree(d_out);
     return GVT_OK;
 }
 
@@ -755,8 +771,9 @@ extern "C" int32_t gvt_taa_resolve_webgl(gvt_renderer* r, uint32_t width, uint32
     if (!r || !cur || !hist || !out || width == 0 || height == 0) return fail(GVT_ERR_INVALID, "bad argument");
     CK(cudaSetDevice(r->device));
     const size_t bytes = (size_t)width * height * sizeof(float4);
-    float4 *d_cur = nullptr, *d_hist = nullptr, *d_out = nullptr;
-    CK(cudaMalloc(&d_cur, bytes)); CK(cudaMalloc(&d_hist, bytes)); CK(cudaMalloc(&d_out, bytes));
+    DevBuf b_cur, b_hist, b_out;
+    CK(b_cur.alloc(bytes)); CK(b_hist.alloc(bytes)); CK(b_out.alloc(bytes));
+    float4 *d_cur = b_cur.as<float4>(), *d_hist = b_hist.as<float4>(), *d_out = b_out.as<float4>();
     CK(cudaMemcpyAsync(d_cur, cur, bytes, cudaMemcpyHostToDevice, r->stream));
     CK(cudaMemcpyAsync(d_hist, hist, bytes, cudaMemcpyHostToDevice, r->stream));
     TaaParams T;
@@ -767,7 +784,6 @@ extern "C" int32_t gvt_taa_resolve_webgl(gvt_renderer* r, uint32_t width, uint32
     CK(launch_taa(T, r->stream));
     CK(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, r->stream));
     CK(cudaStreamSynchronize(r->stream));
-    cudaFree(d_cur); cudaFree(d_hist); cudaFree(d_out);
     return GVT_OK;
 }
 
