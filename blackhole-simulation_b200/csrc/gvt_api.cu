@@ -501,7 +501,8 @@ static int32_t build_frame(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
     if (!r->luts_ready) return fail(GVT_ERR_INVALID, "LUTs not initialised: call gvt_render_init_luts / gvt_render_set_luts first");
     if (rp->coords != GVT_COORDS_KERR_SCHILD)
         return fail(GVT_ERR_UNSUPPORTED, "the render path traces in Kerr-Schild coordinates (lib.rs:64,454); use gvt_engine_integrate_rays for Boyer-Lindquist");
-    if (rp->method > GVT_METHOD_VERLET_GLSL || rp->precision > GVT_PRECISION_F32) return fail(GVT_ERR_INVALID, "bad method/precision");
+    if (rp->method > GVT_METHOD_VERLET_GLSL || rp->precision > GVT_PRECISION_F32 || rp->output_format > GVT_FORMAT_RGBA8_ACES)
+        return fail(GVT_ERR_INVALID, "bad method/precision/output_format");
     if (rp->renormalize_interval == 0) return fail(GVT_ERR_INVALID, "renormalize_interval must be > 0");
     const uint32_t W = (uint32_t)phys->resolution[0], H = (uint32_t)phys->resolution[1];
     if (W == 0 || H == 0) return fail(GVT_ERR_INVALID, "zero resolution");
@@ -549,14 +550,25 @@ static void fill_taa(const GvtCamera* cam, uint32_t W, uint32_t H, TaaParams& T)
     T.mode = 0; T.blend = 0.75f; T.moving = 0;
 }
 
+static size_t format_bytes(uint32_t f) { return f == GVT_FORMAT_RGBA32F ? 16 : (f == GVT_FORMAT_RGBA16F ? 8 : 4); }
+// converts pixels [px0, px0 + npx) of the finished frame into the staging buffer in `format` (not RGBA32F)
+static int32_t convert_frame(gvt_renderer* r, uint32_t format, size_t px0, size_t npx) {
+    const size_t n_px = (size_t)r->width * r->height;
+    if (!r->half_frame) CK(cudaMalloc(&r->half_frame, n_px * 8));
+    char* dst = static_cast<char*>(r->half_frame) + px0 * format_bytes(format);
+    if (format == GVT_FORMAT_RGBA16F) CK(launch_f32_to_f16(r->frame + px0, dst, npx, r->stream));
+    else CK(launch_tonemap_rgba8(r->frame + px0, dst, npx, format == GVT_FORMAT_RGBA8_ACES ? 1 : 0, r->stream));
+    return GVT_OK;
+}
+
 extern "C" int32_t gvt_render_read_frame(gvt_renderer* r, uint32_t format, void* host_rgba) {
-    if (!r || !host_rgba || !r->frame) return fail(GVT_ERR_INVALID, "bad argument / no frame");
+    if (!r || !host_rgba || !r->frame || format > GVT_FORMAT_RGBA8_ACES) return fail(GVT_ERR_INVALID, "bad argument / no frame");
     CK(cudaSetDevice(r->device));
     const size_t n_px = (size_t)r->width * r->height;
-    if (format == GVT_FORMAT_RGBA16F) {
-        if (!r->half_frame) CK(cudaMalloc(&r->half_frame, n_px * 8));
-        CK(launch_f32_to_f16(r->frame, r->half_frame, n_px, r->stream));
-        CK(cudaMemcpyAsync(host_rgba, r->half_frame, n_px * 8, cudaMemcpyDeviceToHost, r->stream));
+    if (format != GVT_FORMAT_RGBA32F) {
+        int32_t rc = convert_frame(r, format, 0, n_px);
+        if (rc != GVT_OK) return rc;
+        CK(cudaMemcpyAsync(host_rgba, r->half_frame, n_px * format_bytes(format), cudaMemcpyDeviceToHost, r->stream));
     } else {
         CK(cudaMemcpyAsync(host_rgba, r->frame, n_px * sizeof(float4), cudaMemcpyDeviceToHost, r->stream));
     }
@@ -665,15 +677,16 @@ extern "C" int32_t gvt_render_frame(gvt_renderer* r, const GvtCamera* cam, const
         const size_t n_px = (size_t)W * H;
         // which pixels go back: the whole frame, or only this rank's row block at its place in the host frame
         const size_t px0 = own ? (size_t)row0 * W : 0, npx = own ? (size_t)(row1 - row0) * W : n_px;
-        if (rp->output_format == GVT_FORMAT_RGBA16F) {
-            if (!r->half_frame) CK(cudaMalloc(&r->half_frame, n_px * 8));
+        if (rp->output_format != GVT_FORMAT_RGBA32F) {
+            const size_t bpp = format_bytes(rp->output_format);
             if (npx) {
-                CK(launch_f32_to_f16(r->frame + px0, static_cast<char*>(r->half_frame) + px0 * 8, npx, r->stream));
+                int32_t crc = convert_frame(r, rp->output_format, px0, npx);
+                if (crc != GVT_OK) return crc;
                 launches++;
-                CK(cudaMemcpyAsync(static_cast<char*>(host_rgba) + px0 * 8, static_cast<char*>(r->half_frame) + px0 * 8,
-                                   npx * 8, cudaMemcpyDeviceToHost, r->stream));
+                CK(cudaMemcpyAsync(static_cast<char*>(host_rgba) + px0 * bpp, static_cast<char*>(r->half_frame) + px0 * bpp,
+                                   npx * bpp, cudaMemcpyDeviceToHost, r->stream));
             }
-            d2h += npx * 8;
+            d2h += npx * bpp;
         } else {
             if (npx)
                 CK(cudaMemcpyAsync(static_cast<char*>(host_rgba) + px0 * sizeof(float4), r->frame + px0, npx * sizeof(float4),

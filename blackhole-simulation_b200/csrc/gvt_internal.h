@@ -80,6 +80,7 @@ cudaError_t launch_trace(const FrameParams& p, int method, int precision, bool b
 cudaError_t launch_integrate_rays(const RayBatchParams& p, cudaStream_t stream);
 cudaError_t launch_taa(const TaaParams& p, cudaStream_t stream);
 cudaError_t launch_f32_to_f16(const float4* src, void* dst, size_t n_px, cudaStream_t stream);
+cudaError_t launch_tonemap_rgba8(const float4* src, void* dst, size_t n_px, int aces, cudaStream_t stream);
 cudaError_t launch_fma_peak(int precision, int sm_count, unsigned long long iters, float* sink, cudaStream_t stream,
                             double* flops_out);
 

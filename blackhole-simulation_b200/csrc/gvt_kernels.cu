@@ -646,6 +646,26 @@ cudaError_t launch_f32_to_f16(const float4* src, void* dst, size_t n_px, cudaStr
     return cudaGetLastError();
 }
 
+// Display-ready 8-bit output: Reinhard (webgpu/renderer.ts:45-47) or ACES + gamma (bloom.glsl.ts:106-124, no bloom).
+__device__ __forceinline__ float aces_gamma(float c) {
+    const float t = fminf(fmaxf((c * (2.51f * c + 0.03f)) / (c * (2.43f * c + 0.59f) + 0.14f), 0.0f), 1.0f);
+    return powf(t, 0.4545f);
+}
+__device__ __forceinline__ uint32_t unorm8(float v) { return (uint32_t)__float2int_rn(fminf(fmaxf(v, 0.0f), 1.0f) * 255.0f); }
+__global__ void k_tonemap_rgba8(const float4* __restrict__ src, uint32_t* __restrict__ dst, size_t n, int aces) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = src[i];
+        float r, g, b;
+        if (aces) { r = aces_gamma(v.x); g = aces_gamma(v.y); b = aces_gamma(v.z); }
+        else { r = v.x / (v.x + 1.0f); g = v.y / (v.y + 1.0f); b = v.z / (v.z + 1.0f); }
+        dst[i] = unorm8(r) | (unorm8(g) << 8) | (unorm8(b) << 16) | (unorm8(v.w) << 24);
+    }
+}
+cudaError_t launch_tonemap_rgba8(const float4* src, void* dst, size_t n_px, int aces, cudaStream_t stream) {
+    k_tonemap_rgba8<<<148 * 8, 256, 0, stream>>>(src, reinterpret_cast<uint32_t*>(dst), n_px, aces);
+    return cudaGetLastError();
+}
+
 // --------------------------------------------------------------------------------------------------
 // FMA-pipe peak micro-benchmark: 8 independent dependent chains per thread.
 // --------------------------------------------------------------------------------------------------

@@ -181,7 +181,7 @@ class KerrRenderer:
             raise err
 
     def pinned_frame(self, width, height, fmt=_lib.FORMAT_RGBA32F):
-        nbytes = width * height * (16 if fmt == _lib.FORMAT_RGBA32F else 8)
+        nbytes = width * height * _lib.FORMAT_BYTES[fmt]
         if self._pinned is None or self._pinned.nbytes != nbytes:
             self._pinned = PinnedBuffer(nbytes)
         return self._pinned
@@ -203,12 +203,10 @@ class KerrRenderer:
         self.last_stats = _stats(st)
         if not readback:
             return None
-        dt = np.float32 if self.params.c.output_format == _lib.FORMAT_RGBA32F else np.float16
-        return buf.array(dt, (H, W, 4))
+        return buf.array(np.dtype(_lib.FORMAT_DTYPE[self.params.c.output_format]), (H, W, 4))
 
     def read_frame(self, fmt=_lib.FORMAT_RGBA32F):
-        dt = np.float32 if fmt == _lib.FORMAT_RGBA32F else np.float16
-        out = np.zeros((self.height, self.width, 4), dt)
+        out = np.zeros((self.height, self.width, 4), np.dtype(_lib.FORMAT_DTYPE[fmt]))
         check(lib().gvt_render_read_frame(self._h, fmt, out.ctypes.data_as(C.c_void_p)))
         return out
 

@@ -53,7 +53,13 @@ enum { GVT_METHOD_RKF45 = 0, GVT_METHOD_RK4 = 1, GVT_METHOD_SYMPLECTIC = 2,
           plays MAX_DIST. Thin-disk light comes from the same LUT composite as the Hamiltonian path. */
        GVT_METHOD_VERLET_GLSL = 3 };
 enum { GVT_PRECISION_F64 = 0, GVT_PRECISION_F32 = 1 };
-enum { GVT_FORMAT_RGBA32F = 0, GVT_FORMAT_RGBA16F = 1 }; /* RGBA16F = reprojection.ts:120-140 texture format */
+enum {
+    GVT_FORMAT_RGBA32F = 0,
+    GVT_FORMAT_RGBA16F = 1,        /* reprojection.ts:120-140 / webgpu/renderer.ts:161-180 texture format (linear HDR) */
+    GVT_FORMAT_RGBA8_REINHARD = 2, /* display-ready: the WebGPU blit's Reinhard map c/(1+c) (webgpu/renderer.ts:45-47), 8-bit unorm */
+    GVT_FORMAT_RGBA8_ACES = 3      /* display-ready: the WebGL final pass without bloom (bloom.glsl.ts:106-124): ACES
+                                      (Narkowicz) then pow(., 0.4545), 8-bit unorm */
+};
 /* step rule for the fixed-step methods: constant `initial_step` (geodesic/mod.rs:218-223) or the per-step rule
  * h = clamp(0.15 (r - r+), 0.05, 1.0) of src/shaders/compute.wgsl.ts:213 */
 enum { GVT_STEP_CONSTANT = 0, GVT_STEP_WGSL = 1 };

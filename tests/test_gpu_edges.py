@@ -134,3 +134,25 @@ def test_default_integration_options_ray(built, oracle):
             got = e.integrate_ray_relativistic(ray, 10000, 1e-8, ks)
             ref = oracle.integrate(1, 0.9, 1 if ks else 0, oracle.Options.default(), ray)["xp"][0]
             np.testing.assert_allclose(got, ref, rtol=1e-7, atol=1e-10)
+
+
+def test_display_ready_rgba8_outputs(renderer):
+    """GVT_FORMAT_RGBA8_REINHARD = the WebGPU blit (webgpu/renderer.ts:45-47); GVT_FORMAT_RGBA8_ACES = the WebGL final pass
+    without bloom (bloom.glsl.ts:106-124). Checked against numpy on the same HDR frame (<= 1 code value: powf/rounding)."""
+    from gravitas_b200 import _lib
+    cam, phys = _setup(renderer, 128, 72, max_steps=160)
+    hdr = np.array(renderer.render(cam, phys)).astype(np.float32)
+    for fmt in (_lib.FORMAT_RGBA8_REINHARD, _lib.FORMAT_RGBA8_ACES):
+        renderer.params.c.output_format = fmt
+        got = np.array(renderer.render(cam, phys))
+        assert got.dtype == np.uint8 and got.shape == (72, 128, 4) and np.all(got[..., 3] == 255)
+        assert np.array_equal(renderer.read_frame(fmt), got)
+        c = hdr[..., :3].astype(np.float64)
+        if fmt == _lib.FORMAT_RGBA8_REINHARD:
+            ref = c / (c + 1.0)
+        else:
+            ref = np.clip((c * (2.51 * c + 0.03)) / (c * (2.43 * c + 0.59) + 0.14), 0.0, 1.0) ** 0.4545
+        ref8 = np.rint(np.clip(ref, 0, 1) * 255.0)
+        assert np.abs(got[..., :3].astype(np.float64) - ref8).max() <= 1
+        assert got[..., :3].max() > 0
+    renderer.params.c.output_format = _lib.FORMAT_RGBA32F
