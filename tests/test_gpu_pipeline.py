@@ -1,0 +1,57 @@
+"""Both seams together, the way the reference app drives them: the worker ticks the PhysicsEngine and publishes the
+SAB (workers/physics.worker.ts:111-176), the main thread reads the CAMERA / PHYSICS blocks through the seqlock
+(engine/physics-bridge.ts:148-188), builds CameraUniforms (components/canvas/WebGPUCanvas.tsx:119-178) and calls
+renderer.render(camera, physics) (rendering/webgpu/renderer.ts:280)."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_engine_tick_to_rendered_frames(built, renderer, oracle):
+    from gravitas_b200 import camera, renderer as R, _lib
+    W, H, steps = 128, 72, 96
+    spin = 0.9
+    eng = built.PhysicsEngine(1.0, spin)
+    sab = np.zeros(2 * 1024 * 1024 // 4, np.float32)           # SharedArrayBuffer(2 MiB) viewed as f32 (physics-bridge.ts:60)
+    eng.attach_sab(sab)
+    eng.set_camera_state(0.0, -3.7, 29.8)                      # position only (lib.rs:120-122)
+    eng.set_auto_spin(True)
+    renderer.init_pipelines(mass=1.0, spin=float(np.float32(spin)), spec_w=64, spec_h=16, max_temp=1e7)
+    renderer.resize(W, H)
+    renderer.reset_history()
+    renderer.params = R.RenderParams(max_steps=steps, flags=_lib.FLAG_TAA | _lib.FLAG_JITTER)
+    prev_vp, frames, seq_prev = None, [], float(sab[built.OFFSETS["TELEMETRY"]])
+    for k in range(4):
+        sab[built.OFFSETS["CONTROL"] + 1] = 0.3                # mouse_dx written by the main thread (physics-bridge.ts:153)
+        sab[built.OFFSETS["CONTROL"] + 4] = 0.016
+        eng.tick_sab(0.0)                                      # dt from CONTROL[4]
+        cam_blk = sab[built.OFFSETS["CAMERA"]:built.OFFSETS["CAMERA"] + 16]
+        phys_blk = sab[built.OFFSETS["PHYSICS"]:built.OFFSETS["PHYSICS"] + 16]
+        assert np.all(np.isfinite(cam_blk)) and sab[built.OFFSETS["CONTROL"] + 1] == 0.0    # input consumed
+        assert phys_blk[0] == np.float32(eng.compute_horizon()) and phys_blk[3] == np.float32(spin)
+        eye = tuple(float(v) for v in cam_blk[0:3])
+        cam, vp = camera.camera_uniforms(eye, W, H, prev_view_proj=prev_vp)
+        phys = R.pack_physics(float(phys_blk[2]), float(phys_blk[3]), W, H, frame_index=k)
+        frame = np.array(renderer.render(cam, phys))
+        assert frame.shape == (H, W, 4) and np.isfinite(frame).all() and (frame[..., :3].sum() > 0)
+        frames.append((eye, frame))
+        prev_vp = vp
+    # the camera orbits (yaw from mouse_dx + auto-spin) at constant radius, and TAA accumulates: frames differ and brighten
+    r = [math.sqrt(sum(c * c for c in e)) for e, _ in frames]
+    assert max(r) - min(r) < 1e-3 and frames[0][0] != frames[-1][0]
+    assert frames[1][1][..., :3].sum() > frames[0][1][..., :3].sum()      # history was zero on the first frame (0.92 blend)
+    # the un-resolved render of the last camera matches the oracle pixel for pixel
+    renderer.params = R.RenderParams(max_steps=steps)
+    cam, _ = camera.camera_uniforms(frames[-1][0], W, H)
+    phys = R.pack_physics(1.0, spin, W, H)
+    got = np.array(renderer.render(cam, phys))
+    s32 = float(np.float32(spin))
+    spec, td = oracle.spectrum_lut(64, 16, 1e7), oracle.disk_lut(1.0, s32)
+    opts = oracle.Options.default(method=2, step_rule=1, max_steps=steps)
+    rp, keep = oracle.make_render_params(W, H, 1.0, s32, opts, spectrum=spec, spec_w=64, spec_h=16, tdisk=td)
+    ref = oracle.render(cam, rp, want=("rgba",))
+    peak = float(ref["rgba"][..., :3].max())
+    assert (np.abs(got - ref["rgba"]) <= 1e-6 * np.maximum(np.abs(ref["rgba"]), 1e-3 * peak) + 1e-30).all()
