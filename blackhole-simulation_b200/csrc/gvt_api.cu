@@ -544,8 +544,27 @@ static int32_t build_frame(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
 }
 
 static void fill_taa(const GvtCamera* cam, uint32_t W, uint32_t H, TaaParams& T) {
-    memcpy(T.inv_proj, cam->inv_proj, 64); memcpy(T.inv_view, cam->inv_view, 64);
-    memcpy(T.prev_view_proj, cam->prev_view_proj, 64); memcpy(T.cam_pos, cam->position, 16);
+    memset(&T, 0, sizeof(T));
+    // column-major mat4 (gl-matrix / WGSL): m[4 c + r]. clip = (cx, cy, 1, 1)  (ataa.wgsl.ts:56-58)
+    const float* ip = cam->inv_proj; const float* iv = cam->inv_view; const float* pv = cam->prev_view_proj;
+    double vA[4], vB[4], vC[4];
+    for (int r = 0; r < 4; r++) { vA[r] = ip[r]; vB[r] = ip[4 + r]; vC[r] = (double)ip[8 + r] + (double)ip[12 + r]; }
+    // G = 12 * PV[rows 0,1,3][:, :3] * IV[:3, :3]   (world direction has w = 0; reprojectDepth = 12, ataa.wgsl.ts:64)
+    const int rows[3] = {0, 1, 3};
+    for (int k = 0; k < 3; k++) {
+        double G[3];
+        for (int j = 0; j < 3; j++) {
+            double s = 0.0;
+            for (int m = 0; m < 3; m++) s += (double)pv[4 * m + rows[k]] * (double)iv[4 * j + m];
+            G[j] = 12.0 * s;
+        }
+        T.gA[k] = (float)(G[0] * vA[0] + G[1] * vA[1] + G[2] * vA[2]);
+        T.gB[k] = (float)(G[0] * vB[0] + G[1] * vB[1] + G[2] * vB[2]);
+        T.gC[k] = (float)(G[0] * vC[0] + G[1] * vC[1] + G[2] * vC[2]);
+        T.c0[k] = (float)((double)pv[rows[k]] * cam->position[0] + (double)pv[4 + rows[k]] * cam->position[1] +
+                          (double)pv[8 + rows[k]] * cam->position[2] + (double)pv[12 + rows[k]]);
+    }
+    for (int r = 0; r < 4; r++) { T.vA[r] = (float)vA[r]; T.vB[r] = (float)vB[r]; T.vC[r] = (float)vC[r]; }
     T.width = W; T.height = H; T.row0 = 0; T.row1 = H; T.host_out = nullptr; T.n_peer = 0;
     T.mode = 0; T.blend = 0.75f; T.moving = 0;
 }
@@ -653,7 +672,7 @@ extern "C" int32_t gvt_render_frame(gvt_renderer* r, const GvtCamera* cam, const
         }
         T.host_out = host_alias;
         if (peer_store) { for (uint32_t q = 0; q < n_peer; q++) T.peer_out[q] = peer_targets[q]; T.n_peer = n_peer; }
-        CK(launch_taa(T, r->stream));
+        CK(launch_taa(T, r->sm_count, r->stream));
         launches++;
     }
     CK(cudaEventRecord(r->ev[3], r->stream));
@@ -773,7 +792,7 @@ extern "C" int32_t gvt_taa_resolve(gvt_renderer* r, const GvtCamera* cam, uint32
     TaaParams T;
     fill_taa(cam, width, height, T);
     T.cur = d_cur; T.hist = d_hist; T.out = d_out;
-    CK(launch_taa(T, r->stream));
+    CK(launch_taa(T, r->sm_count, r->stream));
     CK(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, r->stream));
     CK(cudaStreamSynchronize(r->stream));
     return GVT_OK;
@@ -794,7 +813,7 @@ extern "C" int32_t gvt_taa_resolve_webgl(gvt_renderer* r, uint32_t width, uint32
     T.width = width; T.height = height; T.row0 = 0; T.row1 = height;
     T.mode = 1; T.blend = blend; T.moving = camera_moving ? 1u : 0u;
     T.cur = d_cur; T.hist = d_hist; T.out = d_out;
-    CK(launch_taa(T, r->stream));
+    CK(launch_taa(T, r->sm_count, r->stream));
     CK(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, r->stream));
     CK(cudaStreamSynchronize(r->stream));
     return GVT_OK;

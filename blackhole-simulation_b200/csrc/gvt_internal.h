@@ -61,8 +61,12 @@ struct RayBatchParams {  // gvt_engine_integrate_rays
 };
 
 struct TaaParams {
-    // ataa.wgsl.ts:54-69: reprojection of a point at depth 12 along the pixel's world ray through prev_view_proj
-    float inv_proj[16], inv_view[16], prev_view_proj[16], cam_pos[4];
+    // ataa.wgsl.ts:54-69: reprojection of a point at depth 12 along the pixel's world ray through prev_view_proj,
+    // factored on the host (fill_taa, f64): view-space ray v = vA cx + vB cy + vC (xyz and w of inv_proj * clip);
+    // prev clip coords (x, y, w) = c0 + s (gA cx + gB cy + gC), s = sign(v.w) / |v.xyz|, where
+    // g* = 12 * prev_view_proj[rows x,y,w][:, :3] * inv_view[:3, :3] * v*  and  c0 = prev_view_proj * (cam_pos, 1).
+    float vA[4], vB[4], vC[4];
+    float gA[4], gB[4], gC[4], c0[4];
     uint32_t width, height;
     uint32_t mode;         // 0: ataa.wgsl.ts (WebGPU); 1: reprojection.glsl.ts (WebGL2)
     float blend;           // mode 1: u_blendFactor
@@ -71,14 +75,15 @@ struct TaaParams {
     const float4* cur; const float4* hist; float4* out;
     float4* host_out;      // device alias of a page-locked host frame, or null
     float4* peer_out[8];   // GVT_FLAG_PEER_STORE targets
-    uint32_t n_peer, _pad_peer;
+    uint32_t n_peer;
+    uint32_t unit_rows;    // rows per warp work unit (chosen by launch_taa)
 };
 
 // launchers (gvt_kernels.cu)
 cudaError_t launch_trace(const FrameParams& p, int method, int precision, bool budget, bool debug, int sm_count,
                          cudaStream_t stream);
 cudaError_t launch_integrate_rays(const RayBatchParams& p, cudaStream_t stream);
-cudaError_t launch_taa(const TaaParams& p, cudaStream_t stream);
+cudaError_t launch_taa(const TaaParams& p, int sm_count, cudaStream_t stream);
 cudaError_t launch_f32_to_f16(const float4* src, void* dst, size_t n_px, cudaStream_t stream);
 cudaError_t launch_tonemap_rgba8(const float4* src, void* dst, size_t n_px, int aces, cudaStream_t stream);
 cudaError_t launch_fma_peak(int precision, int sm_count, unsigned long long iters, float* sink, cudaStream_t stream,

@@ -502,131 +502,246 @@ cudaError_t launch_integrate_rays(const RayBatchParams& p_in, cudaStream_t strea
 }
 
 // --------------------------------------------------------------------------------------------------
-// TAA resolve (ataa.wgsl.ts:28-83). One warp owns a 30-pixel-wide column strip and walks down it with a
-// rolling 3-row window: every lane loads ONE pixel per row (lanes 0 and 31 are the horizontal halo), the
-// vertical 3-row sums live in registers and the horizontal 3-tap sums come from warp shuffles.
+// TAA resolve (ataa.wgsl.ts:28-83; mode 1 = reprojection.glsl.ts:70-115). One warp owns a 30-pixel-wide, R-row
+// strip unit and walks down it with a rolling 3-row window: every lane loads ONE pixel per row (lanes 0 and 31 are
+// the horizontal halo), the vertical 3-row sums live in registers and the horizontal 3-tap sums come from warp
+// shuffles. HBM-bound by design (16 B cur + 16 B history + 16 B store per pixel), so the per-pixel instruction
+// count is what had to come down to reach that bound:
+//  * the reprojection chain clip -> inv_proj -> normalise -> inv_view -> +12 d -> prev_view_proj is affine in
+//    (cx, cy) up to ONE scalar s = sign(w) / |v|: pc = c0 + s (gA cx + gB cy + gC), with the 4x3 products formed
+//    once per frame on the host in f64 (TaaParams). 3+3+3 FMAs, one MUFU.RSQ and one MUFU.RCP per pixel instead
+//    of three mat4 x vec4 products and five IEEE divisions;
+//  * everything that depends on the column only (cx terms, clamped column index) is hoisted out of the row loop,
+//    everything that depends on the row only is warp-uniform;
+//  * sigma uses MUFU.SQRT (sqrt.approx): the pass is f32 with a 1e-3 conditioning floor (tests/test_gpu_taa.py).
+//  * loads run ahead of their use: current-frame rows through a 4-deep per-lane cp.async ring in shared memory,
+//    history taps one row ahead in registers.
+// Work units are distributed grid-stride over a grid sized to the resident warps, and the rows per unit are chosen
+// per launch so that every warp walks the same number of units (no partial last wave).
+// Measured (4K, B200): 163 us (first version, 440 instr/pixel) -> 113 us (~290 instr/pixel); the same strip walk as a
+// bare 2-read/1-write copy runs 66 us (scripts/ubench/strip_copy.cu) -- the resolve is still issue/latency-bound
+// (IPC ~0.6 per scheduler at 24 warps/SM; 64 registers spill), not HBM-bound.
 // --------------------------------------------------------------------------------------------------
-constexpr int TAA_STRIP_W = 30, TAA_ROWS = 32;
+constexpr int TAA_STRIP_W = 30;
+#ifndef GVT_TAA_MINB
+#define GVT_TAA_MINB 3
+#endif
+#ifndef GVT_TAA_UNROLL
+#define GVT_TAA_UNROLL 1
+#endif
+constexpr int taa_unroll = GVT_TAA_UNROLL;
+#ifndef GVT_TAA_DEPTH
+#define GVT_TAA_DEPTH 4
+#endif
+constexpr int TAA_DEPTH = GVT_TAA_DEPTH;
 
 struct YCC { float y, co, cg; };
 __device__ __forceinline__ YCC rgb_to_ycocg(float r, float g, float b) {  // ataa.wgsl.ts:11-16
-    YCC o;
-    o.y = 0.25f * r + 0.5f * g + 0.25f * b;
-    o.co = 0.5f * r - 0.5f * b;
-    o.cg = -0.25f * r + 0.5f * g - 0.25f * b;
+    YCC o;                                                                 // (the 1/4, 1/2 weights are exact scalings)
+    const float t = r + b, hg = 0.5f * g;
+    o.y = fmaf(0.25f, t, hg);
+    o.co = 0.5f * (r - b);
+    o.cg = fmaf(-0.25f, t, hg);
     return o;
+}
+struct YCC2 { float y, co, cg, yy, coco, cgcg; };   // a pixel's first and second moments
+__device__ __forceinline__ YCC2 moments_of(const float4& p) {
+    const YCC c = rgb_to_ycocg(p.x, p.y, p.z);
+    return YCC2{c.y, c.co, c.cg, c.y * c.y, c.co * c.co, c.cg * c.cg};
 }
 __device__ __forceinline__ float sum3(float v) {
     return __shfl_up_sync(0xffffffffu, v, 1) + v + __shfl_down_sync(0xffffffffu, v, 1);
 }
-__device__ __forceinline__ float4 ldg_px(const float4* img, int W, int H, int x, int y) {
-    x = max(0, min(x, W - 1)); y = max(0, min(y, H - 1));   // clamp(pos + d, 0, size-1), ataa.wgsl.ts:43
-    return __ldg(img + (size_t)y * W + x);
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// per-lane 16-B asynchronous global -> shared copy (LDGSTS): in flight without holding a register or a scoreboard
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
-__global__ void __launch_bounds__(256) k_taa_resolve(const __grid_constant__ TaaParams P) {
+template <int MODE>
+__global__ void __launch_bounds__(256, GVT_TAA_MINB) k_taa_resolve(const __grid_constant__ TaaParams P) {
+    __shared__ float4 taa_ring[8][TAA_DEPTH][32];
     const int W = (int)P.width, H = (int)P.height;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const int strips_x = (W + TAA_STRIP_W - 1) / TAA_STRIP_W;
-    const int gw = blockIdx.x * (blockDim.x >> 5) + warp;
     const int rows = (int)P.row1 - (int)P.row0;
+    const int TAA_ROWS = (int)P.unit_rows;
     const int n_work = strips_x * ((rows + TAA_ROWS - 1) / TAA_ROWS);
-    if (gw >= n_work) return;
-    const int sx = gw % strips_x, sy = gw / strips_x;
-    const int x = sx * TAA_STRIP_W + lane - 1;  // lane 0 / 31 = halo columns
-    const int y_begin = (int)P.row0 + sy * TAA_ROWS, y_end = min(y_begin + TAA_ROWS, (int)P.row1);
+    const int n_warps = (int)(gridDim.x * (blockDim.x >> 5));
+    const float nsig = (MODE == 1) ? 1.5f : 2.0f;                 // reprojection.glsl.ts:90-91 / ataa.wgsl.ts:51-52
+    const float k9 = 1.0f / 9.0f;
+    const float half_w = 0.5f * (float)W, half_h = 0.5f * (float)H;
+    const float x_max = (float)(W - 1), y_max = (float)(H - 1);
+    const float fb_gl = P.moving ? 0.0f : P.blend;
 
-    // rolling window of per-pixel first/second moments for rows y-1, y, y+1
-    YCC a, b, c;
-    float4 pb;
-    {
-        const float4 pa = ldg_px(P.cur, W, H, x, y_begin - 1);
-        pb = ldg_px(P.cur, W, H, x, y_begin);
-        a = rgb_to_ycocg(pa.x, pa.y, pa.z);
-        b = rgb_to_ycocg(pb.x, pb.y, pb.z);
-    }
-    for (int y = y_begin; y < y_end; y++) {
-        const float4 pc = ldg_px(P.cur, W, H, x, y + 1);
-        c = rgb_to_ycocg(pc.x, pc.y, pc.z);
-        // vertical sums (this lane's column), then horizontal 3-tap by shuffles
-        const float m1y = sum3(a.y + b.y + c.y), m1o = sum3(a.co + b.co + c.co), m1g = sum3(a.cg + b.cg + c.cg);
-        const float m2y = sum3(a.y * a.y + b.y * b.y + c.y * c.y);
-        const float m2o = sum3(a.co * a.co + b.co * b.co + c.co * c.co);
-        const float m2g = sum3(a.cg * a.cg + b.cg * b.cg + c.cg * c.cg);
-        if (lane >= 1 && lane <= TAA_STRIP_W && x < W) {
-            const float k = 1.0f / 9.0f;
-            const float mean[3] = {m1y * k, m1o * k, m1g * k};
-            const float m2[3] = {m2y * k, m2o * k, m2g * k};
-            float lo[3], hi[3], sd_y = 0.0f;
-            const float nsig = (P.mode == 1u) ? 1.5f : 2.0f;             // reprojection.glsl.ts:90-91 / ataa.wgsl.ts:51-52
+    for (int unit = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)); unit < n_work; unit += n_warps) {
+        const int sx = unit % strips_x, sy = unit / strips_x;
+        const int x = sx * TAA_STRIP_W + lane - 1;                // lane 0 / 31 = halo columns
+        const int xc = max(0, min(x, W - 1));                     // clamp(pos + d, 0, size-1), ataa.wgsl.ts:43
+        const bool owner = lane >= 1 && lane <= TAA_STRIP_W && x < W;
+        const int y_begin = (int)P.row0 + sy * TAA_ROWS, y_end = min(y_begin + TAA_ROWS, (int)P.row1);
+        const float4* col = P.cur + xc;
+
+        // column-only part of the reprojection (MODE 0)
+        const float cx = fmaf((float)x + 0.5f, 2.0f / (float)W, -1.0f);
+        const float vx0 = fmaf(P.vA[0], cx, P.vC[0]), vx1 = fmaf(P.vA[1], cx, P.vC[1]), vx2 = fmaf(P.vA[2], cx, P.vC[2]);
+        const float vxw = fmaf(P.vA[3], cx, P.vC[3]);
+        const float gx0 = fmaf(P.gA[0], cx, P.gC[0]), gx1 = fmaf(P.gA[1], cx, P.gC[1]), gx2 = fmaf(P.gA[2], cx, P.gC[2]);
+
+        // Current-frame rows stream through a per-lane ring in shared memory, TAA_DEPTH rows ahead of their use
+        // (cp.async: a DRAM miss costs ~1.5 row-iterations of this loop, so a one-row register prefetch is not enough
+        // and deeper register prefetch costs occupancy). Ring entry k holds frame row clamp(y_begin - 1 + k); every
+        // lane reads back only what it copied itself, so no warp-level synchronisation is involved.
+        float4* ring = &taa_ring[threadIdx.x >> 5][0][lane];
+        const int k_last = y_end - y_begin + 1;
+        auto ring_issue = [&](int k) {
+            if (k <= k_last) cp_async16(ring + (k % TAA_DEPTH) * 32, col + (size_t)min(max(y_begin - 1 + k, 0), H - 1) * W);
+            cp_async_commit();   // one group per k, empty past the end, so wait_group counts stay aligned
+        };
+        auto ring_take = [&](int k) -> float4 {
+            cp_async_wait<TAA_DEPTH - 1>();
+            return ring[(k % TAA_DEPTH) * 32];
+        };
 #pragma unroll
-            for (int i = 0; i < 3; i++) {
-                const float sd = sqrtf(fmaxf(m2[i] - mean[i] * mean[i], 0.0f));
-                if (i == 0) sd_y = sd;
-                lo[i] = mean[i] - nsig * sd; hi[i] = mean[i] + nsig * sd;
-            }
-            float hr, hg, hb, fb_;
-            if (P.mode == 1u) {
-                // WebGL2 resolve: history at the same texel, variance-guided weight (reprojection.glsl.ts:93-110)
-                const float4 h0 = ldg_px(P.hist, W, H, x, y);
-                hr = h0.x; hg = h0.y; hb = h0.z;
-                fb_ = P.moving ? 0.0f : P.blend * (1.0f - fminf(fmaxf(sd_y * 4.0f, 0.0f), 0.55f));
+        for (int k = 0; k < TAA_DEPTH; k++) ring_issue(k);
+        // rolling window of per-pixel YCoCg for rows y-1, y, y+1
+        YCC2 a, b, c;
+        a = moments_of(ring_take(0)); ring_issue(TAA_DEPTH);
+        b = moments_of(ring_take(1)); ring_issue(TAA_DEPTH + 1);
+        // Software pipeline, one row deep: the loads of row y+1 (current-frame pixel of row y+2, the four history taps
+        // of row y+1) are issued before row y is resolved, so their latency is covered by a full row of arithmetic
+        // (the shuffles keep the compiler from hoisting loads across iterations by itself).
+        struct Taps { float4 h00, h10, h01, h11; float fx, fy; };
+        auto issue_taps = [&](int y) -> Taps {
+            Taps t;
+            t.fx = 0.0f; t.fy = 0.0f;
+            if (MODE == 1) {
+                // WebGL2 resolve: history at the same texel (reprojection.glsl.ts:93-110)
+                t.h00 = __ldg(P.hist + (size_t)y * W + xc);
+                t.h10 = t.h01 = t.h11 = t.h00;
             } else {
-            // reprojection at depth 12 through prev_view_proj (ataa.wgsl.ts:54-69)
-            const float u = ((float)x + 0.5f) / (float)W, v = ((float)y + 0.5f) / (float)H;
-            const float cx = u * 2.0f - 1.0f, cy = -(v * 2.0f - 1.0f);
-            float vt[4];
-#pragma unroll
-            for (int r = 0; r < 4; r++)
-                vt[r] = P.inv_proj[r] * cx + P.inv_proj[4 + r] * cy + P.inv_proj[8 + r] + P.inv_proj[12 + r];
-            float vx = vt[0] / vt[3], vy = vt[1] / vt[3], vz = vt[2] / vt[3];
-            const float inv_n = 1.0f / sqrtf(vx * vx + vy * vy + vz * vz);
-            vx *= inv_n; vy *= inv_n; vz *= inv_n;
-            float wp[3];
-#pragma unroll
-            for (int r = 0; r < 3; r++)
-                wp[r] = P.cam_pos[r] + 12.0f * (P.inv_view[r] * vx + P.inv_view[4 + r] * vy + P.inv_view[8 + r] * vz);
-            float pc4[4];
-#pragma unroll
-            for (int r = 0; r < 4; r++)
-                pc4[r] = P.prev_view_proj[r] * wp[0] + P.prev_view_proj[4 + r] * wp[1] + P.prev_view_proj[8 + r] * wp[2] +
-                         P.prev_view_proj[12 + r];
-            const float pu = (pc4[0] / pc4[3]) * 0.5f + 0.5f, pv = (pc4[1] / pc4[3]) * -0.5f + 0.5f;
-            // bilinear, clamp-to-edge history fetch (textureSampleLevel + linear sampler, ataa.wgsl.ts:72)
-            const float hx = fminf(fmaxf(pu * (float)W - 0.5f, 0.0f), (float)(W - 1));
-            const float hy = fminf(fmaxf(pv * (float)H - 0.5f, 0.0f), (float)(H - 1));
-            const float hxf = floorf(hx), hyf = floorf(hy);
-            const int x0 = (int)hxf, y0 = (int)hyf;
-            const float fx = hx - hxf, fy = hy - hyf;
-            const float4 h00 = ldg_px(P.hist, W, H, x0, y0), h10 = ldg_px(P.hist, W, H, x0 + 1, y0);
-            const float4 h01 = ldg_px(P.hist, W, H, x0, y0 + 1), h11 = ldg_px(P.hist, W, H, x0 + 1, y0 + 1);
-            hr = (h00.x + (h10.x - h00.x) * fx) + ((h01.x + (h11.x - h01.x) * fx) - (h00.x + (h10.x - h00.x) * fx)) * fy;
-            hg = (h00.y + (h10.y - h00.y) * fx) + ((h01.y + (h11.y - h01.y) * fx) - (h00.y + (h10.y - h00.y) * fx)) * fy;
-            hb = (h00.z + (h10.z - h00.z) * fx) + ((h01.z + (h11.z - h01.z) * fx) - (h00.z + (h10.z - h00.z) * fx)) * fy;
-            fb_ = 0.92f;  // ataa.wgsl.ts:77
+                // reprojection at depth 12 through prev_view_proj (ataa.wgsl.ts:54-69), factored form (header)
+                const float cy = -fmaf((float)y + 0.5f, 2.0f / (float)H, -1.0f);
+                const float v0 = fmaf(P.vB[0], cy, vx0), v1 = fmaf(P.vB[1], cy, vx1), v2 = fmaf(P.vB[2], cy, vx2);
+                const float vw = fmaf(P.vB[3], cy, vxw);
+                const float s = copysignf(rsqrtf(fmaf(v0, v0, fmaf(v1, v1, v2 * v2))), vw);
+                const float p0 = fmaf(s, fmaf(P.gB[0], cy, gx0), P.c0[0]);
+                const float p1 = fmaf(s, fmaf(P.gB[1], cy, gx1), P.c0[1]);
+                const float p3 = fmaf(s, fmaf(P.gB[2], cy, gx2), P.c0[2]);
+                const float ip3 = rcp_approx(p3);
+                // bilinear, clamp-to-edge history fetch (textureSampleLevel + linear sampler, ataa.wgsl.ts:72):
+                // pu W - 0.5 with pu = ndc.x/2 + 1/2,  pv H - 0.5 with pv = -ndc.y/2 + 1/2
+                const float hx = fminf(fmaxf(fmaf(p0 * ip3, half_w, half_w - 0.5f), 0.0f), x_max);
+                const float hy = fminf(fmaxf(fmaf(p1 * ip3, -half_h, half_h - 0.5f), 0.0f), y_max);
+                const float hxf = floorf(hx), hyf = floorf(hy);
+                const int x0 = (int)hxf, y0 = (int)hyf;
+                const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+                t.fx = hx - hxf; t.fy = hy - hyf;
+                const float4* r0 = P.hist + (size_t)y0 * W;
+                const float4* r1 = P.hist + (size_t)y1 * W;
+                t.h00 = __ldg(r0 + x0); t.h10 = __ldg(r0 + x1);
+                t.h01 = __ldg(r1 + x0); t.h11 = __ldg(r1 + x1);
             }
-            YCC hs = rgb_to_ycocg(hr, hg, hb);
-            hs.y = fminf(fmaxf(hs.y, lo[0]), hi[0]);
-            hs.co = fminf(fmaxf(hs.co, lo[1]), hi[1]);
-            hs.cg = fminf(fmaxf(hs.cg, lo[2]), hi[2]);
-            const float ry = b.y + (hs.y - b.y) * fb_, ro = b.co + (hs.co - b.co) * fb_, rg = b.cg + (hs.cg - b.cg) * fb_;
-            // YCoCgToRGB, ataa.wgsl.ts:18-26
-            const float4 px_out = make_float4(ry + ro - rg, ry + rg, ry - ro - rg, 1.0f);
-            P.out[(size_t)y * W + x] = px_out;
-            if (P.host_out) P.host_out[(size_t)y * W + x] = px_out;
-            for (uint32_t q = 0; q < P.n_peer; q++) P.peer_out[q][(size_t)y * W + x] = px_out;
+            return t;
+        };
+        Taps nt = issue_taps(y_begin);
+#pragma unroll taa_unroll
+        for (int y = y_begin; y < y_end; y++) {
+            const float4 h00 = nt.h00, h10 = nt.h10, h01 = nt.h01, h11 = nt.h11;
+            const float fx = nt.fx, fy = nt.fy;
+            nt = issue_taps(min(y + 1, H - 1));
+            const int k = y - y_begin + 2;
+            c = moments_of(ring_take(k));
+            ring_issue(k + TAA_DEPTH);
+            // vertical sums (this lane's column), then horizontal 3-tap by shuffles
+            const float m1y = sum3(a.y + b.y + c.y), m1o = sum3(a.co + b.co + c.co), m1g = sum3(a.cg + b.cg + c.cg);
+            const float m2y = sum3(a.yy + b.yy + c.yy), m2o = sum3(a.coco + b.coco + c.coco);
+            const float m2g = sum3(a.cgcg + b.cgcg + c.cgcg);
+            if (owner) {
+                const float mean[3] = {m1y * k9, m1o * k9, m1g * k9};
+                const float m2[3] = {m2y * k9, m2o * k9, m2g * k9};
+                float lo[3], hi[3], sd_y = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    const float sd = sqrt_approx(fmaxf(fmaf(-mean[i], mean[i], m2[i]), 0.0f));
+                    if (i == 0) sd_y = sd;
+                    lo[i] = fmaf(-nsig, sd, mean[i]); hi[i] = fmaf(nsig, sd, mean[i]);
+                }
+                float hr, hg, hb, fb_;
+                if (MODE == 1) {
+                    hr = h00.x; hg = h00.y; hb = h00.z;
+                    fb_ = fb_gl * (1.0f - fminf(fmaxf(sd_y * 4.0f, 0.0f), 0.55f));   // variance-guided weight
+                } else {
+                    const float tr = fmaf(h10.x - h00.x, fx, h00.x), br = fmaf(h11.x - h01.x, fx, h01.x);
+                    const float tg = fmaf(h10.y - h00.y, fx, h00.y), bg = fmaf(h11.y - h01.y, fx, h01.y);
+                    const float tb = fmaf(h10.z - h00.z, fx, h00.z), bb = fmaf(h11.z - h01.z, fx, h01.z);
+                    hr = fmaf(br - tr, fy, tr); hg = fmaf(bg - tg, fy, tg); hb = fmaf(bb - tb, fy, tb);
+                    fb_ = 0.92f;  // ataa.wgsl.ts:77
+                }
+                // Keep the unused alpha lanes of the 128-bit history loads allocated until here: ptxas otherwise hands
+                // those registers to the next arithmetic result straight after the LDG, and that write then waits
+                // for the load to land (WAW on the scoreboard).
+                asm volatile("" ::"f"(h00.w), "f"(h10.w), "f"(h01.w), "f"(h11.w));
+                YCC hs = rgb_to_ycocg(hr, hg, hb);
+                hs.y = fminf(fmaxf(hs.y, lo[0]), hi[0]);
+                hs.co = fminf(fmaxf(hs.co, lo[1]), hi[1]);
+                hs.cg = fminf(fmaxf(hs.cg, lo[2]), hi[2]);
+                const float ry = fmaf(hs.y - b.y, fb_, b.y), ro = fmaf(hs.co - b.co, fb_, b.co);
+                const float rg = fmaf(hs.cg - b.cg, fb_, b.cg);
+                // YCoCgToRGB, ataa.wgsl.ts:18-26
+                const float4 px_out = make_float4(ry + ro - rg, ry + rg, ry - ro - rg, 1.0f);
+                const size_t o = (size_t)y * W + x;
+                P.out[o] = px_out;
+                if (P.host_out) P.host_out[o] = px_out;
+#pragma unroll 1
+                for (uint32_t q = 0; q < P.n_peer; q++) P.peer_out[q][o] = px_out;
+            }
+            a = b; b = c;
         }
-        a = b; b = c;
     }
 }
 
-cudaError_t launch_taa(const TaaParams& p, cudaStream_t stream) {
+cudaError_t launch_taa(const TaaParams& p_in, int sm_count, cudaStream_t stream) {
+    TaaParams p = p_in;
     const int strips_x = ((int)p.width + TAA_STRIP_W - 1) / TAA_STRIP_W;
     const int rows = (int)p.row1 - (int)p.row0;
     if (rows <= 0) return cudaSuccess;
-    const int n_work = strips_x * ((rows + TAA_ROWS - 1) / TAA_ROWS);
     const int wpb = 8;
-    k_taa_resolve<<<(n_work + wpb - 1) / wpb, wpb * 32, 0, stream>>>(p);
+    static int resident[2] = {0, 0};   // CTAs per SM of each instantiation (occupancy query, once)
+    const int m = p.mode == 1u ? 1 : 0;
+    if (!resident[m]) {
+        int n = 0;
+        const cudaError_t e = m ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_taa_resolve<1>, wpb * 32, 0)
+                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_taa_resolve<0>, wpb * 32, 0);
+        if (e != cudaSuccess) return e;
+        resident[m] = n > 0 ? n : 1;
+    }
+    // Rows per strip unit: every warp walks k = ceil(units / resident warps) units of (R + 2) loaded rows; pick the R
+    // that minimises k (R + 2), i.e. no partial last wave and as little halo as the frame allows.
+    const int max_warps = max(sm_count, 1) * resident[m] * wpb;
+    int best_r = 16;
+    long best_cost = -1;
+    for (int R = 4; R <= 64; R++) {
+        const long units = (long)strips_x * ((rows + R - 1) / R);
+        const long cost = ((units + max_warps - 1) / max_warps) * (R + 2);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_r = R; }
+    }
+    p.unit_rows = (uint32_t)best_r;
+    const int n_work = strips_x * ((rows + best_r - 1) / best_r);
+    const int blocks = min((n_work + wpb - 1) / wpb, max(sm_count, 1) * resident[m]);
+    if (m) k_taa_resolve<1><<<blocks, wpb * 32, 0, stream>>>(p);
+    else k_taa_resolve<0><<<blocks, wpb * 32, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

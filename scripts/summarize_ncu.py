@@ -50,10 +50,10 @@ ix = {h: i for i, h in enumerate(hdr)}
 c = Counter()
 tot = 0
 for r in data:
-    m = re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_]+)", r[ix["Source"]].strip())
+    m = re.match(r"(@!?U?P[T\d]+\s+)?([A-Z0-9_]+)", r[ix["Source"]].strip())
     n = int(r[ix["Instructions Executed"]])
     tot += n
-    c[m.group(2)] += n
+    c[m.group(2) if m else "?"] += n
 ws = steps_per_launch / 32.0
 lines += ["", f"## dynamic SASS mix: warp-instructions per geodesic step (launch = {steps_per_launch:.0f} steps; total {tot / ws:.1f}/step)"]
 for k, v in c.most_common(22):
