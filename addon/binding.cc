@@ -95,6 +95,28 @@ ENGINE_GETTER(ComputeIsco, gvt_engine_compute_isco(e, &out))                    
 ENGINE_GETTER(ComputePhotonSphere, gvt_engine_compute_photon_sphere(e, &out))    // lib.rs:93
 ENGINE_GETTER(ComputeDilation, gvt_engine_compute_dilation(e, Num(env, argv[0]), &out))             // lib.rs:97
 ENGINE_GETTER(ComputeGFactor, gvt_engine_compute_g_factor(e, Num(env, argv[0]), Num(env, argv[1]), &out))   // lib.rs:203
+ENGINE_GETTER(ComputeShadowRadius, gvt_engine_compute_shadow_radius(e, &out))    // lib.rs:173
+ENGINE_GETTER(ComputeDiskFlux, gvt_engine_compute_disk_flux(e, Num(env, argv[0]), &out))            // lib.rs:199
+napi_value ShadowCurve(napi_env env, napi_callback_info info) {                  // lib.rs:161
+    size_t argc = 2; napi_value argv[2];
+    gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
+    const double theta = Num(env, argv[0]);
+    const uint32_t n_points = (uint32_t)Num(env, argv[1]);
+    uint32_t n = 0;
+    GVT(gvt_engine_compute_shadow_curve(e, theta, n_points, nullptr, 0, &n));
+    float* out = nullptr;
+    napi_value arr = F32Array(env, (size_t)n * 2, &out);
+    if (arr) GVT(gvt_engine_compute_shadow_curve(e, theta, n_points, out, n, &n));
+    return arr;
+}
+napi_value ShadowShift(napi_env env, napi_callback_info info) {                  // lib.rs:179
+    size_t argc = 1; napi_value argv[1];
+    gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
+    float* out = nullptr;
+    napi_value arr = F32Array(env, 2, &out);
+    if (arr) GVT(gvt_engine_compute_shadow_shift(e, Num(env, argv[0]), out));
+    return arr;
+}
 napi_value DiskLut(napi_env env, napi_callback_info info) {                      // lib.rs:107
     size_t argc = 0;
     gvt_engine* e = Self<gvt_engine>(env, info, &argc, nullptr);
@@ -209,6 +231,8 @@ NAPI_MODULE_INIT() {
         {"compute_horizon", 0, ComputeHorizon, 0, 0, 0, napi_default, 0}, {"compute_isco", 0, ComputeIsco, 0, 0, 0, napi_default, 0},
         {"compute_photon_sphere", 0, ComputePhotonSphere, 0, 0, 0, napi_default, 0},
         {"compute_dilation", 0, ComputeDilation, 0, 0, 0, napi_default, 0}, {"compute_g_factor", 0, ComputeGFactor, 0, 0, 0, napi_default, 0},
+        {"compute_shadow_curve", 0, ShadowCurve, 0, 0, 0, napi_default, 0}, {"compute_shadow_shift", 0, ShadowShift, 0, 0, 0, napi_default, 0},
+        {"compute_shadow_radius", 0, ComputeShadowRadius, 0, 0, 0, napi_default, 0}, {"compute_disk_flux", 0, ComputeDiskFlux, 0, 0, 0, napi_default, 0},
         {"generate_disk_lut", 0, DiskLut, 0, 0, 0, napi_default, 0}, {"generate_spectrum_lut", 0, SpectrumLut, 0, 0, 0, napi_default, 0},
         {"integrate_ray_relativistic", 0, IntegrateRay, 0, 0, 0, napi_default, 0}};
     const napi_property_descriptor renderer[] = {

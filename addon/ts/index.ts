@@ -14,6 +14,8 @@ export const PhysicsEngine: new (mass: number, spin: number) => {
   set_auto_spin(enabled: boolean): void;
   compute_horizon(): number; compute_isco(): number; compute_photon_sphere(): number;
   compute_dilation(r: number): number; compute_g_factor(r: number, lambda: number): number;
+  compute_shadow_curve(thetaObs: number, nPoints: number): Float32Array; compute_shadow_shift(thetaObs: number): Float32Array;
+  compute_shadow_radius(): number; compute_disk_flux(r: number): number;
   generate_disk_lut(): Float32Array; generate_spectrum_lut(w: number, h: number, maxTemp: number): Float32Array;
   integrate_ray_relativistic(state: number[], steps: number, tol: number, useKerrSchild: boolean): Float64Array;
 } = addon.PhysicsEngine;

@@ -191,6 +191,38 @@ extern "C" int32_t gvt_engine_compute_g_factor(gvt_engine* e, double r, double l
     *out = host::g_factor(r, e->mass, e->spin, lambda);  // lib.rs:203-205 passes the raw (unclamped) spin
     return GVT_OK;
 }
+extern "C" int32_t gvt_engine_compute_shadow_curve(gvt_engine* e, double theta_obs, uint32_t n_points, float* out_pairs,
+                                                   uint32_t capacity_pairs, uint32_t* n_pairs) {
+    if (!e || !n_pairs) return fail(GVT_ERR_INVALID, "null argument");
+    const auto curve = host::bardeen_shadow(host::Hole(e->mass, e->spin), theta_obs, n_points);
+    *n_pairs = (uint32_t)curve.size();
+    if (out_pairs)
+        for (size_t i = 0; i < curve.size() && i < capacity_pairs; i++) {
+            out_pairs[2 * i] = (float)curve[i].first; out_pairs[2 * i + 1] = (float)curve[i].second;
+        }
+    return GVT_OK;
+}
+extern "C" int32_t gvt_engine_compute_shadow_radius(gvt_engine* e, double* out) {
+    if (!e || !out) return fail(GVT_ERR_INVALID, "null argument");
+    *out = 3.0 * std::sqrt(3.0) * e->mass;   // shadow.rs:191-193
+    return GVT_OK;
+}
+extern "C" int32_t gvt_engine_compute_shadow_shift(gvt_engine* e, double theta_obs, float out2[2]) {
+    if (!e || !out2) return fail(GVT_ERR_INVALID, "null argument");
+    const auto curve = host::bardeen_shadow(host::Hole(e->mass, e->spin), theta_obs, 32);
+    double min_a = 0.0, max_a = 0.0;
+    if (!curve.empty()) {
+        min_a = max_a = curve[0].first;
+        for (const auto& c : curve) { if (c.first < min_a) min_a = c.first; if (c.first > max_a) max_a = c.first; }
+    }
+    out2[0] = (float)min_a; out2[1] = (float)max_a;
+    return GVT_OK;
+}
+extern "C" int32_t gvt_engine_compute_disk_flux(gvt_engine* e, double r, double* out) {
+    if (!e || !out) return fail(GVT_ERR_INVALID, "null argument");
+    *out = host::nt::flux(r, host::Hole(e->mass, e->spin), 1.0);   // page_thorne_flux(r, metric_bl, 1.0)
+    return GVT_OK;
+}
 extern "C" int32_t gvt_engine_generate_disk_lut(gvt_engine* e, float* out512) {
     if (!e || !out512) return fail(GVT_ERR_INVALID, "null argument");
     host::disk_lut(host::Hole(e->mass, e->spin), 512, out512);  // lut_width 512 (lib.rs:65)

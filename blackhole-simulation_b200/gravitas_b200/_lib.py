@@ -84,6 +84,10 @@ SIGNATURES = {
     "gvt_engine_compute_photon_sphere": (_i32, [_vp, _pd]),
     "gvt_engine_compute_dilation": (_i32, [_vp, _d, _pd]),
     "gvt_engine_compute_g_factor": (_i32, [_vp, _d, _d, _pd]),
+    "gvt_engine_compute_shadow_curve": (_i32, [_vp, _d, _u32, _pf, _u32, _pu32]),
+    "gvt_engine_compute_shadow_radius": (_i32, [_vp, _pd]),
+    "gvt_engine_compute_shadow_shift": (_i32, [_vp, _d, _pf]),
+    "gvt_engine_compute_disk_flux": (_i32, [_vp, _d, _pd]),
     "gvt_engine_generate_disk_lut": (_i32, [_vp, _pf]),
     "gvt_engine_generate_spectrum_lut": (_i32, [_vp, _u32, _u32, _d, _pf]),
     "gvt_engine_integrate_ray": (_i32, [_vp, _pd, _u64, _d, _i32, _pd, _pu32, _pu64, _pd]),

@@ -49,6 +49,25 @@ class PhysicsEngine:
     def compute_g_factor(self, r, lam):  # lib.rs:203-205
         return self._scalar(lib().gvt_engine_compute_g_factor, float(r), float(lam))
 
+    def compute_shadow_curve(self, theta_obs, n_points):  # lib.rs:161-170 -> Float32Array [a0, b0, a1, b1, ...]
+        n = C.c_uint32(0)
+        check(lib().gvt_engine_compute_shadow_curve(self._h, float(theta_obs), int(n_points), None, 0, C.byref(n)))
+        out = np.zeros(2 * n.value, np.float32)
+        check(lib().gvt_engine_compute_shadow_curve(self._h, float(theta_obs), int(n_points),
+                                                    out.ctypes.data_as(C.POINTER(C.c_float)), n.value, C.byref(n)))
+        return out
+
+    def compute_shadow_radius(self):  # lib.rs:173-175
+        return self._scalar(lib().gvt_engine_compute_shadow_radius)
+
+    def compute_shadow_shift(self, theta_obs):  # lib.rs:179-196 -> Vec<f32>[min_alpha, max_alpha]
+        out = np.zeros(2, np.float32)
+        check(lib().gvt_engine_compute_shadow_shift(self._h, float(theta_obs), out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def compute_disk_flux(self, r):  # lib.rs:199-201
+        return self._scalar(lib().gvt_engine_compute_disk_flux, float(r))
+
     def generate_disk_lut(self):  # lib.rs:107-110 -> Vec<f32>(512)
         out = np.zeros(512, np.float32)
         check(lib().gvt_engine_generate_disk_lut(self._h, out.ctypes.data_as(C.POINTER(C.c_float))))

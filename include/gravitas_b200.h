@@ -172,6 +172,14 @@ int32_t gvt_engine_compute_isco(gvt_engine* e, double* out);                    
 int32_t gvt_engine_compute_photon_sphere(gvt_engine* e, double* out);               /* lib.rs:93-95 */
 int32_t gvt_engine_compute_dilation(gvt_engine* e, double r, double* out);          /* lib.rs:97-105 */
 int32_t gvt_engine_compute_g_factor(gvt_engine* e, double r, double lambda, double* out); /* redshift.rs:65-95 */
+/* Bardeen critical curve as [alpha0, beta0, alpha1, beta1, ...] f32 pairs (lib.rs:161-170; shadow.rs:81-183). The
+ * curve has n_points points for a* = 0, 2 n_points otherwise; `capacity_pairs` bounds what is written, *n_pairs
+ * receives the curve's full length (call with out = NULL to size the buffer). */
+int32_t gvt_engine_compute_shadow_curve(gvt_engine* e, double theta_obs, uint32_t n_points, float* out_pairs,
+                                        uint32_t capacity_pairs, uint32_t* n_pairs);
+int32_t gvt_engine_compute_shadow_radius(gvt_engine* e, double* out);               /* lib.rs:173-175 */
+int32_t gvt_engine_compute_shadow_shift(gvt_engine* e, double theta_obs, float out2[2]); /* lib.rs:179-196 */
+int32_t gvt_engine_compute_disk_flux(gvt_engine* e, double r, double* out);         /* lib.rs:199-201 */
 int32_t gvt_engine_generate_disk_lut(gvt_engine* e, float* out512);                 /* lib.rs:107-110 */
 int32_t gvt_engine_generate_spectrum_lut(gvt_engine* e, uint32_t width, uint32_t height, double max_temp,
                                          float* out_rgba);                          /* lib.rs:128-136 */

@@ -281,3 +281,67 @@ def render_pixel(cam88, W, H, px, py, mass, spin, max_steps, lut, LW, LH, td, r_
             term = 4
             break
     return col, term, steps
+
+
+# ---- physics/shadow.rs : Bardeen critical curve (independent restatement from the Rust, CPython libm) -----------
+def photon_sphere(m, spin):  # kerr.rs photon_sphere(): prograde circular photon orbit 2M(1 + cos(2/3 acos(-|a*|)))
+    return 2.0 * m * (1.0 + math.cos((2.0 / 3.0) * math.acos(-abs(spin))))
+
+
+def critical_params(r, m, a):  # shadow.rs:38-58
+    r2 = r * r
+    r3 = r2 * r
+    a2 = a * a
+    denom = a * (r - m)
+    if abs(denom) < 1e-30:
+        return 0.0, 0.0
+    xi = -(r3 - 3.0 * m * r2 + a2 * r + a2 * m) / denom
+    denom2 = a2 * (r - m) * (r - m)
+    if abs(denom2) < 1e-30:
+        return xi, 0.0
+    q = r - 3.0 * m
+    eta = r3 * (4.0 * m * a2 - r * (q * q)) / denom2
+    return xi, eta
+
+
+def bardeen_shadow(m, spin, theta_obs, n_points):  # shadow.rs:81-183
+    a = spin * m
+    so, co = math.sin(theta_obs), math.cos(theta_obs)
+    if abs(a) < 1e-10:
+        rad = 3.0 * math.sqrt(3.0) * m
+        return [(rad * math.cos(2.0 * math.pi * i / n_points), rad * math.sin(2.0 * math.pi * i / n_points))
+                for i in range(n_points)]
+    if abs(so) < 1e-10:
+        xi, eta = critical_params(photon_sphere(m, spin), m, a)
+        rad = math.sqrt(max(eta + a * a, 0.0))
+        return [(rad * math.cos(2.0 * math.pi * i / (2.0 * n_points)), rad * math.sin(2.0 * math.pi * i / (2.0 * n_points)))
+                for i in range(2 * n_points)]
+    a_star = a / m
+    r_pro = 2.0 * m * (1.0 + math.cos((2.0 / 3.0) * math.acos(-abs(a_star))))
+    r_ret = 2.0 * m * (1.0 + math.cos((2.0 / 3.0) * math.acos(abs(a_star))))
+
+    def beta_sq(r):
+        xi, eta = critical_params(r, m, a)
+        return eta + a * a * co * co - xi * xi * co * co / (so * so), xi
+
+    r_min, r_max = r_pro, r_ret
+    steps = 1000
+    for i in range(steps + 1):
+        r = r_pro + (i / steps) * (r_ret - r_pro)
+        if beta_sq(r)[0] >= 0.0:
+            r_min = r
+            break
+    for i in range(steps, -1, -1):
+        r = r_pro + (i / steps) * (r_ret - r_pro)
+        if beta_sq(r)[0] >= 0.0:
+            r_max = r
+            break
+    pts = []
+    for sign, order in ((-1.0, range(n_points)), (1.0, range(n_points - 1, -1, -1))):
+        for i in order:
+            phase = math.pi * i / max(n_points - 1, 1)
+            t = 0.5 - 0.5 * math.cos(phase)
+            r = r_min + t * (r_max - r_min)
+            b2, xi = beta_sq(r)
+            pts.append((a * so - xi / so, sign * math.sqrt(max(b2, 0.0))))
+    return pts
