@@ -372,6 +372,9 @@ struct gvt_renderer {
     // debug buffers for gvt_trace_states
     double* d_xp = nullptr; double* d_drift = nullptr; double* d_rgba = nullptr; uint32_t* d_term = nullptr; uint32_t* d_steps = nullptr;
     size_t dbg_cap = 0;
+    // WebGL2 fragment-shader path: red channels of the two noise textures, per-pixel parity hooks
+    uint8_t* d_noise_r = nullptr; uint8_t* d_blue_r = nullptr;
+    uint32_t* d_gsteps = nullptr; uint32_t* d_ghit = nullptr; size_t g_cap = 0;
 };
 
 extern "C" int32_t gvt_render_params_default(GvtRenderParams* p) {
@@ -458,6 +461,10 @@ extern "C" int32_t gvt_render_destroy(gvt_renderer* r) {
     if (r->d_rgba) cudaFree(r->d_rgba);
     if (r->d_term) cudaFree(r->d_term);
     if (r->d_steps) cudaFree(r->d_steps);
+    if (r->d_noise_r) cudaFree(r->d_noise_r);
+    if (r->d_blue_r) cudaFree(r->d_blue_r);
+    if (r->d_gsteps) cudaFree(r->d_gsteps);
+    if (r->d_ghit) cudaFree(r->d_ghit);
     for (auto& e : r->ev) if (e) cudaEventDestroy(e);
     if (r->stream) cudaStreamDestroy(r->stream);
     delete r;
@@ -627,29 +634,53 @@ extern "C" int32_t gvt_render_read_frame(gvt_renderer* r, uint32_t format, void*
     return GVT_OK;
 }
 
-// webgpu/renderer.ts:280-411 render(camera, physics)
-extern "C" int32_t gvt_render_frame(gvt_renderer* r, const GvtCamera* cam, const GvtPhysicsParams* phys,
-                                    const GvtRenderParams* rp, void* host_rgba, GvtFrameStats* stats) {
-    if (!r || !cam || !phys || !rp) return fail(GVT_ERR_INVALID, "null argument");
+// One frame through the shared pipeline: [barrier] -> producing kernel (the fused geodesic trace, or the WebGL2
+// fragment shader when `glsl` is given) -> optional TAA resolve -> gather / peer-store barrier -> host delivery.
+static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysicsParams* phys, const GvtRenderParams* rp,
+                           const GvtGlslUniforms* glsl, uint32_t glsl_precision, void* host_rgba, GvtFrameStats* stats) {
+    if (!r || !rp || (!glsl && (!cam || !phys))) return fail(GVT_ERR_INVALID, "null argument");
     CK(cudaSetDevice(r->device));
-    const uint32_t W = (uint32_t)phys->resolution[0], H = (uint32_t)phys->resolution[1];
+    const uint32_t W = glsl ? (uint32_t)glsl->resolution[0] : (uint32_t)phys->resolution[0];
+    const uint32_t H = glsl ? (uint32_t)glsl->resolution[1] : (uint32_t)phys->resolution[1];
     if (W != r->width || H != r->height || !r->cur) {  // renderer.ts:281-284
         int32_t rc = gvt_render_resize(r, W, H);
         if (rc != GVT_OK) return rc;
     }
     FrameParams P;
-    int32_t rc = build_frame(r, cam, phys, rp, P);
-    if (rc != GVT_OK) return rc;
+    GlslParams G;
+    if (glsl) {
+        if (!r->d_noise_r || !r->d_blue_r) return fail(GVT_ERR_INVALID, "noise textures not set: call gvt_render_set_noise_textures first");
+        if ((rp->flags & GVT_FLAG_TAA) && !(rp->flags & GVT_FLAG_TAA_WEBGL))
+            return fail(GVT_ERR_INVALID, "the fragment-shader path resolves with GVT_FLAG_TAA_WEBGL (reprojection.glsl.ts), it has no CameraUniforms");
+        memset(&G, 0, sizeof(G));
+        G.u = *glsl;
+        G.width = W; G.height = H;
+        G.noise_r = r->d_noise_r; G.blue_r = r->d_blue_r; G.counters = r->d_counters;
+        const size_t n_px = (size_t)W * H;
+        if (r->g_cap < n_px) {
+            if (r->d_gsteps) cudaFree(r->d_gsteps);
+            if (r->d_ghit) cudaFree(r->d_ghit);
+            r->d_gsteps = nullptr; r->d_ghit = nullptr; r->g_cap = 0;
+            CK(cudaMalloc(&r->d_gsteps, n_px * sizeof(uint32_t)));
+            CK(cudaMalloc(&r->d_ghit, n_px * sizeof(uint32_t)));
+            r->g_cap = n_px;
+        }
+        G.dbg_steps = r->d_gsteps; G.dbg_hit = r->d_ghit;
+    } else {
+        int32_t rc = build_frame(r, cam, phys, rp, P);
+        if (rc != GVT_OK) return rc;
+    }
     const bool taa = (rp->flags & GVT_FLAG_TAA) != 0;
-    const bool budget = (rp->flags & GVT_FLAG_BUDGET) != 0 && (rp->method == GVT_METHOD_RK4 || rp->method == GVT_METHOD_SYMPLECTIC);
+    const bool budget = !glsl && (rp->flags & GVT_FLAG_BUDGET) != 0 && (rp->method == GVT_METHOD_RK4 || rp->method == GVT_METHOD_SYMPLECTIC);
     const uint32_t row0 = std::min(H, (uint32_t)r->rank * r->rows_per_rank);
     const uint32_t row1 = std::min(H, row0 + r->rows_per_rank);
     // TAA needs a one-pixel halo of the current frame: trace one redundant row above and below the block
     const uint32_t ty0 = (taa && row0 > 0) ? row0 - 1 : row0, ty1 = (taa && row1 < H) ? row1 + 1 : row1;
-    P.x0 = 0; P.xs = 1; P.y0 = ty0; P.y1 = ty1; P.ys = 1; P.nx = W; P.ny = ty1 - ty0;
+    if (glsl) { G.y0 = ty0; G.y1 = ty1; }
+    else { P.x0 = 0; P.xs = 1; P.y0 = ty0; P.y1 = ty1; P.ys = 1; P.nx = W; P.ny = ty1 - ty0; }
     if (taa && r->history_valid) std::swap(r->frame, r->hist);  // last finished frame becomes the history
     float4* trace_out = taa ? r->cur : r->frame;
-    P.frame = trace_out;
+    if (glsl) G.frame = trace_out; else P.frame = trace_out;
     uint32_t launches = 0;
     uint64_t h2d = 0, d2h = 0;
     // Host frame delivery. If the caller's buffer is page-locked (gvt_host_alloc / gvt_host_register) and this rank
@@ -665,7 +696,7 @@ extern "C" int32_t gvt_render_frame(gvt_renderer* r, const GvtCamera* cam, const
         else
             (void)cudaGetLastError();   // pageable memory: not an error, just the copy path
     }
-    P.host_frame = taa ? nullptr : host_alias;
+    if (glsl) G.host_frame = taa ? nullptr : host_alias; else P.host_frame = taa ? nullptr : host_alias;
     // Fused gather: the producing kernel writes each finished pixel into the same frame on every peer.
     const bool peer_store = (rp->flags & GVT_FLAG_PEER_STORE) != 0 && r->world > 1 && !(rp->flags & GVT_FLAG_NO_GATHER);
     float4* peer_targets[GVT_MAX_PEERS];
@@ -677,12 +708,17 @@ extern "C" int32_t gvt_render_frame(gvt_renderer* r, const GvtCamera* cam, const
             if (p >= GVT_MAX_PEERS || !r->peer_open[p]) return fail(GVT_ERR_INVALID, "GVT_FLAG_PEER_STORE: frames of rank %d not imported (gvt_render_import_peer_frames)", p);
             peer_targets[n_peer++] = r->peer[p][idx];
         }
-        if (!taa) { for (uint32_t q = 0; q < n_peer; q++) P.peer_frame[q] = peer_targets[q]; P.n_peer = n_peer; }
+        if (!taa && glsl) { for (uint32_t q = 0; q < n_peer; q++) G.peer_frame[q] = peer_targets[q]; G.n_peer = n_peer; }
+        else if (!taa) { for (uint32_t q = 0; q < n_peer; q++) P.peer_frame[q] = peer_targets[q]; P.n_peer = n_peer; }
     }
 
     CK(cudaEventRecord(r->ev[0], r->stream));
-    CK(cudaMemcpyAsync(r->d_block, r->h_block, sizeof(FrameBlock), cudaMemcpyHostToDevice, r->stream));
-    h2d += sizeof(FrameBlock);
+    if (!glsl) {
+        CK(cudaMemcpyAsync(r->d_block, r->h_block, sizeof(FrameBlock), cudaMemcpyHostToDevice, r->stream));
+        h2d += sizeof(FrameBlock);
+    } else {
+        h2d += sizeof(GvtGlslUniforms);   // travels in the kernel parameter block
+    }
     CK(cudaMemsetAsync(r->d_counters, 0, sizeof(Counters), r->stream));
     if (peer_store) {
         // peers are about to write into this rank's frame: everything this rank still had queued on the previous
@@ -691,11 +727,21 @@ extern "C" int32_t gvt_render_frame(gvt_renderer* r, const GvtCamera* cam, const
         if (nrc != 0) return fail(GVT_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(nrc));
     }
     CK(cudaEventRecord(r->ev[1], r->stream));
-    if (P.ny > 0) { CK(launch_trace(P, rp->method, rp->precision, budget, false, r->sm_count, r->stream)); launches++; }
+    if (glsl) {
+        if (ty1 > ty0) {
+            if (glsl_precision == GVT_PRECISION_F32_FAST) CK(launch_fragment_glsl_fast(G, r->sm_count, r->stream));
+            else CK(launch_fragment_glsl(G, (int)glsl_precision, r->sm_count, r->stream));
+            launches++;
+        }
+    } else if (P.ny > 0) {
+        CK(launch_trace(P, rp->method, rp->precision, budget, false, r->sm_count, r->stream));
+        launches++;
+    }
     CK(cudaEventRecord(r->ev[2], r->stream));
     if (taa && row1 > row0) {
         TaaParams T;
-        fill_taa(cam, W, H, T);
+        if (cam) fill_taa(cam, W, H, T);
+        else { memset(&T, 0, sizeof(T)); T.width = W; T.height = H; }
         T.cur = r->cur; T.hist = r->hist; T.out = r->frame;
         T.row0 = row0; T.row1 = row1;
         if (rp->flags & GVT_FLAG_TAA_WEBGL) {
@@ -761,6 +807,59 @@ extern "C" int32_t gvt_render_frame(gvt_renderer* r, const GvtCamera* cam, const
         stats->h2d_bytes = h2d; stats->d2h_bytes = d2h; stats->kernel_launches = launches;
         stats->rows_begin = row0; stats->rows_end = row1;
     }
+    return GVT_OK;
+}
+
+// webgpu/renderer.ts:280-411 render(camera, physics)
+extern "C" int32_t gvt_render_frame(gvt_renderer* r, const GvtCamera* cam, const GvtPhysicsParams* phys,
+                                    const GvtRenderParams* rp, void* host_rgba, GvtFrameStats* stats) {
+    if (!r || !cam || !phys || !rp) return fail(GVT_ERR_INVALID, "null argument");
+    return render_impl(r, cam, phys, rp, nullptr, 0, host_rgba, stats);
+}
+
+// webgl-utils.ts:259-303: createNoiseTexture / createBlueNoiseTexture (256x256 RGBA8). Only .r is ever sampled
+// (chunks/noise.ts:7, fragment.glsl.ts:106), so only the red channels are kept on the device.
+extern "C" int32_t gvt_render_set_noise_textures(gvt_renderer* r, const uint8_t* noise_rgba8, const uint8_t* blue_rgba8,
+                                                 uint32_t size) {
+    if (!r || !noise_rgba8 || !blue_rgba8) return fail(GVT_ERR_INVALID, "null argument");
+    if (size != 256) return fail(GVT_ERR_INVALID, "noise textures are 256x256 (webgl/renderer.ts:124-125), got %u", size);
+    CK(cudaSetDevice(r->device));
+    std::vector<uint8_t> red(2 * 65536);
+    for (size_t i = 0; i < 65536; i++) { red[i] = noise_rgba8[4 * i]; red[65536 + i] = blue_rgba8[4 * i]; }
+    if (!r->d_noise_r) CK(cudaMalloc(&r->d_noise_r, 65536));
+    if (!r->d_blue_r) CK(cudaMalloc(&r->d_blue_r, 65536));
+    CK(cudaMemcpyAsync(r->d_noise_r, red.data(), 65536, cudaMemcpyHostToDevice, r->stream));
+    CK(cudaMemcpyAsync(r->d_blue_r, red.data() + 65536, 65536, cudaMemcpyHostToDevice, r->stream));
+    CK(cudaStreamSynchronize(r->stream));
+    return GVT_OK;
+}
+
+// webgl/renderer.ts:173-420 render(params, mouse): the fragment-shader pass (+ the WebGL2 TAA resolve on request)
+extern "C" int32_t gvt_render_fragment_glsl(gvt_renderer* r, const GvtGlslUniforms* u, uint32_t precision, uint32_t flags,
+                                            uint32_t output_format, float taa_blend, uint32_t taa_camera_moving,
+                                            void* host_rgba, GvtFrameStats* stats) {
+    if (!r || !u) return fail(GVT_ERR_INVALID, "null argument");
+    if (u->struct_size != sizeof(GvtGlslUniforms)) return fail(GVT_ERR_INVALID, "GvtGlslUniforms.struct_size = %u, expected %zu", u->struct_size, sizeof(GvtGlslUniforms));
+    if (precision > GVT_PRECISION_F32_FAST || output_format > GVT_FORMAT_RGBA8_ACES) return fail(GVT_ERR_INVALID, "bad precision / output format");
+    if (!(u->resolution[0] >= 1.0f) || !(u->resolution[1] >= 1.0f) || u->resolution[0] > 65536.0f || u->resolution[1] > 65536.0f)
+        return fail(GVT_ERR_INVALID, "bad u_resolution");
+    if (!(u->mass > 0.0f)) return fail(GVT_ERR_INVALID, "u_mass must be positive");
+    GvtRenderParams rp;
+    gvt_render_params_default(&rp);
+    rp.flags = flags & ~(uint32_t)(GVT_FLAG_BUDGET | GVT_FLAG_JITTER);
+    rp.output_format = output_format;
+    rp.taa_blend = taa_blend; rp.taa_camera_moving = taa_camera_moving;
+    return render_impl(r, nullptr, nullptr, &rp, u, precision, host_rgba, stats);
+}
+
+extern "C" int32_t gvt_render_fragment_glsl_debug(gvt_renderer* r, uint32_t* steps, uint32_t* hit) {
+    if (!r || !r->d_gsteps || !r->d_ghit) return fail(GVT_ERR_INVALID, "no fragment-shader frame rendered yet");
+    CK(cudaSetDevice(r->device));
+    const size_t n = (size_t)r->width * r->height;
+    if (n > r->g_cap) return fail(GVT_ERR_INVALID, "frame was resized since the last fragment-shader frame");
+    if (steps) CK(cudaMemcpyAsync(steps, r->d_gsteps, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, r->stream));
+    if (hit) CK(cudaMemcpyAsync(hit, r->d_ghit, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, r->stream));
+    CK(cudaStreamSynchronize(r->stream));
     return GVT_OK;
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "gvt_device.cuh"
+#include "../../include/gravitas_b200.h"
 
 namespace gvt {
 
@@ -79,11 +80,26 @@ struct TaaParams {
     uint32_t unit_rows;    // rows per warp work unit (chosen by launch_taa)
 };
 
+// k_fragment_glsl (gvt_fragment.cu): the production WebGL2 fragment shader
+struct GlslParams {
+    GvtGlslUniforms u;            // chunks/common.ts:9-38 uniforms + feature bits, in the parameter bank
+    uint32_t width, height;       // frame size (= u.resolution)
+    uint32_t y0, y1;              // rows shaded by this launch (a rank's row block)
+    const uint8_t* noise_r;       // 256*256 red channel of u_noiseTex (global; TMA-staged into shared memory)
+    const uint8_t* blue_r;        // 256*256 red channel of u_blueNoiseTex (one tap per pixel, stays in global)
+    float4* frame; float4* host_frame; float4* peer_frame[8];
+    uint32_t n_peer, _pad;
+    Counters* counters;
+    uint32_t* dbg_steps; uint32_t* dbg_hit;   // parity hooks (full-frame arrays) or null
+};
+
 // launchers (gvt_kernels.cu)
 cudaError_t launch_trace(const FrameParams& p, int method, int precision, bool budget, bool debug, int sm_count,
                          cudaStream_t stream);
 cudaError_t launch_integrate_rays(const RayBatchParams& p, cudaStream_t stream);
 cudaError_t launch_taa(const TaaParams& p, int sm_count, cudaStream_t stream);
+cudaError_t launch_fragment_glsl(const GlslParams& p, int precision, int sm_count, cudaStream_t stream);
+cudaError_t launch_fragment_glsl_fast(const GlslParams& p, int sm_count, cudaStream_t stream);   // f32, MUFU maths
 cudaError_t launch_f32_to_f16(const float4* src, void* dst, size_t n_px, cudaStream_t stream);
 cudaError_t launch_tonemap_rgba8(const float4* src, void* dst, size_t n_px, int aces, cudaStream_t stream);
 cudaError_t launch_fma_peak(int precision, int sm_count, unsigned long long iters, float* sink, cudaStream_t stream,

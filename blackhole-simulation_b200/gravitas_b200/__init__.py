@@ -4,6 +4,8 @@
   physics-engine/gravitas-wasm/src/lib.rs:42-465 (Seam A), including the SAB f32-offset protocol.
 * ``KerrRenderer``   — the src/rendering renderer API (webgpu/renderer.ts:82-411: init / resize / render(camera,
   physics) / updateSettings), returning the frame buffer (Seam B).
+* ``WebGLRenderer``  — the WebGL2 pipeline's renderer API (webgl/renderer.ts:36-482: init / resize / render(params,
+  mouse) / cleanup) over the fused fragment-shader kernel.
 * ``camera``         — gl-matrix-compatible orbit camera -> CameraUniforms (components/canvas/WebGPUCanvas.tsx:119-178).
 
 The reference host is TypeScript over wasm-bindgen; node is not available in this image, so this ctypes mirror is
@@ -14,4 +16,5 @@ with ``GravitasError`` when no sm_100 device is present or the shared library is
 from ._lib import GravitasError, lib, lib_path, OFFSETS  # noqa: F401
 from .engine import PhysicsEngine  # noqa: F401
 from .renderer import KerrRenderer, RenderParams, FrameStats  # noqa: F401
-from . import camera, shard  # noqa: F401
+from .webgl import WebGLRenderer  # noqa: F401
+from . import camera, shard, webgl  # noqa: F401

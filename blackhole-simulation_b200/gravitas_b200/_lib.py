@@ -14,7 +14,7 @@ GVT_OK, GVT_ERR_INVALID, GVT_ERR_NO_DEVICE, GVT_ERR_CUDA, GVT_ERR_NCCL, GVT_ERR_
 TERM_NONE, TERM_HORIZON, TERM_ESCAPE, TERM_MAXSTEPS, TERM_DISK = 0, 1, 2, 3, 4
 COORDS_BL, COORDS_KS = 0, 1
 METHOD_RKF45, METHOD_RK4, METHOD_SYMPLECTIC, METHOD_VERLET_GLSL = 0, 1, 2, 3
-PRECISION_F64, PRECISION_F32 = 0, 1
+PRECISION_F64, PRECISION_F32, PRECISION_F32_FAST = 0, 1, 2
 FORMAT_RGBA32F, FORMAT_RGBA16F, FORMAT_RGBA8_REINHARD, FORMAT_RGBA8_ACES = 0, 1, 2, 3
 FORMAT_BYTES = {0: 16, 1: 8, 2: 4, 3: 4}
 FORMAT_DTYPE = {0: "float32", 1: "float16", 2: "uint8", 3: "uint8"}
@@ -47,6 +47,19 @@ class GvtRenderParams(C.Structure):
                 ("taa_blend", C.c_float), ("taa_camera_moving", C.c_uint32)]
 
 
+GLSL_LENSING, GLSL_DISK, GLSL_JETS, GLSL_STARS, GLSL_PHOTON_GLOW, GLSL_DOPPLER, GLSL_REDSHIFT = 1, 2, 4, 8, 16, 32, 64
+GLSL_LINEAR_OUTPUT, GLSL_QUALITY_LOW = 128, 256
+
+
+class GvtGlslUniforms(C.Structure):  # chunks/common.ts:9-38 uniforms + shader-manager #defines (manager.ts:55-82)
+    _fields_ = [("struct_size", C.c_uint32), ("features", C.c_uint32), ("resolution", C.c_float * 2), ("time", C.c_float),
+                ("mass", C.c_float), ("spin", C.c_float), ("disk_density", C.c_float), ("disk_temp", C.c_float),
+                ("mouse", C.c_float * 2), ("zoom", C.c_float), ("lensing_strength", C.c_float), ("disk_size", C.c_float),
+                ("disk_scale_height", C.c_float), ("max_ray_steps", C.c_int32), ("debug", C.c_float),
+                ("show_redshift", C.c_float), ("show_kerr_shadow", C.c_float), ("shadow_count", C.c_float),
+                ("cam_pos", C.c_float * 3), ("cam_quat", C.c_float * 4), ("shadow_curve", C.c_float * 128)]
+
+
 class GvtDeviceConfig(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("rank", C.c_int32), ("world_size", C.c_int32),
                 ("nccl_id", C.c_uint8 * 128)]
@@ -60,7 +73,7 @@ class GvtFrameStats(C.Structure):
                 ("rows_begin", C.c_uint32), ("rows_end", C.c_uint32)]
 
 
-assert C.sizeof(GvtCamera) == 352 and C.sizeof(GvtPhysicsParams) == 32
+assert C.sizeof(GvtCamera) == 352 and C.sizeof(GvtPhysicsParams) == 32 and C.sizeof(GvtGlslUniforms) == 620
 
 _d, _i32, _u32, _u64, _vp = C.c_double, C.c_int32, C.c_uint32, C.c_uint64, C.c_void_p
 _pd, _pf, _pu32, _pu64 = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
@@ -107,6 +120,10 @@ SIGNATURES = {
     "gvt_taa_resolve": (_i32, [_vp, C.POINTER(GvtCamera), _u32, _u32, _pf, _pf, _pf]),
     "gvt_taa_resolve_webgl": (_i32, [_vp, _u32, _u32, _pf, _pf, C.c_float, _i32, _pf]),
     "gvt_render_reset_history": (_i32, [_vp]),
+    "gvt_render_set_noise_textures": (_i32, [_vp, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), _u32]),
+    "gvt_render_fragment_glsl": (_i32, [_vp, C.POINTER(GvtGlslUniforms), _u32, _u32, _u32, C.c_float, _u32, _vp,
+                                        C.POINTER(GvtFrameStats)]),
+    "gvt_render_fragment_glsl_debug": (_i32, [_vp, _pu32, _pu32]),
     "gvt_render_export_frames": (_i32, [_vp, C.POINTER(C.c_uint8)]),
     "gvt_render_import_peer_frames": (_i32, [_vp, _i32, C.POINTER(C.c_uint8)]),
     "gvt_host_alloc": (_i32, [C.c_size_t, C.POINTER(_vp)]),

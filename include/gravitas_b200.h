@@ -52,7 +52,11 @@ enum { GVT_METHOD_RKF45 = 0, GVT_METHOD_RK4 = 1, GVT_METHOD_SYMPLECTIC = 2,
           (fragment.glsl.ts:129-221, chunks/metric.ts:96-149); max_steps is capped at 500 as there (:115); escape_radius
           plays MAX_DIST. Thin-disk light comes from the same LUT composite as the Hamiltonian path. */
        GVT_METHOD_VERLET_GLSL = 3 };
-enum { GVT_PRECISION_F64 = 0, GVT_PRECISION_F32 = 1 };
+enum {
+    GVT_PRECISION_F64 = 0,
+    GVT_PRECISION_F32 = 1,
+    GVT_PRECISION_F32_FAST = 2 /* gvt_render_fragment_glsl only: f32 with MUFU rcp/sqrt/exp2/log2/sin/cos, as a GLSL compiler builds the shader */
+};
 enum {
     GVT_FORMAT_RGBA32F = 0,
     GVT_FORMAT_RGBA16F = 1,        /* reprojection.ts:120-140 / webgpu/renderer.ts:161-180 texture format (linear HDR) */
@@ -127,6 +131,46 @@ typedef struct GvtRenderParams {
     float taa_blend;               /* GVT_FLAG_TAA_WEBGL: u_blendFactor (0.75 in webgl/renderer.ts:380-385) */
     uint32_t taa_camera_moving;    /* GVT_FLAG_TAA_WEBGL: u_cameraMoving */
 } GvtRenderParams;
+
+/* The production WebGL2 fragment shader's uniforms (src/shaders/blackhole/chunks/common.ts:9-38), with the values
+ * webgl/renderer.ts:296-358 uploads, plus the shader manager's #defines (src/shaders/manager.ts:55-82) as bits.
+ * Conventions GLSL leaves to the implementation, fixed here: u_noiseTex is sampled LINEAR + REPEAT with exact bilinear
+ * weights, u_blueNoiseTex NEAREST + REPEAT (webgl-utils.ts:259-303), only their red channels are read (as the shader
+ * does); normalize(v) = v / sqrt(dot(v, v)); row j of the output frame is gl_FragCoord.y = j + 0.5 (bottom-up). */
+enum {
+    GVT_GLSL_LENSING = 1,        /* ENABLE_LENSING */
+    GVT_GLSL_DISK = 2,           /* ENABLE_DISK */
+    GVT_GLSL_JETS = 4,           /* ENABLE_JETS (the manager emits it only together with the disk) */
+    GVT_GLSL_STARS = 8,          /* ENABLE_STARS */
+    GVT_GLSL_PHOTON_GLOW = 16,   /* ENABLE_PHOTON_GLOW */
+    GVT_GLSL_DOPPLER = 32,       /* ENABLE_DOPPLER */
+    GVT_GLSL_REDSHIFT = 64,      /* ENABLE_REDSHIFT */
+    GVT_GLSL_LINEAR_OUTPUT = 128,/* ENABLE_LINEAR_OUTPUT: skip ACES + gamma (the bloom pipeline tone-maps later) */
+    GVT_GLSL_QUALITY_LOW = 256   /* RAY_QUALITY_LOW / RAY_QUALITY_OFF: no march */
+};
+typedef struct GvtGlslUniforms {
+    uint32_t struct_size;        /* sizeof(GvtGlslUniforms) */
+    uint32_t features;           /* GVT_GLSL_* */
+    float resolution[2];         /* u_resolution (pixels) */
+    float time;                  /* u_time */
+    float mass;                  /* u_mass */
+    float spin;                  /* u_spin = a* x mass (renderer.ts:326) */
+    float disk_density;          /* u_disk_density (default 4) */
+    float disk_temp;             /* u_disk_temp = T x mass^-1/4 (renderer.ts:351-354) */
+    float mouse[2];              /* u_mouse: azimuth/2pi, polar/pi */
+    float zoom;                  /* u_zoom = 2 x params.zoom (renderer.ts:327) */
+    float lensing_strength;      /* u_lensing_strength */
+    float disk_size;             /* u_disk_size (default 50) */
+    float disk_scale_height;     /* u_disk_scale_height (default 0.2) */
+    int32_t max_ray_steps;       /* u_maxRaySteps (capped at 500 by the shader) */
+    float debug;                 /* u_debug */
+    float show_redshift;         /* u_show_redshift */
+    float show_kerr_shadow;      /* u_show_kerr_shadow */
+    float shadow_count;          /* u_shadowCount */
+    float cam_pos[3];            /* u_camPos: (0,0,0) selects the mouse/zoom camera, as renderer.ts:314 does */
+    float cam_quat[4];           /* u_camQuat xyzw */
+    float shadow_curve[128];     /* u_shadowCurve: 64 (alpha, beta) pairs, SAB PHYSICS block [16..143] */
+} GvtGlslUniforms;
 
 typedef struct GvtDeviceConfig {
     uint32_t struct_size;
@@ -227,6 +271,22 @@ int32_t gvt_taa_resolve(gvt_renderer* r, const GvtCamera* cam, uint32_t width, u
 int32_t gvt_taa_resolve_webgl(gvt_renderer* r, uint32_t width, uint32_t height, const float* cur, const float* hist,
                               float blend, int32_t camera_moving, float* out);
 int32_t gvt_render_reset_history(gvt_renderer* r);
+
+/* ---- Seam B, WebGL2 pipeline: WebGLRenderer.render(params, mouse) (src/rendering/webgl/renderer.ts:173-420) ----
+ * The two 256x256 RGBA8 noise textures the reference fills with Math.random() at init (webgl-utils.ts:259-303);
+ * here the caller supplies them, so a frame is a pure function of its inputs. */
+int32_t gvt_render_set_noise_textures(gvt_renderer* r, const uint8_t* noise_rgba8, const uint8_t* blue_noise_rgba8,
+                                      uint32_t size /* 256 */);
+/* One frame of the production fragment shader (fragment.glsl.ts) into the renderer's frame buffer (RGBA32F; alpha 1)
+ * and, if host_rgba is not NULL, into the caller's buffer in `output_format`. precision: GVT_PRECISION_F32 is the
+ * shader's own arithmetic with IEEE division / 1-2 ulp libm (the parity build), GVT_PRECISION_F32_FAST the same source
+ * on MUFU approximations (what a GL driver generates), GVT_PRECISION_F64 the rounding-insensitive reference. flags: GVT_FLAG_TAA | GVT_FLAG_TAA_WEBGL runs the WebGL2 TAA resolve after it
+ * (taa_blend / taa_camera_moving as in GvtRenderParams), plus the multi-GPU flags of gvt_render_frame. */
+int32_t gvt_render_fragment_glsl(gvt_renderer* r, const GvtGlslUniforms* u, uint32_t precision, uint32_t flags,
+                                 uint32_t output_format, float taa_blend, uint32_t taa_camera_moving, void* host_rgba,
+                                 GvtFrameStats* stats);
+/* Parity hook: per-pixel step count and horizon flag of the last gvt_render_fragment_glsl frame (width*height each). */
+int32_t gvt_render_fragment_glsl_debug(gvt_renderer* r, uint32_t* steps, uint32_t* hit);
 /* Peer-store gather (GVT_FLAG_PEER_STORE): each rank exports CUDA IPC handles of its two frame buffers; the host
  * exchanges them (any transport) and every rank imports every peer's pair. Call again after gvt_render_resize. All
  * ranks must issue the same sequence of gvt_render_frame calls (the buffers ping-pong in lockstep under TAA). */

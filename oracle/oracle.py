@@ -77,6 +77,8 @@ def lib():
             ("orc_render", d, [pf, C.POINTER(RenderParams), u32, u32, u32, u32, u32, pd, pd, C.POINTER(u32),
                                C.POINTER(u32), pd, C.POINTER(u32), C.POINTER(u64), C.POINTER(u64)]),
             ("orc_flop_census", None, [i, d, pd, d, C.POINTER(u64)]),
+            ("orc_fragment_glsl", d, [C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), i, u32, u32, u32, u32, u32, pd,
+                                      C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)]),
         ]:
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
@@ -244,3 +246,31 @@ def flop_census(what, spin, xp, h=0.1):
     d = {k: int(v) for k, v in zip(keys, out)}
     d["flops"] = d["add"] + d["mul"] + d["div"] + d["sqrt"]
     return d
+
+
+# ---- the production WebGL2 fragment shader (glsl_fragment_oracle.hpp) ------------------------------------------
+class GlslUniforms(C.Structure):  # chunks/common.ts:9-38 + shader-manager #defines; same layout as GvtGlslUniforms
+    _fields_ = [("struct_size", C.c_uint32), ("features", C.c_uint32), ("resolution", C.c_float * 2), ("time", C.c_float),
+                ("mass", C.c_float), ("spin", C.c_float), ("disk_density", C.c_float), ("disk_temp", C.c_float),
+                ("mouse", C.c_float * 2), ("zoom", C.c_float), ("lensing_strength", C.c_float), ("disk_size", C.c_float),
+                ("disk_scale_height", C.c_float), ("max_ray_steps", C.c_int32), ("debug", C.c_float),
+                ("show_redshift", C.c_float), ("show_kerr_shadow", C.c_float), ("shadow_count", C.c_float),
+                ("cam_pos", C.c_float * 3), ("cam_quat", C.c_float * 4), ("shadow_curve", C.c_float * 128)]
+
+
+def fragment_glsl(uniform_bytes, noise_r, blue_r, precision=0, x0=0, xs=1, y0=0, y1=None, ys=1):
+    """Run the GLSL-shader oracle over a pixel lattice. `uniform_bytes`: the raw bytes of a GvtGlslUniforms /
+    GlslUniforms structure. noise_r / blue_r: (256, 256) uint8 (the .r channels of u_noiseTex / u_blueNoiseTex)."""
+    u = GlslUniforms.from_buffer_copy(bytes(uniform_bytes))
+    W, H = int(u.resolution[0]), int(u.resolution[1])
+    y1 = H if y1 is None else y1
+    nx, ny = (W - x0 + xs - 1) // xs, (y1 - y0 + ys - 1) // ys
+    noise_r = np.ascontiguousarray(noise_r, np.uint8); blue_r = np.ascontiguousarray(blue_r, np.uint8)
+    assert noise_r.size == 65536 and blue_r.size == 65536
+    rgba = np.zeros((ny, nx, 4)); steps = np.zeros((ny, nx), np.uint32); hit = np.zeros((ny, nx), np.uint32)
+    photon = np.zeros((ny, nx), np.uint32); total = C.c_uint64(0)
+    pu8 = C.POINTER(C.c_uint8); pu32 = C.POINTER(C.c_uint32)
+    secs = lib().orc_fragment_glsl(C.addressof(u), noise_r.ctypes.data_as(pu8), blue_r.ctypes.data_as(pu8), precision,
+                                   x0, xs, y0, y1, ys, _pd(rgba), steps.ctypes.data_as(pu32), hit.ctypes.data_as(pu32),
+                                   photon.ctypes.data_as(pu32), C.byref(total))
+    return {"rgba": rgba, "steps": steps, "hit": hit, "photon": photon, "total_steps": total.value, "seconds": secs}

@@ -2,6 +2,7 @@
 // cpu_baseline / --impl reference legs ONLY). TEST INFRASTRUCTURE; never linked into the product.
 // PARITY STATUS: see gravitas_oracle.hpp header ("parity unpinned" for integrate/LUT/RGBA values).
 #include "gravitas_oracle.hpp"
+#include "glsl_fragment_oracle.hpp"
 #include <cstring>
 #include <chrono>
 #include <atomic>
@@ -232,6 +233,38 @@ double orc_render(const float* cam88, const orc_render_params* p, uint32_t x0, u
     auto t1 = std::chrono::steady_clock::now();
     if (total_steps) *total_steps = tsteps.load();
     if (total_rhs) *total_rhs = trhs.load();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// The production WebGL2 fragment shader (glsl_fragment_oracle.hpp) over the pixel lattice
+// {x0 + i*xs < width} x {y0 + j*ys < y1}; precision 0 = double, 1 = float (the shader's own arithmetic).
+// Outputs are dense arrays over the lattice; any may be null. Returns wall seconds.
+double orc_fragment_glsl(const orc::glsl::Uniforms* u, const uint8_t* noise_r, const uint8_t* blue_r, int precision,
+                         uint32_t x0, uint32_t xs, uint32_t y0, uint32_t y1, uint32_t ys, double* rgba, uint32_t* steps,
+                         uint32_t* hit, uint32_t* photon, uint64_t* total_steps) {
+    const uint32_t width = (uint32_t)u->resolution[0];
+    const uint32_t nx = (width - x0 + xs - 1) / xs, ny = (y1 - y0 + ys - 1) / ys;
+    orc::glsl::Textures tex{noise_r, blue_r};
+    std::atomic<uint64_t> tsteps{0};
+    auto t0 = std::chrono::steady_clock::now();
+    parallel_for((int64_t)ny, 1, [&](int64_t j) {
+        uint64_t ls = 0;
+        for (uint32_t i = 0; i < nx; i++) {
+            const uint32_t px = x0 + i * xs, py = y0 + (uint32_t)j * ys;
+            const size_t k = (size_t)j * nx + i;
+            double c[4]; uint32_t st, h, ph;
+            if (precision == 1) { auto o = orc::glsl::Shader<float>(*u, tex).main(px, py); for (int q = 0; q < 4; q++) c[q] = o.rgba[q]; st = o.steps; h = o.hit; ph = o.photon; }
+            else { auto o = orc::glsl::Shader<double>(*u, tex).main(px, py); for (int q = 0; q < 4; q++) c[q] = o.rgba[q]; st = o.steps; h = o.hit; ph = o.photon; }
+            if (rgba) for (int q = 0; q < 4; q++) rgba[4 * k + q] = c[q];
+            if (steps) steps[k] = st;
+            if (hit) hit[k] = h;
+            if (photon) photon[k] = ph;
+            ls += st;
+        }
+        tsteps += ls;
+    });
+    auto t1 = std::chrono::steady_clock::now();
+    if (total_steps) *total_steps = tsteps.load();
     return std::chrono::duration<double>(t1 - t0).count();
 }
 

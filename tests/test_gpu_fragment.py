@@ -1,0 +1,169 @@
+"""k_fragment_glsl (the reference's production WebGL2 fragment shader as one fused CUDA kernel) vs the C++ restatement
+of the GLSL in oracle/glsl_fragment_oracle.hpp, through the C ABI (gvt_render_fragment_glsl).
+
+Tolerances. The f64 instantiation must agree with the f64 oracle to rounding on every pixel whose march is not
+sitting on a discontinuity of the shader (floor() star cells, `if (x > threshold)` gates, integer step counts): the
+test requires identical per-pixel step counts / horizon flags on >= 99.9 % of pixels and 1e-9 absolute agreement of
+the (tone-mapped, [0,1]) colours on those. The f32 instantiation is the shader's own arithmetic; CUDA's and glibc's
+single-precision sin/exp/pow/log differ by an ulp or two and a 300-step march amplifies that, so f32 is checked
+statistically against the f32 oracle (median, 99th percentile) and against the f64 oracle as an accuracy statement."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def wgl(built):
+    from gravitas_b200 import webgl
+    r = webgl.WebGLRenderer(device=0, noise_seed=11)
+    assert r.init(), r.error
+    yield r
+    r.cleanup()
+
+
+def run_both(wgl, oracle, u, precision):
+    from gravitas_b200 import _lib
+    wgl.precision = precision
+    wgl.resize(int(u.resolution[0]), int(u.resolution[1]))
+    got = np.array(wgl.render({}, (u.mouse[0], u.mouse[1]), uniforms=u)).astype(np.float64)
+    steps, hit = wgl.debug_counts()
+    ref = oracle.fragment_glsl(bytes(u), wgl.noise_r, wgl.blue_r, precision=1 if precision == _lib.PRECISION_F32 else 0)
+    return got, steps, hit, ref
+
+
+FEATURE_SETS = {
+    "high-quality": dict(),
+    "balanced": dict(rayTracingQuality="medium", dopplerBeaming=False, photonSphereGlow=False, relativisticJets=False),
+    "no-lensing": dict(gravitationalLensing=False),
+    "redshift-overlay": dict(gravitationalRedshift=True),
+    "shadow-guide": dict(kerrShadow=True, relativisticJets=False),
+    "low": dict(rayTracingQuality="low"),
+}
+
+
+@pytest.mark.parametrize("name", list(FEATURE_SETS))
+def test_f64_kernel_matches_f64_oracle(wgl, oracle, name):
+    from gravitas_b200 import webgl, _lib
+    W, H = 160, 90
+    feats = dict(webgl.DEFAULT_FEATURES, **FEATURE_SETS[name])
+    params = dict(mass=1.0, spin=0.9, zoom=30.0, lensing=1.0)
+    u = webgl.make_uniforms(W, H, params, mouse=(0.5, 0.5 + 7.0 / 180.0), time=1.37, features=feats)
+    if name == "shadow-guide":
+        import gravitas_b200 as g
+        e = g.PhysicsEngine(1.0, 0.9)
+        curve = e.compute_shadow_curve(math.radians(97.0), 32)
+        u = webgl.make_uniforms(W, H, params, mouse=(0.5, 0.5 + 7.0 / 180.0), time=1.37, features=feats,
+                                shadow_curve=curve, shadow_count=curve.size // 2)
+    got, steps, hit, ref = run_both(wgl, oracle, u, _lib.PRECISION_F64)
+    assert np.all(np.isfinite(got)) and np.all(got[..., 3] == 1.0)
+    same = (steps == ref["steps"]) & (hit == ref["hit"])
+    assert same.mean() >= 0.999, f"{name}: step/horizon census differs on {(~same).sum()} of {same.size} pixels"
+    err = np.abs(got[..., :3] - ref["rgba"][..., :3])[same]
+    # frame values are stored as float32: 6e-8 relative on [0, ~2] values
+    assert np.percentile(err, 99.9) <= 5e-7, f"{name}: p99.9 abs err {np.percentile(err, 99.9):.3e}"
+    assert err.max() <= 2e-3, f"{name}: max abs err {err.max():.3e}"       # a star-cell / threshold flip on a rare pixel
+    assert wgl.last_stats.steps_committed == int(steps.sum())
+    if name not in ("low",):
+        assert ref["rgba"][..., :3].max() > 0.2 and int(steps.sum()) > W * H * 10   # a real picture, a real march
+
+
+def test_f32_kernel_statistics(wgl, oracle):
+    from gravitas_b200 import webgl, _lib
+    W, H = 192, 108
+    u = webgl.make_uniforms(W, H, dict(mass=1.0, spin=0.9, zoom=30.0, lensing=1.0), mouse=(0.47, 0.5 + 7.0 / 180.0), time=0.5)
+    got, steps, hit, ref = run_both(wgl, oracle, u, _lib.PRECISION_F32)
+    err = np.abs(got[..., :3] - ref["rgba"][..., :3])
+    assert np.median(err) <= 2e-6 and np.percentile(err, 99) <= 2e-3, (np.median(err), np.percentile(err, 99))
+    assert (steps == ref["steps"]).mean() >= 0.97
+    ref64 = oracle.fragment_glsl(bytes(u), wgl.noise_r, wgl.blue_r, precision=0)
+    e64 = np.abs(got[..., :3] - ref64["rgba"][..., :3])
+    assert np.median(e64) <= 5e-6 and np.percentile(e64, 99) <= 5e-3      # accuracy of the shader's f32 arithmetic
+
+
+def test_f32_fast_math_build_statistics(wgl, oracle):
+    """GVT_PRECISION_F32_FAST: the same kernel source built with MUFU approximations (what a GLSL compiler emits).
+    No bit-level claim: compared with the f64 oracle as an accuracy statement on the tone-mapped [0, 1] colours."""
+    from gravitas_b200 import webgl, _lib
+    W, H = 192, 108
+    u = webgl.make_uniforms(W, H, dict(mass=1.0, spin=0.9, zoom=30.0, lensing=1.0), mouse=(0.47, 0.5 + 7.0 / 180.0), time=0.5)
+    wgl.precision = _lib.PRECISION_F32_FAST
+    wgl.resize(W, H)
+    got = np.array(wgl.render({}, (0.47, 0.54), uniforms=u)).astype(np.float64)
+    steps, hit = wgl.debug_counts()
+    ref64 = oracle.fragment_glsl(bytes(u), wgl.noise_r, wgl.blue_r, precision=0)
+    e = np.abs(got[..., :3] - ref64["rgba"][..., :3])
+    assert np.all(np.isfinite(got))
+    assert np.median(e) <= 2e-5 and np.percentile(e, 99) <= 1e-2, (np.median(e), np.percentile(e, 99))
+    assert (steps == ref64["steps"]).mean() >= 0.95 and (hit == ref64["hit"]).mean() >= 0.999
+    wgl.precision = _lib.PRECISION_F32
+
+
+def test_quaternion_camera_mass_scaling_and_debug(wgl, oracle):
+    from gravitas_b200 import webgl, _lib
+    W, H = 97, 61                                   # ragged: partial tiles on both edges
+    q = (0.0, math.sin(0.1), 0.0, math.cos(0.1))    # small yaw
+    u = webgl.make_uniforms(W, H, dict(mass=2.5, spin=-0.6, zoom=40.0, lensing=0.7, diskTemp=20000.0), time=3.0,
+                            cam_pos=(3.0, 6.0, -70.0), cam_quat=q,
+                            features=dict(webgl.DEFAULT_FEATURES, relativisticJets=True))
+    got, steps, hit, ref = run_both(wgl, oracle, u, _lib.PRECISION_F64)
+    same = (steps == ref["steps"]) & (hit == ref["hit"])
+    assert same.mean() >= 0.999
+    assert np.percentile(np.abs(got[..., :3] - ref["rgba"][..., :3])[same], 99.9) <= 5e-7
+    # u_debug: the uv ramp (fragment.glsl.ts:45-48)
+    ud = webgl.make_uniforms(W, H, debug=1.0)
+    gd, _, _, rd = run_both(wgl, oracle, ud, _lib.PRECISION_F32)
+    np.testing.assert_allclose(gd[..., :3], rd["rgba"][..., :3], atol=1e-6)
+    assert abs(gd[H // 2, W // 2, 0] - 0.5) < 0.02 and abs(gd[H // 2, W // 2, 1] - 0.5) < 0.02
+
+
+def test_webgl_pipeline_with_taa_and_formats(wgl, oracle):
+    """render(params, mouse) twice with the TAA resolve on (as the reference with a ReprojectionManager): frame 2 ==
+    reprojection.glsl resolve of (shader frame 2, frame 1); RGBA8 read-back of a linear-output frame."""
+    import taa_oracle
+    from gravitas_b200 import webgl, _lib
+    W, H = 128, 72
+    wgl.precision = _lib.PRECISION_F32
+    wgl.resize(W, H)
+    wgl._k.reset_history()
+    wgl.taa = True
+    wgl.time = 0.0
+    params = dict(mass=1.0, spin=0.9, zoom=30.0, lensing=1.0, features=dict(webgl.DEFAULT_FEATURES, bloom=False))
+    mouse = {"x": 0.5, "y": 0.54}
+    try:
+        f1 = np.array(wgl.render(params, mouse))
+        assert wgl.last_stats.kernel_launches == 2 and wgl.last_stats.taa_ms > 0
+        f2 = np.array(wgl.render(params, mouse))
+        # un-resolved frame 2 from a second renderer with the same textures and time
+        plain = webgl.WebGLRenderer(device=0, noise_seed=11)
+        assert plain.init()
+        plain.resize(W, H)
+        u2 = webgl.make_uniforms(W, H, params, (0.5, 0.54), time=0.02, features=params["features"], has_post=True)
+        cur2 = np.array(plain.render({}, (0.5, 0.54), uniforms=u2))
+        plain.cleanup()
+        ref2 = taa_oracle.taa_resolve_webgl(cur2, f1, 0.75, False)
+        scale = float(np.abs(ref2[..., :3]).max())
+        np.testing.assert_allclose(f2, ref2, rtol=1e-3, atol=1e-3 * scale)
+    finally:
+        wgl.taa = False
+    # 8-bit display output of a tone-mapped frame
+    u = webgl.make_uniforms(W, H, params, (0.5, 0.54), time=0.3)
+    f32 = np.array(wgl.render({}, (0.5, 0.54), uniforms=u))
+    f16 = wgl.read_frame(_lib.FORMAT_RGBA16F)
+    np.testing.assert_allclose(f16.astype(np.float32), f32, rtol=1e-3, atol=1e-3)
+
+
+def test_fragment_validation(wgl):
+    from gravitas_b200 import webgl, _lib
+    import ctypes as C
+    u = webgl.make_uniforms(64, 36)
+    u.struct_size = 12
+    with pytest.raises(_lib.GravitasError):
+        wgl.render({}, (0.5, 0.5), uniforms=u)
+    u = webgl.make_uniforms(64, 36)
+    with pytest.raises(_lib.GravitasError):          # TAA without the WebGL variant has no camera to reproject with
+        wgl.render({}, (0.5, 0.5), uniforms=u, flags=_lib.FLAG_TAA)
+    with pytest.raises(_lib.GravitasError):
+        _lib.check(_lib.lib().gvt_render_set_noise_textures(wgl._k._h, None, None, 256))
