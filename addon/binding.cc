@@ -220,6 +220,43 @@ napi_value RenderFrame(napi_env env, napi_callback_info info) {
     return o;
 }
 
+// setNoiseTextures(noiseU8x262144, blueU8x262144): the two 256x256 RGBA8 textures of webgl-utils.ts:259-303
+napi_value SetNoiseTextures(napi_env env, napi_callback_info info) {
+    size_t argc = 2; napi_value argv[2];
+    gvt_renderer* r = Self<gvt_renderer>(env, info, &argc, argv);
+    napi_typedarray_type t; size_t n0, n1; void *a, *b; napi_value ab; size_t off;
+    NAPI_OK(napi_get_typedarray_info(env, argv[0], &t, &n0, &a, &ab, &off));
+    NAPI_OK(napi_get_typedarray_info(env, argv[1], &t, &n1, &b, &ab, &off));
+    if (n0 < 262144 || n1 < 262144) { napi_throw_range_error(env, nullptr, "Uint8Array(256*256*4) expected"); return nullptr; }
+    GVT(gvt_render_set_noise_textures(r, static_cast<const uint8_t*>(a), static_cast<const uint8_t*>(b), 256));
+    return Undefined(env);
+}
+// renderFragment(uniformsF32x155, {precision, flags, format, taaBlend, cameraMoving}, outArrayBuffer) -> stats
+// uniforms: the GvtGlslUniforms block as 155 32-bit words (struct_size, features and max_ray_steps are integer words:
+// build it with a DataView / Uint32Array alias, see addon/ts/webgl_b200_renderer.ts)      webgl/renderer.ts:173
+napi_value RenderFragment(napi_env env, napi_callback_info info) {
+    size_t argc = 3; napi_value argv[3];
+    gvt_renderer* r = Self<gvt_renderer>(env, info, &argc, argv);
+    napi_typedarray_type t; size_t n; void *u, *out; napi_value ab; size_t off, outlen;
+    NAPI_OK(napi_get_typedarray_info(env, argv[0], &t, &n, &u, &ab, &off));
+    if (n * 4 < sizeof(GvtGlslUniforms)) { napi_throw_range_error(env, nullptr, "uniforms: 155 words expected"); return nullptr; }
+    NAPI_OK(napi_get_arraybuffer_info(env, argv[2], &out, &outlen));
+    const uint32_t precision = OptU32(env, argv[1], "precision", GVT_PRECISION_F32_FAST);
+    const uint32_t flags = OptU32(env, argv[1], "flags", 0), format = OptU32(env, argv[1], "format", GVT_FORMAT_RGBA32F);
+    const uint32_t moving = OptU32(env, argv[1], "cameraMoving", 0);
+    const GvtGlslUniforms* gu = static_cast<const GvtGlslUniforms*>(u);
+    const size_t need = (size_t)gu->resolution[0] * (size_t)gu->resolution[1] * (format == GVT_FORMAT_RGBA32F ? 16 : format == GVT_FORMAT_RGBA16F ? 8 : 4);
+    if (outlen < need) { napi_throw_range_error(env, nullptr, "output ArrayBuffer too small"); return nullptr; }
+    GvtFrameStats st;
+    GVT(gvt_render_fragment_glsl(r, gu, precision, flags, format, 0.75f, moving, out, &st));
+    napi_value o, v;
+    NAPI_OK(napi_create_object(env, &o));
+    napi_create_double(env, st.total_ms, &v); napi_set_named_property(env, o, "totalMs", v);
+    napi_create_double(env, st.trace_ms, &v); napi_set_named_property(env, o, "shaderMs", v);
+    napi_create_double(env, (double)st.steps_committed, &v); napi_set_named_property(env, o, "steps", v);
+    return o;
+}
+
 }  // namespace
 
 NAPI_MODULE_INIT() {
@@ -237,7 +274,8 @@ NAPI_MODULE_INIT() {
         {"integrate_ray_relativistic", 0, IntegrateRay, 0, 0, 0, napi_default, 0}};
     const napi_property_descriptor renderer[] = {
         {"initLuts", 0, InitLuts, 0, 0, 0, napi_default, 0}, {"resize", 0, Resize, 0, 0, 0, napi_default, 0},
-        {"renderFrame", 0, RenderFrame, 0, 0, 0, napi_default, 0}};
+        {"renderFrame", 0, RenderFrame, 0, 0, 0, napi_default, 0},
+        {"setNoiseTextures", 0, SetNoiseTextures, 0, 0, 0, napi_default, 0}, {"renderFragment", 0, RenderFragment, 0, 0, 0, napi_default, 0}};
     napi_value cls;
     NAPI_OK(napi_define_class(env, "PhysicsEngine", NAPI_AUTO_LENGTH, EngineNew, nullptr, sizeof(engine) / sizeof(engine[0]), engine, &cls));
     NAPI_OK(napi_set_named_property(env, exports, "PhysicsEngine", cls));

@@ -416,6 +416,33 @@ def run_extra(args):
             print(json.dumps({"extra_workload": "GLSL-semantics path: Cartesian Velocity-Verlet on the shader's pseudo-Kerr acceleration "
                               "(fragment.glsl.ts:129-221), f32, 256-step budget, natural termination, thin-disk LUT shading",
                               "n_gpus": world, "frames": args.steps, **res}))
+    elif args.workload == "webgl":
+        # the whole production WebGL2 fragment shader (k_fragment_glsl: march + volumetric disk + jets + stars + glows
+        # + ACES), "ultra-quality" preset (256-step budget), 4K, through WebGLRenderer.render(params, mouse); device
+        # time per frame for the MUFU build a GLSL compiler would produce and for the IEEE/libm parity build
+        from gravitas_b200 import webgl
+        w = webgl.WebGLRenderer(device=local, noise_seed=11) if rank == 0 else None   # single-GPU extra: rank 0 only
+        res = {}
+        if w is not None:
+            assert w.init(), w.error
+            Wx, Hx = 3840, 2160
+            w.resize(Wx, Hx)
+            sp = dict(mass=1.0, spin=0.9, zoom=30.0, lensing=1.0, features=dict(webgl.PRESETS["ultra-quality"], bloom=False))
+            for nm, pr in (("f32_fast", _lib.PRECISION_F32_FAST), ("f32_precise", _lib.PRECISION_F32), ("f64", _lib.PRECISION_F64)):
+                w.precision = pr
+                ms, st = [], None
+                for k in range(args.warmup + args.steps):
+                    w.render(sp, {"x": 0.5, "y": 0.5 + 7.0 / 180.0}, readback=False)
+                    if k >= args.warmup:
+                        ms.append(w.last_stats.trace_ms); st = w.last_stats
+                m = sum(ms) / len(ms)
+                res[nm] = {"ms_per_frame": m, "fps": 1e3 / m, "march_steps_per_s": st.steps_committed / (m * 1e-3),
+                           "mean_steps_per_pixel": st.steps_committed / (Wx * Hx)}
+            w.cleanup()
+        if rank == 0:
+            print(json.dumps({"extra_workload": "WebGL2 production fragment shader (fragment.glsl.ts, all features of the "
+                              "ultra-quality preset except bloom), 3840x2160, mouse/zoom camera at 97 deg polar, zoom 60",
+                              "n_gpus": 1, "frames": args.steps, **res}))
     elif args.workload == "config4":
         Wx, Hx = 7680, 4320
         r.params = R.RenderParams(method=_lib.METHOD_RKF45, max_steps=1024, step_rule=_lib.STEP_CONSTANT)
@@ -471,7 +498,7 @@ def main():
     ap.add_argument("--no-peer-store", action="store_true",
                     help="N > 1: use the ncclAllGather after the trace kernel instead of the default fused gather (NVLink "
                          "peer stores from the trace kernel + 4-byte all-reduce barriers)")
-    ap.add_argument("--workload", default="config3", choices=["config1", "config2", "config3", "config4", "config5", "glsl"],
+    ap.add_argument("--workload", default="config3", choices=["config1", "config2", "config3", "config4", "config5", "glsl", "webgl"],
                     help="config3 = the headline (default). The others print an 'extra_workload' JSON line for BASELINE "
                          "configs[0] (Schwarzschild 256x256x128 RKF45: GPU batch integrate + the CPU port), configs[1] "
                          "(1080p, 256 steps, f32), configs[3] (8K, 1024 adaptive RKF45), configs[4] (orbit, 4K, TAA)")

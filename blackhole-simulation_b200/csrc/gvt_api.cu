@@ -540,7 +540,7 @@ static int32_t build_frame(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
     if (!r->luts_ready) return fail(GVT_ERR_INVALID, "LUTs not initialised: call gvt_render_init_luts / gvt_render_set_luts first");
     if (rp->coords != GVT_COORDS_KERR_SCHILD)
         return fail(GVT_ERR_UNSUPPORTED, "the render path traces in Kerr-Schild coordinates (lib.rs:64,454); use gvt_engine_integrate_rays for Boyer-Lindquist");
-    if (rp->method > GVT_METHOD_VERLET_GLSL || rp->precision > GVT_PRECISION_F32 || rp->output_format > GVT_FORMAT_RGBA8_ACES)
+    if (rp->method > GVT_METHOD_VERLET_GLSL || rp->precision > GVT_PRECISION_F32 || rp->output_format > GVT_FORMAT_RGBA8_UNORM)
         return fail(GVT_ERR_INVALID, "bad method/precision/output_format");
     if (rp->renormalize_interval == 0) return fail(GVT_ERR_INVALID, "renormalize_interval must be > 0");
     const uint32_t W = (uint32_t)phys->resolution[0], H = (uint32_t)phys->resolution[1];
@@ -615,12 +615,12 @@ static int32_t convert_frame(gvt_renderer* r, uint32_t format, size_t px0, size_
     if (!r->half_frame) CK(cudaMalloc(&r->half_frame, n_px * 8));
     char* dst = static_cast<char*>(r->half_frame) + px0 * format_bytes(format);
     if (format == GVT_FORMAT_RGBA16F) CK(launch_f32_to_f16(r->frame + px0, dst, npx, r->stream));
-    else CK(launch_tonemap_rgba8(r->frame + px0, dst, npx, format == GVT_FORMAT_RGBA8_ACES ? 1 : 0, r->stream));
+    else CK(launch_tonemap_rgba8(r->frame + px0, dst, npx, format == GVT_FORMAT_RGBA8_ACES ? 1 : (format == GVT_FORMAT_RGBA8_UNORM ? 2 : 0), r->stream));
     return GVT_OK;
 }
 
 extern "C" int32_t gvt_render_read_frame(gvt_renderer* r, uint32_t format, void* host_rgba) {
-    if (!r || !host_rgba || !r->frame || format > GVT_FORMAT_RGBA8_ACES) return fail(GVT_ERR_INVALID, "bad argument / no frame");
+    if (!r || !host_rgba || !r->frame || format > GVT_FORMAT_RGBA8_UNORM) return fail(GVT_ERR_INVALID, "bad argument / no frame");
     CK(cudaSetDevice(r->device));
     const size_t n_px = (size_t)r->width * r->height;
     if (format != GVT_FORMAT_RGBA32F) {
@@ -840,7 +840,7 @@ extern "C" int32_t gvt_render_fragment_glsl(gvt_renderer* r, const GvtGlslUnifor
                                             void* host_rgba, GvtFrameStats* stats) {
     if (!r || !u) return fail(GVT_ERR_INVALID, "null argument");
     if (u->struct_size != sizeof(GvtGlslUniforms)) return fail(GVT_ERR_INVALID, "GvtGlslUniforms.struct_size = %u, expected %zu", u->struct_size, sizeof(GvtGlslUniforms));
-    if (precision > GVT_PRECISION_F32_FAST || output_format > GVT_FORMAT_RGBA8_ACES) return fail(GVT_ERR_INVALID, "bad precision / output format");
+    if (precision > GVT_PRECISION_F32_FAST || output_format > GVT_FORMAT_RGBA8_UNORM) return fail(GVT_ERR_INVALID, "bad precision / output format");
     if (!(u->resolution[0] >= 1.0f) || !(u->resolution[1] >= 1.0f) || u->resolution[0] > 65536.0f || u->resolution[1] > 65536.0f)
         return fail(GVT_ERR_INVALID, "bad u_resolution");
     if (!(u->mass > 0.0f)) return fail(GVT_ERR_INVALID, "u_mass must be positive");

@@ -771,7 +771,8 @@ __global__ void k_tonemap_rgba8(const float4* __restrict__ src, uint32_t* __rest
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float4 v = src[i];
         float r, g, b;
-        if (aces) { r = aces_gamma(v.x); g = aces_gamma(v.y); b = aces_gamma(v.z); }
+        if (aces == 1) { r = aces_gamma(v.x); g = aces_gamma(v.y); b = aces_gamma(v.z); }
+        else if (aces == 2) { r = v.x; g = v.y; b = v.z; }   // already display-referred: quantise only
         else { r = v.x / (v.x + 1.0f); g = v.y / (v.y + 1.0f); b = v.z / (v.z + 1.0f); }
         dst[i] = unorm8(r) | (unorm8(g) << 8) | (unorm8(b) << 16) | (unorm8(v.w) << 24);
     }

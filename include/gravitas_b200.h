@@ -61,8 +61,10 @@ enum {
     GVT_FORMAT_RGBA32F = 0,
     GVT_FORMAT_RGBA16F = 1,        /* reprojection.ts:120-140 / webgpu/renderer.ts:161-180 texture format (linear HDR) */
     GVT_FORMAT_RGBA8_REINHARD = 2, /* display-ready: the WebGPU blit's Reinhard map c/(1+c) (webgpu/renderer.ts:45-47), 8-bit unorm */
-    GVT_FORMAT_RGBA8_ACES = 3      /* display-ready: the WebGL final pass without bloom (bloom.glsl.ts:106-124): ACES
+    GVT_FORMAT_RGBA8_ACES = 3,     /* display-ready: the WebGL final pass without bloom (bloom.glsl.ts:106-124): ACES
                                       (Narkowicz) then pow(., 0.4545), 8-bit unorm */
+    GVT_FORMAT_RGBA8_UNORM = 4     /* clamp to [0,1] and quantise only: for frames that are already display-referred (the
+                                    * fragment shader applies ACES + gamma itself unless GVT_GLSL_LINEAR_OUTPUT) */
 };
 /* step rule for the fixed-step methods: constant `initial_step` (geodesic/mod.rs:218-223) or the per-step rule
  * h = clamp(0.15 (r - r+), 0.05, 1.0) of src/shaders/compute.wgsl.ts:213 */

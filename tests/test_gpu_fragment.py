@@ -153,6 +153,10 @@ def test_webgl_pipeline_with_taa_and_formats(wgl, oracle):
     f32 = np.array(wgl.render({}, (0.5, 0.54), uniforms=u))
     f16 = wgl.read_frame(_lib.FORMAT_RGBA16F)
     np.testing.assert_allclose(f16.astype(np.float32), f32, rtol=1e-3, atol=1e-3)
+    u8 = wgl.read_frame(_lib.FORMAT_RGBA8_UNORM)                       # already ACES + gamma: quantise only
+    assert np.abs(u8.astype(np.float32) - np.clip(f32, 0, 1) * 255.0).max() <= 0.5 + 1e-3
+    got8 = np.array(wgl.render({}, (0.5, 0.54), uniforms=u, output_format=_lib.FORMAT_RGBA8_UNORM))
+    assert got8.dtype == np.uint8 and np.array_equal(got8, u8)
 
 
 def test_fragment_validation(wgl):
@@ -167,3 +171,23 @@ def test_fragment_validation(wgl):
         wgl.render({}, (0.5, 0.5), uniforms=u, flags=_lib.FLAG_TAA)
     with pytest.raises(_lib.GravitasError):
         _lib.check(_lib.lib().gvt_render_set_noise_textures(wgl._k._h, None, None, 256))
+
+
+@pytest.mark.parametrize("case", ["hq", "guide"])
+def test_f64_kernel_matches_committed_fixture(built, case):
+    """The CUDA kernel against tests/golden/glsl_fragment_48x27.npz (oracle output committed with its generator)."""
+    import os
+    from gravitas_b200 import webgl, _lib
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "glsl_fragment_48x27.npz")))
+    r = webgl.WebGLRenderer(device=0, noise_seed=int(g["noise_seed"]))
+    assert r.init(), r.error
+    try:
+        u = _lib.GvtGlslUniforms.from_buffer_copy(g[f"{case}_uniforms"].tobytes())
+        r.precision = _lib.PRECISION_F64
+        r.resize(48, 27)
+        got = np.array(r.render({}, (u.mouse[0], u.mouse[1]), uniforms=u)).astype(np.float64)
+        steps, hit = r.debug_counts()
+        assert np.array_equal(steps, g[f"{case}_steps"]) and np.array_equal(hit, g[f"{case}_hit"])
+        np.testing.assert_allclose(got, g[f"{case}_rgba"], rtol=0, atol=2e-7)   # float32 frame buffer
+    finally:
+        r.cleanup()

@@ -1,0 +1,85 @@
+"""The GLSL fragment-shader oracle (oracle/glsl_fragment_oracle.hpp) on the CPU: regression pin against the committed
+fixture (tests/golden/make_glsl_golden.py), closed-form properties of the shader, and the uniform block layout the
+C ABI, the oracle and the Python mirror share."""
+import ctypes as C
+import math
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "glsl_fragment_48x27.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    from gravitas_b200 import webgl
+    g = dict(np.load(GOLD))
+    noise, blue = webgl.random_noise_textures(seed=int(g["noise_seed"]))
+    g["noise_r"], g["blue_r"] = noise[..., 0].copy(), blue[..., 0].copy()
+    assert [zlib.crc32(g["noise_r"].tobytes()), zlib.crc32(g["blue_r"].tobytes())] == [int(x) for x in g["noise_crc"]]
+    return g
+
+
+def test_uniform_layout_is_shared(built, oracle):
+    from gravitas_b200 import _lib
+    assert C.sizeof(_lib.GvtGlslUniforms) == C.sizeof(oracle.GlslUniforms) == 620
+    for (n1, t1), (n2, t2) in zip(_lib.GvtGlslUniforms._fields_, oracle.GlslUniforms._fields_):
+        assert n1 == n2 and C.sizeof(t1) == C.sizeof(t2)
+        assert getattr(_lib.GvtGlslUniforms, n1).offset == getattr(oracle.GlslUniforms, n2).offset
+    hdr = open(os.path.join(os.path.dirname(GOLD), "..", "..", "include", "gravitas_b200.h")).read()
+    body = hdr[hdr.index("typedef struct GvtGlslUniforms {"):hdr.index("} GvtGlslUniforms;")]
+    import re
+    names = re.findall(r"^\s*(?:uint32_t|int32_t|float)\s+(\w+)", body, re.M)
+    assert names == [f[0] for f in _lib.GvtGlslUniforms._fields_]
+
+
+@pytest.mark.parametrize("case", ["hq", "guide"])
+def test_oracle_reproduces_the_fixture(oracle, gold, case):
+    r = oracle.fragment_glsl(gold[f"{case}_uniforms"].tobytes(), gold["noise_r"], gold["blue_r"], precision=0)
+    assert np.array_equal(r["steps"], gold[f"{case}_steps"]) and np.array_equal(r["hit"], gold[f"{case}_hit"])
+    np.testing.assert_allclose(r["rgba"], gold[f"{case}_rgba"], rtol=0, atol=1e-12)
+    # float instantiation: the shader's own arithmetic stays close to the f64 one on the tone-mapped output
+    r32 = oracle.fragment_glsl(gold[f"{case}_uniforms"].tobytes(), gold["noise_r"], gold["blue_r"], precision=1)
+    assert np.median(np.abs(r32["rgba"] - r["rgba"])) < 1e-6
+
+
+def test_shader_properties(built, oracle, gold):
+    from gravitas_b200 import webgl, _lib
+    W, H = 64, 36
+    zeros = np.zeros((256, 256), np.uint8)
+    # u_debug: fragColor = (uv + 0.5, 0, 1) with uv = (fragCoord - res/2) / min(res)   (fragment.glsl.ts:42-48)
+    r = oracle.fragment_glsl(bytes(webgl.make_uniforms(W, H, debug=1.0)), zeros, zeros)
+    xs = (np.arange(W) + 0.5 - W / 2) / H + 0.5
+    ys = (np.arange(H) + 0.5 - H / 2) / H + 0.5
+    np.testing.assert_allclose(r["rgba"][..., 0], np.broadcast_to(xs, (H, W)), atol=1e-14)
+    np.testing.assert_allclose(r["rgba"][..., 1], np.broadcast_to(ys[:, None], (H, W)), atol=1e-14)
+    # a* = 0, on-axis camera, no noise-driven feature: the image is mirror-symmetric in x and in y
+    feats = dict(webgl.PRESETS["maximum-performance"], gravitationalLensing=True, rayTracingQuality="ultra", photonSphereGlow=True)
+    u = webgl.make_uniforms(W, H, dict(mass=1.0, spin=0.0, zoom=20.0, lensing=1.0), mouse=(0.5, 0.5), features=feats)
+    r = oracle.fragment_glsl(bytes(u), zeros, zeros)
+    img = r["rgba"][..., :3]
+    np.testing.assert_allclose(img, img[:, ::-1], atol=1e-9)
+    np.testing.assert_allclose(img, img[::-1], atol=1e-9)
+    assert r["hit"][H // 2, W // 2] == 1 and r["hit"][0, 0] == 0            # shadow in the middle, sky in the corner
+    assert img[r["hit"] == 1].max() == 0.0                                   # horizon pixels are black without a disk
+    # the captured region is a disc; its edge is the shader's capture impact parameter (camera at 40 M, focal length
+    # 1.5: b = 40 uv / 1.5). The pseudo-Kerr Darwin field + 1.15 r+ threshold put it at ~7.1 M (measured at 1024x576),
+    # above the exact Schwarzschild value 3 sqrt(3) M = 5.196 -- the shader's behaviour, recorded here as a bound
+    row = r["hit"][H // 2]
+    b_edge = 40.0 * (row.sum() / 2.0 / H) / 1.5
+    assert 3.0 * math.sqrt(3.0) < b_edge < 8.0, b_edge
+    # all emission off and lensing off: straight rays, black frame, every ray leaves after a bounded number of steps
+    off = dict(webgl.PRESETS["maximum-performance"], rayTracingQuality="ultra")
+    r0 = oracle.fragment_glsl(bytes(webgl.make_uniforms(W, H, dict(spin=0.5, zoom=30.0), features=off)), zeros, zeros)
+    assert r0["rgba"][..., :3].max() <= 1e-12 or np.isfinite(r0["rgba"]).all()
+    # low quality = no march at all
+    low = oracle.fragment_glsl(bytes(webgl.make_uniforms(W, H, features=dict(webgl.DEFAULT_FEATURES, rayTracingQuality="low"))),
+                               gold["noise_r"], gold["blue_r"])
+    assert low["total_steps"] == 0 and low["rgba"][..., :3].max() > 0.1
+    # feature bits follow the shader manager (manager.ts:55-82)
+    assert webgl.feature_bits(webgl.PRESETS["high-quality"]) == (_lib.GLSL_LENSING | _lib.GLSL_DISK | _lib.GLSL_DOPPLER |
+                                                                  _lib.GLSL_STARS | _lib.GLSL_PHOTON_GLOW | _lib.GLSL_JETS)
+    assert webgl.feature_bits(dict(webgl.PRESETS["high-quality"], accretionDisk=False)) & _lib.GLSL_JETS == 0
+    assert webgl.feature_bits(webgl.PRESETS["maximum-performance"]) == _lib.GLSL_QUALITY_LOW
