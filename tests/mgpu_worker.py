@@ -88,5 +88,32 @@ assert np.array_equal(np.array(shared.array()), b), f"rank {rank}: shared host f
 dist.barrier()
 shared.close()
 multi.cleanup(); single.cleanup()
+
+# the WebGL2 fragment-shader path shares the pipeline: sharded rows + all-gather / fused peer stores, with and without
+# the WebGL TAA resolve, bit-identical to the single-GPU frames
+from gravitas_b200 import webgl
+ids = [g.KerrRenderer.nccl_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(ids, src=0)
+wm = webgl.WebGLRenderer(device=local, rank=rank, world_size=world, nccl_id=ids[0], noise_seed=3)
+ws = webgl.WebGLRenderer(device=local, noise_seed=3)
+assert wm.init() and ws.init(), (wm.error, ws.error)
+sp = dict(mass=1.0, spin=0.9, zoom=30.0, lensing=1.0, features=dict(webgl.PRESETS["high-quality"], bloom=False))
+for (W, H) in ((192, 108), (157, 83)):
+    for taa in (False, True):
+        for peer in (False, True):
+            wm.resize(W, H); ws.resize(W, H)
+            wm._k.reset_history(); ws._k.reset_history()
+            if peer:
+                wm._k.connect_peers(dist)
+            wm.taa = ws.taa = taa
+            wm.time = ws.time = 0.0
+            for k in range(2):
+                mouse = {"x": 0.5 + 0.001 * k, "y": 0.54}
+                a = np.array(wm.render(sp, mouse, flags=_lib.FLAG_PEER_STORE if peer else 0))
+                b = np.array(ws.render(sp, mouse))
+                assert (wm.last_stats.rows_begin, wm.last_stats.rows_end) == shard.shard_rows(H, rank, world)
+                assert np.array_equal(a, b), f"rank {rank}: fragment-shader frame differs (W={W} H={H} taa={taa} peer={peer} k={k})"
+dist.barrier()
+wm.cleanup(); ws.cleanup()
 dist.destroy_process_group()
 print(f"rank {rank} ok")
