@@ -246,7 +246,8 @@ napi_value RenderFragment(napi_env env, napi_callback_info info) {
     const uint32_t moving = OptU32(env, argv[1], "cameraMoving", 0);
     const GvtGlslUniforms* gu = static_cast<const GvtGlslUniforms*>(u);
     const size_t need = (size_t)gu->resolution[0] * (size_t)gu->resolution[1] * (format == GVT_FORMAT_RGBA32F ? 16 : format == GVT_FORMAT_RGBA16F ? 8 : 4);
-    if (outlen < need) { napi_throw_range_error(env, nullptr, "output ArrayBuffer too small"); return nullptr; }
+    if (outlen == 0) out = nullptr;                                               // frame stays on the device (bloom follows)
+    else if (outlen < need) { napi_throw_range_error(env, nullptr, "output ArrayBuffer too small"); return nullptr; }
     GvtFrameStats st;
     GVT(gvt_render_fragment_glsl(r, gu, precision, flags, format, 0.75f, moving, out, &st));
     napi_value o, v;
@@ -254,6 +255,26 @@ napi_value RenderFragment(napi_env env, napi_callback_info info) {
     napi_create_double(env, st.total_ms, &v); napi_set_named_property(env, o, "totalMs", v);
     napi_create_double(env, st.trace_ms, &v); napi_set_named_property(env, o, "shaderMs", v);
     napi_create_double(env, (double)st.steps_committed, &v); napi_set_named_property(env, o, "steps", v);
+    return o;
+}
+
+// bloom({enabled, intensity, threshold, blurPasses, format}, outArrayBuffer) -> ms      rendering/bloom.ts:446-632
+napi_value Bloom(napi_env env, napi_callback_info info) {
+    size_t argc = 2; napi_value argv[2];
+    gvt_renderer* r = Self<gvt_renderer>(env, info, &argc, argv);
+    GvtBloomConfig cfg; memset(&cfg, 0, sizeof(cfg));
+    cfg.struct_size = sizeof(cfg);
+    cfg.enabled = OptU32(env, argv[0], "enabled", 1); cfg.blur_passes = OptU32(env, argv[0], "blurPasses", 2);
+    cfg.intensity = 0.5f; cfg.threshold = 0.8f;                                   // bloom.ts:32-39
+    bool has = false; napi_value v;
+    if (napi_has_named_property(env, argv[0], "intensity", &has) == napi_ok && has) { napi_get_named_property(env, argv[0], "intensity", &v); cfg.intensity = (float)Num(env, v); }
+    if (napi_has_named_property(env, argv[0], "threshold", &has) == napi_ok && has) { napi_get_named_property(env, argv[0], "threshold", &v); cfg.threshold = (float)Num(env, v); }
+    void* out; size_t outlen;
+    NAPI_OK(napi_get_arraybuffer_info(env, argv[1], &out, &outlen));
+    double ms = 0;
+    if (outlen == 0) out = nullptr;
+    GVT(gvt_render_bloom(r, &cfg, OptU32(env, argv[0], "format", GVT_FORMAT_RGBA8_UNORM), out, &ms));
+    napi_value o; napi_create_double(env, ms, &o);
     return o;
 }
 
@@ -275,7 +296,8 @@ NAPI_MODULE_INIT() {
     const napi_property_descriptor renderer[] = {
         {"initLuts", 0, InitLuts, 0, 0, 0, napi_default, 0}, {"resize", 0, Resize, 0, 0, 0, napi_default, 0},
         {"renderFrame", 0, RenderFrame, 0, 0, 0, napi_default, 0},
-        {"setNoiseTextures", 0, SetNoiseTextures, 0, 0, 0, napi_default, 0}, {"renderFragment", 0, RenderFragment, 0, 0, 0, napi_default, 0}};
+        {"setNoiseTextures", 0, SetNoiseTextures, 0, 0, 0, napi_default, 0}, {"renderFragment", 0, RenderFragment, 0, 0, 0, napi_default, 0},
+        {"bloom", 0, Bloom, 0, 0, 0, napi_default, 0}};
     napi_value cls;
     NAPI_OK(napi_define_class(env, "PhysicsEngine", NAPI_AUTO_LENGTH, EngineNew, nullptr, sizeof(engine) / sizeof(engine[0]), engine, &cls));
     NAPI_OK(napi_set_named_property(env, exports, "PhysicsEngine", cls));

@@ -74,7 +74,14 @@ export class WebGLB200Renderer {
       for (let i = 0; i < 64; i++) { const phi = (i / 64) * Math.PI * 2; u[27 + 2 * i] = Math.cos(phi) * b; u[28 + 2 * i] = Math.sin(phi) * b; }
     }
     u[19] = count;
-    const stats = this.r.renderFragment(u, { format: 4 /* RGBA8_UNORM: the shader already applied ACES + gamma */, cameraMoving: moving ? 1 : 0 }, this.out);
+    let stats;
+    if (f.bloom) {                                                // renderer.ts:366-399: linear HDR scene -> bloom -> final pass
+      w[1] = bits | F.LINEAR_OUTPUT;
+      stats = this.r.renderFragment(u, { format: 0, cameraMoving: moving ? 1 : 0 }, new ArrayBuffer(0));
+      this.r.bloom({ enabled: 1, format: 4 }, this.out);          // bloom.ts:32-39 defaults
+    } else {
+      stats = this.r.renderFragment(u, { format: 4 /* RGBA8_UNORM: the shader already applied ACES + gamma */, cameraMoving: moving ? 1 : 0 }, this.out);
+    }
     if (this.onMetricsUpdate) this.onMetricsUpdate(stats);
     if (this.ctx) {                                               // rows arrive bottom-up (gl_FragCoord): flip while blitting
       const img = this.ctx.createImageData(this.width, this.height), src = new Uint8Array(this.out), rb = this.width * 4;

@@ -438,6 +438,13 @@ def run_extra(args):
                 m = sum(ms) / len(ms)
                 res[nm] = {"ms_per_frame": m, "fps": 1e3 / m, "march_steps_per_s": st.steps_committed / (m * 1e-3),
                            "mean_steps_per_pixel": st.steps_committed / (Wx * Hx)}
+            # post tail on the last frame: WebGL TAA resolve is part of render() when w.taa; bloom + final pass here
+            bl = []
+            for k in range(args.warmup + args.steps):
+                w._k.bloom(enabled=True, readback=False)
+                if k >= args.warmup:
+                    bl.append(w._k.last_bloom_ms)
+            res["bloom_final_pass_ms"] = sum(bl) / len(bl)
             w.cleanup()
         if rank == 0:
             print(json.dumps({"extra_workload": "WebGL2 production fragment shader (fragment.glsl.ts, all features of the "

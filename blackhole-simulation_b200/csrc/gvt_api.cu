@@ -375,6 +375,9 @@ struct gvt_renderer {
     // WebGL2 fragment-shader path: red channels of the two noise textures, per-pixel parity hooks
     uint8_t* d_noise_r = nullptr; uint8_t* d_blue_r = nullptr;
     uint32_t* d_gsteps = nullptr; uint32_t* d_ghit = nullptr; size_t g_cap = 0;
+    // bloom: display-referred output + RGBA16F scratch (half-res bright texture, two quarter-res blur textures)
+    float4* display = nullptr; uint2* bloom_half = nullptr; uint2* bloom_q1 = nullptr; uint2* bloom_q2 = nullptr;
+    uint32_t bloom_w = 0, bloom_h = 0;
 };
 
 extern "C" int32_t gvt_render_params_default(GvtRenderParams* p) {
@@ -465,6 +468,10 @@ extern "C" int32_t gvt_render_destroy(gvt_renderer* r) {
     if (r->d_blue_r) cudaFree(r->d_blue_r);
     if (r->d_gsteps) cudaFree(r->d_gsteps);
     if (r->d_ghit) cudaFree(r->d_ghit);
+    if (r->display) cudaFree(r->display);
+    if (r->bloom_half) cudaFree(r->bloom_half);
+    if (r->bloom_q1) cudaFree(r->bloom_q1);
+    if (r->bloom_q2) cudaFree(r->bloom_q2);
     for (auto& e : r->ev) if (e) cudaEventDestroy(e);
     if (r->stream) cudaStreamDestroy(r->stream);
     delete r;
@@ -850,6 +857,51 @@ extern "C" int32_t gvt_render_fragment_glsl(gvt_renderer* r, const GvtGlslUnifor
     rp.output_format = output_format;
     rp.taa_blend = taa_blend; rp.taa_camera_moving = taa_camera_moving;
     return render_impl(r, nullptr, nullptr, &rp, u, precision, host_rgba, stats);
+}
+
+// rendering/bloom.ts:446-632 on the finished frame
+extern "C" int32_t gvt_render_bloom(gvt_renderer* r, const GvtBloomConfig* cfg, uint32_t output_format, void* host_out, double* ms) {
+    if (!r || !cfg) return fail(GVT_ERR_INVALID, "null argument");
+    if (cfg->struct_size != sizeof(GvtBloomConfig)) return fail(GVT_ERR_INVALID, "GvtBloomConfig.struct_size = %u", cfg->struct_size);
+    if (!r->frame || r->width == 0) return fail(GVT_ERR_INVALID, "no frame rendered yet");
+    if (output_format != GVT_FORMAT_RGBA32F && output_format != GVT_FORMAT_RGBA16F && output_format != GVT_FORMAT_RGBA8_UNORM)
+        return fail(GVT_ERR_INVALID, "bloom output is display-referred: RGBA32F, RGBA16F or RGBA8_UNORM");
+    if (cfg->blur_passes > 16) return fail(GVT_ERR_INVALID, "blur_passes > 16");
+    CK(cudaSetDevice(r->device));
+    const int W = (int)r->width, H = (int)r->height;
+    if (r->bloom_w != r->width || r->bloom_h != r->height || !r->display) {
+        CK(cudaStreamSynchronize(r->stream));
+        if (r->display) cudaFree(r->display);
+        if (r->bloom_half) cudaFree(r->bloom_half);
+        if (r->bloom_q1) cudaFree(r->bloom_q1);
+        if (r->bloom_q2) cudaFree(r->bloom_q2);
+        r->display = nullptr; r->bloom_half = r->bloom_q1 = r->bloom_q2 = nullptr; r->bloom_w = r->bloom_h = 0;
+        const size_t hw = (size_t)std::max(1, W / 2), hh = (size_t)std::max(1, H / 2), bw = (size_t)std::max(1, W / 4), bh = (size_t)std::max(1, H / 4);
+        CK(cudaMalloc(&r->display, (size_t)W * H * sizeof(float4)));
+        CK(cudaMalloc(&r->bloom_half, hw * hh * sizeof(uint2)));
+        CK(cudaMalloc(&r->bloom_q1, bw * bh * sizeof(uint2)));
+        CK(cudaMalloc(&r->bloom_q2, bw * bh * sizeof(uint2)));
+        r->bloom_w = r->width; r->bloom_h = r->height;
+    }
+    int launches = 0;
+    CK(cudaEventRecord(r->ev[0], r->stream));
+    CK(launch_bloom(r->frame, W, H, r->bloom_half, r->bloom_q1, r->bloom_q2, r->display, cfg->threshold, cfg->intensity,
+                    (int)cfg->blur_passes, cfg->enabled ? 1 : 0, r->sm_count, r->stream, &launches));
+    CK(cudaEventRecord(r->ev[1], r->stream));
+    if (host_out) {
+        const size_t n_px = (size_t)W * H;
+        if (output_format == GVT_FORMAT_RGBA32F) {
+            CK(cudaMemcpyAsync(host_out, r->display, n_px * sizeof(float4), cudaMemcpyDeviceToHost, r->stream));
+        } else {
+            if (!r->half_frame) CK(cudaMalloc(&r->half_frame, n_px * 8));
+            if (output_format == GVT_FORMAT_RGBA16F) CK(launch_f32_to_f16(r->display, r->half_frame, n_px, r->stream));
+            else CK(launch_tonemap_rgba8(r->display, r->half_frame, n_px, 2, r->stream));
+            CK(cudaMemcpyAsync(host_out, r->half_frame, n_px * format_bytes(output_format), cudaMemcpyDeviceToHost, r->stream));
+        }
+    }
+    CK(cudaStreamSynchronize(r->stream));
+    if (ms) { float t = 0.f; cudaEventElapsedTime(&t, r->ev[0], r->ev[1]); *ms = t; }
+    return GVT_OK;
 }
 
 extern "C" int32_t gvt_render_fragment_glsl_debug(gvt_renderer* r, uint32_t* steps, uint32_t* hit) {

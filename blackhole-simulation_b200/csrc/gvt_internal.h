@@ -99,6 +99,9 @@ cudaError_t launch_trace(const FrameParams& p, int method, int precision, bool b
 cudaError_t launch_integrate_rays(const RayBatchParams& p, cudaStream_t stream);
 cudaError_t launch_taa(const TaaParams& p, int sm_count, cudaStream_t stream);
 cudaError_t launch_fragment_glsl(const GlslParams& p, int precision, int sm_count, cudaStream_t stream);
+cudaError_t launch_bloom(const float4* frame, int W, int H, uint2* half_tex, uint2* q1, uint2* q2, float4* display,
+                         float threshold, float intensity, int blur_passes, int enabled, int sm_count, cudaStream_t stream,
+                         int* launches);
 cudaError_t launch_fragment_glsl_fast(const GlslParams& p, int sm_count, cudaStream_t stream);   // f32, MUFU maths
 cudaError_t launch_f32_to_f16(const float4* src, void* dst, size_t n_px, cudaStream_t stream);
 cudaError_t launch_tonemap_rgba8(const float4* src, void* dst, size_t n_px, int aces, cudaStream_t stream);

@@ -60,6 +60,11 @@ class GvtGlslUniforms(C.Structure):  # chunks/common.ts:9-38 uniforms + shader-m
                 ("cam_pos", C.c_float * 3), ("cam_quat", C.c_float * 4), ("shadow_curve", C.c_float * 128)]
 
 
+class GvtBloomConfig(C.Structure):  # rendering/bloom.ts:22-39
+    _fields_ = [("struct_size", C.c_uint32), ("enabled", C.c_uint32), ("intensity", C.c_float), ("threshold", C.c_float),
+                ("blur_passes", C.c_uint32)]
+
+
 class GvtDeviceConfig(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("rank", C.c_int32), ("world_size", C.c_int32),
                 ("nccl_id", C.c_uint8 * 128)]
@@ -124,6 +129,7 @@ SIGNATURES = {
     "gvt_render_fragment_glsl": (_i32, [_vp, C.POINTER(GvtGlslUniforms), _u32, _u32, _u32, C.c_float, _u32, _vp,
                                         C.POINTER(GvtFrameStats)]),
     "gvt_render_fragment_glsl_debug": (_i32, [_vp, _pu32, _pu32]),
+    "gvt_render_bloom": (_i32, [_vp, C.POINTER(GvtBloomConfig), _u32, _vp, _pd]),
     "gvt_render_export_frames": (_i32, [_vp, C.POINTER(C.c_uint8)]),
     "gvt_render_import_peer_frames": (_i32, [_vp, _i32, C.POINTER(C.c_uint8)]),
     "gvt_host_alloc": (_i32, [C.c_size_t, C.POINTER(_vp)]),

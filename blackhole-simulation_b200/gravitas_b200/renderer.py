@@ -250,6 +250,18 @@ class KerrRenderer:
                                           1 if camera_moving else 0, out.ctypes.data_as(pf)))
         return out
 
+    def bloom(self, enabled=True, intensity=0.5, threshold=0.8, blur_passes=2, fmt=_lib.FORMAT_RGBA32F, readback=True):
+        """BloomManager.applyBloomToTexture / drawTextureToScreen (rendering/bloom.ts:446-632) on the finished frame:
+        returns the display-referred frame (ACES + gamma applied) in ``fmt``."""
+        cfg = _lib.GvtBloomConfig()
+        cfg.struct_size = C.sizeof(cfg)
+        cfg.enabled, cfg.intensity, cfg.threshold, cfg.blur_passes = 1 if enabled else 0, intensity, threshold, blur_passes
+        out = np.zeros((self.height, self.width, 4), np.dtype(_lib.FORMAT_DTYPE[fmt])) if readback else None
+        ms = C.c_double()
+        check(lib().gvt_render_bloom(self._h, C.byref(cfg), fmt, out.ctypes.data_as(C.c_void_p) if readback else None, C.byref(ms)))
+        self.last_bloom_ms = ms.value
+        return out
+
     def reset_history(self):
         check(lib().gvt_render_reset_history(self._h))
 

@@ -182,6 +182,12 @@ class WebGLRenderer:
             return None
         return buf.array(np.dtype(_lib.FORMAT_DTYPE[output_format]), (H, W, 4))
 
+    def present(self, params=None, fmt=_lib.FORMAT_RGBA8_UNORM, readback=True):
+        """The post-processing tail of render() (renderer.ts:366-414) once a linear-HDR frame exists: bloom when
+        ``features.bloom`` (BloomManager.applyBloomToTexture), else the plain ACES + gamma draw (drawTextureToScreen)."""
+        f = dict(DEFAULT_FEATURES, **((params or {}).get("features") or {}))
+        return self._k.bloom(enabled=bool(f["bloom"]), fmt=fmt, readback=readback)
+
     def debug_counts(self):
         """Parity hook: per-pixel march steps and horizon flags of the last frame."""
         steps = np.zeros((self.height, self.width), np.uint32)

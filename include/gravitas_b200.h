@@ -287,6 +287,20 @@ int32_t gvt_render_set_noise_textures(gvt_renderer* r, const uint8_t* noise_rgba
 int32_t gvt_render_fragment_glsl(gvt_renderer* r, const GvtGlslUniforms* u, uint32_t precision, uint32_t flags,
                                  uint32_t output_format, float taa_blend, uint32_t taa_camera_moving, void* host_rgba,
                                  GvtFrameStats* stats);
+/* BloomManager (src/rendering/bloom.ts:22-39 config, :446-632 applyBloomToTexture / drawTextureToScreen) on the
+ * renderer's finished linear-HDR frame: bright pass -> `blur_passes` x (horizontal, vertical) 9-tap Gaussian at quarter
+ * resolution in RGBA16F -> scene + bloom * intensity -> ACES -> gamma (postprocess/bloom.glsl.ts). enabled = 0 is
+ * drawTextureToScreen: the final ACES + gamma pass alone. The display-referred result stays on the device (it does
+ * not replace the frame, which remains the TAA history) and is copied to host_out in `output_format`
+ * (RGBA32F, RGBA16F or RGBA8_UNORM) when host_out is not NULL. *ms receives the device time. */
+typedef struct GvtBloomConfig {
+    uint32_t struct_size;
+    uint32_t enabled;      /* features.bloom */
+    float intensity;       /* 0.5 */
+    float threshold;       /* 0.8 */
+    uint32_t blur_passes;  /* 2 */
+} GvtBloomConfig;
+int32_t gvt_render_bloom(gvt_renderer* r, const GvtBloomConfig* cfg, uint32_t output_format, void* host_out, double* ms);
 /* Parity hook: per-pixel step count and horizon flag of the last gvt_render_fragment_glsl frame (width*height each). */
 int32_t gvt_render_fragment_glsl_debug(gvt_renderer* r, uint32_t* steps, uint32_t* hit);
 /* Peer-store gather (GVT_FLAG_PEER_STORE): each rank exports CUDA IPC handles of its two frame buffers; the host

@@ -191,3 +191,30 @@ def test_f64_kernel_matches_committed_fixture(built, case):
         np.testing.assert_allclose(got, g[f"{case}_rgba"], rtol=0, atol=2e-7)   # float32 frame buffer
     finally:
         r.cleanup()
+
+
+@pytest.mark.parametrize("W,H,passes", [(128, 72, 2), (157, 83, 1), (64, 36, 0), (5, 3, 2)])
+def test_bloom_matches_numpy_restatement(wgl, W, H, passes):
+    """gvt_render_bloom (bright pass, RGBA16F quarter-res Gaussian ping-pong, combine + ACES + gamma) vs the numpy
+    restatement of bloom.glsl.ts / bloom.ts. Tolerance: intermediates are RGBA16F, so an FMA-vs-separate rounding
+    difference can flip a half-float ulp (2^-11 relative) in a blurred texel; the output is display-referred [0, 1]."""
+    import bloom_oracle
+    from gravitas_b200 import webgl, _lib
+    wgl.precision = _lib.PRECISION_F32
+    wgl.taa = False
+    wgl.resize(W, H)
+    feats = dict(webgl.PRESETS["ultra-quality"], bloom=True)
+    u = webgl.make_uniforms(W, H, dict(mass=1.0, spin=0.9, zoom=30.0, lensing=1.0), (0.5, 0.54), time=0.4, features=feats, has_post=True)
+    scene = np.array(wgl.render({}, (0.5, 0.54), uniforms=u))            # linear HDR (ENABLE_LINEAR_OUTPUT); stays the frame
+    got_plain = wgl._k.bloom(enabled=False)                               # drawTextureToScreen: ACES + gamma only
+    ref_plain = bloom_oracle.apply_bloom(scene, enabled=False)
+    np.testing.assert_allclose(got_plain, ref_plain, atol=2e-6)
+    got = wgl._k.bloom(enabled=True, intensity=0.5, threshold=0.05, blur_passes=passes)   # low threshold: most of the disk blooms
+    ref = bloom_oracle.apply_bloom(scene, True, 0.5, 0.05, passes)
+    assert np.abs(got - ref).max() <= 2e-3 and np.median(np.abs(got - ref)) <= 1e-6, (np.abs(got - ref).max(), passes)
+    assert np.abs(ref - ref_plain).max() > 0.01 or W < 16                 # the bloom actually contributes
+    u8 = wgl._k.bloom(enabled=True, intensity=0.5, threshold=0.05, blur_passes=passes, fmt=_lib.FORMAT_RGBA8_UNORM)
+    assert u8.dtype == np.uint8 and np.abs(u8.astype(np.float32) - got * 255.0).max() <= 0.5 + 1e-3
+    # present(): the renderer's post tail picks bloom or the plain draw from features.bloom
+    out = wgl.present(dict(features=dict(feats, bloom=False)), fmt=_lib.FORMAT_RGBA32F)
+    np.testing.assert_allclose(out, got_plain, atol=0)
