@@ -282,6 +282,52 @@ def run_own(args):
     f_ms, _, f_stats = timed_frames(r, cam, phys, max(2, args.steps // 3), dist, readback=False)
     f_steps = allreduce_sum(dist, float(sum(s.steps_executed for s in f_stats)))
 
+    # ---- beside the headline (one GPU only): the two other kernels of the path, a few frames each ----
+    side = {}
+    if world == 1:
+        import math
+        hbm_gbs, hbm_src = 6650.0, "fallback of /opt/skills/guides/B200_PROFILING.md"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                hbm_gbs, hbm_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            pass
+        # TAA resolve (config-5 style frames: jitter + TAA, short march so the resolve is not lost in event noise)
+        r.params = R.RenderParams(method=_lib.METHOD_SYMPLECTIC, precision=_lib.PRECISION_F32, max_steps=32,
+                                  step_rule=_lib.STEP_WGSL, flags=_lib.FLAG_TAA | _lib.FLAG_JITTER)
+        prev, taa_ms = None, []
+        for k in range(6):
+            c5, vp = camera.default_camera(W, H, azimuth=math.pi + 0.005 * k, prev_view_proj=prev)
+            r.render(c5, R.pack_physics(MASS, SPIN, W, H, frame_index=k), readback=False)
+            prev = vp
+            if k >= 2:
+                taa_ms.append(r.last_stats.taa_ms)
+        t = sorted(taa_ms)[len(taa_ms) // 2]
+        taa_bytes = 48 * W * H                      # 16 B current + 16 B history + 16 B store per pixel
+        side["taa_resolve"] = {"kernel": "k_taa_resolve<0>", "ms": t, "bound": "hbm", "algorithmic_bytes": taa_bytes,
+                               "achieved_gbs": taa_bytes / (t * 1e-3) * 1e-9, "peak_gbs": hbm_gbs, "peak_source": hbm_src,
+                               "frac": taa_bytes / (t * 1e-3) * 1e-9 / hbm_gbs}
+        # the whole WebGL2 fragment shader (k_fragment_glsl, MUFU build), ultra-quality preset, + bloom / final pass
+        from gravitas_b200 import webgl
+        wr = webgl.WebGLRenderer(device=local, noise_seed=11)
+        if wr.init():
+            wr.precision = _lib.PRECISION_F32_FAST
+            wr.resize(W, H)
+            sp = dict(mass=1.0, spin=0.9, zoom=30.0, lensing=1.0, features=dict(webgl.PRESETS["ultra-quality"], bloom=False))
+            ms = []
+            for k in range(5):
+                wr.render(sp, {"x": 0.5, "y": 0.5 + 7.0 / 180.0}, readback=False)
+                if k >= 2:
+                    ms.append(wr.last_stats.trace_ms)
+            st = wr.last_stats
+            m = sorted(ms)[len(ms) // 2]
+            wr._k.bloom(enabled=True, readback=False); wr._k.bloom(enabled=True, readback=False)
+            side["webgl_fragment_shader"] = {"kernel": "k_fragment_glsl<float> (MUFU build)", "preset": "ultra-quality, 256-step budget",
+                                             "ms": m, "fps": 1e3 / m, "march_steps_per_s": st.steps_committed / (m * 1e-3),
+                                             "mean_steps_per_pixel": st.steps_committed / (W * H),
+                                             "bloom_final_pass_ms": wr._k.last_bloom_ms}
+            wr.cleanup()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_sample(15.0)
@@ -319,6 +365,7 @@ def run_own(args):
                                                          "max_steps": int(s0.n_maxsteps), "disk_opaque": int(s0.n_disk)}},
                 "f32_budget": {"steps_per_s": f_steps / (f_ms * 1e-3), "ms_per_frame": f_ms / len(f_stats),
                                "frac_of_fp32_peak": (f_steps / (f_ms * 1e-3)) * fl * 1e-12 / peak32 / world},
+                **side,
             },
         }
         print(json.dumps(out))
