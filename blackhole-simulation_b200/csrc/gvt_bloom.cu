@@ -86,9 +86,10 @@ __device__ __forceinline__ float aces_gamma_f(float x) {   // bloom.glsl.ts:106-
 }
 
 __global__ void k_bloom_combine(Tex32 scene, Tex16 bloom, float4* __restrict__ dst, float intensity, int use_bloom) {
-    const size_t n = (size_t)scene.w * scene.h;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const int x = (int)(i % scene.w), y = (int)(i / scene.w);
+    // one thread per pixel, rows on blockIdx.y (no 64-bit division in the index arithmetic)
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int y = blockIdx.y; y < scene.h && x < scene.w; y += gridDim.y) {
+        const size_t i = (size_t)y * scene.w + x;
         const float4 s = __ldg(scene.p + i);                      // the scene is sampled at its own texel centres
         float r = s.x, g = s.y, b = s.z;
         if (use_bloom) {
@@ -121,7 +122,7 @@ cudaError_t launch_bloom(const float4* frame, int W, int H, uint2* half_tex, uin
         }
         result = src;   // blurPasses = 0: the bright texture itself is combined (bloom.ts:517-546)
     }
-    k_bloom_combine<<<grid, 256, 0, stream>>>(scene, result, display, intensity, enabled);
+    k_bloom_combine<<<dim3((unsigned)((W + 255) / 256), (unsigned)min(H, 65535)), 256, 0, stream>>>(scene, result, display, intensity, enabled);
     (*launches)++;
     return cudaGetLastError();
 }

@@ -514,24 +514,24 @@ cudaError_t launch_integrate_rays(const RayBatchParams& p_in, cudaStream_t strea
 //  * everything that depends on the column only (cx terms, clamped column index) is hoisted out of the row loop,
 //    everything that depends on the row only is warp-uniform;
 //  * sigma uses MUFU.SQRT (sqrt.approx): the pass is f32 with a 1e-3 conditioning floor (tests/test_gpu_taa.py).
-//  * loads run ahead of their use: current-frame rows through a 4-deep per-lane cp.async ring in shared memory,
-//    history taps one row ahead in registers.
+//  * every global load runs ahead of its use at no register cost: current-frame rows AND the four history taps go
+//    through per-lane cp.async rings in shared memory, two row-iterations deep (45 KB per CTA).
 // Work units are distributed grid-stride over a grid sized to the resident warps, and the rows per unit are chosen
 // per launch so that every warp walks the same number of units (no partial last wave).
-// Measured (4K, B200): 163 us (first version, 440 instr/pixel) -> 113 us (~290 instr/pixel); the same strip walk as a
-// bare 2-read/1-write copy runs 66 us (scripts/ubench/strip_copy.cu) -- the resolve is still issue/latency-bound
-// (IPC ~0.6 per scheduler at 24 warps/SM; 64 registers spill), not HBM-bound.
+// Measured (4K, B200): 163 us (first version, 440 instr/pixel) -> 113 us (factored reprojection, register prefetch)
+// -> 101 us with the tap ring (64 registers, 32 warps/SM); the WebGL2 variant (one tap) 87 us. The same strip walk as a
+// bare 2-read/1-write copy runs 66 us (scripts/ubench/strip_copy.cu): the rest is the resolve's own arithmetic.
 // --------------------------------------------------------------------------------------------------
 constexpr int TAA_STRIP_W = 30;
 #ifndef GVT_TAA_MINB
-#define GVT_TAA_MINB 3
+#define GVT_TAA_MINB 4
 #endif
 #ifndef GVT_TAA_UNROLL
 #define GVT_TAA_UNROLL 1
 #endif
 constexpr int taa_unroll = GVT_TAA_UNROLL;
 #ifndef GVT_TAA_DEPTH
-#define GVT_TAA_DEPTH 4
+#define GVT_TAA_DEPTH 2
 #endif
 constexpr int TAA_DEPTH = GVT_TAA_DEPTH;
 
@@ -571,9 +571,17 @@ __device__ __forceinline__ float rcp_approx(float x) {
 
 template <int MODE>
 __global__ void __launch_bounds__(256, GVT_TAA_MINB) k_taa_resolve(const __grid_constant__ TaaParams P) {
-    __shared__ float4 taa_ring[8][TAA_DEPTH][32];
+    constexpr int NT = (MODE == 1) ? 1 : 4;                        // history taps per pixel
+    // per-warp, per-lane rings: every lane reads back only what it copied itself, so no warp-level synchronisation
+    extern __shared__ __align__(16) unsigned char taa_smem[];     // dynamic: TAA_DEPTH = 3 already exceeds the 48 KB static limit
+    typedef float4 (*RingCur)[TAA_DEPTH][32];
+    typedef float4 (*RingTap)[TAA_DEPTH][NT][32];
+    typedef float2 (*RingFrac)[TAA_DEPTH][32];
+    RingCur ring_cur = reinterpret_cast<RingCur>(taa_smem);
+    RingTap ring_tap = reinterpret_cast<RingTap>(taa_smem + sizeof(float4) * 8 * TAA_DEPTH * 32);
+    RingFrac ring_frac = reinterpret_cast<RingFrac>(taa_smem + sizeof(float4) * 8 * TAA_DEPTH * 32 * (1 + NT));
     const int W = (int)P.width, H = (int)P.height;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int strips_x = (W + TAA_STRIP_W - 1) / TAA_STRIP_W;
     const int rows = (int)P.row1 - (int)P.row0;
     const int TAA_ROWS = (int)P.unit_rows;
@@ -585,12 +593,13 @@ __global__ void __launch_bounds__(256, GVT_TAA_MINB) k_taa_resolve(const __grid_
     const float x_max = (float)(W - 1), y_max = (float)(H - 1);
     const float fb_gl = P.moving ? 0.0f : P.blend;
 
-    for (int unit = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)); unit < n_work; unit += n_warps) {
+    for (int unit = (int)(blockIdx.x * (blockDim.x >> 5) + wid); unit < n_work; unit += n_warps) {
         const int sx = unit % strips_x, sy = unit / strips_x;
         const int x = sx * TAA_STRIP_W + lane - 1;                // lane 0 / 31 = halo columns
         const int xc = max(0, min(x, W - 1));                     // clamp(pos + d, 0, size-1), ataa.wgsl.ts:43
         const bool owner = lane >= 1 && lane <= TAA_STRIP_W && x < W;
         const int y_begin = (int)P.row0 + sy * TAA_ROWS, y_end = min(y_begin + TAA_ROWS, (int)P.row1);
+        const int n_rows = y_end - y_begin;
         const float4* col = P.cur + xc;
 
         // column-only part of the reprojection (MODE 0)
@@ -599,71 +608,61 @@ __global__ void __launch_bounds__(256, GVT_TAA_MINB) k_taa_resolve(const __grid_
         const float vxw = fmaf(P.vA[3], cx, P.vC[3]);
         const float gx0 = fmaf(P.gA[0], cx, P.gC[0]), gx1 = fmaf(P.gA[1], cx, P.gC[1]), gx2 = fmaf(P.gA[2], cx, P.gC[2]);
 
-        // Current-frame rows stream through a per-lane ring in shared memory, TAA_DEPTH rows ahead of their use
-        // (cp.async: a DRAM miss costs ~1.5 row-iterations of this loop, so a one-row register prefetch is not enough
-        // and deeper register prefetch costs occupancy). Ring entry k holds frame row clamp(y_begin - 1 + k); every
-        // lane reads back only what it copied itself, so no warp-level synchronisation is involved.
-        float4* ring = &taa_ring[threadIdx.x >> 5][0][lane];
-        const int k_last = y_end - y_begin + 1;
-        auto ring_issue = [&](int k) {
-            if (k <= k_last) cp_async16(ring + (k % TAA_DEPTH) * 32, col + (size_t)min(max(y_begin - 1 + k, 0), H - 1) * W);
+        // Every global load of the walk is a 16-B cp.async into the rings, TAA_DEPTH rows ahead of its use and at no
+        // register cost (a DRAM miss costs more than one row-iteration of this loop, and holding a row of taps in
+        // registers ahead of time costs a quarter of the occupancy). Group k carries what row-iteration j = k - 2
+        // consumes: current-frame row clamp(y_begin - 1 + k) -- the bottom row of j's 3x3 window -- and the history
+        // taps (+ bilinear fractions) of row y_begin + j.
+        auto issue = [&](int k) {
+            const int slot = k % TAA_DEPTH;
+            if (k <= n_rows + 1) cp_async16(&ring_cur[wid][slot][lane], col + (size_t)min(max(y_begin - 1 + k, 0), H - 1) * W);
+            const int j = k - 2;
+            if (j >= 0 && j < n_rows) {
+                const int y = y_begin + j;
+                if (MODE == 1) {
+                    // WebGL2 resolve: history at the same texel (reprojection.glsl.ts:93-110)
+                    cp_async16(&ring_tap[wid][slot][0][lane], P.hist + (size_t)y * W + xc);
+                } else {
+                    // reprojection at depth 12 through prev_view_proj (ataa.wgsl.ts:54-69), factored form (header)
+                    const float cy = -fmaf((float)y + 0.5f, 2.0f / (float)H, -1.0f);
+                    const float v0 = fmaf(P.vB[0], cy, vx0), v1 = fmaf(P.vB[1], cy, vx1), v2 = fmaf(P.vB[2], cy, vx2);
+                    const float vw = fmaf(P.vB[3], cy, vxw);
+                    const float s = copysignf(rsqrtf(fmaf(v0, v0, fmaf(v1, v1, v2 * v2))), vw);
+                    const float p0 = fmaf(s, fmaf(P.gB[0], cy, gx0), P.c0[0]);
+                    const float p1 = fmaf(s, fmaf(P.gB[1], cy, gx1), P.c0[1]);
+                    const float p3 = fmaf(s, fmaf(P.gB[2], cy, gx2), P.c0[2]);
+                    const float ip3 = rcp_approx(p3);
+                    // bilinear, clamp-to-edge history fetch (textureSampleLevel + linear sampler, ataa.wgsl.ts:72):
+                    // pu W - 0.5 with pu = ndc.x/2 + 1/2,  pv H - 0.5 with pv = -ndc.y/2 + 1/2
+                    const float hx = fminf(fmaxf(fmaf(p0 * ip3, half_w, half_w - 0.5f), 0.0f), x_max);
+                    const float hy = fminf(fmaxf(fmaf(p1 * ip3, -half_h, half_h - 0.5f), 0.0f), y_max);
+                    const float hxf = floorf(hx), hyf = floorf(hy);
+                    const int x0 = (int)hxf, y0 = (int)hyf;
+                    const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+                    const float4* r0 = P.hist + (size_t)y0 * W;
+                    const float4* r1 = P.hist + (size_t)y1 * W;
+                    cp_async16(&ring_tap[wid][slot][0][lane], r0 + x0); cp_async16(&ring_tap[wid][slot][1][lane], r0 + x1);
+                    cp_async16(&ring_tap[wid][slot][2][lane], r1 + x0); cp_async16(&ring_tap[wid][slot][3][lane], r1 + x1);
+                    ring_frac[wid][slot][lane] = make_float2(hx - hxf, hy - hyf);
+                }
+            }
             cp_async_commit();   // one group per k, empty past the end, so wait_group counts stay aligned
         };
-        auto ring_take = [&](int k) -> float4 {
-            cp_async_wait<TAA_DEPTH - 1>();
-            return ring[(k % TAA_DEPTH) * 32];
-        };
 #pragma unroll
-        for (int k = 0; k < TAA_DEPTH; k++) ring_issue(k);
-        // rolling window of per-pixel YCoCg for rows y-1, y, y+1
+        for (int k = 0; k < TAA_DEPTH; k++) issue(k);
+        // rolling window of per-pixel YCoCg moments for rows y-1, y, y+1
         YCC2 a, b, c;
-        a = moments_of(ring_take(0)); ring_issue(TAA_DEPTH);
-        b = moments_of(ring_take(1)); ring_issue(TAA_DEPTH + 1);
-        // Software pipeline, one row deep: the loads of row y+1 (current-frame pixel of row y+2, the four history taps
-        // of row y+1) are issued before row y is resolved, so their latency is covered by a full row of arithmetic
-        // (the shuffles keep the compiler from hoisting loads across iterations by itself).
-        struct Taps { float4 h00, h10, h01, h11; float fx, fy; };
-        auto issue_taps = [&](int y) -> Taps {
-            Taps t;
-            t.fx = 0.0f; t.fy = 0.0f;
-            if (MODE == 1) {
-                // WebGL2 resolve: history at the same texel (reprojection.glsl.ts:93-110)
-                t.h00 = __ldg(P.hist + (size_t)y * W + xc);
-                t.h10 = t.h01 = t.h11 = t.h00;
-            } else {
-                // reprojection at depth 12 through prev_view_proj (ataa.wgsl.ts:54-69), factored form (header)
-                const float cy = -fmaf((float)y + 0.5f, 2.0f / (float)H, -1.0f);
-                const float v0 = fmaf(P.vB[0], cy, vx0), v1 = fmaf(P.vB[1], cy, vx1), v2 = fmaf(P.vB[2], cy, vx2);
-                const float vw = fmaf(P.vB[3], cy, vxw);
-                const float s = copysignf(rsqrtf(fmaf(v0, v0, fmaf(v1, v1, v2 * v2))), vw);
-                const float p0 = fmaf(s, fmaf(P.gB[0], cy, gx0), P.c0[0]);
-                const float p1 = fmaf(s, fmaf(P.gB[1], cy, gx1), P.c0[1]);
-                const float p3 = fmaf(s, fmaf(P.gB[2], cy, gx2), P.c0[2]);
-                const float ip3 = rcp_approx(p3);
-                // bilinear, clamp-to-edge history fetch (textureSampleLevel + linear sampler, ataa.wgsl.ts:72):
-                // pu W - 0.5 with pu = ndc.x/2 + 1/2,  pv H - 0.5 with pv = -ndc.y/2 + 1/2
-                const float hx = fminf(fmaxf(fmaf(p0 * ip3, half_w, half_w - 0.5f), 0.0f), x_max);
-                const float hy = fminf(fmaxf(fmaf(p1 * ip3, -half_h, half_h - 0.5f), 0.0f), y_max);
-                const float hxf = floorf(hx), hyf = floorf(hy);
-                const int x0 = (int)hxf, y0 = (int)hyf;
-                const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
-                t.fx = hx - hxf; t.fy = hy - hyf;
-                const float4* r0 = P.hist + (size_t)y0 * W;
-                const float4* r1 = P.hist + (size_t)y1 * W;
-                t.h00 = __ldg(r0 + x0); t.h10 = __ldg(r0 + x1);
-                t.h01 = __ldg(r1 + x0); t.h11 = __ldg(r1 + x1);
-            }
-            return t;
-        };
-        Taps nt = issue_taps(y_begin);
+        cp_async_wait<TAA_DEPTH - 1>();
+        a = moments_of(ring_cur[wid][0][lane]);
+        issue(TAA_DEPTH);
+        cp_async_wait<TAA_DEPTH - 1>();
+        b = moments_of(ring_cur[wid][1 % TAA_DEPTH][lane]);
+        issue(TAA_DEPTH + 1);
 #pragma unroll taa_unroll
         for (int y = y_begin; y < y_end; y++) {
-            const float4 h00 = nt.h00, h10 = nt.h10, h01 = nt.h01, h11 = nt.h11;
-            const float fx = nt.fx, fy = nt.fy;
-            nt = issue_taps(min(y + 1, H - 1));
-            const int k = y - y_begin + 2;
-            c = moments_of(ring_take(k));
-            ring_issue(k + TAA_DEPTH);
+            const int k = y - y_begin + 2, slot = k % TAA_DEPTH;
+            cp_async_wait<TAA_DEPTH - 1>();
+            c = moments_of(ring_cur[wid][slot][lane]);
             // vertical sums (this lane's column), then horizontal 3-tap by shuffles
             const float m1y = sum3(a.y + b.y + c.y), m1o = sum3(a.co + b.co + c.co), m1g = sum3(a.cg + b.cg + c.cg);
             const float m2y = sum3(a.yy + b.yy + c.yy), m2o = sum3(a.coco + b.coco + c.coco);
@@ -679,20 +678,20 @@ __global__ void __launch_bounds__(256, GVT_TAA_MINB) k_taa_resolve(const __grid_
                     lo[i] = fmaf(-nsig, sd, mean[i]); hi[i] = fmaf(nsig, sd, mean[i]);
                 }
                 float hr, hg, hb, fb_;
+                const float4 h00 = ring_tap[wid][slot][0][lane];
                 if (MODE == 1) {
                     hr = h00.x; hg = h00.y; hb = h00.z;
                     fb_ = fb_gl * (1.0f - fminf(fmaxf(sd_y * 4.0f, 0.0f), 0.55f));   // variance-guided weight
                 } else {
-                    const float tr = fmaf(h10.x - h00.x, fx, h00.x), br = fmaf(h11.x - h01.x, fx, h01.x);
-                    const float tg = fmaf(h10.y - h00.y, fx, h00.y), bg = fmaf(h11.y - h01.y, fx, h01.y);
-                    const float tb = fmaf(h10.z - h00.z, fx, h00.z), bb = fmaf(h11.z - h01.z, fx, h01.z);
-                    hr = fmaf(br - tr, fy, tr); hg = fmaf(bg - tg, fy, tg); hb = fmaf(bb - tb, fy, tb);
+                    const float4 h10 = ring_tap[wid][slot][NT > 1 ? 1 : 0][lane], h01 = ring_tap[wid][slot][NT > 1 ? 2 : 0][lane],
+                                 h11 = ring_tap[wid][slot][NT > 1 ? 3 : 0][lane];
+                    const float2 fr = ring_frac[wid][slot][lane];
+                    const float tr = fmaf(h10.x - h00.x, fr.x, h00.x), br = fmaf(h11.x - h01.x, fr.x, h01.x);
+                    const float tg = fmaf(h10.y - h00.y, fr.x, h00.y), bg = fmaf(h11.y - h01.y, fr.x, h01.y);
+                    const float tb = fmaf(h10.z - h00.z, fr.x, h00.z), bb = fmaf(h11.z - h01.z, fr.x, h01.z);
+                    hr = fmaf(br - tr, fr.y, tr); hg = fmaf(bg - tg, fr.y, tg); hb = fmaf(bb - tb, fr.y, tb);
                     fb_ = 0.92f;  // ataa.wgsl.ts:77
                 }
-                // Keep the unused alpha lanes of the 128-bit history loads allocated until here: ptxas otherwise hands
-                // those registers to the next arithmetic result straight after the LDG, and that write then waits
-                // for the load to land (WAW on the scoreboard).
-                asm volatile("" ::"f"(h00.w), "f"(h10.w), "f"(h01.w), "f"(h11.w));
                 YCC hs = rgb_to_ycocg(hr, hg, hb);
                 hs.y = fminf(fmaxf(hs.y, lo[0]), hi[0]);
                 hs.co = fminf(fmaxf(hs.co, lo[1]), hi[1]);
@@ -708,7 +707,9 @@ __global__ void __launch_bounds__(256, GVT_TAA_MINB) k_taa_resolve(const __grid_
                 for (uint32_t q = 0; q < P.n_peer; q++) P.peer_out[q][o] = px_out;
             }
             a = b; b = c;
+            issue(k + TAA_DEPTH);   // refills the slot this iteration has just finished reading
         }
+        cp_async_wait<0>();         // nothing of this unit may land after the next unit starts reusing the slots
     }
 }
 
@@ -720,10 +721,15 @@ cudaError_t launch_taa(const TaaParams& p_in, int sm_count, cudaStream_t stream)
     const int wpb = 8;
     static int resident[2] = {0, 0};   // CTAs per SM of each instantiation (occupancy query, once)
     const int m = p.mode == 1u ? 1 : 0;
+    // rings per CTA: 8 warps x TAA_DEPTH x 32 lanes x (16 B current + NT x 16 B taps + 8 B fractions)
+    const size_t smem = (size_t)8 * TAA_DEPTH * 32 * (16 + (m ? 1 : 4) * 16 + 8);
     if (!resident[m]) {
         int n = 0;
-        const cudaError_t e = m ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_taa_resolve<1>, wpb * 32, 0)
-                                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_taa_resolve<0>, wpb * 32, 0);
+        cudaError_t e = m ? cudaFuncSetAttribute(k_taa_resolve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                          : cudaFuncSetAttribute(k_taa_resolve<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = m ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_taa_resolve<1>, wpb * 32, smem)
+              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_taa_resolve<0>, wpb * 32, smem);
         if (e != cudaSuccess) return e;
         resident[m] = n > 0 ? n : 1;
     }
@@ -740,8 +746,8 @@ cudaError_t launch_taa(const TaaParams& p_in, int sm_count, cudaStream_t stream)
     p.unit_rows = (uint32_t)best_r;
     const int n_work = strips_x * ((rows + best_r - 1) / best_r);
     const int blocks = min((n_work + wpb - 1) / wpb, max(sm_count, 1) * resident[m]);
-    if (m) k_taa_resolve<1><<<blocks, wpb * 32, 0, stream>>>(p);
-    else k_taa_resolve<0><<<blocks, wpb * 32, 0, stream>>>(p);
+    if (m) k_taa_resolve<1><<<blocks, wpb * 32, smem, stream>>>(p);
+    else k_taa_resolve<0><<<blocks, wpb * 32, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
