@@ -661,7 +661,7 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
             return fail(GVT_ERR_INVALID, "the fragment-shader path resolves with GVT_FLAG_TAA_WEBGL (reprojection.glsl.ts), it has no CameraUniforms");
         memset(&G, 0, sizeof(G));
         G.u = *glsl;
-        G.width = W; G.height = H;
+        G.width = W; G.height = H; G.ys = 1;
         G.noise_r = r->d_noise_r; G.blue_r = r->d_blue_r; G.counters = r->d_counters;
         const size_t n_px = (size_t)W * H;
         if (r->g_cap < n_px) {
@@ -683,8 +683,19 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
     const uint32_t row1 = std::min(H, row0 + r->rows_per_rank);
     // TAA needs a one-pixel halo of the current frame: trace one redundant row above and below the block
     const uint32_t ty0 = (taa && row0 > 0) ? row0 - 1 : row0, ty1 = (taa && row1 < H) ? row1 + 1 : row1;
-    if (glsl) { G.y0 = ty0; G.y1 = ty1; }
-    else { P.x0 = 0; P.xs = 1; P.y0 = ty0; P.y1 = ty1; P.ys = 1; P.nx = W; P.ny = ty1 - ty0; }
+    // GVT_FLAG_ROW_INTERLEAVE: rows rank, rank + world, ... (peer stores only: nothing needs contiguous blocks)
+    const bool interleave = (rp->flags & GVT_FLAG_ROW_INTERLEAVE) != 0 && r->world > 1;
+    if (interleave && (taa || !(rp->flags & GVT_FLAG_PEER_STORE) || (rp->flags & GVT_FLAG_NO_GATHER)))
+        return fail(GVT_ERR_INVALID, "GVT_FLAG_ROW_INTERLEAVE needs GVT_FLAG_PEER_STORE and no TAA");
+    const uint32_t n_own = interleave ? ((uint32_t)r->rank < H ? (H - (uint32_t)r->rank + (uint32_t)r->world - 1) / (uint32_t)r->world : 0u)
+                                      : row1 - row0;
+    if (glsl) {
+        G.y0 = interleave ? (uint32_t)r->rank : ty0; G.y1 = interleave ? H : ty1; G.ys = interleave ? (uint32_t)r->world : 1u;
+    } else if (interleave) {
+        P.x0 = 0; P.xs = 1; P.y0 = (uint32_t)r->rank; P.y1 = H; P.ys = (uint32_t)r->world; P.nx = W; P.ny = n_own;
+    } else {
+        P.x0 = 0; P.xs = 1; P.y0 = ty0; P.y1 = ty1; P.ys = 1; P.nx = W; P.ny = ty1 - ty0;
+    }
     if (taa && r->history_valid) std::swap(r->frame, r->hist);  // last finished frame becomes the history
     float4* trace_out = taa ? r->cur : r->frame;
     if (glsl) G.frame = trace_out; else P.frame = trace_out;
@@ -735,7 +746,7 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
     }
     CK(cudaEventRecord(r->ev[1], r->stream));
     if (glsl) {
-        if (ty1 > ty0) {
+        if (G.y1 > G.y0) {
             if (glsl_precision == GVT_PRECISION_F32_FAST) CK(launch_fragment_glsl_fast(G, r->sm_count, r->stream));
             else CK(launch_fragment_glsl(G, (int)glsl_precision, r->sm_count, r->stream));
             launches++;
@@ -776,7 +787,15 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
     CK(cudaMemcpyAsync(r->h_counters, r->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, r->stream));
     d2h += sizeof(Counters);
     if (host_rgba && host_alias) {
-        d2h += (size_t)(row1 - row0) * W * sizeof(float4);   // delivered by the kernel's own stores
+        d2h += (size_t)n_own * W * sizeof(float4);   // delivered by the kernel's own stores
+    } else if (host_rgba && own && interleave) {
+        if (rp->output_format != GVT_FORMAT_RGBA32F) return fail(GVT_ERR_UNSUPPORTED, "interleaved own-row delivery is RGBA32F only");
+        const size_t row_bytes = (size_t)W * sizeof(float4), pitch = row_bytes * (size_t)r->world;
+        if (n_own)
+            CK(cudaMemcpy2DAsync(static_cast<char*>(host_rgba) + (size_t)r->rank * row_bytes, pitch,
+                                 reinterpret_cast<const char*>(r->frame) + (size_t)r->rank * row_bytes, pitch, row_bytes, n_own,
+                                 cudaMemcpyDeviceToHost, r->stream));
+        d2h += (size_t)n_own * row_bytes;
     } else if (host_rgba) {
         const size_t n_px = (size_t)W * H;
         // which pixels go back: the whole frame, or only this rank's row block at its place in the host frame
@@ -812,7 +831,7 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
         stats->steps_committed = c.steps_committed; stats->steps_executed = c.steps_executed; stats->rhs_evals = c.rhs_evals;
         stats->n_horizon = c.n_horizon; stats->n_escape = c.n_escape; stats->n_maxsteps = c.n_maxsteps; stats->n_disk = c.n_disk;
         stats->h2d_bytes = h2d; stats->d2h_bytes = d2h; stats->kernel_launches = launches;
-        stats->rows_begin = row0; stats->rows_end = row1;
+        stats->rows_begin = interleave ? (uint32_t)r->rank : row0; stats->rows_end = interleave ? H : row1;   // interleaved: every world-th row from rows_begin
     }
     return GVT_OK;
 }

@@ -295,7 +295,8 @@ __global__ void __launch_bounds__(256, 2) k_fragment_glsl(const __grid_constant_
     const bool show_red = U.show_redshift > 0.5f;
 
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t tiles_x = (P.width + 7u) / 8u, tiles_y = (P.y1 - P.y0 + 3u) / 4u;
+    const uint32_t n_rows = (P.y1 - P.y0 + P.ys - 1u) / P.ys;
+    const uint32_t tiles_x = (P.width + 7u) / 8u, tiles_y = (n_rows + 3u) / 4u;
     const uint32_t n_tiles = tiles_x * tiles_y;
     unsigned long long acc_steps = 0;
     uint32_t acc_hit = 0, acc_other = 0;
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(256, 2) k_fragment_glsl(const __grid_constant_
         if (lane == 0) tile = atomicAdd(&P.counters->tile_counter, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= n_tiles) break;
-        const uint32_t px = (tile % tiles_x) * 8u + (lane & 7u), py = P.y0 + (tile / tiles_x) * 4u + (lane >> 3);
+        const uint32_t px = (tile % tiles_x) * 8u + (lane & 7u), py = P.y0 + ((tile / tiles_x) * 4u + (lane >> 3)) * P.ys;
         const bool valid = px < P.width && py < P.y1;
         R out[3] = {R(0), R(0), R(0)};
         uint32_t steps = 0;
@@ -568,7 +569,7 @@ __global__ void __launch_bounds__(256, 2) k_fragment_glsl(const __grid_constant_
 }
 
 static cudaError_t launch_impl(const GlslParams& p, int precision, int sm_count, cudaStream_t stream) {
-    if (p.y1 <= p.y0 || p.width == 0) return cudaSuccess;
+    if (p.y1 <= p.y0 || p.width == 0 || p.ys == 0) return cudaSuccess;
     const size_t smem = 65536;
 #ifdef GVT_FRAGMENT_FAST
     (void)precision;
@@ -578,7 +579,8 @@ static cudaError_t launch_impl(const GlslParams& p, int precision, int sm_count,
 #endif
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const uint32_t tiles = ((p.width + 7u) / 8u) * ((p.y1 - p.y0 + 3u) / 4u);
+    const uint32_t n_rows = (p.y1 - p.y0 + p.ys - 1u) / p.ys;
+    const uint32_t tiles = ((p.width + 7u) / 8u) * ((n_rows + 3u) / 4u);
     int per_sm = 1;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
     if (e != cudaSuccess) return e;

@@ -84,11 +84,11 @@ struct TaaParams {
 struct GlslParams {
     GvtGlslUniforms u;            // chunks/common.ts:9-38 uniforms + feature bits, in the parameter bank
     uint32_t width, height;       // frame size (= u.resolution)
-    uint32_t y0, y1;              // rows shaded by this launch (a rank's row block)
+    uint32_t y0, y1, ys;          // rows shaded by this launch: y0, y0 + ys, ... < y1 (a rank's block, or its interleaved rows)
     const uint8_t* noise_r;       // 256*256 red channel of u_noiseTex (global; TMA-staged into shared memory)
     const uint8_t* blue_r;        // 256*256 red channel of u_blueNoiseTex (one tap per pixel, stays in global)
     float4* frame; float4* host_frame; float4* peer_frame[8];
-    uint32_t n_peer, _pad;
+    uint32_t n_peer;
     Counters* counters;
     uint32_t* dbg_steps; uint32_t* dbg_hit;   // parity hooks (full-frame arrays) or null
 };

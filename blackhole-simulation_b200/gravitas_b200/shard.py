@@ -26,3 +26,8 @@ def gather_counts(width, height, world):
     """floats each rank contributes to the single ncclAllGather, and the padded frame height it implies."""
     rpr = rows_per_rank(height, world)
     return rpr * width * 4, rpr * world
+
+
+def interleaved_rows(height, rank, world):
+    """GVT_FLAG_ROW_INTERLEAVE: rank k produces rows k, k + world, k + 2 world, ... (peer-store gather only)."""
+    return list(range(rank, height, world))

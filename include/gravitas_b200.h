@@ -85,6 +85,10 @@ enum {
                                        into every peer's frame over NVLink (peer frames imported with
                                        gvt_render_import_peer_frames) and a 4-byte ncclAllReduce closes the frame as the
                                        cross-GPU barrier; replaces the ncclAllGather */
+    GVT_FLAG_ROW_INTERLEAVE = 1u << 8, /* multi-GPU, with GVT_FLAG_PEER_STORE and without TAA: rank k produces rows k, k + world,
+                                       k + 2 world, ... instead of one contiguous block, so that rows of very different cost
+                                       (sky / disk / shadow under natural termination) spread evenly over the GPUs
+                                       (interleaved stripes); the peer stores need no contiguous blocks */
     GVT_FLAG_D2H_OWN_ROWS = 1u << 5 /* multi-GPU: copy only this rank's row block into host_rgba (at its place in the
                                        full-size buffer). With one host frame shared by all ranks (POSIX shm registered
                                        through gvt_host_register) the ranks assemble the frame in parallel, one

@@ -113,7 +113,46 @@ for (W, H) in ((192, 108), (157, 83)):
                 b = np.array(ws.render(sp, mouse))
                 assert (wm.last_stats.rows_begin, wm.last_stats.rows_end) == shard.shard_rows(H, rank, world)
                 assert np.array_equal(a, b), f"rank {rank}: fragment-shader frame differs (W={W} H={H} taa={taa} peer={peer} k={k})"
+# row-interleaved shards (GVT_FLAG_ROW_INTERLEAVE, peer stores): same frames again, on both producing kernels
+for (W, H) in ((192, 108), (157, 83)):
+    wm.resize(W, H); ws.resize(W, H)
+    wm._k.connect_peers(dist)
+    wm.taa = ws.taa = False
+    wm.time = ws.time = 0.0
+    a = np.array(wm.render(sp, {"x": 0.5, "y": 0.54}, flags=_lib.FLAG_PEER_STORE | _lib.FLAG_ROW_INTERLEAVE))
+    b = np.array(ws.render(sp, {"x": 0.5, "y": 0.54}))
+    assert (wm.last_stats.rows_begin, wm.last_stats.rows_end) == (rank, H)
+    assert np.array_equal(a, b), f"rank {rank}: interleaved fragment-shader frame differs (W={W} H={H})"
 dist.barrier()
 wm.cleanup(); ws.cleanup()
+ids = [g.KerrRenderer.nccl_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(ids, src=0)
+multi = g.KerrRenderer(device=local, rank=rank, world_size=world, nccl_id=ids[0]); multi.init()
+multi.init_pipelines(mass=1.0, spin=spin, spec_w=64, spec_h=16, max_temp=1e7)
+single = g.KerrRenderer(device=local); single.init()
+single.init_pipelines(mass=1.0, spin=spin, spec_w=64, spec_h=16, max_temp=1e7)
+for (W, H, method) in ((256, 144, _lib.METHOD_SYMPLECTIC), (157, 83, _lib.METHOD_RKF45)):
+    multi.resize(W, H); single.resize(W, H)
+    multi.connect_peers(dist)
+    cam, _ = camera.default_camera(W, H)
+    phys = R.pack_physics(1.0, spin, W, H)
+    kw = dict(method=method, max_steps=96, step_rule=_lib.STEP_WGSL if method == _lib.METHOD_SYMPLECTIC else _lib.STEP_CONSTANT)
+    multi.params = R.RenderParams(flags=_lib.FLAG_PEER_STORE | _lib.FLAG_ROW_INTERLEAVE, **kw)
+    single.params = R.RenderParams(**kw)
+    a = np.array(multi.render(cam, phys))
+    b = np.array(single.render(cam, phys))
+    assert np.array_equal(a, b), f"rank {rank}: interleaved trace frame differs (W={W} H={H} method={method})"
+    t = torch.tensor([float(multi.last_stats.steps_committed)]); dist.all_reduce(t)
+    assert int(t[0]) == int(single.last_stats.steps_committed)
+    # the flag is refused where it cannot work: with TAA (halo rows) or without the peer-store gather
+    for bad in (_lib.FLAG_ROW_INTERLEAVE, _lib.FLAG_ROW_INTERLEAVE | _lib.FLAG_PEER_STORE | _lib.FLAG_TAA):
+        multi.params = R.RenderParams(flags=bad, **kw)
+        try:
+            multi.render(cam, phys)
+            raise AssertionError("GVT_FLAG_ROW_INTERLEAVE accepted in an unsupported combination")
+        except g.GravitasError as e:
+            assert e.code == _lib.GVT_ERR_INVALID
+dist.barrier()
+multi.cleanup(); single.cleanup()
 dist.destroy_process_group()
 print(f"rank {rank} ok")
