@@ -466,37 +466,54 @@ def run_extra(args):
     elif args.workload == "webgl":
         # the whole production WebGL2 fragment shader (k_fragment_glsl: march + volumetric disk + jets + stars + glows
         # + ACES), "ultra-quality" preset (256-step budget), 4K, through WebGLRenderer.render(params, mouse); device
-        # time per frame for the MUFU build a GLSL compiler would produce and for the IEEE/libm parity build
+        # time per frame for the MUFU build a GLSL compiler would produce and, on one GPU, for the parity builds.
+        # At N > 1: row-block shards + ncclAllGather, and row-interleaved shards + fused peer stores.
         from gravitas_b200 import webgl
-        w = webgl.WebGLRenderer(device=local, noise_seed=11) if rank == 0 else None   # single-GPU extra: rank 0 only
+        wid = None
+        if world > 1:
+            objs = [g.KerrRenderer.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(objs, src=0)
+            wid = objs[0]
+        w = webgl.WebGLRenderer(device=local, rank=rank, world_size=world, nccl_id=wid, noise_seed=11)
+        assert w.init(), w.error
+        Wx, Hx = 3840, 2160
+        w.resize(Wx, Hx)
+        sp = dict(mass=1.0, spin=0.9, zoom=30.0, lensing=1.0, features=dict(webgl.PRESETS["ultra-quality"], bloom=False))
         res = {}
-        if w is not None:
-            assert w.init(), w.error
-            Wx, Hx = 3840, 2160
-            w.resize(Wx, Hx)
-            sp = dict(mass=1.0, spin=0.9, zoom=30.0, lensing=1.0, features=dict(webgl.PRESETS["ultra-quality"], bloom=False))
-            for nm, pr in (("f32_fast", _lib.PRECISION_F32_FAST), ("f32_precise", _lib.PRECISION_F32), ("f64", _lib.PRECISION_F64)):
-                w.precision = pr
-                ms, st = [], None
-                for k in range(args.warmup + args.steps):
-                    w.render(sp, {"x": 0.5, "y": 0.5 + 7.0 / 180.0}, readback=False)
-                    if k >= args.warmup:
-                        ms.append(w.last_stats.trace_ms); st = w.last_stats
-                m = sum(ms) / len(ms)
-                res[nm] = {"ms_per_frame": m, "fps": 1e3 / m, "march_steps_per_s": st.steps_committed / (m * 1e-3),
-                           "mean_steps_per_pixel": st.steps_committed / (Wx * Hx)}
-            # post tail on the last frame: WebGL TAA resolve is part of render() when w.taa; bloom + final pass here
-            bl = []
+
+        def run(nm, pr, flags):
+            w.precision = pr
+            tot, shader, steps = 0.0, 0.0, 0.0
+            barrier(dist)
             for k in range(args.warmup + args.steps):
+                w.render(sp, {"x": 0.5, "y": 0.5 + 7.0 / 180.0}, readback=False, flags=flags)
+                if k >= args.warmup:
+                    tot += w.last_stats.total_ms; shader += w.last_stats.trace_ms; steps += w.last_stats.steps_committed
+            tot = allreduce_max(dist, tot) / args.steps
+            res[nm] = {"ms_per_frame": tot, "fps": 1e3 / tot, "slowest_rank_shader_ms": allreduce_max(dist, shader) / args.steps,
+                       "march_steps_per_s": allreduce_sum(dist, steps) / args.steps / (tot * 1e-3),
+                       "mean_steps_per_pixel": allreduce_sum(dist, steps) / args.steps / (Wx * Hx)}
+
+        if world == 1:
+            for nm, pr in (("f32_fast", _lib.PRECISION_F32_FAST), ("f32_precise", _lib.PRECISION_F32), ("f64", _lib.PRECISION_F64)):
+                run(nm, pr, 0)
+            bl = []
+            for k in range(args.warmup + args.steps):   # post tail on the last frame: bloom + final pass
                 w._k.bloom(enabled=True, readback=False)
                 if k >= args.warmup:
                     bl.append(w._k.last_bloom_ms)
             res["bloom_final_pass_ms"] = sum(bl) / len(bl)
-            w.cleanup()
+        else:
+            run("f32_fast_row_blocks_allgather", _lib.PRECISION_F32_FAST, 0)
+            w._k.connect_peers(dist)
+            run("f32_fast_row_blocks_peer_store", _lib.PRECISION_F32_FAST, _lib.FLAG_PEER_STORE)
+            run("f32_fast_row_interleaved_peer_store", _lib.PRECISION_F32_FAST, _lib.FLAG_PEER_STORE | _lib.FLAG_ROW_INTERLEAVE)
+        barrier(dist)
+        w.cleanup()
         if rank == 0:
             print(json.dumps({"extra_workload": "WebGL2 production fragment shader (fragment.glsl.ts, all features of the "
                               "ultra-quality preset except bloom), 3840x2160, mouse/zoom camera at 97 deg polar, zoom 60",
-                              "n_gpus": 1, "frames": args.steps, **res}))
+                              "n_gpus": world, "frames": args.steps, **res}))
     elif args.workload == "config4":
         Wx, Hx = 7680, 4320
         r.params = R.RenderParams(method=_lib.METHOD_RKF45, max_steps=1024, step_rule=_lib.STEP_CONSTANT)
@@ -507,9 +524,23 @@ def run_extra(args):
         ev_ms, wall_ms, stats = timed_frames(r, cam, phys, args.steps, dist, readback=False)
         steps = allreduce_sum(dist, float(sum(s.steps_committed for s in stats)))
         rhs = allreduce_sum(dist, float(sum(s.rhs_evals for s in stats)))
+        inter = None
+        if world > 1:
+            # the same frames with row-interleaved shards over the fused peer-store gather (natural
+            # termination makes rows unequal; interleaving spreads them)
+            r.resize(Wx, Hx)
+            r.connect_peers(dist)
+            r.params = R.RenderParams(method=_lib.METHOD_RKF45, max_steps=1024, step_rule=_lib.STEP_CONSTANT,
+                                      flags=_lib.FLAG_PEER_STORE | _lib.FLAG_ROW_INTERLEAVE)
+            r.render(cam, phys, readback=False)
+            i_ms, _, i_stats = timed_frames(r, cam, phys, args.steps, dist, readback=False)
+            t_max = allreduce_max(dist, sum(s.trace_ms for s in i_stats) / len(i_stats))
+            inter = {"ms_per_frame": i_ms / args.steps, "slowest_rank_trace_ms": t_max}
+        b_max = allreduce_max(dist, sum(s.trace_ms for s in stats) / len(stats))
         if rank == 0:
             print(json.dumps({"extra_workload": "config 4: Kerr a*=0.999, 7680x4320, <=1024 adaptive RKF45 steps (tol 1e-8, escape "
                               "1000), natural termination, row-block shard", "n_gpus": world, "frames": args.steps,
+                              "slowest_rank_trace_ms": b_max, "row_interleaved_peer_store": inter,
                               "ms_per_frame": ev_ms / args.steps, "accepted_steps_per_s": steps / (ev_ms * 1e-3),
                               "rhs_evals_per_s": rhs / (ev_ms * 1e-3), "accepted_steps_per_frame": steps / args.steps,
                               "mean_steps_per_pixel": steps / args.steps / (Wx * Hx),
