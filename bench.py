@@ -195,6 +195,54 @@ def timed_frames(r, cam, phys, n, dist, readback, out=None):
     return allreduce_max(dist, ev_ms), allreduce_max(dist, wall), stats
 
 
+def side_kernels(r, local, camera, R, _lib):
+    """Beside the headline (one GPU): the two other kernels of the path, a few 4K frames each."""
+    side = {}
+    import math
+    hbm_gbs, hbm_src = 6650.0, "fallback of /opt/skills/guides/B200_PROFILING.md"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm_gbs, hbm_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        pass
+    # TAA resolve (config-5 style frames: jitter + TAA, short march so the resolve is not lost in event noise)
+    r.params = R.RenderParams(method=_lib.METHOD_SYMPLECTIC, precision=_lib.PRECISION_F32, max_steps=32,
+                              step_rule=_lib.STEP_WGSL, flags=_lib.FLAG_TAA | _lib.FLAG_JITTER)
+    prev, taa_ms = None, []
+    for k in range(6):
+        c5, vp = camera.default_camera(W, H, azimuth=math.pi + 0.005 * k, prev_view_proj=prev)
+        r.render(c5, R.pack_physics(MASS, SPIN, W, H, frame_index=k), readback=False)
+        prev = vp
+        if k >= 2:
+            taa_ms.append(r.last_stats.taa_ms)
+    t = sorted(taa_ms)[len(taa_ms) // 2]
+    taa_bytes = 48 * W * H                      # 16 B current + 16 B history + 16 B store per pixel
+    side["taa_resolve"] = {"kernel": "k_taa_resolve<0>", "ms": t, "bound": "hbm", "algorithmic_bytes": taa_bytes,
+                           "achieved_gbs": taa_bytes / (t * 1e-3) * 1e-9, "peak_gbs": hbm_gbs, "peak_source": hbm_src,
+                           "frac": taa_bytes / (t * 1e-3) * 1e-9 / hbm_gbs}
+    # the whole WebGL2 fragment shader (k_fragment_glsl, MUFU build), ultra-quality preset, + bloom / final pass
+    from gravitas_b200 import webgl
+    wr = webgl.WebGLRenderer(device=local, noise_seed=11)
+    if wr.init():
+        wr.precision = _lib.PRECISION_F32_FAST
+        wr.resize(W, H)
+        sp = dict(mass=1.0, spin=0.9, zoom=30.0, lensing=1.0, features=dict(webgl.PRESETS["ultra-quality"], bloom=False))
+        ms = []
+        for k in range(5):
+            wr.render(sp, {"x": 0.5, "y": 0.5 + 7.0 / 180.0}, readback=False)
+            if k >= 2:
+                ms.append(wr.last_stats.trace_ms)
+        st = wr.last_stats
+        m = sorted(ms)[len(ms) // 2]
+        wr._k.bloom(enabled=True, readback=False); wr._k.bloom(enabled=True, readback=False)
+        side["webgl_fragment_shader"] = {"kernel": "k_fragment_glsl<float> (MUFU build)", "preset": "ultra-quality, 256-step budget",
+                                         "ms": m, "fps": 1e3 / m, "march_steps_per_s": st.steps_committed / (m * 1e-3),
+                                         "mean_steps_per_pixel": st.steps_committed / (W * H),
+                                         "bloom_final_pass_ms": wr._k.last_bloom_ms}
+        wr.cleanup()
+    return side
+
+
 def run_own(args):
     import gravitas_b200 as g
     from gravitas_b200 import _lib, camera, renderer as R
@@ -285,49 +333,10 @@ def run_own(args):
     # ---- beside the headline (one GPU only): the two other kernels of the path, a few frames each ----
     side = {}
     if world == 1:
-        import math
-        hbm_gbs, hbm_src = 6650.0, "fallback of /opt/skills/guides/B200_PROFILING.md"
         try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                hbm_gbs, hbm_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
-        except Exception:
-            pass
-        # TAA resolve (config-5 style frames: jitter + TAA, short march so the resolve is not lost in event noise)
-        r.params = R.RenderParams(method=_lib.METHOD_SYMPLECTIC, precision=_lib.PRECISION_F32, max_steps=32,
-                                  step_rule=_lib.STEP_WGSL, flags=_lib.FLAG_TAA | _lib.FLAG_JITTER)
-        prev, taa_ms = None, []
-        for k in range(6):
-            c5, vp = camera.default_camera(W, H, azimuth=math.pi + 0.005 * k, prev_view_proj=prev)
-            r.render(c5, R.pack_physics(MASS, SPIN, W, H, frame_index=k), readback=False)
-            prev = vp
-            if k >= 2:
-                taa_ms.append(r.last_stats.taa_ms)
-        t = sorted(taa_ms)[len(taa_ms) // 2]
-        taa_bytes = 48 * W * H                      # 16 B current + 16 B history + 16 B store per pixel
-        side["taa_resolve"] = {"kernel": "k_taa_resolve<0>", "ms": t, "bound": "hbm", "algorithmic_bytes": taa_bytes,
-                               "achieved_gbs": taa_bytes / (t * 1e-3) * 1e-9, "peak_gbs": hbm_gbs, "peak_source": hbm_src,
-                               "frac": taa_bytes / (t * 1e-3) * 1e-9 / hbm_gbs}
-        # the whole WebGL2 fragment shader (k_fragment_glsl, MUFU build), ultra-quality preset, + bloom / final pass
-        from gravitas_b200 import webgl
-        wr = webgl.WebGLRenderer(device=local, noise_seed=11)
-        if wr.init():
-            wr.precision = _lib.PRECISION_F32_FAST
-            wr.resize(W, H)
-            sp = dict(mass=1.0, spin=0.9, zoom=30.0, lensing=1.0, features=dict(webgl.PRESETS["ultra-quality"], bloom=False))
-            ms = []
-            for k in range(5):
-                wr.render(sp, {"x": 0.5, "y": 0.5 + 7.0 / 180.0}, readback=False)
-                if k >= 2:
-                    ms.append(wr.last_stats.trace_ms)
-            st = wr.last_stats
-            m = sorted(ms)[len(ms) // 2]
-            wr._k.bloom(enabled=True, readback=False); wr._k.bloom(enabled=True, readback=False)
-            side["webgl_fragment_shader"] = {"kernel": "k_fragment_glsl<float> (MUFU build)", "preset": "ultra-quality, 256-step budget",
-                                             "ms": m, "fps": 1e3 / m, "march_steps_per_s": st.steps_committed / (m * 1e-3),
-                                             "mean_steps_per_pixel": st.steps_committed / (W * H),
-                                             "bloom_final_pass_ms": wr._k.last_bloom_ms}
-            wr.cleanup()
-
+            side = side_kernels(r, local, camera, R, _lib)
+        except Exception as ex:   # the side measurements must never cost the headline line
+            side = {"side_kernels_error": repr(ex)}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_sample(15.0)

@@ -218,3 +218,31 @@ def test_bloom_matches_numpy_restatement(wgl, W, H, passes):
     # present(): the renderer's post tail picks bloom or the plain draw from features.bloom
     out = wgl.present(dict(features=dict(feats, bloom=False)), fmt=_lib.FORMAT_RGBA32F)
     np.testing.assert_allclose(out, got_plain, atol=0)
+
+
+@pytest.mark.parametrize("W,H", [(1, 1), (7, 3), (33, 2), (8, 4)])
+def test_fragment_degenerate_sizes_and_budgets(wgl, oracle, W, H):
+    """Edge cases: frames smaller than one 8x4 warp tile, a zero / one-step ray budget, a camera beyond MAX_DIST (every
+    ray leaves on its first test), a camera inside 1.5 r+ (the shader's kamikaze clamp), a near-extremal and a
+    retrograde spin — all against the f64 oracle."""
+    from gravitas_b200 import webgl, _lib
+    feats = dict(webgl.PRESETS["ultra-quality"], bloom=False)
+    cases = [dict(params=dict(spin=0.9, zoom=30.0, lensing=1.0), steps=None),
+             dict(params=dict(spin=0.9, zoom=30.0, lensing=1.0), steps=0),
+             dict(params=dict(spin=0.9, zoom=30.0, lensing=1.0), steps=1),
+             dict(params=dict(spin=0.5, zoom=6000.0, lensing=1.0), steps=None),      # ro at 12000 > MAX_DIST
+             dict(params=dict(spin=0.5, zoom=1.0, lensing=1.0), steps=None),         # ro at 2 M < 1.5 r+ ~ 2.8 M
+             dict(params=dict(spin=0.999, zoom=20.0, lensing=2.0, mass=0.5), steps=None),
+             dict(params=dict(spin=-0.99, zoom=20.0, lensing=0.3, mass=3.0), steps=None)]
+    for c in cases:
+        u = webgl.make_uniforms(W, H, c["params"], mouse=(0.37, 0.58), time=2.0, features=feats)
+        if c["steps"] is not None:
+            u.max_ray_steps = c["steps"]
+        got, steps, hit, ref = run_both(wgl, oracle, u, _lib.PRECISION_F64)
+        assert np.all(np.isfinite(got)), c
+        assert np.array_equal(steps, ref["steps"]) and np.array_equal(hit, ref["hit"]), c
+        np.testing.assert_allclose(got[..., :3], ref["rgba"][..., :3], rtol=0, atol=2e-7)
+        if c["steps"] is not None:
+            assert int(steps.max()) <= c["steps"]
+    if (W, H) == (8, 4):
+        assert wgl.last_stats.n_horizon + wgl.last_stats.n_escape == W * H
