@@ -203,8 +203,9 @@ template <class R> __device__ __forceinline__ void blackbody(R temp, R c[3]) {
 
 // chunks/metric.ts:96-149 kerr_geodesic_accel, as the shader writes it (divisions kept: this path is a behavioural
 // restatement of the f32 shader, not the headline kernel)
+// `pn` = |p| = sqrt(dot(p, p)), which the march already holds (it is the step's r or r_new): normalize(p) reuses it.
 template <class R>
-__device__ __forceinline__ void shader_accel(const Vec3<R>& p, const Vec3<R>& v, R M, R a, Vec3<R>& acc, R& omega) {
+__device__ __forceinline__ void shader_accel(const Vec3<R>& p, const Vec3<R>& v, R pn, R M, R a, Vec3<R>& acc, R& omega) {
     using G = GM<R>;
     const R a2 = a * a;
     const R rho2 = p.x * p.x + p.y * p.y + p.z * p.z;
@@ -220,7 +221,6 @@ __device__ __forceinline__ void shader_accel(const Vec3<R>& p, const Vec3<R>& v,
     const R r2_inv = r_inv * r_inv;
     const R r4_inv = r2_inv * r2_inv;
     const R sigma_ratio = r2 / gl_max(R(1e-8), sigma);
-    const R pn = G::sqrt_(rho2);
     const R f = M * r2_inv * sigma_ratio + R(3.0) * M * gl_max(R(0.0), L2_eff) * r4_inv * sigma_ratio;
     const R r3_p_a2r = r_k * r2 + a2 * r_k;
     const R drag = R(2.0) * M * a / gl_max(R(1e-8), r3_p_a2r);
@@ -359,9 +359,10 @@ __global__ void __launch_bounds__(256, 2) k_fragment_glsl(const __grid_constant_
                     R prevY = p.y;
                     bool red_init = false;
                     if (len3(cross3(ro, rd)) < rh * R(0.9)) hitHorizon = true;                       // inner shadow culling
+                    R r_next = len3(p);                                                              // |p| is carried from step to step
                     for (int i = 0; i < maxSteps; i++) {
                         const Vec3<R> pp = p;
-                        const R r = len3(p);
+                        const R r = r_next;
                         if (r < rh * R(1.15)) { hitHorizon = true; break; }
                         if (r > MAX_DIST) break;
                         const R distFactor = R(1.0) + r * R(0.05);
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(256, 2) k_fragment_glsl(const __grid_constant_
                         Vec3<R> acc = {R(0), R(0), R(0)};
                         if (feat & GVT_GLSL_LENSING) {
                             R omega;
-                            shader_accel<R>(p, v, M, a, acc, omega);
+                            shader_accel<R>(p, v, r, M, a, acc, omega);
                             acc.x *= lens; acc.y *= lens; acc.z *= lens;
                             rot_pair(omega * cdt, v.x, v.z);                                           // ZAMO twist of v.xz
                         }
@@ -383,9 +384,10 @@ __global__ void __launch_bounds__(256, 2) k_fragment_glsl(const __grid_constant_
                         p.y += v.y * cdt + acc.y * R(0.5) * cdt * cdt;
                         p.z += v.z * cdt + acc.z * R(0.5) * cdt * cdt;
                         const R r_new = len3(p);
+                        r_next = r_new;
                         if ((feat & GVT_GLSL_LENSING) && alpha < R(0.95)) {
                             Vec3<R> acc2; R om2;
-                            shader_accel<R>(p, v, M, a, acc2, om2);
+                            shader_accel<R>(p, v, r_new, M, a, acc2, om2);
                             v.x += (acc.x + acc2.x * lens) * R(0.5) * cdt;
                             v.y += (acc.y + acc2.y * lens) * R(0.5) * cdt;
                             v.z += (acc.z + acc2.z * lens) * R(0.5) * cdt;
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(256, 2) k_fragment_glsl(const __grid_constant_
                                     const R t = G::abs_(pp.y) / gl_max(R(0.0001), G::abs_(pp.y) + G::abs_(p.y));
                                     sp = {gl_mix(pp.x, p.x, t), gl_mix(pp.y, p.y, t), gl_mix(pp.z, p.z, t)};
                                 }
-                                const R sr = len3(sp);
+                                const R sr = crossed ? len3(sp) : r_new;
                                 const R esh = gl_min(R(U.disk_scale_height), R(0.450));
                                 const R diskOuter = gl_max(M * R(U.disk_size), isco * R(1.1));
                                 if ((G::abs_(sp.y) < sr * esh || crossed) && sr > isco && sr < diskOuter) {
