@@ -561,6 +561,22 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async16_s(uint32_t dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, float x, float y) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -580,6 +596,11 @@ __global__ void __launch_bounds__(256, GVT_TAA_MINB) k_taa_resolve(const __grid_
     RingCur ring_cur = reinterpret_cast<RingCur>(taa_smem);
     RingTap ring_tap = reinterpret_cast<RingTap>(taa_smem + sizeof(float4) * 8 * TAA_DEPTH * 32);
     RingFrac ring_frac = reinterpret_cast<RingFrac>(taa_smem + sizeof(float4) * 8 * TAA_DEPTH * 32 * (1 + NT));
+    // this lane's ring entries, as shared-space byte addresses fixed for the whole kernel: slot s of the current-frame
+    // ring is at my_cur + s * 512, tap t of slot s at my_tap + (s * NT + t) * 512, the fractions at my_frac + s * 256
+    const uint32_t my_cur = smem_u32(&ring_cur[threadIdx.x >> 5][0][threadIdx.x & 31]);
+    const uint32_t my_tap = smem_u32(&ring_tap[threadIdx.x >> 5][0][0][threadIdx.x & 31]);
+    const uint32_t my_frac = smem_u32(&ring_frac[threadIdx.x >> 5][0][threadIdx.x & 31]);
     const int W = (int)P.width, H = (int)P.height;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int strips_x = (W + TAA_STRIP_W - 1) / TAA_STRIP_W;
@@ -614,14 +635,15 @@ __global__ void __launch_bounds__(256, GVT_TAA_MINB) k_taa_resolve(const __grid_
         // consumes: current-frame row clamp(y_begin - 1 + k) -- the bottom row of j's 3x3 window -- and the history
         // taps (+ bilinear fractions) of row y_begin + j.
         auto issue = [&](int k) {
-            const int slot = k % TAA_DEPTH;
-            if (k <= n_rows + 1) cp_async16(&ring_cur[wid][slot][lane], col + (size_t)min(max(y_begin - 1 + k, 0), H - 1) * W);
+            const uint32_t slot = (uint32_t)k % TAA_DEPTH;
+            if (k <= n_rows + 1) cp_async16_s(my_cur + slot * 512u, col + (size_t)min(max(y_begin - 1 + k, 0), H - 1) * W);
             const int j = k - 2;
             if (j >= 0 && j < n_rows) {
                 const int y = y_begin + j;
+                const uint32_t tap = my_tap + slot * (NT * 512u);
                 if (MODE == 1) {
                     // WebGL2 resolve: history at the same texel (reprojection.glsl.ts:93-110)
-                    cp_async16(&ring_tap[wid][slot][0][lane], P.hist + (size_t)y * W + xc);
+                    cp_async16_s(tap, P.hist + (size_t)y * W + xc);
                 } else {
                     // reprojection at depth 12 through prev_view_proj (ataa.wgsl.ts:54-69), factored form (header)
                     const float cy = -fmaf((float)y + 0.5f, 2.0f / (float)H, -1.0f);
@@ -638,12 +660,12 @@ __global__ void __launch_bounds__(256, GVT_TAA_MINB) k_taa_resolve(const __grid_
                     const float hy = fminf(fmaxf(fmaf(p1 * ip3, -half_h, half_h - 0.5f), 0.0f), y_max);
                     const float hxf = floorf(hx), hyf = floorf(hy);
                     const int x0 = (int)hxf, y0 = (int)hyf;
-                    const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
-                    const float4* r0 = P.hist + (size_t)y0 * W;
-                    const float4* r1 = P.hist + (size_t)y1 * W;
-                    cp_async16(&ring_tap[wid][slot][0][lane], r0 + x0); cp_async16(&ring_tap[wid][slot][1][lane], r0 + x1);
-                    cp_async16(&ring_tap[wid][slot][2][lane], r1 + x0); cp_async16(&ring_tap[wid][slot][3][lane], r1 + x1);
-                    ring_frac[wid][slot][lane] = make_float2(hx - hxf, hy - hyf);
+                    // one 64-bit address, the other three taps by small element offsets (0 or 1 column, 0 or W rows)
+                    const float4* t00 = P.hist + ((size_t)y0 * W + x0);
+                    const int dx = (x0 + 1 < W) ? 1 : 0, dy = (y0 + 1 < H) ? W : 0;
+                    cp_async16_s(tap, t00); cp_async16_s(tap + 512u, t00 + dx);
+                    cp_async16_s(tap + 1024u, t00 + dy); cp_async16_s(tap + 1536u, t00 + dy + dx);
+                    sts64(my_frac + slot * 256u, hx - hxf, hy - hyf);
                 }
             }
             cp_async_commit();   // one group per k, empty past the end, so wait_group counts stay aligned
@@ -653,16 +675,17 @@ __global__ void __launch_bounds__(256, GVT_TAA_MINB) k_taa_resolve(const __grid_
         // rolling window of per-pixel YCoCg moments for rows y-1, y, y+1
         YCC2 a, b, c;
         cp_async_wait<TAA_DEPTH - 1>();
-        a = moments_of(ring_cur[wid][0][lane]);
+        a = moments_of(lds128(my_cur));
         issue(TAA_DEPTH);
         cp_async_wait<TAA_DEPTH - 1>();
-        b = moments_of(ring_cur[wid][1 % TAA_DEPTH][lane]);
+        b = moments_of(lds128(my_cur + (1u % TAA_DEPTH) * 512u));
         issue(TAA_DEPTH + 1);
 #pragma unroll taa_unroll
         for (int y = y_begin; y < y_end; y++) {
-            const int k = y - y_begin + 2, slot = k % TAA_DEPTH;
+            const int k = y - y_begin + 2;
+            const uint32_t slot = (uint32_t)k % TAA_DEPTH;
             cp_async_wait<TAA_DEPTH - 1>();
-            c = moments_of(ring_cur[wid][slot][lane]);
+            c = moments_of(lds128(my_cur + slot * 512u));
             // vertical sums (this lane's column), then horizontal 3-tap by shuffles
             const float m1y = sum3(a.y + b.y + c.y), m1o = sum3(a.co + b.co + c.co), m1g = sum3(a.cg + b.cg + c.cg);
             const float m2y = sum3(a.yy + b.yy + c.yy), m2o = sum3(a.coco + b.coco + c.coco);
@@ -678,14 +701,14 @@ __global__ void __launch_bounds__(256, GVT_TAA_MINB) k_taa_resolve(const __grid_
                     lo[i] = fmaf(-nsig, sd, mean[i]); hi[i] = fmaf(nsig, sd, mean[i]);
                 }
                 float hr, hg, hb, fb_;
-                const float4 h00 = ring_tap[wid][slot][0][lane];
+                const uint32_t tap = my_tap + slot * (NT * 512u);
+                const float4 h00 = lds128(tap);
                 if (MODE == 1) {
                     hr = h00.x; hg = h00.y; hb = h00.z;
                     fb_ = fb_gl * (1.0f - fminf(fmaxf(sd_y * 4.0f, 0.0f), 0.55f));   // variance-guided weight
                 } else {
-                    const float4 h10 = ring_tap[wid][slot][NT > 1 ? 1 : 0][lane], h01 = ring_tap[wid][slot][NT > 1 ? 2 : 0][lane],
-                                 h11 = ring_tap[wid][slot][NT > 1 ? 3 : 0][lane];
-                    const float2 fr = ring_frac[wid][slot][lane];
+                    const float4 h10 = lds128(tap + 512u), h01 = lds128(tap + 1024u), h11 = lds128(tap + 1536u);
+                    const float2 fr = lds64(my_frac + slot * 256u);
                     const float tr = fmaf(h10.x - h00.x, fr.x, h00.x), br = fmaf(h11.x - h01.x, fr.x, h01.x);
                     const float tg = fmaf(h10.y - h00.y, fr.x, h00.y), bg = fmaf(h11.y - h01.y, fr.x, h01.y);
                     const float tb = fmaf(h10.z - h00.z, fr.x, h00.z), bb = fmaf(h11.z - h01.z, fr.x, h01.z);
