@@ -246,3 +246,45 @@ def test_fragment_degenerate_sizes_and_budgets(wgl, oracle, W, H):
             assert int(steps.max()) <= c["steps"]
     if (W, H) == (8, 4):
         assert wgl.last_stats.n_horizon + wgl.last_stats.n_escape == W * H
+
+
+def test_both_seams_webgl_pipeline(built, oracle):
+    """Seam A feeds Seam B exactly as in the reference's WebGL canvas: PhysicsEngine.tick_sab publishes the Bardeen
+    curve in the SAB PHYSICS block -> WebGLRenderer.render() uploads it as u_shadowCurve / u_shadowCount
+    (webgl/renderer.ts:277-303) -> the shader's Kerr-shadow guide draws it; frame checked against the oracle fed the
+    same uniform block, then TAA + bloom tail."""
+    import bloom_oracle
+    import gravitas_b200 as g
+    from gravitas_b200 import webgl, _lib
+    W, H = 144, 81
+    eng = g.PhysicsEngine(1.0, 0.9)
+    eng.set_camera_state(0.0, 60.0 * math.cos(math.radians(97.0)), -60.0 * math.sin(math.radians(97.0)))
+    r = webgl.WebGLRenderer(device=0, noise_seed=2)
+    assert r.init(), r.error
+    try:
+        r.physics_bridge = eng
+        r.precision = _lib.PRECISION_F64
+        r.resize(W, H)
+        params = dict(mass=1.0, spin=0.9, zoom=30.0, lensing=1.0,
+                      features=dict(webgl.PRESETS["high-quality"], kerrShadow=True, bloom=False))
+        u = r.uniforms(params, (0.5, 0.5 + 7.0 / 180.0))
+        sab = eng.get_sab_ptr()
+        assert u.shadow_count == sab[128 + 15] == 64.0
+        np.testing.assert_array_equal(np.array(u.shadow_curve[:]), sab[128 + 16:128 + 16 + 128])
+        got = np.array(r.render(params, (0.5, 0.5 + 7.0 / 180.0), uniforms=u)).astype(np.float64)
+        ref = oracle.fragment_glsl(bytes(u), r.noise_r, r.blue_r, precision=0)
+        np.testing.assert_allclose(got[..., :3], ref["rgba"][..., :3], rtol=0, atol=2e-7)
+        u_off = _lib.GvtGlslUniforms.from_buffer_copy(bytes(u))
+        u_off.show_kerr_shadow = 0.0
+        plain = oracle.fragment_glsl(bytes(u_off), r.noise_r, r.blue_r, precision=0)
+        drawn = np.abs(ref["rgba"][..., :3] - plain["rgba"][..., :3]).max(-1) > 1e-3
+        # the guide is 0.045 M thick and a pixel spans ~0.5 M here, so it touches only a few pixel centres
+        assert 1 <= drawn.sum() < W * H // 10
+        # linear-HDR frame -> bloom + final pass, as render() does when features.bloom (renderer.ts:366-399)
+        u2 = r.uniforms(dict(params, features=dict(params["features"], bloom=True)), (0.5, 0.54), has_post=True)
+        lin = np.array(r.render(params, (0.5, 0.54), uniforms=u2))
+        out = r.present(dict(features=dict(bloom=True)), fmt=_lib.FORMAT_RGBA32F)
+        refb = bloom_oracle.apply_bloom(lin, True, 0.5, 0.8, 2)
+        assert np.abs(out - refb).max() <= 2e-3
+    finally:
+        r.cleanup()
