@@ -374,7 +374,7 @@ struct gvt_renderer {
     size_t dbg_cap = 0;
     // WebGL2 fragment-shader path: red channels of the two noise textures, per-pixel parity hooks
     uint8_t* d_noise_r = nullptr; uint8_t* d_blue_r = nullptr;
-    uint32_t* d_gsteps = nullptr; uint32_t* d_ghit = nullptr; size_t g_cap = 0;
+    uint32_t* d_gsteps = nullptr; uint32_t* d_ghit = nullptr; size_t g_cap = 0; bool g_valid = false;
     // bloom: display-referred output + RGBA16F scratch (half-res bright texture, two quarter-res blur textures)
     float4* display = nullptr; uint2* bloom_half = nullptr; uint2* bloom_q1 = nullptr; uint2* bloom_q2 = nullptr;
     uint32_t bloom_w = 0, bloom_h = 0;
@@ -664,7 +664,9 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
         G.width = W; G.height = H; G.ys = 1;
         G.noise_r = r->d_noise_r; G.blue_r = r->d_blue_r; G.counters = r->d_counters;
         const size_t n_px = (size_t)W * H;
-        if (r->g_cap < n_px) {
+        const bool counts = (rp->flags & GVT_FLAG_DEBUG_COUNTS) != 0;
+        r->g_valid = counts;
+        if (counts && r->g_cap < n_px) {
             if (r->d_gsteps) cudaFree(r->d_gsteps);
             if (r->d_ghit) cudaFree(r->d_ghit);
             r->d_gsteps = nullptr; r->d_ghit = nullptr; r->g_cap = 0;
@@ -672,7 +674,7 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
             CK(cudaMalloc(&r->d_ghit, n_px * sizeof(uint32_t)));
             r->g_cap = n_px;
         }
-        G.dbg_steps = r->d_gsteps; G.dbg_hit = r->d_ghit;
+        G.dbg_steps = counts ? r->d_gsteps : nullptr; G.dbg_hit = counts ? r->d_ghit : nullptr;
     } else {
         int32_t rc = build_frame(r, cam, phys, rp, P);
         if (rc != GVT_OK) return rc;
@@ -924,7 +926,7 @@ extern "C" int32_t gvt_render_bloom(gvt_renderer* r, const GvtBloomConfig* cfg, 
 }
 
 extern "C" int32_t gvt_render_fragment_glsl_debug(gvt_renderer* r, uint32_t* steps, uint32_t* hit) {
-    if (!r || !r->d_gsteps || !r->d_ghit) return fail(GVT_ERR_INVALID, "no fragment-shader frame rendered yet");
+    if (!r || !r->d_gsteps || !r->d_ghit || !r->g_valid) return fail(GVT_ERR_INVALID, "the last fragment-shader frame was not rendered with GVT_FLAG_DEBUG_COUNTS");
     CK(cudaSetDevice(r->device));
     const size_t n = (size_t)r->width * r->height;
     if (n > r->g_cap) return fail(GVT_ERR_INVALID, "frame was resized since the last fragment-shader frame");

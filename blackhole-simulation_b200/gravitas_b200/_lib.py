@@ -21,6 +21,7 @@ FORMAT_DTYPE = {0: "float32", 1: "float16", 2: "uint8", 3: "uint8", 4: "uint8"}
 STEP_CONSTANT, STEP_WGSL = 0, 1
 FLAG_JITTER, FLAG_BUDGET, FLAG_TAA, FLAG_NO_GATHER, FLAG_D2H_OWN_ROWS, FLAG_PEER_STORE, FLAG_TAA_WEBGL = 1, 2, 8, 16, 32, 64, 128
 FLAG_ROW_INTERLEAVE = 256
+FLAG_DEBUG_COUNTS = 512
 
 
 class GravitasError(RuntimeError):

@@ -116,6 +116,7 @@ class WebGLRenderer:
         self.last_mouse = (0.0, 0.0)
         self.last_stats = None
         self._noise_seed = noise_seed
+        self.debug = False                      # record per-pixel steps / horizon flags (parity hook, debug_counts())
         self.physics_bridge = None              # optional PhysicsEngine: supplies the SAB shadow curve (renderer.ts:277-287)
 
     def init(self, canvas=None):                # renderer.ts:58-161
@@ -167,6 +168,8 @@ class WebGLRenderer:
         st = GvtFrameStats()
         if self.taa:
             flags |= _lib.FLAG_TAA | _lib.FLAG_TAA_WEBGL
+        if self.debug:
+            flags |= _lib.FLAG_DEBUG_COUNTS
         host = None
         if readback:
             buf = self._k.pinned_frame(W, H, output_format)

@@ -89,6 +89,8 @@ enum {
                                        k + 2 world, ... instead of one contiguous block, so that rows of very different cost
                                        (sky / disk / shadow under natural termination) spread evenly over the GPUs
                                        (interleaved stripes); the peer stores need no contiguous blocks */
+    GVT_FLAG_DEBUG_COUNTS = 1u << 9, /* gvt_render_fragment_glsl: also record per-pixel march steps and horizon flags for
+                                       gvt_render_fragment_glsl_debug (8 B per pixel of extra stores; off by default) */
     GVT_FLAG_D2H_OWN_ROWS = 1u << 5 /* multi-GPU: copy only this rank's row block into host_rgba (at its place in the
                                        full-size buffer). With one host frame shared by all ranks (POSIX shm registered
                                        through gvt_host_register) the ranks assemble the frame in parallel, one
@@ -305,7 +307,8 @@ typedef struct GvtBloomConfig {
     uint32_t blur_passes;  /* 2 */
 } GvtBloomConfig;
 int32_t gvt_render_bloom(gvt_renderer* r, const GvtBloomConfig* cfg, uint32_t output_format, void* host_out, double* ms);
-/* Parity hook: per-pixel step count and horizon flag of the last gvt_render_fragment_glsl frame (width*height each). */
+/* Parity hook: per-pixel step count and horizon flag of the last gvt_render_fragment_glsl frame rendered with
+ * GVT_FLAG_DEBUG_COUNTS (width*height each). */
 int32_t gvt_render_fragment_glsl_debug(gvt_renderer* r, uint32_t* steps, uint32_t* hit);
 /* Peer-store gather (GVT_FLAG_PEER_STORE): each rank exports CUDA IPC handles of its two frame buffers; the host
  * exchanges them (any transport) and every rank imports every peer's pair. Call again after gvt_render_resize. All

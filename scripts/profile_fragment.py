@@ -29,6 +29,7 @@ if len(sys.argv) > 4 and sys.argv[4] == "parity":
     import oracle as O
     Wp, Hp = 480, 270
     r.resize(Wp, Hp)
+    r.debug = True
     for pr, nm in ((_lib.PRECISION_F64, "f64"), (_lib.PRECISION_F32, "f32"), (_lib.PRECISION_F32_FAST, "f32-fast")):
         r.precision = pr
         u = webgl.make_uniforms(Wp, Hp, params, (0.5, 0.5 + 7.0 / 180.0), time=0.77, features=feats)

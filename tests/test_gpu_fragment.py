@@ -20,6 +20,7 @@ def wgl(built):
     from gravitas_b200 import webgl
     r = webgl.WebGLRenderer(device=0, noise_seed=11)
     assert r.init(), r.error
+    r.debug = True      # GVT_FLAG_DEBUG_COUNTS: the tests read per-pixel step counts
     yield r
     r.cleanup()
 
@@ -181,6 +182,7 @@ def test_f64_kernel_matches_committed_fixture(built, case):
     g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "glsl_fragment_48x27.npz")))
     r = webgl.WebGLRenderer(device=0, noise_seed=int(g["noise_seed"]))
     assert r.init(), r.error
+    r.debug = True
     try:
         u = _lib.GvtGlslUniforms.from_buffer_copy(g[f"{case}_uniforms"].tobytes())
         r.precision = _lib.PRECISION_F64
