@@ -70,6 +70,7 @@ struct NcclApi {
     int (*AllGather)(const void*, void*, size_t, int, ncclComm_t_, cudaStream_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t_, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
+    int (*CommGetAsyncError)(ncclComm_t_, int*) = nullptr;   // optional (NCCL >= 2.4)
     bool load() {
         if (handle) return true;
         const char* names[] = {"libnccl.so.2", "libnccl.so"};
@@ -81,6 +82,7 @@ struct NcclApi {
         AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t_, cudaStream_t))dlsym(handle, "ncclAllGather");
         AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t_, cudaStream_t))dlsym(handle, "ncclAllReduce");
         GetErrorString = (const char* (*)(int))dlsym(handle, "ncclGetErrorString");
+        CommGetAsyncError = (int (*)(ncclComm_t_, int*))dlsym(handle, "ncclCommGetAsyncError");
         return GetUniqueId && CommInitRank && CommDestroy && AllGather && AllReduce && GetErrorString;
     }
 };
@@ -821,6 +823,13 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
     }
     CK(cudaEventRecord(r->ev[5], r->stream));
     CK(cudaStreamSynchronize(r->stream));
+    if (r->comm && g_nccl.CommGetAsyncError) {
+        // a collective can fail after it was enqueued (peer death, link error): surface it instead of a silent bad frame
+        int aerr = 0;
+        const int qrc = g_nccl.CommGetAsyncError(r->comm, &aerr);
+        if (qrc != 0 || aerr != 0)
+            return fail(GVT_ERR_NCCL, "NCCL asynchronous error: %s", g_nccl.GetErrorString(qrc != 0 ? qrc : aerr));
+    }
     if (taa) r->history_valid = true;
     if (stats) {
         memset(stats, 0, sizeof(*stats));
