@@ -548,7 +548,9 @@ __global__ void __launch_bounds__(256, 2) k_fragment_glsl(const __grid_constant_
                     }
                 }
             }
-            const float4 px_out = make_float4((float)out[0], (float)out[1], (float)out[2], 1.0f);
+            float4 px_out = make_float4((float)out[0], (float)out[1], (float)out[2], 1.0f);
+            // NaN guard: GLSL leaves a NaN fragment undefined; here it becomes black instead of poisoning TAA / bloom
+            if (!(px_out.x == px_out.x) || !(px_out.y == px_out.y) || !(px_out.z == px_out.z)) px_out = make_float4(0.f, 0.f, 0.f, 1.0f);
             const size_t o = (size_t)py * P.width + px;
             if (P.frame) P.frame[o] = px_out;
             if (P.host_frame) P.host_frame[o] = px_out;

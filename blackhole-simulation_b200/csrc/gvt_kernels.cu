@@ -359,7 +359,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
 
         // ---- epilogue: coalesced float4 store + census ----
         if (valid) {
-            const float4 px_out = make_float4((float)col[0], (float)col[1], (float)col[2], 1.0f);
+            // NaN guard (failure detection): a ray that went non-finite must not poison the TAA history
+            float4 px_out = make_float4((float)col[0], (float)col[1], (float)col[2], 1.0f);
+            if (!(px_out.x == px_out.x) || !(px_out.y == px_out.y) || !(px_out.z == px_out.z)) px_out = make_float4(0.f, 0.f, 0.f, 1.0f);
             if (P.frame) P.frame[(size_t)py * P.width + px] = px_out;
             if (P.host_frame) P.host_frame[(size_t)py * P.width + px] = px_out;   // posted PCIe write, off the critical path
             for (uint32_t q = 0; q < P.n_peer; q++)                               // fused gather: NVLink peer stores
