@@ -232,8 +232,17 @@ __device__ __forceinline__ void shader_accel(const Vec3<R>& p, const Vec3<R>& v,
 
 }  // namespace
 
+// resident CTAs per SM: three 64 KB noise copies fit in shared memory; the MUFU build fits 3 x 256 threads in 77
+// registers without spilling (15.6 ms vs 16.2 ms at 4K), the IEEE/libm builds need ~104-128 registers
+#ifndef GVT_FRAG_MINB
+#ifdef GVT_FRAGMENT_FAST
+#define GVT_FRAG_MINB 3
+#else
+#define GVT_FRAG_MINB 2
+#endif
+#endif
 template <class R>
-__global__ void __launch_bounds__(256, 2) k_fragment_glsl(const __grid_constant__ GlslParams P) {
+__global__ void __launch_bounds__(256, GVT_FRAG_MINB) k_fragment_glsl(const __grid_constant__ GlslParams P) {
     using G = GM<R>;
     extern __shared__ __align__(128) unsigned char smem_noise[];
     __shared__ uint64_t bar;
