@@ -234,6 +234,9 @@ __device__ __forceinline__ void shader_accel(const Vec3<R>& p, const Vec3<R>& v,
 
 // resident CTAs per SM: three 64 KB noise copies fit in shared memory; the MUFU build fits 3 x 256 threads in 77
 // registers without spilling (15.6 ms vs 16.2 ms at 4K), the IEEE/libm builds need ~104-128 registers
+#ifndef GVT_FRAG_THREADS
+#define GVT_FRAG_THREADS 256
+#endif
 #ifndef GVT_FRAG_MINB
 #ifdef GVT_FRAGMENT_FAST
 #define GVT_FRAG_MINB 3
@@ -242,7 +245,7 @@ __device__ __forceinline__ void shader_accel(const Vec3<R>& p, const Vec3<R>& v,
 #endif
 #endif
 template <class R>
-__global__ void __launch_bounds__(256, GVT_FRAG_MINB) k_fragment_glsl(const __grid_constant__ GlslParams P) {
+__global__ void __launch_bounds__(GVT_FRAG_THREADS, GVT_FRAG_MINB) k_fragment_glsl(const __grid_constant__ GlslParams P) {
     using G = GM<R>;
     extern __shared__ __align__(128) unsigned char smem_noise[];
     __shared__ uint64_t bar;
@@ -595,12 +598,13 @@ static cudaError_t launch_impl(const GlslParams& p, int precision, int sm_count,
     const uint32_t n_rows = (p.y1 - p.y0 + p.ys - 1u) / p.ys;
     const uint32_t tiles = ((p.width + 7u) / 8u) * ((n_rows + 3u) / 4u);
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GVT_FRAG_THREADS, smem);
     if (e != cudaSuccess) return e;
-    uint32_t ctas = (tiles + 7u) / 8u;
+    const uint32_t wpc = GVT_FRAG_THREADS / 32;
+    uint32_t ctas = (tiles + wpc - 1u) / wpc;
     const uint32_t resident = (uint32_t)sm_count * (uint32_t)(per_sm > 0 ? per_sm : 1);
     if (ctas > resident) ctas = resident;   // persistent CTAs: as many as are resident at once
-    kern<<<ctas, 256, smem, stream>>>(p);
+    kern<<<ctas, GVT_FRAG_THREADS, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
