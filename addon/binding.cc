@@ -117,6 +117,37 @@ napi_value ShadowShift(napi_env env, napi_callback_info info) {                 
     if (arr) GVT(gvt_engine_compute_shadow_shift(e, Num(env, argv[0]), out));
     return arr;
 }
+// ---- spacetime-visualisation helpers (lib.rs:139-305) ----
+ENGINE_GETTER(ComputeKretschner, gvt_engine_compute_kretschner(e, Num(env, argv[0]), Num(env, argv[1]), &out))        // lib.rs:213
+ENGINE_GETTER(ComputeLightConeTilt, gvt_engine_compute_light_cone_tilt(e, Num(env, argv[0]), Num(env, argv[1]), &out)) // lib.rs:238
+ENGINE_GETTER(ComputeFrameDragOmega, gvt_engine_compute_frame_drag_omega(e, Num(env, argv[0]), Num(env, argv[1]), &out)) // lib.rs:267
+ENGINE_GETTER(ComputeFlammHeight, gvt_engine_compute_flamm_height(e, Num(env, argv[0]), &out))                       // lib.rs:296
+napi_value ComputeProperDistance(napi_env env, napi_callback_info info) {                                           // lib.rs:302
+    size_t argc = 3; napi_value argv[3];
+    gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
+    double out = 0;
+    GVT(gvt_engine_compute_proper_distance(e, Num(env, argv[0]), Num(env, argv[1]), (uint32_t)Num(env, argv[2]), &out));
+    napi_value v; napi_create_double(env, out, &v); return v;
+}
+typedef int32_t (*FieldFn)(gvt_engine*, double, double, uint32_t, uint32_t, float*);
+template <FieldFn FN> napi_value Field(napi_env env, napi_callback_info info) {   // (rMin, rMax, n1, n2) -> Float32Array(3 n1 n2)
+    size_t argc = 4; napi_value argv[4];
+    gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
+    const uint32_t n1 = (uint32_t)Num(env, argv[2]), n2 = (uint32_t)Num(env, argv[3]);
+    float* out = nullptr;
+    napi_value arr = F32Array(env, (size_t)3 * n1 * n2, &out);
+    if (arr) GVT(FN(e, Num(env, argv[0]), Num(env, argv[1]), n1, n2, out));
+    return arr;
+}
+napi_value ErgosphereMesh(napi_env env, napi_callback_info info) {                                                  // lib.rs:153
+    size_t argc = 2; napi_value argv[2];
+    gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
+    const uint32_t n1 = (uint32_t)Num(env, argv[0]), n2 = (uint32_t)Num(env, argv[1]);
+    float* out = nullptr;
+    napi_value arr = F32Array(env, (size_t)3 * n1 * n2, &out);
+    if (arr) GVT(gvt_engine_generate_ergosphere_mesh(e, n1, n2, out));
+    return arr;
+}
 napi_value DiskLut(napi_env env, napi_callback_info info) {                      // lib.rs:107
     size_t argc = 0;
     gvt_engine* e = Self<gvt_engine>(env, info, &argc, nullptr);
@@ -291,6 +322,14 @@ NAPI_MODULE_INIT() {
         {"compute_dilation", 0, ComputeDilation, 0, 0, 0, napi_default, 0}, {"compute_g_factor", 0, ComputeGFactor, 0, 0, 0, napi_default, 0},
         {"compute_shadow_curve", 0, ShadowCurve, 0, 0, 0, napi_default, 0}, {"compute_shadow_shift", 0, ShadowShift, 0, 0, 0, napi_default, 0},
         {"compute_shadow_radius", 0, ComputeShadowRadius, 0, 0, 0, napi_default, 0}, {"compute_disk_flux", 0, ComputeDiskFlux, 0, 0, 0, napi_default, 0},
+        {"compute_kretschner", 0, ComputeKretschner, 0, 0, 0, napi_default, 0}, {"compute_light_cone_tilt", 0, ComputeLightConeTilt, 0, 0, 0, napi_default, 0},
+        {"compute_frame_drag_omega", 0, ComputeFrameDragOmega, 0, 0, 0, napi_default, 0}, {"compute_flamm_height", 0, ComputeFlammHeight, 0, 0, 0, napi_default, 0},
+        {"compute_proper_distance", 0, ComputeProperDistance, 0, 0, 0, napi_default, 0},
+        {"generate_curvature_field", 0, Field<gvt_engine_generate_curvature_field>, 0, 0, 0, napi_default, 0},
+        {"generate_tilt_field", 0, Field<gvt_engine_generate_tilt_field>, 0, 0, 0, napi_default, 0},
+        {"generate_frame_drag_field", 0, Field<gvt_engine_generate_frame_drag_field>, 0, 0, 0, napi_default, 0},
+        {"generate_embedding_mesh", 0, Field<gvt_engine_generate_embedding_mesh>, 0, 0, 0, napi_default, 0},
+        {"generate_ergosphere_mesh", 0, ErgosphereMesh, 0, 0, 0, napi_default, 0},
         {"generate_disk_lut", 0, DiskLut, 0, 0, 0, napi_default, 0}, {"generate_spectrum_lut", 0, SpectrumLut, 0, 0, 0, napi_default, 0},
         {"integrate_ray_relativistic", 0, IntegrateRay, 0, 0, 0, napi_default, 0}};
     const napi_property_descriptor renderer[] = {

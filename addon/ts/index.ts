@@ -16,6 +16,14 @@ export const PhysicsEngine: new (mass: number, spin: number) => {
   compute_dilation(r: number): number; compute_g_factor(r: number, lambda: number): number;
   compute_shadow_curve(thetaObs: number, nPoints: number): Float32Array; compute_shadow_shift(thetaObs: number): Float32Array;
   compute_shadow_radius(): number; compute_disk_flux(r: number): number;
+  compute_kretschner(r: number, theta: number): number; compute_light_cone_tilt(r: number, theta: number): number;
+  compute_frame_drag_omega(r: number, theta: number): number; compute_flamm_height(r: number): number;
+  compute_proper_distance(r1: number, r2: number, nSteps: number): number;
+  generate_curvature_field(rMin: number, rMax: number, nRadial: number, nPolar: number): Float32Array;
+  generate_tilt_field(rMin: number, rMax: number, nRadial: number, nPolar: number): Float32Array;
+  generate_frame_drag_field(rMin: number, rMax: number, nRadial: number, nPolar: number): Float32Array;
+  generate_embedding_mesh(rMin: number, rMax: number, nRadial: number, nAngular: number): Float32Array;
+  generate_ergosphere_mesh(nPolar: number, nAzimuthal: number): Float32Array;
   generate_disk_lut(): Float32Array; generate_spectrum_lut(w: number, h: number, maxTemp: number): Float32Array;
   integrate_ray_relativistic(state: number[], steps: number, tol: number, useKerrSchild: boolean): Float64Array;
 } = addon.PhysicsEngine;

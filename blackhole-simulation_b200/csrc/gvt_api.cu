@@ -225,6 +225,74 @@ extern "C" int32_t gvt_engine_compute_disk_flux(gvt_engine* e, double r, double*
     *out = host::nt::flux(r, host::Hole(e->mass, e->spin), 1.0);   // page_thorne_flux(r, metric_bl, 1.0)
     return GVT_OK;
 }
+// ---- spacetime-visualisation helpers (lib.rs:139-305) ----
+extern "C" int32_t gvt_engine_compute_kretschner(gvt_engine* e, double r, double theta, double* out) {
+    if (!e || !out) return fail(GVT_ERR_INVALID, "null argument");
+    *out = host::viz::kretschner(r, theta, e->mass, e->spin);
+    return GVT_OK;
+}
+extern "C" int32_t gvt_engine_compute_light_cone_tilt(gvt_engine* e, double r, double theta, double* out) {
+    if (!e || !out) return fail(GVT_ERR_INVALID, "null argument");
+    *out = host::viz::light_cone_tilt(host::Hole(e->mass, e->spin), r, theta);
+    return GVT_OK;
+}
+extern "C" int32_t gvt_engine_compute_frame_drag_omega(gvt_engine* e, double r, double theta, double* out) {
+    if (!e || !out) return fail(GVT_ERR_INVALID, "null argument");
+    *out = host::viz::frame_drag_omega(host::Hole(e->mass, e->spin), r, theta);
+    return GVT_OK;
+}
+static int32_t check_field(gvt_engine* e, uint32_t n1, uint32_t n2, const float* out) {
+    if (!e || !out) return fail(GVT_ERR_INVALID, "null argument");
+    if (n1 < 2 || n2 < 2) return fail(GVT_ERR_INVALID, "sampling lattices need at least 2 points per axis (the reference divides by n - 1)");
+    return GVT_OK;
+}
+extern "C" int32_t gvt_engine_generate_curvature_field(gvt_engine* e, double r_min, double r_max, uint32_t n_radial,
+                                                       uint32_t n_polar, float* out3) {
+    const int32_t rc = check_field(e, n_radial, n_polar, out3);
+    if (rc != GVT_OK) return rc;
+    const double m = e->mass, s = e->spin;
+    host::viz::field(r_min, r_max, n_radial, n_polar, out3, [&](double r, double th) { return host::viz::kretschner(r, th, m, s); });
+    return GVT_OK;
+}
+extern "C" int32_t gvt_engine_generate_tilt_field(gvt_engine* e, double r_min, double r_max, uint32_t n_radial, uint32_t n_polar,
+                                                  float* out3) {
+    const int32_t rc = check_field(e, n_radial, n_polar, out3);
+    if (rc != GVT_OK) return rc;
+    const host::Hole bh(e->mass, e->spin);
+    host::viz::field(r_min, r_max, n_radial, n_polar, out3, [&](double r, double th) { return host::viz::light_cone_tilt(bh, r, th); });
+    return GVT_OK;
+}
+extern "C" int32_t gvt_engine_generate_frame_drag_field(gvt_engine* e, double r_min, double r_max, uint32_t n_radial,
+                                                        uint32_t n_polar, float* out3) {
+    const int32_t rc = check_field(e, n_radial, n_polar, out3);
+    if (rc != GVT_OK) return rc;
+    const host::Hole bh(e->mass, e->spin);
+    host::viz::field(r_min, r_max, n_radial, n_polar, out3, [&](double r, double th) { return host::viz::frame_drag_omega(bh, r, th); });
+    return GVT_OK;
+}
+extern "C" int32_t gvt_engine_compute_flamm_height(gvt_engine* e, double r, double* out) {
+    if (!e || !out) return fail(GVT_ERR_INVALID, "null argument");
+    *out = host::viz::flamm_height(r, e->mass);
+    return GVT_OK;
+}
+extern "C" int32_t gvt_engine_compute_proper_distance(gvt_engine* e, double r1, double r2, uint32_t n_steps, double* out) {
+    if (!e || !out) return fail(GVT_ERR_INVALID, "null argument");
+    *out = host::viz::proper_distance(host::Hole(e->mass, e->spin), r1, r2, n_steps);
+    return GVT_OK;
+}
+extern "C" int32_t gvt_engine_generate_embedding_mesh(gvt_engine* e, double r_min, double r_max, uint32_t n_radial,
+                                                      uint32_t n_angular, float* out3) {
+    if (!e || !out3) return fail(GVT_ERR_INVALID, "null argument");
+    if (n_radial < 2 || n_angular < 1) return fail(GVT_ERR_INVALID, "embedding mesh needs n_radial >= 2 and n_angular >= 1");
+    host::viz::embedding_mesh(e->mass, e->spin, r_min, r_max, n_radial, n_angular, out3);
+    return GVT_OK;
+}
+extern "C" int32_t gvt_engine_generate_ergosphere_mesh(gvt_engine* e, uint32_t n_polar, uint32_t n_azimuthal, float* out3) {
+    if (!e || !out3) return fail(GVT_ERR_INVALID, "null argument");
+    if (n_polar < 2 || n_azimuthal < 1) return fail(GVT_ERR_INVALID, "ergosphere mesh needs n_polar >= 2 and n_azimuthal >= 1");
+    host::viz::ergosphere_mesh(host::Hole(e->mass, e->spin), n_polar, n_azimuthal, out3);
+    return GVT_OK;
+}
 extern "C" int32_t gvt_engine_generate_disk_lut(gvt_engine* e, float* out512) {
     if (!e || !out512) return fail(GVT_ERR_INVALID, "null argument");
     host::disk_lut(host::Hole(e->mass, e->spin), 512, out512);  // lut_width 512 (lib.rs:65)

@@ -242,6 +242,106 @@ inline std::vector<std::pair<double, double>> bardeen_shadow(const Hole& bh, dou
     return pts;
 }
 
+// ---- gravitas-core/src/spacetime/{curvature,lightcone,frame_drag,embedding}.rs : the visualisation helpers the
+// PhysicsEngine exposes (lib.rs:139-305). One-off host maths in the reference too; all on the Boyer-Lindquist metric
+// (lib.rs:63 `metric_bl`), covariant components as kerr.rs:241-264. -----------------------------------------------
+namespace viz {
+struct CovBL { double g_tt, g_rr, g_thth, g_phph, g_tph; };
+inline CovBL covariant_bl(const Hole& bh, double r, double theta) {
+    const double m = bh.mass, a = bh.a(), r2 = r * r, a2 = a * a;
+    const double st = std::sin(theta), ct = std::cos(theta), sin2 = st * st, cos2 = ct * ct;
+    const double sigma = r2 + a2 * cos2, delta = r2 - 2.0 * m * r + a2;
+    CovBL g;
+    g.g_tt = -(1.0 - (2.0 * m * r) / sigma);
+    g.g_rr = sigma / delta;
+    g.g_thth = sigma;
+    g.g_phph = (r2 + a2 + (2.0 * m * r * a2 * sin2) / sigma) * sin2;
+    g.g_tph = -(2.0 * m * r * a * sin2) / sigma;
+    return g;
+}
+// curvature.rs:13-36 (raw mass / spin, as lib.rs:213-215 passes them)
+inline double kretschner(double r, double theta, double mass, double spin) {
+    const double a = spin * mass, r2 = r * r, a2 = a * a, c = std::cos(theta);
+    const double cos2 = c * c, cos4 = cos2 * cos2, cos6 = cos4 * cos2;
+    const double r4 = r2 * r2, r6 = r4 * r2, a4 = a2 * a2, a6 = a4 * a2;
+    const double sigma = r2 + a2 * cos2, s2 = sigma * sigma, s4 = s2 * s2, sigma6 = s2 * s4;   // powi(6) by squaring
+    if (sigma6 < 1e-30) return INFINITY;
+    const double num = r6 - 15.0 * r4 * a2 * cos2 + 15.0 * r2 * a4 * cos4 - a6 * cos6;
+    return 48.0 * mass * mass * num / sigma6;
+}
+// lightcone.rs:18-49 (the BL metric is diagonal in (t, r): only the first branch can be taken)
+inline double light_cone_tilt(const Hole& bh, double r, double theta) {
+    const CovBL g = covariant_bl(bh, r, theta);
+    if (g.g_tt >= 0.0) return 1.5707963267948966;
+    return std::atan(std::sqrt(std::max(-g.g_tt / g.g_rr, 0.0)));
+}
+// frame_drag.rs:13-15 over kerr.rs:143-152
+inline double frame_drag_omega(const Hole& bh, double r, double theta) {
+    const CovBL g = covariant_bl(bh, r, theta);
+    return std::fabs(g.g_phph) < 1e-30 ? 0.0 : -g.g_tph / g.g_phph;
+}
+// the (r, theta, value) sampling lattice shared by curvature_field / tilt_field / frame_drag_field
+template <class F> inline void field(double r_min, double r_max, size_t n_radial, size_t n_polar, float* out, F f) {
+    const double PI = 3.14159265358979323846;
+    for (size_t i = 0; i < n_radial; i++) {
+        const double r = r_min + (r_max - r_min) * (double)i / (double)(n_radial - 1);
+        for (size_t j = 0; j < n_polar; j++) {
+            const double theta = 0.1 + (PI - 0.2) * (double)j / (double)(n_polar - 1);
+            float* o = out + 3 * (i * n_polar + j);
+            o[0] = (float)r; o[1] = (float)theta; o[2] = (float)f(r, theta);
+        }
+    }
+}
+inline double flamm_height(double r, double mass) {   // embedding.rs:14-20
+    const double rs = 2.0 * mass;
+    return r <= rs ? 0.0 : 2.0 * std::sqrt(rs * (r - rs));
+}
+inline double kerr_embedding_height(const Hole& bh, double r, double r_ref, size_t n_steps) {   // embedding.rs:28-44
+    const double dr = (r_ref - r) / (double)n_steps;
+    double z = 0.0;
+    for (size_t i = 0; i < n_steps; i++) {
+        const double r_i = r + ((double)i + 0.5) * dr;
+        z += std::sqrt(std::fabs(covariant_bl(bh, r_i, 1.5707963267948966).g_rr - 1.0)) * dr;
+    }
+    return z;
+}
+inline double proper_distance(const Hole& bh, double r1, double r2, size_t n_steps) {   // embedding.rs:49-63
+    const double lo = r1 < r2 ? r1 : r2, hi = r1 < r2 ? r2 : r1, dr = (hi - lo) / (double)n_steps;
+    double d = 0.0;
+    for (size_t i = 0; i < n_steps; i++) {
+        const double r_i = lo + ((double)i + 0.5) * dr;
+        d += std::sqrt(std::fabs(covariant_bl(bh, r_i, 1.5707963267948966).g_rr)) * dr;
+    }
+    return d;
+}
+inline void embedding_mesh(double mass, double spin, double r_min, double r_max, size_t n_radial, size_t n_angular, float* out) {
+    const double PI = 3.14159265358979323846;   // embedding.rs:72-110
+    const Hole bh(mass, spin);
+    for (size_t i = 0; i < n_radial; i++) {
+        const double t = (double)i / (double)(n_radial - 1), r = r_min + t * (r_max - r_min);
+        const double height = std::fabs(spin) < 1e-6 ? flamm_height(r, mass) : kerr_embedding_height(bh, r, r_max, 100);
+        for (size_t j = 0; j < n_angular; j++) {
+            const double phi = 2.0 * PI * (double)j / (double)n_angular;
+            float* o = out + 3 * (i * n_angular + j);
+            o[0] = (float)(r * std::cos(phi)); o[1] = (float)(-height); o[2] = (float)(r * std::sin(phi));
+        }
+    }
+}
+inline void ergosphere_mesh(const Hole& bh, size_t n_polar, size_t n_azimuthal, float* out) {   // frame_drag.rs:48-68
+    const double PI = 3.14159265358979323846, m = bh.mass, a = bh.a();
+    for (size_t i = 0; i < n_polar; i++) {
+        const double theta = PI * (double)i / (double)(n_polar - 1), c = std::cos(theta);
+        const double disc = m * m - a * a * c * c, r_ergo = disc < 0.0 ? m : m + std::sqrt(disc);   // kerr.rs:157-167
+        for (size_t j = 0; j < n_azimuthal; j++) {
+            const double phi = 2.0 * PI * (double)j / (double)n_azimuthal;
+            float* o = out + 3 * (i * n_azimuthal + j);
+            o[0] = (float)(r_ergo * std::sin(theta) * std::cos(phi)); o[1] = (float)(r_ergo * std::cos(theta));
+            o[2] = (float)(r_ergo * std::sin(theta) * std::sin(phi));
+        }
+    }
+}
+}  // namespace viz
+
 // ---- gravitas-wasm/src/camera.rs:9-70 : camera state + kinematic filter (glam DVec3/DQuat maths inlined) --
 struct Vec3 { double x, y, z; };
 struct CameraState {

@@ -108,6 +108,16 @@ SIGNATURES = {
     "gvt_engine_compute_shadow_radius": (_i32, [_vp, _pd]),
     "gvt_engine_compute_shadow_shift": (_i32, [_vp, _d, _pf]),
     "gvt_engine_compute_disk_flux": (_i32, [_vp, _d, _pd]),
+    "gvt_engine_compute_kretschner": (_i32, [_vp, _d, _d, _pd]),
+    "gvt_engine_generate_curvature_field": (_i32, [_vp, _d, _d, _u32, _u32, _pf]),
+    "gvt_engine_compute_light_cone_tilt": (_i32, [_vp, _d, _d, _pd]),
+    "gvt_engine_generate_tilt_field": (_i32, [_vp, _d, _d, _u32, _u32, _pf]),
+    "gvt_engine_compute_frame_drag_omega": (_i32, [_vp, _d, _d, _pd]),
+    "gvt_engine_generate_frame_drag_field": (_i32, [_vp, _d, _d, _u32, _u32, _pf]),
+    "gvt_engine_compute_flamm_height": (_i32, [_vp, _d, _pd]),
+    "gvt_engine_compute_proper_distance": (_i32, [_vp, _d, _d, _u32, _pd]),
+    "gvt_engine_generate_embedding_mesh": (_i32, [_vp, _d, _d, _u32, _u32, _pf]),
+    "gvt_engine_generate_ergosphere_mesh": (_i32, [_vp, _u32, _u32, _pf]),
     "gvt_engine_generate_disk_lut": (_i32, [_vp, _pf]),
     "gvt_engine_generate_spectrum_lut": (_i32, [_vp, _u32, _u32, _d, _pf]),
     "gvt_engine_integrate_ray": (_i32, [_vp, _pd, _u64, _d, _i32, _pd, _pu32, _pu64, _pd]),

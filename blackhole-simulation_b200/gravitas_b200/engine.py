@@ -68,6 +68,44 @@ class PhysicsEngine:
     def compute_disk_flux(self, r):  # lib.rs:199-201
         return self._scalar(lib().gvt_engine_compute_disk_flux, float(r))
 
+    # ---- spacetime visualisation helpers (lib.rs:139-305): Float32Array results as flat numpy f32 arrays ----
+    def _field(self, fn, r_min, r_max, n_radial, n_polar):
+        out = np.zeros(3 * int(n_radial) * int(n_polar), np.float32)
+        check(fn(self._h, float(r_min), float(r_max), int(n_radial), int(n_polar), out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def compute_kretschner(self, r, theta):  # lib.rs:213-215
+        return self._scalar(lib().gvt_engine_compute_kretschner, float(r), float(theta))
+
+    def generate_curvature_field(self, r_min, r_max, n_radial, n_polar):  # lib.rs:219-234 -> (r, theta, K) triples
+        return self._field(lib().gvt_engine_generate_curvature_field, r_min, r_max, n_radial, n_polar)
+
+    def compute_light_cone_tilt(self, r, theta):  # lib.rs:238-240
+        return self._scalar(lib().gvt_engine_compute_light_cone_tilt, float(r), float(theta))
+
+    def generate_tilt_field(self, r_min, r_max, n_radial, n_polar):  # lib.rs:244-263
+        return self._field(lib().gvt_engine_generate_tilt_field, r_min, r_max, n_radial, n_polar)
+
+    def compute_frame_drag_omega(self, r, theta):  # lib.rs:267-269
+        return self._scalar(lib().gvt_engine_compute_frame_drag_omega, float(r), float(theta))
+
+    def generate_frame_drag_field(self, r_min, r_max, n_radial, n_polar):  # lib.rs:273-292
+        return self._field(lib().gvt_engine_generate_frame_drag_field, r_min, r_max, n_radial, n_polar)
+
+    def compute_flamm_height(self, r):  # lib.rs:296-298
+        return self._scalar(lib().gvt_engine_compute_flamm_height, float(r))
+
+    def compute_proper_distance(self, r1, r2, n_steps):  # lib.rs:302-304
+        return self._scalar(lib().gvt_engine_compute_proper_distance, float(r1), float(r2), int(n_steps))
+
+    def generate_embedding_mesh(self, r_min, r_max, n_radial, n_angular):  # lib.rs:139-150 -> (x, y, z) triples
+        return self._field(lib().gvt_engine_generate_embedding_mesh, r_min, r_max, n_radial, n_angular)
+
+    def generate_ergosphere_mesh(self, n_polar, n_azimuthal):  # lib.rs:153-157
+        out = np.zeros(3 * int(n_polar) * int(n_azimuthal), np.float32)
+        check(lib().gvt_engine_generate_ergosphere_mesh(self._h, int(n_polar), int(n_azimuthal), out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
     def generate_disk_lut(self):  # lib.rs:107-110 -> Vec<f32>(512)
         out = np.zeros(512, np.float32)
         check(lib().gvt_engine_generate_disk_lut(self._h, out.ctypes.data_as(C.POINTER(C.c_float))))

@@ -232,6 +232,23 @@ int32_t gvt_engine_compute_shadow_curve(gvt_engine* e, double theta_obs, uint32_
 int32_t gvt_engine_compute_shadow_radius(gvt_engine* e, double* out);               /* lib.rs:173-175 */
 int32_t gvt_engine_compute_shadow_shift(gvt_engine* e, double theta_obs, float out2[2]); /* lib.rs:179-196 */
 int32_t gvt_engine_compute_disk_flux(gvt_engine* e, double r, double* out);         /* lib.rs:199-201 */
+/* Spacetime-visualisation helpers of the class (lib.rs:139-305 over gravitas-core/src/spacetime/): one-off host maths on the
+ * Boyer-Lindquist metric, as in the reference. Fields are (r, theta, value) f32 triples over n_radial x n_polar samples
+ * (r linear in [r_min, r_max], theta in [0.1, pi - 0.1]); meshes are (x, y, z) f32 triples. n_radial / n_polar >= 2. */
+int32_t gvt_engine_compute_kretschner(gvt_engine* e, double r, double theta, double* out);        /* lib.rs:213-215 */
+int32_t gvt_engine_generate_curvature_field(gvt_engine* e, double r_min, double r_max, uint32_t n_radial, uint32_t n_polar,
+                                            float* out3);                                          /* lib.rs:219-234 */
+int32_t gvt_engine_compute_light_cone_tilt(gvt_engine* e, double r, double theta, double* out);   /* lib.rs:238-240 */
+int32_t gvt_engine_generate_tilt_field(gvt_engine* e, double r_min, double r_max, uint32_t n_radial, uint32_t n_polar,
+                                       float* out3);                                               /* lib.rs:244-263 */
+int32_t gvt_engine_compute_frame_drag_omega(gvt_engine* e, double r, double theta, double* out);  /* lib.rs:267-269 */
+int32_t gvt_engine_generate_frame_drag_field(gvt_engine* e, double r_min, double r_max, uint32_t n_radial, uint32_t n_polar,
+                                             float* out3);                                         /* lib.rs:273-292 */
+int32_t gvt_engine_compute_flamm_height(gvt_engine* e, double r, double* out);                    /* lib.rs:296-298 */
+int32_t gvt_engine_compute_proper_distance(gvt_engine* e, double r1, double r2, uint32_t n_steps, double* out); /* :302-304 */
+int32_t gvt_engine_generate_embedding_mesh(gvt_engine* e, double r_min, double r_max, uint32_t n_radial, uint32_t n_angular,
+                                           float* out3);                                           /* lib.rs:139-150 */
+int32_t gvt_engine_generate_ergosphere_mesh(gvt_engine* e, uint32_t n_polar, uint32_t n_azimuthal, float* out3); /* :153-157 */
 int32_t gvt_engine_generate_disk_lut(gvt_engine* e, float* out512);                 /* lib.rs:107-110 */
 int32_t gvt_engine_generate_spectrum_lut(gvt_engine* e, uint32_t width, uint32_t height, double max_temp,
                                          float* out_rgba);                          /* lib.rs:128-136 */

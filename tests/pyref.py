@@ -345,3 +345,96 @@ def bardeen_shadow(m, spin, theta_obs, n_points):  # shadow.rs:81-183
             b2, xi = beta_sq(r)
             pts.append((a * so - xi / so, sign * math.sqrt(max(b2, 0.0))))
     return pts
+
+
+# ---- gravitas-core/src/spacetime/*.rs : visualisation helpers (independent restatement from the Rust) ----------------
+def covariant_bl(m, spin, r, theta):  # kerr.rs:241-264 -> (g_tt, g_rr, g_thth, g_phph, g_tph)
+    a = spin * m
+    r2, a2 = r * r, a * a
+    s, c = math.sin(theta), math.cos(theta)
+    sin2, cos2 = s * s, c * c
+    sigma = r2 + a2 * cos2
+    delta = r2 - 2.0 * m * r + a2
+    return (-(1.0 - (2.0 * m * r) / sigma), sigma / delta, sigma, (r2 + a2 + (2.0 * m * r * a2 * sin2) / sigma) * sin2,
+            -(2.0 * m * r * a * sin2) / sigma)
+
+
+def kretschner_kerr(r, theta, mass, spin):  # curvature.rs:13-36
+    a = spin * mass
+    r2, a2 = r * r, a * a
+    cos2 = math.cos(theta) ** 2
+    cos4 = cos2 * cos2
+    cos6 = cos4 * cos2
+    r4 = r2 * r2
+    r6 = r4 * r2
+    a4 = a2 * a2
+    a6 = a4 * a2
+    sigma = r2 + a2 * cos2
+    sigma6 = (sigma * sigma) * ((sigma * sigma) * (sigma * sigma))
+    if sigma6 < 1e-30:
+        return math.inf
+    return 48.0 * mass * mass * (r6 - 15.0 * r4 * a2 * cos2 + 15.0 * r2 * a4 * cos4 - a6 * cos6) / sigma6
+
+
+def light_cone_tilt_bl(m, spin, r, theta):  # lightcone.rs:18-34 (diagonal branch)
+    g_tt, g_rr = covariant_bl(m, spin, r, theta)[:2]
+    if g_tt >= 0.0:
+        return math.pi / 2
+    return math.atan(math.sqrt(max(-g_tt / g_rr, 0.0)))
+
+
+def frame_dragging(m, spin, r, theta):  # kerr.rs:143-152
+    g = covariant_bl(m, spin, r, theta)
+    return 0.0 if abs(g[3]) < 1e-30 else -g[4] / g[3]
+
+
+def field_lattice(r_min, r_max, n_radial, n_polar):
+    for i in range(n_radial):
+        r = r_min + (r_max - r_min) * i / (n_radial - 1)
+        for j in range(n_polar):
+            yield r, 0.1 + (math.pi - 0.2) * j / (n_polar - 1)
+
+
+def flamm_height(r, mass):  # embedding.rs:14-20
+    rs = 2.0 * mass
+    return 0.0 if r <= rs else 2.0 * math.sqrt(rs * (r - rs))
+
+
+def kerr_embedding_height(m, spin, r, r_ref, n_steps):  # embedding.rs:28-44
+    dr = (r_ref - r) / n_steps
+    z = 0.0
+    for i in range(n_steps):
+        g_rr = covariant_bl(m, spin, r + (i + 0.5) * dr, math.pi / 2)[1]
+        z += math.sqrt(abs(g_rr - 1.0)) * dr
+    return z
+
+
+def proper_distance(m, spin, r1, r2, n_steps):  # embedding.rs:49-63
+    lo, hi = (r1, r2) if r1 < r2 else (r2, r1)
+    dr = (hi - lo) / n_steps
+    return sum(math.sqrt(abs(covariant_bl(m, spin, lo + (i + 0.5) * dr, math.pi / 2)[1])) * dr for i in range(n_steps))
+
+
+def embedding_mesh(mass, spin, r_min, r_max, n_radial, n_angular):  # embedding.rs:72-110
+    cl = max(-1.0, min(1.0, spin))
+    out = []
+    for i in range(n_radial):
+        r = r_min + (i / (n_radial - 1)) * (r_max - r_min)
+        h = flamm_height(r, mass) if abs(spin) < 1e-6 else kerr_embedding_height(mass, cl, r, r_max, 100)
+        for j in range(n_angular):
+            phi = 2.0 * math.pi * j / n_angular
+            out += [r * math.cos(phi), -h, r * math.sin(phi)]
+    return out
+
+
+def ergosphere_mesh(m, spin, n_polar, n_azimuthal):  # frame_drag.rs:48-68, kerr.rs:157-167
+    a = spin * m
+    out = []
+    for i in range(n_polar):
+        theta = math.pi * i / (n_polar - 1)
+        disc = m * m - a * a * math.cos(theta) ** 2
+        r_e = m if disc < 0.0 else m + math.sqrt(disc)
+        for j in range(n_azimuthal):
+            phi = 2.0 * math.pi * j / n_azimuthal
+            out += [r_e * math.sin(theta) * math.cos(phi), r_e * math.cos(theta), r_e * math.sin(theta) * math.sin(phi)]
+    return out

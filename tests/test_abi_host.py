@@ -197,3 +197,46 @@ def test_shadow_and_flux_methods(built, oracle):
     cam = sab[64:67].astype(np.float64)
     th_cam = math.acos(cam[1] / np.linalg.norm(cam))
     np.testing.assert_allclose(sab[144:144 + 112], e.compute_shadow_curve(th_cam, 32)[:112], rtol=1e-5, atol=1e-5)
+
+
+def test_spacetime_visualisation_helpers(built):
+    """The PhysicsEngine's visualisation helpers (lib.rs:139-305 over gravitas-core/src/spacetime/) against an independent
+    Python restatement of the Rust, plus the reference's own unit tests for them (embedding.rs:113-129) and closed forms."""
+    import pyref
+    # embedding.rs tests: flamm_height(2, 1) == 0; at r = 100: |z - 2 sqrt(2 * 98)| < 0.1
+    e1 = built.PhysicsEngine(1.0, 0.0)
+    assert e1.compute_flamm_height(2.0) == 0.0
+    assert abs(e1.compute_flamm_height(100.0) - 2.0 * math.sqrt(2.0 * 98.0)) < 0.1
+    # Schwarzschild closed forms: K = 48 M^2 / r^6 (curvature.rs:41-43); no frame dragging; tan(tilt) = 1 - 2M/r
+    assert abs(e1.compute_kretschner(5.0, 1.0) - 48.0 / 5.0 ** 6) < 1e-18
+    assert e1.compute_frame_drag_omega(7.0, 1.1) == 0.0
+    assert abs(math.tan(e1.compute_light_cone_tilt(10.0, 0.7)) - (1.0 - 2.0 / 10.0)) < 1e-14
+    assert e1.compute_light_cone_tilt(1.9, 0.7) == math.pi / 2                      # inside the horizon
+    # proper distance from 4M to 10M in Schwarzschild: closed form of int dr / sqrt(1 - 2M/r)
+    F = lambda r: math.sqrt(r * (r - 2.0)) + 2.0 * math.atanh(math.sqrt(1.0 - 2.0 / r))
+    assert abs(e1.compute_proper_distance(4.0, 10.0, 4000) - (F(10.0) - F(4.0))) < 1e-6
+    assert e1.compute_proper_distance(10.0, 4.0, 50) == e1.compute_proper_distance(4.0, 10.0, 50)
+    for m, a in [(1.0, 0.9), (2.5, -0.6), (1.0, 0.0), (0.7, 0.999)]:
+        e = built.PhysicsEngine(m, a)
+        for r, th in [(3.0 * m, 0.4), (6.0 * m, 1.5707963267948966), (20.0 * m, 2.9), (1.2 * m, 1.0)]:
+            np.testing.assert_allclose(e.compute_kretschner(r, th), pyref.kretschner_kerr(r, th, m, a), rtol=1e-13)
+            np.testing.assert_allclose(e.compute_light_cone_tilt(r, th), pyref.light_cone_tilt_bl(m, a, r, th), rtol=1e-14, atol=1e-16)
+            np.testing.assert_allclose(e.compute_frame_drag_omega(r, th), pyref.frame_dragging(m, a, r, th), rtol=1e-14, atol=1e-300)
+        np.testing.assert_allclose(e.compute_proper_distance(3.0 * m, 9.0 * m, 64), pyref.proper_distance(m, a, 3.0 * m, 9.0 * m, 64), rtol=1e-13)
+        nr, npol = 5, 7
+        lat = list(pyref.field_lattice(2.5 * m, 12.0 * m, nr, npol))
+        for gen, fn in [(e.generate_curvature_field, lambda r, t: pyref.kretschner_kerr(r, t, m, a)),
+                        (e.generate_tilt_field, lambda r, t: pyref.light_cone_tilt_bl(m, a, r, t)),
+                        (e.generate_frame_drag_field, lambda r, t: pyref.frame_dragging(m, a, r, t))]:
+            got = gen(2.5 * m, 12.0 * m, nr, npol).reshape(-1, 3)
+            ref = np.array([[r, t, fn(r, t)] for r, t in lat]).astype(np.float32)
+            np.testing.assert_allclose(got, ref, rtol=2e-7, atol=1e-30)
+        np.testing.assert_allclose(e.generate_embedding_mesh(2.2 * m, 15.0 * m, 6, 8),
+                                   np.array(pyref.embedding_mesh(m, a, 2.2 * m, 15.0 * m, 6, 8)).astype(np.float32), rtol=2e-7, atol=1e-6)
+        np.testing.assert_allclose(e.generate_ergosphere_mesh(9, 12),
+                                   np.array(pyref.ergosphere_mesh(m, a, 9, 12)).astype(np.float32), rtol=2e-7, atol=1e-6)
+        # the ergosphere touches the horizon at the poles and reaches 2M at the equator
+        mesh = e.generate_ergosphere_mesh(9, 12).reshape(9, 12, 3)
+        assert abs(np.linalg.norm(mesh[4, 0]) - 2.0 * m) < 1e-5 * m and abs(abs(mesh[0, 0, 1]) - e.compute_horizon()) < 1e-5 * m
+    with pytest.raises(built.GravitasError):
+        e1.generate_curvature_field(2.0, 10.0, 1, 5)          # the reference divides by (n - 1)
