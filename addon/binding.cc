@@ -156,6 +156,16 @@ napi_value DiskLut(napi_env env, napi_callback_info info) {                     
     if (arr) GVT(gvt_engine_generate_disk_lut(e, out));
     return arr;
 }
+napi_value DiskLutPtr(napi_env env, napi_callback_info info) {                   // lib.rs:112: a copy of the engine-owned LUT
+    size_t argc = 0;
+    gvt_engine* e = Self<gvt_engine>(env, info, &argc, nullptr);
+    const float* p = nullptr; uint32_t n = 0;
+    GVT(gvt_engine_get_disk_lut_ptr(e, &p, &n));
+    float* out = nullptr;
+    napi_value arr = F32Array(env, n, &out);
+    if (arr && n) memcpy(out, p, (size_t)n * sizeof(float));
+    return arr;
+}
 napi_value SpectrumLut(napi_env env, napi_callback_info info) {                  // lib.rs:128
     size_t argc = 3; napi_value argv[3];
     gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
@@ -330,7 +340,7 @@ NAPI_MODULE_INIT() {
         {"generate_frame_drag_field", 0, Field<gvt_engine_generate_frame_drag_field>, 0, 0, 0, napi_default, 0},
         {"generate_embedding_mesh", 0, Field<gvt_engine_generate_embedding_mesh>, 0, 0, 0, napi_default, 0},
         {"generate_ergosphere_mesh", 0, ErgosphereMesh, 0, 0, 0, napi_default, 0},
-        {"generate_disk_lut", 0, DiskLut, 0, 0, 0, napi_default, 0}, {"generate_spectrum_lut", 0, SpectrumLut, 0, 0, 0, napi_default, 0},
+        {"generate_disk_lut", 0, DiskLut, 0, 0, 0, napi_default, 0}, {"get_disk_lut_ptr", 0, DiskLutPtr, 0, 0, 0, napi_default, 0}, {"generate_spectrum_lut", 0, SpectrumLut, 0, 0, 0, napi_default, 0},
         {"integrate_ray_relativistic", 0, IntegrateRay, 0, 0, 0, napi_default, 0}};
     const napi_property_descriptor renderer[] = {
         {"initLuts", 0, InitLuts, 0, 0, 0, napi_default, 0}, {"resize", 0, Resize, 0, 0, 0, napi_default, 0},

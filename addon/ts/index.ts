@@ -24,11 +24,12 @@ export const PhysicsEngine: new (mass: number, spin: number) => {
   generate_frame_drag_field(rMin: number, rMax: number, nRadial: number, nPolar: number): Float32Array;
   generate_embedding_mesh(rMin: number, rMax: number, nRadial: number, nAngular: number): Float32Array;
   generate_ergosphere_mesh(nPolar: number, nAzimuthal: number): Float32Array;
-  generate_disk_lut(): Float32Array; generate_spectrum_lut(w: number, h: number, maxTemp: number): Float32Array;
+  generate_disk_lut(): Float32Array; get_disk_lut_ptr(): Float32Array; generate_spectrum_lut(w: number, h: number, maxTemp: number): Float32Array;
   integrate_ray_relativistic(state: number[], steps: number, tol: number, useKerrSchild: boolean): Float64Array;
 } = addon.PhysicsEngine;
 
 export const KerrRenderer = addon.KerrRenderer;
+export function init_hooks(): void {}                           // lib.rs:30-33: the wasm panic hook has no native counterpart
 
 // physics.worker.ts:61,68 and physics-bridge.ts:87-88 only use `.memory.buffer` to build Float32Array views over the
 // engine's SAB block; with attach_sab() the engine writes the caller's SharedArrayBuffer directly.

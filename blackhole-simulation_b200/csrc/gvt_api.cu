@@ -108,6 +108,7 @@ struct gvt_engine {
     double mass, spin;
     std::vector<float> sab;     // engine-owned 2048 f32 (lib.rs:67)
     float* ext_sab = nullptr;   // lib.rs:74-76
+    std::vector<float> lut_buffer;   // lib.rs:48,66: empty until generate_disk_lut() fills it
     host::CameraState camera, last_good;
     // device scratch for integrate_rays
     cudaStream_t stream = nullptr;
@@ -296,6 +297,13 @@ extern "C" int32_t gvt_engine_generate_ergosphere_mesh(gvt_engine* e, uint32_t n
 extern "C" int32_t gvt_engine_generate_disk_lut(gvt_engine* e, float* out512) {
     if (!e || !out512) return fail(GVT_ERR_INVALID, "null argument");
     host::disk_lut(host::Hole(e->mass, e->spin), 512, out512);  // lut_width 512 (lib.rs:65)
+    e->lut_buffer.assign(out512, out512 + 512);                 // lib.rs:108: the engine keeps its own copy
+    return GVT_OK;
+}
+extern "C" int32_t gvt_engine_get_disk_lut_ptr(gvt_engine* e, const float** out, uint32_t* n) {
+    if (!e || !out) return fail(GVT_ERR_INVALID, "null argument");
+    *out = e->lut_buffer.empty() ? nullptr : e->lut_buffer.data();   // lib.rs:112-114 (dangling-free: null while empty)
+    if (n) *n = (uint32_t)e->lut_buffer.size();
     return GVT_OK;
 }
 extern "C" int32_t gvt_engine_generate_spectrum_lut(gvt_engine* e, uint32_t w, uint32_t h, double max_temp, float* out) {

@@ -14,7 +14,7 @@ There is NO CPU fallback: importing works without a GPU (symbols resolve), but a
 with ``GravitasError`` when no sm_100 device is present or the shared library is missing.
 """
 from ._lib import GravitasError, lib, lib_path, OFFSETS  # noqa: F401
-from .engine import PhysicsEngine  # noqa: F401
+from .engine import PhysicsEngine, init_hooks  # noqa: F401
 from .renderer import KerrRenderer, RenderParams, FrameStats  # noqa: F401
 from .webgl import WebGLRenderer  # noqa: F401
 from . import camera, shard, webgl  # noqa: F401

@@ -119,6 +119,7 @@ SIGNATURES = {
     "gvt_engine_generate_embedding_mesh": (_i32, [_vp, _d, _d, _u32, _u32, _pf]),
     "gvt_engine_generate_ergosphere_mesh": (_i32, [_vp, _u32, _u32, _pf]),
     "gvt_engine_generate_disk_lut": (_i32, [_vp, _pf]),
+    "gvt_engine_get_disk_lut_ptr": (_i32, [_vp, C.POINTER(_pf), _pu32]),
     "gvt_engine_generate_spectrum_lut": (_i32, [_vp, _u32, _u32, _d, _pf]),
     "gvt_engine_integrate_ray": (_i32, [_vp, _pd, _u64, _d, _i32, _pd, _pu32, _pu64, _pd]),
     "gvt_engine_integrate_rays": (_i32, [_vp, C.POINTER(GvtRenderParams), _u64, _pd, _pd, _pu32, _pu32, _pd, _pu32]),

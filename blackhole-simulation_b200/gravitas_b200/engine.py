@@ -7,6 +7,10 @@ from . import _lib
 from ._lib import check, lib
 
 
+def init_hooks():  # lib.rs:30-33 installs the wasm panic hook; errors here are status codes -> GravitasError
+    return None
+
+
 class PhysicsEngine:
     """Same surface as the reference's JS-visible ``PhysicsEngine`` (method names and argument meaning kept).
 
@@ -110,6 +114,11 @@ class PhysicsEngine:
         out = np.zeros(512, np.float32)
         check(lib().gvt_engine_generate_disk_lut(self._h, out.ctypes.data_as(C.POINTER(C.c_float))))
         return out
+
+    def get_disk_lut_ptr(self):  # lib.rs:112-114 -> a view of the engine-owned copy (empty before generate_disk_lut)
+        p, n = C.POINTER(C.c_float)(), C.c_uint32(0)
+        check(lib().gvt_engine_get_disk_lut_ptr(self._h, C.byref(p), C.byref(n)))
+        return np.ctypeslib.as_array(p, shape=(n.value,)) if n.value else np.zeros(0, np.float32)
 
     def generate_spectrum_lut(self, width, height, max_temp):  # lib.rs:128-136 -> Float32Array(4wh)
         out = np.zeros(int(width) * int(height) * 4, np.float32)

@@ -250,6 +250,8 @@ int32_t gvt_engine_generate_embedding_mesh(gvt_engine* e, double r_min, double r
                                            float* out3);                                           /* lib.rs:139-150 */
 int32_t gvt_engine_generate_ergosphere_mesh(gvt_engine* e, uint32_t n_polar, uint32_t n_azimuthal, float* out3); /* :153-157 */
 int32_t gvt_engine_generate_disk_lut(gvt_engine* e, float* out512);                 /* lib.rs:107-110 */
+/* the engine-owned copy the last generate_disk_lut left behind (lib.rs:112-114); NULL / 0 before the first call */
+int32_t gvt_engine_get_disk_lut_ptr(gvt_engine* e, const float** out, uint32_t* n);
 int32_t gvt_engine_generate_spectrum_lut(gvt_engine* e, uint32_t width, uint32_t height, double max_temp,
                                          float* out_rgba);                          /* lib.rs:128-136 */
 /* lib.rs:422-464 integrate_ray_relativistic: RKF45, h0 0.01, escape 1000, renorm 10. Runs on the GPU.

@@ -18,6 +18,30 @@ def header_symbols():
     return sorted(set(re.findall(r"\b(gvt_[a-z0-9_]+)\s*\(", src)))
 
 
+def test_every_method_of_the_reference_class_is_mirrored(built):
+    """Every `pub fn` of the wasm-bindgen PhysicsEngine (gravitas-wasm/src/lib.rs; list frozen here because
+    /root/reference does not exist on the GPU box) has a same-named method on the Python mirror and a C-ABI symbol."""
+    ref = """new update_params compute_horizon compute_isco compute_photon_sphere compute_dilation generate_disk_lut
+             get_disk_lut_ptr get_sab_ptr attach_sab set_camera_state set_auto_spin generate_spectrum_lut
+             generate_embedding_mesh generate_ergosphere_mesh compute_shadow_curve compute_shadow_radius compute_shadow_shift
+             compute_disk_flux compute_g_factor compute_kretschner generate_curvature_field compute_light_cone_tilt
+             generate_tilt_field compute_frame_drag_omega generate_frame_drag_field compute_flamm_height
+             compute_proper_distance tick_sab get_sab_layout integrate_ray_relativistic""".split()
+    syms = header_symbols()
+    for m in ref:
+        if m == "new":
+            assert "gvt_engine_create" in syms
+            continue
+        assert hasattr(built.PhysicsEngine, m), m
+        c_name = {"integrate_ray_relativistic": "gvt_engine_integrate_ray"}.get(m, "gvt_engine_" + m)
+        assert c_name in syms, c_name
+    assert callable(built.init_hooks)
+    src = os.path.join("/root/reference", "physics-engine", "gravitas-wasm", "src", "lib.rs")
+    if os.path.exists(src):       # in the build container: the frozen list really is the reference's
+        names = set(re.findall(r"pub fn (\w+)", open(src).read())) - {"init_hooks"}
+        assert names == set(ref), names ^ set(ref)
+
+
 def test_library_exports_every_declared_symbol(built):
     from gravitas_b200 import _lib
     L = C.CDLL(built.lib_path())
@@ -59,8 +83,12 @@ def test_luts_match_oracle_bitwise(built, oracle):
     assert np.array_equal(e.generate_spectrum_lut(48, 12, 1e7), oracle.spectrum_lut(48, 12, 1e7, serial=True))
     e2 = built.PhysicsEngine(1.0, 0.0)
     assert np.array_equal(e2.generate_disk_lut(), oracle.disk_lut(1.0, 0.0))
+    e_new = built.PhysicsEngine(1.0, 0.9)
+    assert e_new.get_disk_lut_ptr().size == 0                    # lib.rs:66: the engine-owned copy starts empty
     lut = e.generate_disk_lut()
     assert lut.shape == (512,) and lut[0] == 0.0 and lut.max() == 1.0
+    assert np.array_equal(e.get_disk_lut_ptr(), lut)              # lib.rs:108-114
+    assert built.init_hooks() is None
 
 
 def test_tick_sab_protocol(built):
