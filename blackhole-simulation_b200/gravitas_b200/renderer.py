@@ -153,6 +153,9 @@ class KerrRenderer:
     def update_settings(self, max_steps):  # renderer.ts:256-263
         self.params.c.max_steps = int(max_steps)
 
+    def get_format(self):  # renderer.ts:265-267 getFormat(): the frame-buffer format delivered to the host
+        return {_lib.FORMAT_RGBA32F: "rgba32float", _lib.FORMAT_RGBA16F: "rgba16float"}.get(self.params.c.output_format, "rgba8unorm")
+
     def resize(self, width, height):  # renderer.ts:269-278
         check(lib().gvt_render_resize(self._h, int(width), int(height)))
         self.width, self.height = int(width), int(height)

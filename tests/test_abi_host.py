@@ -36,6 +36,14 @@ def test_every_method_of_the_reference_class_is_mirrored(built):
         c_name = {"integrate_ray_relativistic": "gvt_engine_integrate_ray"}.get(m, "gvt_engine_" + m)
         assert c_name in syms, c_name
     assert callable(built.init_hooks)
+    # Seam B: the public methods of WebGPURenderer (webgpu/renderer.ts:82-280) and WebGLRenderer (webgl/renderer.ts:36-471)
+    for m in ("init", "init_pipelines", "update_settings", "get_format", "resize", "render"):
+        assert hasattr(built.KerrRenderer, m), m
+    for m in ("init", "resize", "render", "cleanup"):
+        assert hasattr(built.WebGLRenderer, m), m
+    w = built.WebGLRenderer.__new__(built.WebGLRenderer)
+    built.WebGLRenderer.__init__(w)
+    assert w.error is None and w.on_metrics_update is None and built.KerrRenderer().get_format() == "rgba32float"
     src = os.path.join("/root/reference", "physics-engine", "gravitas-wasm", "src", "lib.rs")
     if os.path.exists(src):       # in the build container: the frozen list really is the reference's
         names = set(re.findall(r"pub fn (\w+)", open(src).read())) - {"init_hooks"}
