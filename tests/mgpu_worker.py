@@ -152,6 +152,47 @@ for (W, H, method) in ((256, 144, _lib.METHOD_SYMPLECTIC), (157, 83, _lib.METHOD
             raise AssertionError("GVT_FLAG_ROW_INTERLEAVE accepted in an unsupported combination")
         except g.GravitasError as e:
             assert e.code == _lib.GVT_ERR_INVALID
+# own-row delivery of interleaved shards into host frames: a page-locked shared frame (the kernel stores straight into
+# it) and a pageable private buffer (strided cudaMemcpy2D of this rank's rows)
+import ctypes as C
+W, H = 157, 83
+multi.resize(W, H); single.resize(W, H)
+multi.connect_peers(dist)
+cam, _ = camera.default_camera(W, H)
+phys = R.pack_physics(1.0, spin, W, H)
+kw = dict(method=_lib.METHOD_SYMPLECTIC, max_steps=64, step_rule=_lib.STEP_WGSL)
+single.params = R.RenderParams(**kw)
+b = np.array(single.render(cam, phys))
+multi.params = R.RenderParams(flags=_lib.FLAG_PEER_STORE | _lib.FLAG_ROW_INTERLEAVE | _lib.FLAG_D2H_OWN_ROWS, **kw)
+names = [None]
+if rank == 0:
+    shared = R.SharedFrame(W, H)
+    names = [shared.name]
+dist.broadcast_object_list(names, src=0)
+if rank != 0:
+    shared = R.SharedFrame(W, H, name=names[0], create=False)
+multi.render(cam, phys, out=shared)
+dist.barrier()
+assert np.array_equal(np.array(shared.array()), b), f"rank {rank}: interleaved shared host frame differs"
+dist.barrier()
+shared.close()
+
+
+class Pageable:   # an ordinary (not page-locked) host buffer
+    def __init__(self, shape):
+        self.a = np.full(shape, -1.0, np.float32)
+        self.ptr = C.c_void_p(self.a.ctypes.data)
+    def array(self, dtype, shape):
+        return self.a
+
+
+pg = Pageable((H, W, 4))
+multi.render(cam, phys, out=pg)
+mine = shard.interleaved_rows(H, rank, world)
+others = [y for y in range(H) if y not in mine]
+assert np.array_equal(pg.a[mine], b[mine]), f"rank {rank}: own interleaved rows differ in the pageable buffer"
+assert np.all(pg.a[others] == -1.0)                       # nothing but this rank's rows was touched
+assert multi.last_stats.d2h_bytes == len(mine) * W * 16 + 64
 dist.barrier()
 multi.cleanup(); single.cleanup()
 dist.destroy_process_group()
