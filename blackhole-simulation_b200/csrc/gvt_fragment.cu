@@ -593,17 +593,24 @@ static cudaError_t launch_impl(const GlslParams& p, int precision, int sm_count,
 #else
     auto kern = precision == 1 ? k_fragment_glsl<float> : k_fragment_glsl<double>;
 #endif
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    // the shared-memory opt-in and the occupancy query are per kernel, not per frame (they cost ~10 us each on the host)
+    static int resident[2] = {0, 0};
+    const int ki = precision == 1 ? 1 : 0;
+    if (!resident[ki]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int n = 1;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, GVT_FRAG_THREADS, smem);
+        if (e != cudaSuccess) return e;
+        resident[ki] = n > 0 ? n : 1;
+    }
+    const int per_sm = resident[ki];
     const uint32_t n_rows = (p.y1 - p.y0 + p.ys - 1u) / p.ys;
     const uint32_t tiles = ((p.width + 7u) / 8u) * ((n_rows + 3u) / 4u);
-    int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GVT_FRAG_THREADS, smem);
-    if (e != cudaSuccess) return e;
     const uint32_t wpc = GVT_FRAG_THREADS / 32;
     uint32_t ctas = (tiles + wpc - 1u) / wpc;
-    const uint32_t resident = (uint32_t)sm_count * (uint32_t)(per_sm > 0 ? per_sm : 1);
-    if (ctas > resident) ctas = resident;   // persistent CTAs: as many as are resident at once
+    const uint32_t max_ctas = (uint32_t)sm_count * (uint32_t)per_sm;
+    if (ctas > max_ctas) ctas = max_ctas;   // persistent CTAs: as many as are resident at once
     kern<<<ctas, GVT_FRAG_THREADS, smem, stream>>>(p);
     return cudaGetLastError();
 }
