@@ -55,3 +55,32 @@ def test_engine_tick_to_rendered_frames(built, renderer, oracle):
     ref = oracle.render(cam, rp, want=("rgba",))
     peak = float(ref["rgba"][..., :3].max())
     assert (np.abs(got - ref["rgba"]) <= 1e-6 * np.maximum(np.abs(ref["rgba"]), 1e-3 * peak) + 1e-30).all()
+
+
+def test_bench_own_arm_json_contract():
+    """`python bench.py` (product arm, one GPU): one JSON line with the contract's keys; e2e measured through host
+    buffers; roofline / clocks / gpu_launches present; side kernels reported without error."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "3", "--warmup", "3", "--no-cpu"],
+                       capture_output=True, text=True, timeout=900, cwd=root)
+    assert p.returncode == 0, p.stderr[-3000:]
+    lines = [l for l in p.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert d["value"] > 5e10 and abs(d["value"] * d["ms_per_step"] * 1e-3 - 3840 * 2160 * 512) < 1e-3 * 3840 * 2160 * 512
+    assert d["gpu_launches"] == 3 and "workload" in d["config"] and "model" not in d["config"]
+    e = d["e2e"]
+    assert e["value"] > 5e10 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] >= 3840 * 2160 * 16
+    r = d["roofline"]
+    assert 0.5 < r["frac"] < 1.0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
+    assert d["clocks"]["sm_mhz"] > 0 and isinstance(d["clocks"]["reasons"], list)
+    x = d["extra"]
+    assert "side_kernels_error" not in x and 0.2 < x["taa_resolve"]["frac"] < 1.0 and x["webgl_fragment_shader"]["ms"] > 0
