@@ -560,9 +560,6 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     return y;
 }
 // per-lane 16-B asynchronous global -> shared copy (LDGSTS): in flight without holding a register or a scoreboard
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
 __device__ __forceinline__ void cp_async16_s(uint32_t dst_smem, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
