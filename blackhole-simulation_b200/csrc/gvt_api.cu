@@ -690,6 +690,7 @@ static void fill_taa(const GvtCamera* cam, uint32_t W, uint32_t H, TaaParams& T)
     }
     for (int r = 0; r < 4; r++) { T.vA[r] = (float)vA[r]; T.vB[r] = (float)vB[r]; T.vC[r] = (float)vC[r]; }
     T.width = W; T.height = H; T.row0 = 0; T.row1 = H; T.host_out = nullptr; T.n_peer = 0;
+    T.stripe = StripeMap{0u, 0u, 1u, 0u}; T.n_stripes = 0;
     T.mode = 0; T.blend = 0.75f; T.moving = 0;
 }
 
@@ -763,18 +764,29 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
     const uint32_t row1 = std::min(H, row0 + r->rows_per_rank);
     // TAA needs a one-pixel halo of the current frame: trace one redundant row above and below the block
     const uint32_t ty0 = (taa && row0 > 0) ? row0 - 1 : row0, ty1 = (taa && row1 < H) ? row1 + 1 : row1;
-    // GVT_FLAG_ROW_INTERLEAVE: rows rank, rank + world, ... (peer stores only: nothing needs contiguous blocks)
+    // GVT_FLAG_ROW_INTERLEAVE (peer stores only: nothing needs contiguous blocks): stripes dealt round-robin to the ranks.
+    // Without TAA a stripe is one row (rows rank, rank + world, ...: the finest balance); with TAA it is 16 rows traced
+    // with one halo row on each side, so the 3x3 resolve stays local for 12 % redundant rows.
     const bool interleave = (rp->flags & GVT_FLAG_ROW_INTERLEAVE) != 0 && r->world > 1;
-    if (interleave && (taa || !(rp->flags & GVT_FLAG_PEER_STORE) || (rp->flags & GVT_FLAG_NO_GATHER)))
-        return fail(GVT_ERR_INVALID, "GVT_FLAG_ROW_INTERLEAVE needs GVT_FLAG_PEER_STORE and no TAA");
-    const uint32_t n_own = interleave ? ((uint32_t)r->rank < H ? (H - (uint32_t)r->rank + (uint32_t)r->world - 1) / (uint32_t)r->world : 0u)
-                                      : row1 - row0;
+    if (interleave && (!(rp->flags & GVT_FLAG_PEER_STORE) || (rp->flags & GVT_FLAG_NO_GATHER)))
+        return fail(GVT_ERR_INVALID, "GVT_FLAG_ROW_INTERLEAVE needs the GVT_FLAG_PEER_STORE gather");
+    StripeMap sm = {0u, 0u, (uint32_t)r->world, (uint32_t)r->rank};
+    uint32_t n_my = 0, n_own = row1 - row0;
+    if (interleave) {
+        sm.s = taa ? 16u : 1u; sm.halo = taa ? 1u : 0u;
+        const uint32_t n_total = (H + sm.s - 1u) / sm.s;
+        n_my = (uint32_t)r->rank < n_total ? (n_total - (uint32_t)r->rank + (uint32_t)r->world - 1u) / (uint32_t)r->world : 0u;
+        n_own = 0;
+        for (uint32_t t = 0; t < n_my; t++) n_own += std::min(sm.s, H - (t * (uint32_t)r->world + (uint32_t)r->rank) * sm.s);
+    }
+    const uint32_t lattice_rows = n_my * (sm.s + 2u * sm.halo);
     if (glsl) {
-        G.y0 = interleave ? (uint32_t)r->rank : ty0; G.y1 = interleave ? H : ty1; G.ys = interleave ? (uint32_t)r->world : 1u;
+        G.y0 = interleave ? 0u : ty0; G.y1 = interleave ? H : ty1; G.ys = 1u;
+        G.stripe = sm; G.n_lattice_rows = lattice_rows;
     } else if (interleave) {
-        P.x0 = 0; P.xs = 1; P.y0 = (uint32_t)r->rank; P.y1 = H; P.ys = (uint32_t)r->world; P.nx = W; P.ny = n_own;
+        P.x0 = 0; P.xs = 1; P.y0 = 0; P.y1 = H; P.ys = 1; P.nx = W; P.ny = lattice_rows; P.stripe = sm;
     } else {
-        P.x0 = 0; P.xs = 1; P.y0 = ty0; P.y1 = ty1; P.ys = 1; P.nx = W; P.ny = ty1 - ty0;
+        P.x0 = 0; P.xs = 1; P.y0 = ty0; P.y1 = ty1; P.ys = 1; P.nx = W; P.ny = ty1 - ty0; P.stripe = sm;
     }
     if (taa && r->history_valid) std::swap(r->frame, r->hist);  // last finished frame becomes the history
     float4* trace_out = taa ? r->cur : r->frame;
@@ -826,7 +838,7 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
     }
     CK(cudaEventRecord(r->ev[1], r->stream));
     if (glsl) {
-        if (G.y1 > G.y0) {
+        if (interleave ? lattice_rows > 0 : G.y1 > G.y0) {
             if (glsl_precision == GVT_PRECISION_F32_FAST) CK(launch_fragment_glsl_fast(G, r->sm_count, r->stream));
             else CK(launch_fragment_glsl(G, (int)glsl_precision, r->sm_count, r->stream));
             launches++;
@@ -836,12 +848,13 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
         launches++;
     }
     CK(cudaEventRecord(r->ev[2], r->stream));
-    if (taa && row1 > row0) {
+    if (taa && (interleave ? n_my > 0 : row1 > row0)) {
         TaaParams T;
         if (cam) fill_taa(cam, W, H, T);
         else { memset(&T, 0, sizeof(T)); T.width = W; T.height = H; }
         T.cur = r->cur; T.hist = r->hist; T.out = r->frame;
         T.row0 = row0; T.row1 = row1;
+        T.stripe = sm; T.n_stripes = n_my;
         if (rp->flags & GVT_FLAG_TAA_WEBGL) {
             const bool has = rp->struct_size >= offsetof(GvtRenderParams, taa_camera_moving) + sizeof(uint32_t);
             T.mode = 1; T.blend = has ? rp->taa_blend : 0.75f; T.moving = has ? rp->taa_camera_moving : 0u;
@@ -870,11 +883,21 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
         d2h += (size_t)n_own * W * sizeof(float4);   // delivered by the kernel's own stores
     } else if (host_rgba && own && interleave) {
         if (rp->output_format != GVT_FORMAT_RGBA32F) return fail(GVT_ERR_UNSUPPORTED, "interleaved own-row delivery is RGBA32F only");
-        const size_t row_bytes = (size_t)W * sizeof(float4), pitch = row_bytes * (size_t)r->world;
-        if (n_own)
-            CK(cudaMemcpy2DAsync(static_cast<char*>(host_rgba) + (size_t)r->rank * row_bytes, pitch,
-                                 reinterpret_cast<const char*>(r->frame) + (size_t)r->rank * row_bytes, pitch, row_bytes, n_own,
-                                 cudaMemcpyDeviceToHost, r->stream));
+        const size_t row_bytes = (size_t)W * sizeof(float4);
+        if (sm.s == 1u) {   // every world-th row: one strided copy
+            const size_t pitch = row_bytes * (size_t)r->world;
+            if (n_own)
+                CK(cudaMemcpy2DAsync(static_cast<char*>(host_rgba) + (size_t)r->rank * row_bytes, pitch,
+                                     reinterpret_cast<const char*>(r->frame) + (size_t)r->rank * row_bytes, pitch, row_bytes, n_own,
+                                     cudaMemcpyDeviceToHost, r->stream));
+        } else {            // 16-row stripes: one contiguous copy each
+            for (uint32_t t = 0; t < n_my; t++) {
+                const size_t y = (size_t)(t * (uint32_t)r->world + (uint32_t)r->rank) * sm.s;
+                const size_t n = std::min<size_t>(sm.s, H - y);
+                CK(cudaMemcpyAsync(static_cast<char*>(host_rgba) + y * row_bytes, reinterpret_cast<const char*>(r->frame) + y * row_bytes,
+                                   n * row_bytes, cudaMemcpyDeviceToHost, r->stream));
+            }
+        }
         d2h += (size_t)n_own * row_bytes;
     } else if (host_rgba) {
         const size_t n_px = (size_t)W * H;

@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(GVT_FRAG_THREADS, GVT_FRAG_MINB) k_fragment_gl
     const bool show_red = U.show_redshift > 0.5f;
 
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n_rows = (P.y1 - P.y0 + P.ys - 1u) / P.ys;
+    const uint32_t n_rows = P.stripe.s ? P.n_lattice_rows : (P.y1 - P.y0 + P.ys - 1u) / P.ys;
     const uint32_t tiles_x = (P.width + 7u) / 8u, tiles_y = (n_rows + 3u) / 4u;
     const uint32_t n_tiles = tiles_x * tiles_y;
     unsigned long long acc_steps = 0;
@@ -318,8 +318,12 @@ __global__ void __launch_bounds__(GVT_FRAG_THREADS, GVT_FRAG_MINB) k_fragment_gl
         if (lane == 0) tile = atomicAdd(&P.counters->tile_counter, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= n_tiles) break;
-        const uint32_t px = (tile % tiles_x) * 8u + (lane & 7u), py = P.y0 + ((tile / tiles_x) * 4u + (lane >> 3)) * P.ys;
-        const bool valid = px < P.width && py < P.y1;
+        const uint32_t px = (tile % tiles_x) * 8u + (lane & 7u), lj = (tile / tiles_x) * 4u + (lane >> 3);
+        uint32_t py = P.y0 + lj * P.ys;
+        bool valid = px < P.width && py < P.y1;
+        if (P.stripe.s) {   // GVT_FLAG_ROW_INTERLEAVE: this rank's stripes (+ TAA halo rows)
+            valid = lj < n_rows && stripe_row(P.stripe, lj, P.height, py) && px < P.width;
+        }
         R out[3] = {R(0), R(0), R(0)};
         uint32_t steps = 0;
         bool hitHorizon = false;
@@ -585,7 +589,7 @@ __global__ void __launch_bounds__(GVT_FRAG_THREADS, GVT_FRAG_MINB) k_fragment_gl
 }
 
 static cudaError_t launch_impl(const GlslParams& p, int precision, int sm_count, cudaStream_t stream) {
-    if (p.y1 <= p.y0 || p.width == 0 || p.ys == 0) return cudaSuccess;
+    if (p.width == 0 || (p.stripe.s ? p.n_lattice_rows == 0 : (p.y1 <= p.y0 || p.ys == 0))) return cudaSuccess;
     const size_t smem = 65536;
 #ifdef GVT_FRAGMENT_FAST
     (void)precision;
@@ -605,7 +609,7 @@ static cudaError_t launch_impl(const GlslParams& p, int precision, int sm_count,
         resident[ki] = n > 0 ? n : 1;
     }
     const int per_sm = resident[ki];
-    const uint32_t n_rows = (p.y1 - p.y0 + p.ys - 1u) / p.ys;
+    const uint32_t n_rows = p.stripe.s ? p.n_lattice_rows : (p.y1 - p.y0 + p.ys - 1u) / p.ys;
     const uint32_t tiles = ((p.width + 7u) / 8u) * ((n_rows + 3u) / 4u);
     const uint32_t wpc = GVT_FRAG_THREADS / 32;
     uint32_t ctas = (tiles + wpc - 1u) / wpc;

@@ -29,6 +29,19 @@ struct Counters {  // device-side accumulators, one set per frame
     unsigned int _pad;
 };
 
+// GVT_FLAG_ROW_INTERLEAVE: which frame rows a rank produces. Stripes of `s` rows are dealt round-robin to the ranks
+// (stripe j belongs to rank j % world); with TAA every stripe is traced with `halo` redundant rows on each side so the
+// 3x3 resolve stays local. s = 0: off (contiguous rows). Lattice row lj of a launch -> frame row:
+struct StripeMap {
+    uint32_t s, halo, world, rank;
+};
+__host__ __device__ inline bool stripe_row(const StripeMap& m, uint32_t lj, uint32_t height, uint32_t& row) {
+    const uint32_t sh = m.s + 2u * m.halo, t = lj / sh, o = lj - t * sh;
+    const long long r = (long long)(t * m.world + m.rank) * (long long)m.s - (long long)m.halo + (long long)o;
+    row = r < 0 ? 0u : (uint32_t)r;
+    return r >= 0 && r < (long long)height;
+}
+
 // Kernel parameters (constant bank): the scalars of the step loop are direct c[][] operands.
 struct FrameParams {
     TrigTable trig;                                           // set by the launcher (GVT_TRIG_TABLE_INIT)
@@ -48,6 +61,7 @@ struct FrameParams {
                                                               // epilogue stores the pixel there too, so no D2H copy follows
     float4* peer_frame[8];                                    // GVT_FLAG_PEER_STORE: the same frame on every other rank
     uint32_t n_peer, _pad_peer;
+    StripeMap stripe;                                         // s != 0: lattice rows map to frame rows through stripe_row()
     Counters* counters;
     // parity-hook outputs (DEBUG instantiations only), dense over the lattice
     double* dbg_xp; uint32_t* dbg_term; uint32_t* dbg_steps; double* dbg_drift; double* dbg_rgba;
@@ -78,13 +92,17 @@ struct TaaParams {
     float4* peer_out[8];   // GVT_FLAG_PEER_STORE targets
     uint32_t n_peer;
     uint32_t unit_rows;    // rows per warp work unit (chosen by launch_taa)
+    StripeMap stripe;      // s != 0: resolve this rank's n_stripes stripes (rows [(t world + rank) s, +s)) instead of [row0, row1)
+    uint32_t n_stripes;
 };
 
 // k_fragment_glsl (gvt_fragment.cu): the production WebGL2 fragment shader
 struct GlslParams {
     GvtGlslUniforms u;            // chunks/common.ts:9-38 uniforms + feature bits, in the parameter bank
     uint32_t width, height;       // frame size (= u.resolution)
-    uint32_t y0, y1, ys;          // rows shaded by this launch: y0, y0 + ys, ... < y1 (a rank's block, or its interleaved rows)
+    uint32_t y0, y1, ys;          // rows shaded by this launch: y0, y0 + ys, ... < y1 (a rank's block)
+    StripeMap stripe;             // s != 0: n_lattice_rows lattice rows map to frame rows through stripe_row() instead
+    uint32_t n_lattice_rows;
     const uint8_t* noise_r;       // 256*256 red channel of u_noiseTex (global; TMA-staged into shared memory)
     const uint8_t* blue_r;        // 256*256 red channel of u_blueNoiseTex (one tap per pixel, stays in global)
     float4* frame; float4* host_frame; float4* peer_frame[8];

@@ -162,8 +162,14 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
         if (tile >= n_tiles) break;
         const uint32_t ti = tile % tiles_x, tj = tile / tiles_x;
         const uint32_t li = ti * TILE_W + lx, lj = tj * TILE_H + ly;  // lattice coordinates
-        const bool valid = (li < P.nx) && (lj < P.ny);
-        const uint32_t px = P.x0 + min(li, P.nx - 1) * P.xs, py = P.y0 + min(lj, P.ny - 1) * P.ys;
+        bool valid = (li < P.nx) && (lj < P.ny);
+        const uint32_t px = P.x0 + min(li, P.nx - 1) * P.xs;
+        uint32_t py = P.y0 + min(lj, P.ny - 1) * P.ys;
+        if (P.stripe.s) {   // GVT_FLAG_ROW_INTERLEAVE: this rank's stripes (+ TAA halo rows); rows off the frame are skipped
+            uint32_t row;
+            valid = stripe_row(P.stripe, min(lj, P.ny - 1), P.height, row) && valid;
+            py = min(row, P.height - 1);
+        }
 
         // ---- camera -> (x, p): compute.wgsl.ts:159-187 ----
         Ray<R> y;
@@ -604,8 +610,9 @@ __global__ void __launch_bounds__(256, GVT_TAA_MINB) k_taa_resolve(const __grid_
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int strips_x = (W + TAA_STRIP_W - 1) / TAA_STRIP_W;
     const int rows = (int)P.row1 - (int)P.row0;
-    const int TAA_ROWS = (int)P.unit_rows;
-    const int n_work = strips_x * ((rows + TAA_ROWS - 1) / TAA_ROWS);
+    const bool striped = P.stripe.s != 0u;                        // GVT_FLAG_ROW_INTERLEAVE: one unit row-range per owned stripe
+    const int TAA_ROWS = striped ? (int)P.stripe.s : (int)P.unit_rows;
+    const int n_work = strips_x * (striped ? (int)P.n_stripes : (rows + TAA_ROWS - 1) / TAA_ROWS);
     const int n_warps = (int)(gridDim.x * (blockDim.x >> 5));
     const float nsig = (MODE == 1) ? 1.5f : 2.0f;                 // reprojection.glsl.ts:90-91 / ataa.wgsl.ts:51-52
     const float k9 = 1.0f / 9.0f;
@@ -618,8 +625,10 @@ __global__ void __launch_bounds__(256, GVT_TAA_MINB) k_taa_resolve(const __grid_
         const int x = sx * TAA_STRIP_W + lane - 1;                // lane 0 / 31 = halo columns
         const int xc = max(0, min(x, W - 1));                     // clamp(pos + d, 0, size-1), ataa.wgsl.ts:43
         const bool owner = lane >= 1 && lane <= TAA_STRIP_W && x < W;
-        const int y_begin = (int)P.row0 + sy * TAA_ROWS, y_end = min(y_begin + TAA_ROWS, (int)P.row1);
+        const int y_begin = striped ? (sy * (int)P.stripe.world + (int)P.stripe.rank) * TAA_ROWS : (int)P.row0 + sy * TAA_ROWS;
+        const int y_end = min(y_begin + TAA_ROWS, striped ? H : (int)P.row1);
         const int n_rows = y_end - y_begin;
+        if (n_rows <= 0) continue;
         const float4* col = P.cur + xc;
 
         // column-only part of the reprojection (MODE 0)
@@ -739,7 +748,8 @@ cudaError_t launch_taa(const TaaParams& p_in, int sm_count, cudaStream_t stream)
     TaaParams p = p_in;
     const int strips_x = ((int)p.width + TAA_STRIP_W - 1) / TAA_STRIP_W;
     const int rows = (int)p.row1 - (int)p.row0;
-    if (rows <= 0) return cudaSuccess;
+    const bool striped = p.stripe.s != 0u;
+    if (striped ? p.n_stripes == 0u : rows <= 0) return cudaSuccess;
     const int wpb = 8;
     static int resident[2] = {0, 0};   // CTAs per SM of each instantiation (occupancy query, once)
     const int m = p.mode == 1u ? 1 : 0;
@@ -766,7 +776,7 @@ cudaError_t launch_taa(const TaaParams& p_in, int sm_count, cudaStream_t stream)
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_r = R; }
     }
     p.unit_rows = (uint32_t)best_r;
-    const int n_work = strips_x * ((rows + best_r - 1) / best_r);
+    const int n_work = striped ? strips_x * (int)p.n_stripes : strips_x * ((rows + best_r - 1) / best_r);
     const int blocks = min((n_work + wpb - 1) / wpb, max(sm_count, 1) * resident[m]);
     if (m) k_taa_resolve<1><<<blocks, wpb * 32, smem, stream>>>(p);
     else k_taa_resolve<0><<<blocks, wpb * 32, smem, stream>>>(p);

@@ -28,6 +28,8 @@ def gather_counts(width, height, world):
     return rpr * width * 4, rpr * world
 
 
-def interleaved_rows(height, rank, world):
-    """GVT_FLAG_ROW_INTERLEAVE: rank k produces rows k, k + world, k + 2 world, ... (peer-store gather only)."""
-    return list(range(rank, height, world))
+def interleaved_rows(height, rank, world, taa=False):
+    """GVT_FLAG_ROW_INTERLEAVE (peer-store gather only): stripes dealt round-robin, stripe j to rank j % world. Without
+    TAA a stripe is one row (rows k, k + world, ...); with TAA it is 16 rows (each traced with a one-row halo)."""
+    s = 16 if taa else 1
+    return [y for y in range(height) if (y // s) % world == rank]

@@ -123,6 +123,14 @@ for (W, H) in ((192, 108), (157, 83)):
     b = np.array(ws.render(sp, {"x": 0.5, "y": 0.54}))
     assert (wm.last_stats.rows_begin, wm.last_stats.rows_end) == (rank, H)
     assert np.array_equal(a, b), f"rank {rank}: interleaved fragment-shader frame differs (W={W} H={H})"
+    wm._k.reset_history(); ws._k.reset_history()
+    wm.taa = ws.taa = True                      # WebGL TAA over 16-row stripes + halo
+    wm.time = ws.time = 0.0
+    for k in range(3):
+        mouse = {"x": 0.5 + 0.001 * k, "y": 0.54}
+        a = np.array(wm.render(sp, mouse, flags=_lib.FLAG_PEER_STORE | _lib.FLAG_ROW_INTERLEAVE))
+        b = np.array(ws.render(sp, mouse))
+        assert np.array_equal(a, b), f"rank {rank}: striped fragment-shader TAA frame differs (W={W} H={H} k={k})"
 dist.barrier()
 wm.cleanup(); ws.cleanup()
 ids = [g.KerrRenderer.nccl_unique_id() if rank == 0 else None]
@@ -144,14 +152,26 @@ for (W, H, method) in ((256, 144, _lib.METHOD_SYMPLECTIC), (157, 83, _lib.METHOD
     assert np.array_equal(a, b), f"rank {rank}: interleaved trace frame differs (W={W} H={H} method={method})"
     t = torch.tensor([float(multi.last_stats.steps_committed)]); dist.all_reduce(t)
     assert int(t[0]) == int(single.last_stats.steps_committed)
-    # the flag is refused where it cannot work: with TAA (halo rows) or without the peer-store gather
-    for bad in (_lib.FLAG_ROW_INTERLEAVE, _lib.FLAG_ROW_INTERLEAVE | _lib.FLAG_PEER_STORE | _lib.FLAG_TAA):
-        multi.params = R.RenderParams(flags=bad, **kw)
-        try:
-            multi.render(cam, phys)
-            raise AssertionError("GVT_FLAG_ROW_INTERLEAVE accepted in an unsupported combination")
-        except g.GravitasError as e:
-            assert e.code == _lib.GVT_ERR_INVALID
+    # the flag is refused without the peer-store gather (an all-gather needs contiguous blocks)
+    multi.params = R.RenderParams(flags=_lib.FLAG_ROW_INTERLEAVE, **kw)
+    try:
+        multi.render(cam, phys)
+        raise AssertionError("GVT_FLAG_ROW_INTERLEAVE accepted without GVT_FLAG_PEER_STORE")
+    except g.GravitasError as e:
+        assert e.code == _lib.GVT_ERR_INVALID
+    # with TAA the stripes are 16 rows + halo: three frames of an orbiting, jittered camera equal the single-GPU frames
+    multi.reset_history(); single.reset_history()
+    prev = None
+    for k in range(3):
+        camk, vp = camera.default_camera(W, H, azimuth=math.pi + 0.005 * k, prev_view_proj=prev)
+        physk = R.pack_physics(1.0, spin, W, H, frame_index=k)
+        fl = _lib.FLAG_TAA | _lib.FLAG_JITTER
+        multi.params = R.RenderParams(flags=fl | _lib.FLAG_PEER_STORE | _lib.FLAG_ROW_INTERLEAVE, **kw)
+        single.params = R.RenderParams(flags=fl, **kw)
+        a = np.array(multi.render(camk, physk))
+        b = np.array(single.render(camk, physk))
+        assert np.array_equal(a, b), f"rank {rank}: striped TAA frame differs (W={W} H={H} method={method} k={k})"
+        prev = vp
 # own-row delivery of interleaved shards into host frames: a page-locked shared frame (the kernel stores straight into
 # it) and a pageable private buffer (strided cudaMemcpy2D of this rank's rows)
 import ctypes as C

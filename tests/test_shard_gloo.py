@@ -30,9 +30,9 @@ WORKER = textwrap.dedent('''
             rpr = shard.rows_per_rank(H, world)
             assert all(e - b <= rpr for b, e in own)
             il = [None] * world
-            dist.all_gather_object(il, shard.interleaved_rows(H, rank, world))
+            dist.all_gather_object(il, shard.interleaved_rows(H, rank, world, taa))
             assert sorted(sum(il, [])) == list(range(H))          # GVT_FLAG_ROW_INTERLEAVE: a partition of the rows too
-            assert max(len(x) for x in il) - min(len(x) for x in il) <= 1
+            assert max(len(x) for x in il) - min(len(x) for x in il) <= (16 if taa else 1)
             cnt, padded = shard.gather_counts(W, H, world)
             assert cnt == rpr * W * 4 and padded >= H and padded - H < world
             for (b, e), (tb, te) in allr:
