@@ -517,6 +517,13 @@ def run_extra(args):
             w._k.connect_peers(dist)
             run("f32_fast_row_blocks_peer_store", _lib.PRECISION_F32_FAST, _lib.FLAG_PEER_STORE)
             run("f32_fast_row_interleaved_peer_store", _lib.PRECISION_F32_FAST, _lib.FLAG_PEER_STORE | _lib.FLAG_ROW_INTERLEAVE)
+            # the reference's default WebGL pipeline resolves every frame (ReprojectionManager): shader -> WebGL TAA
+            w.taa = True
+            w._k.reset_history()
+            run("f32_fast_taa_row_blocks_peer_store", _lib.PRECISION_F32_FAST, _lib.FLAG_PEER_STORE)
+            w._k.reset_history()
+            run("f32_fast_taa_16row_stripes_peer_store", _lib.PRECISION_F32_FAST, _lib.FLAG_PEER_STORE | _lib.FLAG_ROW_INTERLEAVE)
+            w.taa = False
         barrier(dist)
         w.cleanup()
         if rank == 0:

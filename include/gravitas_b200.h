@@ -85,10 +85,11 @@ enum {
                                        into every peer's frame over NVLink (peer frames imported with
                                        gvt_render_import_peer_frames) and a 4-byte ncclAllReduce closes the frame as the
                                        cross-GPU barrier; replaces the ncclAllGather */
-    GVT_FLAG_ROW_INTERLEAVE = 1u << 8, /* multi-GPU, with GVT_FLAG_PEER_STORE and without TAA: rank k produces rows k, k + world,
-                                       k + 2 world, ... instead of one contiguous block, so that rows of very different cost
+    GVT_FLAG_ROW_INTERLEAVE = 1u << 8, /* multi-GPU, with GVT_FLAG_PEER_STORE: stripes of rows are dealt round-robin to the
+                                       ranks instead of one contiguous block each, so that rows of very different cost
                                        (sky / disk / shadow under natural termination) spread evenly over the GPUs
-                                       (interleaved stripes); the peer stores need no contiguous blocks */
+                                       (SURVEY 8e). Without TAA a stripe is one row (rank k: rows k, k + world, ...); with
+                                       TAA it is 16 rows traced with a one-row halo. The peer stores need no blocks. */
     GVT_FLAG_DEBUG_COUNTS = 1u << 9, /* gvt_render_fragment_glsl: also record per-pixel march steps and horizon flags for
                                        gvt_render_fragment_glsl_debug (8 B per pixel of extra stores; off by default) */
     GVT_FLAG_D2H_OWN_ROWS = 1u << 5 /* multi-GPU: copy only this rank's row block into host_rgba (at its place in the
