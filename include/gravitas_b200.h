@@ -3,15 +3,18 @@
  *
  *   Seam A  `PhysicsEngine` (wasm-bindgen class, physics-engine/gravitas-wasm/src/lib.rs:42-465) and the
  *           SharedArrayBuffer f32-offset protocol (lib.rs:36-40, sab.rs:18-22, src/engine/physics-bridge.ts:5-11).
- *   Seam B  the src/rendering renderer / frame-buffer API (src/rendering/webgpu/renderer.ts:280 `render(camera,
- *           physics)`; uniform layouts src/types/webgpu.ts:25,42,67-116 and src/shaders/types.wgsl.ts:6-29).
+ *   Seam B  the src/rendering renderer / frame-buffer API: the WebGPU pipeline (src/rendering/webgpu/renderer.ts:280
+ *           `render(camera, physics)`; uniform layouts src/types/webgpu.ts:25,42,67-116 and
+ *           src/shaders/types.wgsl.ts:6-29) and the WebGL2 pipeline (src/rendering/webgl/renderer.ts:173
+ *           `render(params, mouse)`: fragment shader -> TAA resolve -> bloom / final pass).
  *
  * Conventions: every entry point returns an int32 status (GVT_OK = 0, negative = error; the reference has no
  * error returns — Rust panics go to console_error_panic_hook, lib.rs:30-33 — so hosts may ignore it exactly as
  * they do today, or read gvt_last_error()). No exceptions cross the boundary. Handles are opaque. The caller
  * owns every buffer it passes. Thread-compatible, not thread-safe: one handle per thread (the worker model of
- * src/workers/physics.worker.ts). All arithmetic on this path runs in hand-written sm_100a CUDA kernels; there
- * is no CPU fallback — creation fails with GVT_ERR_NO_DEVICE when no CUDA device is usable.
+ * src/workers/physics.worker.ts). All per-pixel / per-ray arithmetic runs in hand-written sm_100a CUDA kernels; there
+ * is no CPU fallback — creation fails with GVT_ERR_NO_DEVICE when no CUDA device is usable. (The engine's once-per-tick
+ * closed forms, LUT generators and visualisation helpers are host maths, as they are one-off host calls in the reference.)
  */
 #ifndef GRAVITAS_B200_H
 #define GRAVITAS_B200_H
