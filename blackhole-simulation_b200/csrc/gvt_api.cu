@@ -625,8 +625,11 @@ static int32_t build_frame(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
     if (!r->luts_ready) return fail(GVT_ERR_INVALID, "LUTs not initialised: call gvt_render_init_luts / gvt_render_set_luts first");
     if (rp->coords != GVT_COORDS_KERR_SCHILD)
         return fail(GVT_ERR_UNSUPPORTED, "the render path traces in Kerr-Schild coordinates (lib.rs:64,454); use gvt_engine_integrate_rays for Boyer-Lindquist");
-    if (rp->method > GVT_METHOD_VERLET_GLSL || rp->precision > GVT_PRECISION_F32 || rp->output_format > GVT_FORMAT_RGBA8_UNORM)
+    if (rp->method > GVT_METHOD_VERLET_GLSL || (rp->precision > GVT_PRECISION_F32 && rp->precision != GVT_PRECISION_MIXED) ||
+        rp->output_format > GVT_FORMAT_RGBA8_UNORM)
         return fail(GVT_ERR_INVALID, "bad method/precision/output_format");
+    if (rp->precision == GVT_PRECISION_MIXED && rp->method != GVT_METHOD_SYMPLECTIC)
+        return fail(GVT_ERR_UNSUPPORTED, "GVT_PRECISION_MIXED is defined for GVT_METHOD_SYMPLECTIC only (f32 predictors of the implicit midpoint)");
     if (rp->renormalize_interval == 0) return fail(GVT_ERR_INVALID, "renormalize_interval must be > 0");
     const uint32_t W = (uint32_t)phys->resolution[0], H = (uint32_t)phys->resolution[1];
     if (W == 0 || H == 0) return fail(GVT_ERR_INVALID, "zero resolution");
@@ -658,6 +661,11 @@ static int32_t build_frame(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
     P.sqrtM = std::sqrt(bh.mass);
     P.escape_r = rp->escape_radius; P.r_in = bh.isco(true); P.r_out = rp->disk_r_out;
     P.tol = rp->tolerance; P.h0 = rp->initial_step;
+    {   // GVT_PRECISION_MIXED: r_switch = 35 M, plus the distance a ray can fall back within one 8-step chunk (|dr/dlambda| <= 1)
+        const char* e = getenv("GVT_MIXED_RSWITCH");   // tuning experiments only
+        const double r_switch = (e && atof(e) > 0.0 ? atof(e) : 35.0) * bh.mass;
+        P.r_far = r_switch + 8.0 * (rp->step_rule == GVT_STEP_WGSL ? 1.0 : std::fabs(rp->initial_step));
+    }
     P.tdisk_rin = r->tdisk_rin; P.tdisk_scale = 511.0 / (r->tdisk_rout - r->tdisk_rin);
     P.width = W; P.height = H;
     P.max_steps = rp->max_steps; P.renorm_interval = rp->renormalize_interval; P.step_rule = rp->step_rule;

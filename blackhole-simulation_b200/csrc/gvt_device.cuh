@@ -118,7 +118,9 @@ __device__ __forceinline__ void trig_pair(const TrigTable& T, double x, double& 
     const int k = __double2loint(kd_m);
     const double kd = kd_m - K[1];
     double r = fma(-kd, K[2], x);
+#ifndef GVT_TRIG_CW1
     r = fma(-kd, K[3], r);
+#endif
     const double z = r * r;
     double ps = K[9];
     ps = fma(ps, z, K[8]);
@@ -195,6 +197,35 @@ template <class R> __device__ __forceinline__ R clampR(R x, R lo, R hi) {
 }
 template <class R> __device__ __forceinline__ R floorAt(R x, R lo) { return (x > lo) ? x : lo; }
 
+// x < c / x > c against a POSITIVE threshold c without touching the FP64 pipe: IEEE doubles are sign-magnitude, so for
+// c > 0 the signed 64-bit compare of the bit patterns orders every non-NaN x (negatives and -0 sort below c) exactly
+// as the floating-point compare does. DSETP issues on the FP64 pipe (2 cycles per warp, the pipe this kernel is bound
+// by); the two ISETPs this compiles to run on the ALU pipe, which idles. NaN: a positive-sign NaN sorts above
+// everything, a negative-sign one below (the FP compare would be false both ways) -- only ever seen on rays that
+// have already blown up, and the termination test below treats both as "not alive" exactly like the FP form.
+#ifdef GVT_NO_INTCMP   // A/B switch: plain FP64 compares (DSETP)
+__device__ __forceinline__ bool lt_pos(double x, double c) { return !(x >= c); }
+__device__ __forceinline__ bool gt_pos(double x, double c) { return !(x <= c); }
+#else
+__device__ __forceinline__ bool lt_pos(double x, double c) { return __double_as_longlong(x) < __double_as_longlong(c); }
+__device__ __forceinline__ bool gt_pos(double x, double c) { return __double_as_longlong(x) > __double_as_longlong(c); }
+#endif
+__device__ __forceinline__ bool abs_lt_pos(double x, double c) {   // |x| < c  (hi/lo words: a 64-bit AND would come back as a DADD |x|)
+#ifdef GVT_NO_INTCMP
+    return fabs(x) < c;
+#else
+    const uint32_t xh = (uint32_t)__double2hiint(x) & 0x7fffffffu, ch = (uint32_t)__double2hiint(c);
+    return xh < ch || (xh == ch && (uint32_t)__double2loint(x) < (uint32_t)__double2loint(c));
+#endif
+}
+__device__ __forceinline__ bool abs_lt_pos(float x, float c) { return fabsf(x) < c; }
+__device__ __forceinline__ bool lt_pos(float x, float c) { return !(x >= c); }  // FP32 compares are cheap; NaN counts as
+__device__ __forceinline__ bool gt_pos(float x, float c) { return !(x <= c); }  // "beyond" here too
+template <class R> __device__ __forceinline__ R clampPos(R x, R lo, R hi) {     // clampR for 0 < lo < hi
+    x = lt_pos(x, lo) ? lo : x;
+    return gt_pos(x, hi) ? hi : x;
+}
+
 // --------------------------------------------------------------------------------------------------
 // Per-ray state. t (x[0]) is carried only when WITH_T (the parity hook); p_t and p_phi are constants.
 // --------------------------------------------------------------------------------------------------
@@ -215,10 +246,12 @@ struct HoleRay {
     R M, a, a2, twoM;
     R pt, pph;
     R pt2, pph2, two_pt, two_a_pph, a_pph;
+    R twoM_pt, twoM_pt2, M_two_pt, M_pt2;     // 2M pt, 2M pt^2, 2M pt (= M * 2pt), M pt^2
     __device__ __forceinline__ void set_hole(R M_, R a_) { M = M_; a = a_; a2 = a_ * a_; twoM = R(2) * M_; }
     __device__ __forceinline__ void set_ray(R pt_, R pph_) {
         pt = pt_; pph = pph_; pt2 = pt_ * pt_; pph2 = pph_ * pph_; two_pt = R(2) * pt_;
         a_pph = a * pph_; two_a_pph = R(2) * a_pph;
+        twoM_pt = twoM * pt_; twoM_pt2 = twoM * pt2; M_two_pt = M * two_pt; M_pt2 = M * pt2;
     }
 };
 
@@ -236,11 +269,11 @@ __device__ __forceinline__ DerivU<R> rhs_ks_u(const HoleRay<R>& c, R r, R a, R s
     using N = Num<R>;
     R sin2 = a * a;
     // Within 1e-6 rad of the polar axis (rare): clamp sin^2 and zero dH/dtheta below |sin| = 1e-10 (both of its
-    // terms carry sc). f64: nested rare path (ptxas predicates it; cheapest on the FP64 pipe). f32: two plain selects.
+    // terms carry sc). f64: nested rare path behind an integer compare (ptxas predicates it). f32: two plain selects.
     if (sizeof(R) == 8) {
-        if (sin2 < R(1e-12)) {
+        if (lt_pos(sin2, R(1e-12))) {
             sin2 = R(1e-12);
-            if (N::abs_(a) < R(1e-10)) sc = R(0);
+            if (abs_lt_pos(a, R(1e-10))) sc = R(0);
         }
     } else {
         if (sin2 < R(1e-20)) sc = R(0);
@@ -253,25 +286,26 @@ __device__ __forceinline__ DerivU<R> rhs_ks_u(const HoleRay<R>& c, R r, R a, R s
     const R t = N::rcp(sigma * sin2);
     const R isig = t * sin2;
     const R w = t * sigma;                          // 1/sin^2
-    const R twoMr = c.twoM * r;
     const R A1 = c.pph2 * w;                        // pph^2 / sin^2
-    const R K = N::fma_(c.two_pt, pr, -c.pt2);      // 2 pt pr - pt^2
     const R pr2 = pr * pr;
-    // N = 2Mr K + Delta pr^2 + pth^2 + A1 + 2 a pph pr
-    R Nn = N::fma_(twoMr, K, A1);
-    Nn = N::fma_(delta, pr2, Nn);
-    Nn = N::fma_(pth, pth, Nn);
-    Nn = N::fma_(c.two_a_pph, pr, Nn);
-    const R q = Nn * isig;
-    const R halfNr = N::fma_(r - c.M, pr2, c.M * K);
+    // dr/dlambda * Sigma = Delta pr + D0,  D0 = 2Mr pt + a pph.  Grouping N by powers of pr reuses it:
+    //   N = 2Mr (2 pt pr - pt^2) + Delta pr^2 + pth^2 + A1 + 2 a pph pr = pr (dr + D0) + pth^2 + A1 - 2M pt^2 r
+    // (4 FP64 ops after dr instead of 6: every instruction here is a slot on the pipe that bounds the kernel)
+    const R D0 = N::fma_(c.twoM_pt, r, c.a_pph);
     DerivU<R> d;
     d.isig = isig;
-    d.dr = N::fma_(delta, pr, N::fma_(twoMr, c.pt, c.a_pph));
+    d.dr = N::fma_(delta, pr, D0);
+    R Nn = N::fma_(-c.twoM_pt2, r, A1);
+    Nn = N::fma_(pth, pth, Nn);
+    Nn = N::fma_(pr, d.dr + D0, Nn);
+    const R q = Nn * isig;
+    // N_r / 2 = M (2 pt pr - pt^2) + (r - M) pr^2
+    const R halfNr = N::fma_(r - c.M, pr2, N::fma_(c.M_two_pt, pr, -c.M_pt2));
     d.dth = pth;
     d.dpr = N::fma_(r, q, -halfNr);                          // -(N_r/2 - r N/Sigma)
     d.dpth = sc * N::fma_(-c.a2, q, A1 * w);                 // -(sc (a^2 N/Sigma - pph^2/sin^4))
     d.dph = WITH_PHI ? N::fma_(c.pph, w, c.a * pr) : R(0);
-    d.dt = WITH_T ? N::fma_(twoMr * isig, pr - c.pt, -c.pt) : R(0);
+    d.dt = WITH_T ? N::fma_((c.twoM * r) * isig, pr - c.pt, -c.pt) : R(0);
     return d;
 }
 template <class R, bool WITH_T>
@@ -455,6 +489,45 @@ __device__ __forceinline__ void step_symplectic(const HoleRay<R>& c, Ray<R>& y, 
     y.pr = N::fma_(d.dpr, h, y.pr);
     y.pth = N::fma_(d.dpth, h, y.pth);
     if (WITH_T) y.t = N::fma_(d.dt, h, y.t);
+}
+
+// GVT_PRECISION_MIXED: the same implicit-midpoint step with its two fixed-point (predictor) evaluations in f32 and the
+// final evaluation -- the only one whose value reaches the state directly -- in f64 on the f64 state.
+// Why this is allowed: the predictors only locate the midpoint. An error e in a predictor's derivative moves the
+// midpoint by (h/2) e and the final derivative by (h/2) J e, J = d(rhs)/d(state): far from the hole (r >~ 35 M:
+// |J| ~ M/r^2, h <= 1) that factor is < 5e-4 for the second predictor and its square for the first, so f32's 6e-8
+// reaches the state as <~ 3e-11 per step, on the ray's final outbound leg where nothing amplifies it afterwards.
+// Measured with the CPU oracle on the headline frame (oracle/experiments/mixed_probe.cpp): worst RGBA component
+// 1.3e-9 relative against all-f64 with r_switch = 35 M, against 1.6e-4 when the f32 predictors are used everywhere.
+// `frozen` lanes (finished rays, h = 0) must not let an f32 overflow on their parked state turn 0 * inf into NaN.
+// The predictors' trigonometry is MUFU.SIN / MUFU.COS (sin.approx.f32, |error| < 4e-7 on [-pi, pi]): the same damping
+// argument covers it (measured: worst RGBA component 4e-10 with polynomial f32 trig, see DESIGN.md for the MUFU figure).
+template <bool WITH_T, bool WGSL_RULE, class RS>   // RS = double (a template parameter only so that the f32 instantiations of the caller compile)
+__device__ __forceinline__ void step_symplectic_mixed(const HoleRay<RS>& c, const HoleRay<float>& cf, Ray<RS>& y, RS h, float hs_bias_f,
+                                                       float h0f, bool frozen) {
+    const float rf = (float)y.r, thf = (float)y.th, prf = (float)y.pr, pthf = (float)y.pth;
+    // the predictors' own copy of the step rule, from the f32 radius (saves converting h)
+    const float hh = 0.5f * (WGSL_RULE ? fminf(fmaxf(fmaf(rf, 0.15f, hs_bias_f), 0.05f), 1.0f) : h0f);
+    float sn = __sinf(thf), cs = __cosf(thf);
+    DerivU<float> d = rhs_ks_u<float, false, false>(cf, rf, sn, sn * cs, prf, pthf);
+    float f = hh * d.isig;
+    const float mr = fmaf(d.dr, f, rf), mth = fmaf(d.dth, f, thf), mpr = fmaf(d.dpr, f, prf), mpth = fmaf(d.dpth, f, pthf);
+    sn = __sinf(mth); cs = __cosf(mth);
+    d = rhs_ks_u<float, false, false>(cf, mr, sn, sn * cs, mpr, mpth);
+    f = hh * d.isig;
+    float ir = d.dr * f, ith = d.dth * f, ipr = d.dpr * f, ipth = d.dpth * f;
+    if (frozen) { ir = 0.0f; ith = 0.0f; ipr = 0.0f; ipth = 0.0f; }
+    // midpoint = f64 state + f32 increment; final evaluation and state update in f64
+    using N = Num<RS>;
+    RS a64, sc64;
+    trig_pair(*c.trig, y.th + (RS)ith, a64, sc64);
+    const DerivU<RS> D = rhs_ks_u<RS, WITH_T, WITH_T>(c, y.r + (RS)ir, a64, sc64, y.pr + (RS)ipr, y.pth + (RS)ipth);
+    const RS F = h * D.isig;
+    y.r = N::fma_(D.dr, F, y.r);
+    y.th = N::fma_(D.dth, F, y.th);
+    y.pr = N::fma_(D.dpr, F, y.pr);
+    y.pth = N::fma_(D.dpth, F, y.pth);
+    if (WITH_T) { y.ph = N::fma_(D.dph, F, y.ph); y.t = N::fma_(D.dt, h, y.t); }
 }
 
 // geodesic/integrator.rs:193-203 classic RK4

@@ -48,6 +48,7 @@ struct FrameParams {
     double M, a, spin, rh, r_term, escape_r, r_in, r_out;   // r_term = 1.001 * r+ (geodesic/mod.rs:257)
     double sqrtM;                                             // sqrt(M) for the Keplerian frequency (redshift.rs:72)
     double tol, h0;
+    double r_far;                                             // GVT_PRECISION_MIXED: f32 predictors beyond this radius
     double tdisk_rin, tdisk_scale;                            // (n-1)/(rout-rin)
     uint32_t width, height;                                   // full frame
     uint32_t x0, xs, y0, y1, ys;                              // pixel lattice traced by this launch

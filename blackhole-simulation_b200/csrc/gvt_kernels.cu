@@ -99,18 +99,34 @@ __device__ __forceinline__ void sample_spectrum(const float4* lut, uint32_t W, u
 #ifndef GVT_MAXT_F32
 #define GVT_MAXT_F32 512
 #endif
+#ifndef GVT_UNROLL_NEAR
+#define GVT_UNROLL_NEAR 4          // step-loop unroll of the fixed-step methods
+#endif
+#ifndef GVT_UNROLL_NEAR_MIXED
+#define GVT_UNROLL_NEAR_MIXED 1    // the same in the GVT_PRECISION_MIXED instantiation: its two step loops share the instruction
+                                   // cache (measured at 4K x 512: unroll 4/2 -> 51.0 ms with no_instruction stalls, 1/1 -> 44.4 ms)
+#endif
+#ifndef GVT_UNROLL_FAR
+#define GVT_UNROLL_FAR 1           // unroll of the f32-predictor step loop
+#endif
+constexpr int kUnrollNear = GVT_UNROLL_NEAR, kUnrollNearMixed = GVT_UNROLL_NEAR_MIXED, kUnrollFar = GVT_UNROLL_FAR;
 constexpr int TILE_W = 8, TILE_H = 4;
 
-// (a)(b) <= 0 without FP64-pipe work: compare sign words, and test either operand for +-0 with integer ops.
-__device__ __forceinline__ bool sign_differs_or_zero(double a, double b) {
-    const int ah = __double2hiint(a), bh = __double2hiint(b);
-    const bool az = ((ah & 0x7fffffff) | __double2loint(a)) == 0, bz = ((bh & 0x7fffffff) | __double2loint(b)) == 0;
-    return ((ah ^ bh) < 0) || az || bz;
-}
-__device__ __forceinline__ bool sign_differs_or_zero(float a, float b) { return a * b <= 0.0f; }  // FP32 ops are cheap  // one warp = one 8x4 pixel tile (compute.wgsl.ts:147 uses 8x8 groups)
+template <bool V> struct FarStep { static constexpr bool value = V; };
 
-template <class R, int METHOD, bool BUDGET, bool DEBUG, int MAXT, bool WGSL_RULE>
+// Which side of the equatorial plane: sign of (theta - pi/2) as -1 / 0 / +1. The subtraction is sign-exact in IEEE
+// arithmetic, so comparing the bit patterns (pi/2 > 0: sign-magnitude order, see lt_pos) gives the same answer with
+// two integer compares on the idle ALU pipe instead of a DADD on the FP64 pipe.
+__device__ __forceinline__ int equator_side(double th) {
+    const long long b = __double_as_longlong(th), h = __double_as_longlong(1.5707963267948966);
+    return (int)(b > h) - (int)(b < h);
+}
+__device__ __forceinline__ int equator_side(float th) { return (int)(th > 1.5707963267948966f) - (int)(th < 1.5707963267948966f); }
+// one warp = one 8x4 pixel tile (compute.wgsl.ts:147 uses 8x8 groups)
+
+template <class R, int METHOD, bool BUDGET, bool DEBUG, int MAXT, bool WGSL_RULE, bool MIXED = false>
 __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ FrameParams P) {
+    static_assert(!MIXED || (sizeof(R) == 8 && METHOD == 2), "GVT_PRECISION_MIXED: f64 state, implicit-midpoint stepper");
     using N = Num<R>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bars[2];
@@ -151,9 +167,19 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
     hc.set_hole(R(P.M), R(P.a));
     const R r_term = R(P.r_term), escape_r = R(P.escape_r), rh = R(P.rh);
     const R half_pi = R(1.5707963267948966);
+    const R hs_bias = R(-0.15) * rh;              // step rule compute.wgsl.ts:213 as one FMA: 0.15 r - 0.15 r+
+    HoleRay<float> hcf;                           // GVT_PRECISION_MIXED: the predictor evaluations' f32 constants
+    if (MIXED) { hcf.trig = &P.trig; hcf.set_hole((float)P.M, (float)P.a); }
 
-    unsigned long long acc_commit = 0, acc_exec = 0, acc_rhs = 0;
-    uint32_t acc_term[4] = {0, 0, 0, 0};
+    // per-warp census accumulators live in shared memory (lane 0 owns its warp's row): seven values that are touched
+    // once per tile must not hold ten registers across the march
+    __shared__ unsigned long long s_acc[MAXT / 32][3];
+    __shared__ uint32_t s_term[MAXT / 32][4];
+    const uint32_t wid = threadIdx.x >> 5;
+    if ((threadIdx.x & 31u) == 0) {
+        s_acc[wid][0] = s_acc[wid][1] = s_acc[wid][2] = 0ull;
+        s_term[wid][0] = s_term[wid][1] = s_term[wid][2] = s_term[wid][3] = 0u;
+    }
 
     for (;;) {
         uint32_t tile = 0;
@@ -203,6 +229,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
             y.pr = pr_far;
             y.pth = pth_far * r0 * r0;
             hc.set_ray(R(-1), pph_far * r0 * r0 * st * st);
+            if (MIXED) hcf.set_ray(-1.0f, (float)hc.pph);
         }
 
         // The spectral-LUT copy was issued before ray generation; by now it has had a tile's worth of set-up time to
@@ -294,70 +321,84 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
         y.pr = renormalize_pr<R, 1>(hc, y.r, y.th, y.pr, y.pth);  // mod.rs:200
         uint32_t renorm_in = 0;          // steps until the next renormalisation (steps % interval == 0, mod.rs:229)
         bool done = false, by_radius = false;
-        // side of the equatorial plane before the step, as the sign word of (theta - pi/2) and an "exactly on it" flag
-        R dprev = y.th - half_pi;
+        int side_prev = equator_side(y.th);   // side of the equatorial plane before the step
         // The warp-uniform early exit (all 32 rays finished) is voted once per chunk of 8 steps, outside the inner
         // loop: a vote.sync inside the step loop, like any warp-synchronising instruction there, stops ptxas from
         // keeping the loop's FP64 constants in uniform registers (3-register DFMAs cost 3 cycles instead of 2).
         // Fixed-step methods unroll the inner loop x4 to amortise its bookkeeping; the adaptive stepper's body is far
         // too large for that (it spills when unrolled).
         constexpr uint32_t CHUNK = 8;
-        for (uint32_t it0 = 0; it0 < P.max_steps; it0 += CHUNK) {
-        if (!BUDGET) { if (__all_sync(0xffffffffu, done)) break; }
-        const uint32_t it1 = min(it0 + CHUNK, P.max_steps);
-#pragma unroll(METHOD == 0 ? 1 : 4)
-        for (uint32_t it = it0; it < it1; it++) {
+        // One march step; FAR (GVT_PRECISION_MIXED only) selects the stepper whose two predictor evaluations run in f32.
+        auto march_step = [&](auto far_tag) {
+            constexpr bool FAR = decltype(far_tag)::value;
             // mod.rs:204,255-265: alive iff 1.001 r+ <= r <= escape radius (which of the two ended it is resolved
             // after the loop from the frozen state)
-            if (!done && !(y.r >= r_term && y.r <= escape_r)) { done = true; by_radius = true; }
+            if (!done && (lt_pos(y.r, r_term) || gt_pos(y.r, escape_r))) { done = true; by_radius = true; }
             // Fixed-step methods run the step for every lane, finished rays with h = 0 on their frozen state (nothing to
             // select back afterwards): in budget accounting that IS the definition; with natural termination the lanes
             // would idle under predication anyway, and keeping the step out of a divergent region lets ptxas feed its
             // constants from uniform registers. The adaptive stepper does the same per attempt (adaptive_step_warp).
-            {
-                const R th0 = y.th, r_prev = y.r;
-                if (METHOD == 0) {
-                    adaptive_step_warp<R, 1>(hc, y, h, R(P.tol), !done, rhs_evals);
-                } else {
-                    R hs = WGSL_RULE ? clampR<R>((y.r - rh) * R(0.15), R(0.05), R(1.0)) : R(P.h0);
-                    if (done) hs = R(0);
-                    if (METHOD == 1) { step_rk4<R, 1, DEBUG>(hc, y, hs); rhs_evals += (BUDGET || !done) ? 4u : 0u; }
-                    else { step_symplectic<R, 1, DEBUG>(hc, y, hs); rhs_evals += (BUDGET || !done) ? 3u : 0u; }
+            const R th0 = y.th, r_prev = y.r;
+            if (METHOD == 0) {
+                adaptive_step_warp<R, 1>(hc, y, h, R(P.tol), !done, rhs_evals);
+            } else {
+                R hs = WGSL_RULE ? clampPos<R>(N::fma_(y.r, R(0.15), hs_bias), R(0.05), R(1.0)) : R(P.h0);
+                if (done) hs = R(0);
+                if (METHOD == 1) { step_rk4<R, 1, DEBUG>(hc, y, hs); rhs_evals += (BUDGET || !done) ? 4u : 0u; }
+                else {
+                    if constexpr (MIXED && FAR) step_symplectic_mixed<DEBUG, WGSL_RULE>(hc, hcf, y, hs, (float)hs_bias, (float)P.h0, done);
+                    else step_symplectic<R, 1, DEBUG>(hc, y, hs);
+                    rhs_evals += (BUDGET || !done) ? 3u : 0u;
                 }
-                if (!done) {
-                    if (renorm_in == 0u) { y.pr = renormalize_pr<R, 1>(hc, y.r, y.th, y.pr, y.pth); renorm_in = P.renorm_interval; }
-                    renorm_in--;
-                    steps++;
-                    if (DEBUG) max_drift = N::max_(max_drift, N::abs_(hamiltonian_of<R, 1>(hc, y.r, y.th, y.pr, y.pth)));
-                    // ---- thin-disk crossing (compute.wgsl.ts:216-254 with a18 + a19 + a20):
-                    //      (th0 - pi/2)(th1 - pi/2) <= 0  <=>  the signs differ or either factor is zero
-                    const R dcur = y.th - half_pi;
-                    const bool crossed = sign_differs_or_zero(dprev, dcur);
-                    dprev = dcur;
-                    if (crossed) {
-                        const R dth = y.th - th0;
-                        const R f = (dth == R(0)) ? R(0) : (half_pi - th0) * N::rcp(dth);
-                        const R r_c = N::fma_(f, y.r - r_prev, r_prev);
-                        if (r_c > R(P.r_in) && r_c < R(P.r_out)) {
-                            const R lambda = hc.pph * N::rcp(-hc.pt);
-                            const R g = g_factor<R>(r_c, R(P.M), R(P.sqrtM), R(P.spin), lambda);
-                            const R tn = sample_tdisk<R>(fb->tdisk, P.tdisk_n, R(P.tdisk_rin), R(P.tdisk_scale), r_c);
-                            const R u = pow04(tn);
-                            const R v = (g - R(0.05)) * R(1.0 / 4.95);
-                            R rgb[3];
-                            sample_spectrum<R>(lut, P.spec_w, P.spec_h, u, v, rgb);
-                            const R opacity = R(0.6) * tn * g;
-                            const R wgt = (R(1) - alpha) * opacity;
-                            col[0] = N::fma_(rgb[0], wgt, col[0]);
-                            col[1] = N::fma_(rgb[1], wgt, col[1]);
-                            col[2] = N::fma_(rgb[2], wgt, col[2]);
-                            alpha += opacity;
-                            if (alpha > R(0.99)) { term = 4u; done = true; }
-                        }
+            }
+            if (!done) {
+                if (renorm_in == 0u) { y.pr = renormalize_pr<R, 1>(hc, y.r, y.th, y.pr, y.pth); renorm_in = P.renorm_interval; }
+                renorm_in--;
+                steps++;
+                if (DEBUG) max_drift = N::max_(max_drift, N::abs_(hamiltonian_of<R, 1>(hc, y.r, y.th, y.pr, y.pth)));
+                // ---- thin-disk crossing (compute.wgsl.ts:216-254 with a18 + a19 + a20):
+                //      (th0 - pi/2)(th1 - pi/2) <= 0  <=>  the sides differ or the ray sits exactly on the plane
+                const int side = equator_side(y.th);
+                const bool crossed = (side != side_prev) || (side == 0);
+                side_prev = side;
+                if (crossed) {
+                    const R dth = y.th - th0;
+                    const R f = (dth == R(0)) ? R(0) : (half_pi - th0) * N::rcp(dth);
+                    const R r_c = N::fma_(f, y.r - r_prev, r_prev);
+                    if (r_c > R(P.r_in) && r_c < R(P.r_out)) {
+                        const R lambda = hc.pph * N::rcp(-hc.pt);
+                        const R g = g_factor<R>(r_c, R(P.M), R(P.sqrtM), R(P.spin), lambda);
+                        const R tn = sample_tdisk<R>(fb->tdisk, P.tdisk_n, R(P.tdisk_rin), R(P.tdisk_scale), r_c);
+                        const R u = pow04(tn);
+                        const R v = (g - R(0.05)) * R(1.0 / 4.95);
+                        R rgb[3];
+                        sample_spectrum<R>(lut, P.spec_w, P.spec_h, u, v, rgb);
+                        const R opacity = R(0.6) * tn * g;
+                        const R wgt = (R(1) - alpha) * opacity;
+                        col[0] = N::fma_(rgb[0], wgt, col[0]);
+                        col[1] = N::fma_(rgb[1], wgt, col[1]);
+                        col[2] = N::fma_(rgb[2], wgt, col[2]);
+                        alpha += opacity;
+                        if (alpha > R(0.99)) { term = 4u; done = true; }
                     }
                 }
             }
-        }
+        };
+        for (uint32_t it0 = 0; it0 < P.max_steps; it0 += CHUNK) {
+            if (!BUDGET) { if (__all_sync(0xffffffffu, done)) break; }
+            const uint32_t it1 = min(it0 + CHUNK, P.max_steps);
+            // GVT_PRECISION_MIXED: the warp takes the f32-predictor stepper for this chunk iff every live ray is on its
+            // way out (p_r > 0) beyond r_far, a chunk's worth of steps clear of r_switch, and away from the polar axis.
+            // Voted once per chunk, like the early exit, so the step loops stay free of warp-synchronising instructions.
+            bool far_chunk = false;
+            if (MIXED) far_chunk = __all_sync(0xffffffffu, done || (y.r > R(P.r_far) && y.pr > R(0) && N::abs_(y.th - half_pi) < R(1.45)));
+            if (MIXED && far_chunk) {
+#pragma unroll(kUnrollFar)
+                for (uint32_t it = it0; it < it1; it++) march_step(FarStep<true>{});
+            } else {
+#pragma unroll(METHOD == 0 ? 1 : (MIXED ? kUnrollNearMixed : kUnrollNear))
+                for (uint32_t it = it0; it < it1; it++) march_step(FarStep<false>{});
+            }
         }
         if (by_radius) term = (y.r < r_term) ? 1u : 2u;   // Horizon is tested first (mod.rs:257-263)
         else if (!done) term = 3u;
@@ -393,31 +434,39 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
             }
         }
         const uint32_t vsteps = valid ? steps : 0u, vrhs = valid ? rhs_evals : 0u;
-        acc_commit += __reduce_add_sync(0xffffffffu, vsteps);
-        acc_rhs += __reduce_add_sync(0xffffffffu, vrhs);
-        acc_exec += BUDGET ? (unsigned long long)__popc(__ballot_sync(0xffffffffu, valid)) * P.max_steps
-                           : (unsigned long long)__reduce_add_sync(0xffffffffu, vsteps);
+        {
+            const uint32_t t_commit = __reduce_add_sync(0xffffffffu, vsteps), t_rhs = __reduce_add_sync(0xffffffffu, vrhs);
+            const uint32_t n_valid = __popc(__ballot_sync(0xffffffffu, valid));
+            uint32_t t_term[4];
 #pragma unroll
-        for (uint32_t c = 0; c < 4; c++) acc_term[c] += __popc(__ballot_sync(0xffffffffu, valid && term == c + 1u));
+            for (uint32_t c = 0; c < 4; c++) t_term[c] = __popc(__ballot_sync(0xffffffffu, valid && term == c + 1u));
+            if (lane == 0) {
+                s_acc[wid][0] += t_commit;
+                s_acc[wid][1] += BUDGET ? (unsigned long long)n_valid * P.max_steps : (unsigned long long)t_commit;
+                s_acc[wid][2] += t_rhs;
+#pragma unroll
+                for (uint32_t c = 0; c < 4; c++) s_term[wid][c] += t_term[c];
+            }
+        }
     }
     // a CTA must not exit while its bulk copy is still in flight
     if (P.lut_in_smem && !lut_ready) mbar_wait(&bars[1], 0);
     if (lane == 0) {
-        atomicAdd(&P.counters->steps_committed, acc_commit);
-        atomicAdd(&P.counters->steps_executed, acc_exec);
-        atomicAdd(&P.counters->rhs_evals, acc_rhs);
-        if (acc_term[0]) atomicAdd(&P.counters->n_horizon, (unsigned long long)acc_term[0]);
-        if (acc_term[1]) atomicAdd(&P.counters->n_escape, (unsigned long long)acc_term[1]);
-        if (acc_term[2]) atomicAdd(&P.counters->n_maxsteps, (unsigned long long)acc_term[2]);
-        if (acc_term[3]) atomicAdd(&P.counters->n_disk, (unsigned long long)acc_term[3]);
+        atomicAdd(&P.counters->steps_committed, s_acc[wid][0]);
+        atomicAdd(&P.counters->steps_executed, s_acc[wid][1]);
+        atomicAdd(&P.counters->rhs_evals, s_acc[wid][2]);
+        if (s_term[wid][0]) atomicAdd(&P.counters->n_horizon, (unsigned long long)s_term[wid][0]);
+        if (s_term[wid][1]) atomicAdd(&P.counters->n_escape, (unsigned long long)s_term[wid][1]);
+        if (s_term[wid][2]) atomicAdd(&P.counters->n_maxsteps, (unsigned long long)s_term[wid][2]);
+        if (s_term[wid][3]) atomicAdd(&P.counters->n_disk, (unsigned long long)s_term[wid][3]);
     }
 }
 
-template <class R, int METHOD, bool BUDGET, bool DEBUG, int MAXT>
+template <class R, int METHOD, bool BUDGET, bool DEBUG, int MAXT, bool MIXED = false>
 static cudaError_t launch_trace_t(const FrameParams& p, int sm_count, cudaStream_t stream) {
     // the per-step rule of compute.wgsl.ts:213 is a compile-time switch for the fixed-step methods
-    auto kern = (METHOD != 0 && p.step_rule == 1u) ? k_trace_tile<R, METHOD, BUDGET, DEBUG, MAXT, true>
-                                                    : k_trace_tile<R, METHOD, BUDGET, DEBUG, MAXT, false>;
+    auto kern = (METHOD != 0 && p.step_rule == 1u) ? k_trace_tile<R, METHOD, BUDGET, DEBUG, MAXT, true, MIXED>
+                                                    : k_trace_tile<R, METHOD, BUDGET, DEBUG, MAXT, false, MIXED>;
     size_t smem = ((sizeof(FrameBlock) + 127) / 128) * 128;
     if (p.lut_in_smem) smem += (size_t)p.spec_w * p.spec_h * sizeof(float4);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -450,6 +499,12 @@ cudaError_t launch_trace(const FrameParams& p_in, int method, int precision, boo
                      : launch_trace_t<RT, 2, false, false, MT>(p, sm_count, stream);                             \
     } while (0)
     if (precision == 1) GVT_DISPATCH(float, GVT_MAXT_F32);
+    if (precision == 3) {   // GVT_PRECISION_MIXED (implicit midpoint only; validated by the caller)
+        if (budget) return debug ? launch_trace_t<double, 2, true, true, GVT_MAXT_F64, true>(p, sm_count, stream)
+                                 : launch_trace_t<double, 2, true, false, GVT_MAXT_F64, true>(p, sm_count, stream);
+        return debug ? launch_trace_t<double, 2, false, true, GVT_MAXT_F64, true>(p, sm_count, stream)
+                     : launch_trace_t<double, 2, false, false, GVT_MAXT_F64, true>(p, sm_count, stream);
+    }
     GVT_DISPATCH(double, GVT_MAXT_F64);
 #undef GVT_DISPATCH
 }

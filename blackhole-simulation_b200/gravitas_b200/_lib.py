@@ -14,7 +14,7 @@ GVT_OK, GVT_ERR_INVALID, GVT_ERR_NO_DEVICE, GVT_ERR_CUDA, GVT_ERR_NCCL, GVT_ERR_
 TERM_NONE, TERM_HORIZON, TERM_ESCAPE, TERM_MAXSTEPS, TERM_DISK = 0, 1, 2, 3, 4
 COORDS_BL, COORDS_KS = 0, 1
 METHOD_RKF45, METHOD_RK4, METHOD_SYMPLECTIC, METHOD_VERLET_GLSL = 0, 1, 2, 3
-PRECISION_F64, PRECISION_F32, PRECISION_F32_FAST = 0, 1, 2
+PRECISION_F64, PRECISION_F32, PRECISION_F32_FAST, PRECISION_MIXED = 0, 1, 2, 3
 FORMAT_RGBA32F, FORMAT_RGBA16F, FORMAT_RGBA8_REINHARD, FORMAT_RGBA8_ACES, FORMAT_RGBA8_UNORM = 0, 1, 2, 3, 4
 FORMAT_BYTES = {0: 16, 1: 8, 2: 4, 3: 4, 4: 4}
 FORMAT_DTYPE = {0: "float32", 1: "float16", 2: "uint8", 3: "uint8", 4: "uint8"}
