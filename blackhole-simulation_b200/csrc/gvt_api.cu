@@ -661,10 +661,29 @@ static int32_t build_frame(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
     P.sqrtM = std::sqrt(bh.mass);
     P.escape_r = rp->escape_radius; P.r_in = bh.isco(true); P.r_out = rp->disk_r_out;
     P.tol = rp->tolerance; P.h0 = rp->initial_step;
-    {   // GVT_PRECISION_MIXED: r_switch = 35 M, plus the distance a ray can fall back within one 8-step chunk (|dr/dlambda| <= 1)
+    {   // Zone radii. A chunk is 8 steps and |dr/dlambda| <= 1 for a null ray with p_t = -1, so a ray moves at most
+        // 8 h_max in r within a chunk.
+        const double h_max = rp->step_rule == GVT_STEP_WGSL ? 1.0 : std::fabs(rp->initial_step);
+        const double travel = 1.5 * 8.0 * h_max;   // |dr/dlambda| <= (r^2 + a^2 + a |L|) / Sigma: up to ~1.1 near the hole, 1.5 is generous
+        // step rule saturated (compute.wgsl.ts:213: 0.15 (r - r+) >= 1), with one chunk of margin; the constant rule is
+        // saturated everywhere, but the horizon test still needs r > 1.001 r+ for the whole chunk
+        P.h_const = rp->step_rule == GVT_STEP_WGSL ? 1.0 : rp->initial_step;
+        P.r_hconst = (rp->step_rule == GVT_STEP_WGSL ? P.rh + 1.0 / 0.15 : P.r_term) + travel + 1e-3;
+        P.r_escape_guard = rp->escape_radius - travel - 1e-3;
+        P.r_sat = rp->step_rule == GVT_STEP_WGSL ? P.rh + 1.0 / 0.15 + 1e-9 : P.r_term;
+        // high-word windows: hi(r) in [hi(lo) + 1, hi(escape_r) - 1] implies lo < r < escape_r for positive finite lo, escape_r
+        auto hi_of = [](double x) { uint64_t b; memcpy(&b, &x, 8); return (uint32_t)(b >> 32); };
+        const double los[2] = {P.r_term, P.r_sat};
+        for (int z = 0; z < 2; z++) {
+            const uint32_t lo = hi_of(los[z]) + 1u, hi = hi_of(rp->escape_radius);
+            P.alive_lo[z] = lo;
+            P.alive_span[z] = (rp->escape_radius > los[z] && los[z] > 0.0 && hi > lo) ? hi - lo : 0u;   // 0: always take the exact tests
+        }
+        // GVT_PRECISION_MIXED: r_switch = 35 M
         const char* e = getenv("GVT_MIXED_RSWITCH");   // tuning experiments only
         const double r_switch = (e && atof(e) > 0.0 ? atof(e) : 35.0) * bh.mass;
-        P.r_far = r_switch + 8.0 * (rp->step_rule == GVT_STEP_WGSL ? 1.0 : std::fabs(rp->initial_step));
+        P.r_far = std::max(r_switch + travel, P.r_hconst);
+        P.f32_M = (float)bh.mass; P.f32_a = (float)bh.a(); P.f32_a2 = (float)(bh.a() * bh.a()); P.f32_twoM = (float)(2.0 * bh.mass); P.f32_hconst = (float)P.h_const;
     }
     P.tdisk_rin = r->tdisk_rin; P.tdisk_scale = 511.0 / (r->tdisk_rout - r->tdisk_rin);
     P.width = W; P.height = H;

@@ -117,10 +117,10 @@ __device__ __forceinline__ void trig_pair(const TrigTable& T, double x, double& 
     const double kd_m = fma(x, K[0], K[1]);
     const int k = __double2loint(kd_m);
     const double kd = kd_m - K[1];
-    double r = fma(-kd, K[2], x);
-#ifndef GVT_TRIG_CW1
-    r = fma(-kd, K[3], r);
-#endif
+    // one-term Cody-Waite: pi/2 as a single double. The dropped tail (6.1e-17 per quadrant) moves the reduced argument
+    // by < ulp(theta)/2 for the |k| <= a few that geodesic polar angles reach -- below the rounding theta itself carries
+    // -- and saves one FP64 instruction per evaluation (3 per step; measured -1.3 % frame time, identical parity).
+    const double r = fma(-kd, K[2], x);
     const double z = r * r;
     double ps = K[9];
     ps = fma(ps, z, K[8]);
@@ -264,13 +264,15 @@ template <class R>
 struct DerivU {
     R dr, dth, dph, dpr, dpth, dt, isig;
 };
-template <class R, bool WITH_T, bool WITH_PHI>
+// POLAR = false drops the polar clamp: only for rays that provably stay away from the axis (see kPolarSafePph).
+template <class R, bool WITH_T, bool WITH_PHI, bool POLAR = true>
 __device__ __forceinline__ DerivU<R> rhs_ks_u(const HoleRay<R>& c, R r, R a, R sc, R pr, R pth) {
     using N = Num<R>;
     R sin2 = a * a;
     // Within 1e-6 rad of the polar axis (rare): clamp sin^2 and zero dH/dtheta below |sin| = 1e-10 (both of its
     // terms carry sc). f64: nested rare path behind an integer compare (ptxas predicates it). f32: two plain selects.
-    if (sizeof(R) == 8) {
+    if (!POLAR) {
+    } else if (sizeof(R) == 8) {
         if (lt_pos(sin2, R(1e-12))) {
             sin2 = R(1e-12);
             if (abs_lt_pos(a, R(1e-10))) sc = R(0);
@@ -450,24 +452,24 @@ __device__ __forceinline__ R hamiltonian_of(const HoleRay<R>& c, R r, R th, R pr
 // --------------------------------------------------------------------------------------------------
 // geodesic/integrator.rs:209-226 implicit midpoint: 2 fixed-point iterations + final evaluation.
 // s_mid = 0.5 (s + (s + d h)) = s + d h/2.
-template <class R, int COORDS, bool WITH_T>
+template <class R, int COORDS, bool WITH_T, bool POLAR = true>
 __device__ __forceinline__ void step_symplectic(const HoleRay<R>& c, Ray<R>& y, R h) {
     using N = Num<R>;
     const R hh = R(0.5) * h;
     if (COORDS == 1) {
         R a, sc;
         trig_pair(*c.trig, y.th, a, sc);
-        DerivU<R> d = rhs_ks_u<R, false, false>(c, y.r, a, sc, y.pr, y.pth);
+        DerivU<R> d = rhs_ks_u<R, false, false, POLAR>(c, y.r, a, sc, y.pr, y.pth);
         R f = hh * d.isig;
         R mr = N::fma_(d.dr, f, y.r), mth = N::fma_(d.dth, f, y.th);
         R mpr = N::fma_(d.dpr, f, y.pr), mpth = N::fma_(d.dpth, f, y.pth);
         trig_pair(*c.trig, mth, a, sc);
-        d = rhs_ks_u<R, false, false>(c, mr, a, sc, mpr, mpth);
+        d = rhs_ks_u<R, false, false, POLAR>(c, mr, a, sc, mpr, mpth);
         f = hh * d.isig;
         mr = N::fma_(d.dr, f, y.r); mth = N::fma_(d.dth, f, y.th);
         mpr = N::fma_(d.dpr, f, y.pr); mpth = N::fma_(d.dpth, f, y.pth);
         trig_pair(*c.trig, mth, a, sc);
-        d = rhs_ks_u<R, WITH_T, WITH_T>(c, mr, a, sc, mpr, mpth);
+        d = rhs_ks_u<R, WITH_T, WITH_T, POLAR>(c, mr, a, sc, mpr, mpth);
         f = h * d.isig;
         y.r = N::fma_(d.dr, f, y.r);
         y.th = N::fma_(d.dth, f, y.th);
@@ -501,27 +503,26 @@ __device__ __forceinline__ void step_symplectic(const HoleRay<R>& c, Ray<R>& y, 
 // 1.3e-9 relative against all-f64 with r_switch = 35 M, against 1.6e-4 when the f32 predictors are used everywhere.
 // `frozen` lanes (finished rays, h = 0) must not let an f32 overflow on their parked state turn 0 * inf into NaN.
 // The predictors' trigonometry is MUFU.SIN / MUFU.COS (sin.approx.f32, |error| < 4e-7 on [-pi, pi]): the same damping
-// argument covers it (measured: worst RGBA component 4e-10 with polynomial f32 trig, see DESIGN.md for the MUFU figure).
-template <bool WITH_T, bool WGSL_RULE, class RS>   // RS = double (a template parameter only so that the f32 instantiations of the caller compile)
-__device__ __forceinline__ void step_symplectic_mixed(const HoleRay<RS>& c, const HoleRay<float>& cf, Ray<RS>& y, RS h, float hs_bias_f,
-                                                       float h0f, bool frozen) {
+// argument covers it (measured on the headline frame: worst RGBA component 7e-10 with MUFU, 4e-10 with polynomial f32 trig).
+// Callers guarantee a ray off the polar axis (kPolarSafePph), so neither precision carries the polar clamp here; hf is
+// the predictors' copy of the step (0 for frozen lanes: their increments are then exactly 0, the f32 derivatives of a
+// parked state being finite).
+template <bool WITH_T, class RS>   // RS = double (a template parameter only so that the f32 instantiations of the caller compile)
+__device__ __forceinline__ void step_symplectic_mixed(const HoleRay<RS>& c, const HoleRay<float>& cf, Ray<RS>& y, RS h, float hf) {
     const float rf = (float)y.r, thf = (float)y.th, prf = (float)y.pr, pthf = (float)y.pth;
-    // the predictors' own copy of the step rule, from the f32 radius (saves converting h)
-    const float hh = 0.5f * (WGSL_RULE ? fminf(fmaxf(fmaf(rf, 0.15f, hs_bias_f), 0.05f), 1.0f) : h0f);
+    const float hh = 0.5f * hf;
     float sn = __sinf(thf), cs = __cosf(thf);
-    DerivU<float> d = rhs_ks_u<float, false, false>(cf, rf, sn, sn * cs, prf, pthf);
+    DerivU<float> d = rhs_ks_u<float, false, false, false>(cf, rf, sn, sn * cs, prf, pthf);
     float f = hh * d.isig;
     const float mr = fmaf(d.dr, f, rf), mth = fmaf(d.dth, f, thf), mpr = fmaf(d.dpr, f, prf), mpth = fmaf(d.dpth, f, pthf);
     sn = __sinf(mth); cs = __cosf(mth);
-    d = rhs_ks_u<float, false, false>(cf, mr, sn, sn * cs, mpr, mpth);
+    d = rhs_ks_u<float, false, false, false>(cf, mr, sn, sn * cs, mpr, mpth);
     f = hh * d.isig;
-    float ir = d.dr * f, ith = d.dth * f, ipr = d.dpr * f, ipth = d.dpth * f;
-    if (frozen) { ir = 0.0f; ith = 0.0f; ipr = 0.0f; ipth = 0.0f; }
     // midpoint = f64 state + f32 increment; final evaluation and state update in f64
     using N = Num<RS>;
     RS a64, sc64;
-    trig_pair(*c.trig, y.th + (RS)ith, a64, sc64);
-    const DerivU<RS> D = rhs_ks_u<RS, WITH_T, WITH_T>(c, y.r + (RS)ir, a64, sc64, y.pr + (RS)ipr, y.pth + (RS)ipth);
+    trig_pair(*c.trig, y.th + (RS)(d.dth * f), a64, sc64);
+    const DerivU<RS> D = rhs_ks_u<RS, WITH_T, WITH_T, false>(c, y.r + (RS)(d.dr * f), a64, sc64, y.pr + (RS)(d.dpr * f), y.pth + (RS)(d.dpth * f));
     const RS F = h * D.isig;
     y.r = N::fma_(D.dr, F, y.r);
     y.th = N::fma_(D.dth, F, y.th);

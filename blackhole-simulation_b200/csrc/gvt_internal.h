@@ -48,7 +48,15 @@ struct FrameParams {
     double M, a, spin, rh, r_term, escape_r, r_in, r_out;   // r_term = 1.001 * r+ (geodesic/mod.rs:257)
     double sqrtM;                                             // sqrt(M) for the Keplerian frequency (redshift.rs:72)
     double tol, h0;
+    // Zone radii of the march (chunk-level, warp-uniform specialisations of the step loop; see k_trace_tile):
+    double r_hconst;                                          // beyond it the step rule has saturated: h == h_const, and the
+    double h_const;                                           //   horizon cannot be reached within one chunk
+    double r_escape_guard;                                    // below it the escape radius cannot be reached within one chunk
+    double r_sat;                                             // where the step rule saturates (r+ + 1/0.15; r_term for the constant rule)
+    uint32_t alive_lo[2], alive_span[2];                      // hot-path "alive" window on the high word of r: [0] (r_term, escape_r),
+                                                              //   [1] (r_sat, escape_r): inside iff (hi(r) - lo) < span (unsigned)
     double r_far;                                             // GVT_PRECISION_MIXED: f32 predictors beyond this radius
+    float f32_M, f32_a, f32_a2, f32_twoM, f32_hconst;         // the predictors' hole constants and (float)h_const
     double tdisk_rin, tdisk_scale;                            // (n-1)/(rout-rin)
     uint32_t width, height;                                   // full frame
     uint32_t x0, xs, y0, y1, ys;                              // pixel lattice traced by this launch

@@ -100,8 +100,11 @@ __device__ __forceinline__ void sample_spectrum(const float4* lut, uint32_t W, u
 #define GVT_MAXT_F32 512
 #endif
 #ifndef GVT_UNROLL_NEAR
-#define GVT_UNROLL_NEAR 4          // step-loop unroll of the fixed-step methods
+#define GVT_UNROLL_NEAR 4          // step-loop unroll of RK4
 #endif
+#ifndef GVT_UNROLL_SYMP
+#define GVT_UNROLL_SYMP 1          // step-loop unroll of the implicit-midpoint zones (measured at 4K x 512, one loop: unroll 1 / 2 /
+#endif                             // 4 / 8 -> 51.60 / 51.72 / 51.59 / 53.93 ms; with one loop per zone the small body is kinder to the I-cache)
 #ifndef GVT_UNROLL_NEAR_MIXED
 #define GVT_UNROLL_NEAR_MIXED 1    // the same in the GVT_PRECISION_MIXED instantiation: its two step loops share the instruction
                                    // cache (measured at 4K x 512: unroll 4/2 -> 51.0 ms with no_instruction stalls, 1/1 -> 44.4 ms)
@@ -109,14 +112,27 @@ __device__ __forceinline__ void sample_spectrum(const float4* lut, uint32_t W, u
 #ifndef GVT_UNROLL_FAR
 #define GVT_UNROLL_FAR 1           // unroll of the f32-predictor step loop
 #endif
-constexpr int kUnrollNear = GVT_UNROLL_NEAR, kUnrollNearMixed = GVT_UNROLL_NEAR_MIXED, kUnrollFar = GVT_UNROLL_FAR;
+constexpr int kUnrollSymp = GVT_UNROLL_SYMP, kUnrollNear = GVT_UNROLL_NEAR, kUnrollNearMixed = GVT_UNROLL_NEAR_MIXED, kUnrollFar = GVT_UNROLL_FAR;
 constexpr int TILE_W = 8, TILE_H = 4;
 
-template <bool V> struct FarStep { static constexpr bool value = V; };
+// Compile-time flavour of one march step (the step loop is instantiated once per flavour a kernel needs and the warp
+// picks one per 8-step chunk): FAR = f32 predictors (GVT_PRECISION_MIXED), HCONST = the step rule has saturated and
+// neither termination radius is within reach, so h is a constant and the radius tests are dropped, POLAR = the ray
+// may come within reach of the polar clamp (kerr.rs:417,448,494) and the RHS carries it.
+template <bool FAR, bool HCONST, bool POLAR> struct StepKind {
+    static constexpr bool far = FAR, hconst = HCONST, polar = POLAR;
+};
+// A ray whose conserved L_z = p_phi satisfies L^2 > kPolarSafe (Q + a^2 + L^2) cannot approach the axis: the polar
+// potential Theta = Q + a^2 cos^2 - L^2 cot^2 >= 0 gives sin^2(theta) >= L^2 / (Q + a^2 + L^2) > 1e-4 along the whole
+// geodesic, eight orders of magnitude above the 1e-12 clamp, so the clamp code is dead for it. Tiles holding any other
+// ray (a few pixel columns around the image of the spin axis) run the generic step.
+constexpr double kPolarSafe = 1e-4;
 
 // Which side of the equatorial plane: sign of (theta - pi/2) as -1 / 0 / +1. The subtraction is sign-exact in IEEE
 // arithmetic, so comparing the bit patterns (pi/2 > 0: sign-magnitude order, see lt_pos) gives the same answer with
 // two integer compares on the idle ALU pipe instead of a DADD on the FP64 pipe.
+__device__ __forceinline__ int hiword(double x) { return __double2hiint(x); }
+__device__ __forceinline__ int hiword(float x) { return __float_as_int(x); }
 __device__ __forceinline__ int equator_side(double th) {
     const long long b = __double_as_longlong(th), h = __double_as_longlong(1.5707963267948966);
     return (int)(b > h) - (int)(b < h);
@@ -169,7 +185,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
     const R half_pi = R(1.5707963267948966);
     const R hs_bias = R(-0.15) * rh;              // step rule compute.wgsl.ts:213 as one FMA: 0.15 r - 0.15 r+
     HoleRay<float> hcf;                           // GVT_PRECISION_MIXED: the predictor evaluations' f32 constants
-    if (MIXED) { hcf.trig = &P.trig; hcf.set_hole((float)P.M, (float)P.a); }
+    if (MIXED) { hcf.trig = &P.trig; hcf.M = P.f32_M; hcf.a = P.f32_a; hcf.a2 = P.f32_a2; hcf.twoM = P.f32_twoM; }
 
     // per-warp census accumulators live in shared memory (lane 0 owns its warp's row): seven values that are touched
     // once per tile must not hold ten registers across the march
@@ -200,6 +216,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
         // ---- camera -> (x, p): compute.wgsl.ts:159-187 ----
         Ray<R> y;
         Vec3<R> wdir;          // world-space ray direction (the Cartesian march of METHOD 3 starts from it)
+        bool polar_ray = true;
         {
             const R ndcx = N::fma_(N::fma_(R((double)px), R(fb->inv_width), R(fb->jx)), R(2), R(-1));
             const R ndcy = N::fma_(N::fma_(R((double)py), R(fb->inv_height), R(fb->jy)), R(2), R(-1));
@@ -230,6 +247,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
             y.pth = pth_far * r0 * r0;
             hc.set_ray(R(-1), pph_far * r0 * r0 * st * st);
             if (MIXED) hcf.set_ray(-1.0f, (float)hc.pph);
+            // Carter constant of the ray at the camera, for the polar-safety test (kPolarSafe)
+            const R ct2 = ct * ct;
+            const R Q = N::fma_(y.pth, y.pth, ct2 * N::fma_(hc.pph2, N::rcp(R(fb->safe_st) * R(fb->safe_st)), -hc.a2));
+            polar_ray = !(hc.pph2 > R(kPolarSafe) * (Q + hc.a2 + hc.pph2));
         }
 
         // The spectral-LUT copy was issued before ray generation; by now it has had a tile's worth of set-up time to
@@ -328,26 +349,44 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
         // Fixed-step methods unroll the inner loop x4 to amortise its bookkeeping; the adaptive stepper's body is far
         // too large for that (it spills when unrolled).
         constexpr uint32_t CHUNK = 8;
-        // One march step; FAR (GVT_PRECISION_MIXED only) selects the stepper whose two predictor evaluations run in f32.
-        auto march_step = [&](auto far_tag) {
-            constexpr bool FAR = decltype(far_tag)::value;
-            // mod.rs:204,255-265: alive iff 1.001 r+ <= r <= escape radius (which of the two ended it is resolved
-            // after the loop from the frozen state)
-            if (!done && (lt_pos(y.r, r_term) || gt_pos(y.r, escape_r))) { done = true; by_radius = true; }
-            // Fixed-step methods run the step for every lane, finished rays with h = 0 on their frozen state (nothing to
-            // select back afterwards): in budget accounting that IS the definition; with natural termination the lanes
-            // would idle under predication anyway, and keeping the step out of a divergent region lets ptxas feed its
-            // constants from uniform registers. The adaptive stepper does the same per attempt (adaptive_step_warp).
+        // One march step, in the flavour `kind` (StepKind).
+        auto march_step = [&](auto kind) {
+            using K = decltype(kind);
             const R th0 = y.th, r_prev = y.r;
+            R hs = R(0);
             if (METHOD == 0) {
+                // mod.rs:204,255-265: alive iff 1.001 r+ <= r <= escape radius (which of the two ended it is resolved
+                // after the loop from the frozen state)
+                if (!done && (lt_pos(y.r, r_term) || gt_pos(y.r, escape_r))) { done = true; by_radius = true; }
                 adaptive_step_warp<R, 1>(hc, y, h, R(P.tol), !done, rhs_evals);
             } else {
-                R hs = WGSL_RULE ? clampPos<R>(N::fma_(y.r, R(0.15), hs_bias), R(0.05), R(1.0)) : R(P.h0);
+                // Hot path of the radius tests (f64): ONE unsigned range test on the high word of r says "strictly inside
+                // (lo, escape_r)", lo = 1.001 r+ or, in HCONST chunks, the radius where the step rule saturates. Only a
+                // ray outside that window -- at a boundary, or a numerically blown-up one that broke the chunk's travel
+                // bound -- takes the exact tests and the generic step rule, so termination and step size are exact for
+                // every ray in every f64 zone. (Measured alternatives: no test at all is 0.9 % faster and gets the step
+                // count of ~10 blown-up rays per 4K frame wrong; parking such rays and replaying them after the chunk is
+                // exact too, and 1 % slower than these predicated instructions.)
+                bool inside;
+                if (sizeof(R) == 8) inside = ((uint32_t)hiword(y.r) - P.alive_lo[K::hconst ? 1 : 0]) < P.alive_span[K::hconst ? 1 : 0];
+                else inside = K::hconst ? (y.r > R(P.r_sat) && y.r < escape_r) : false;
+                hs = K::hconst ? R(P.h_const) : (WGSL_RULE ? clampPos<R>(N::fma_(y.r, R(0.15), hs_bias), R(0.05), R(1.0)) : R(P.h0));
+                if (!inside && !done) {
+                    if (lt_pos(y.r, r_term) || gt_pos(y.r, escape_r)) { done = true; by_radius = true; }
+                    // f32-predictor (FAR) chunks hold rays on their way out beyond r_far; one that blew up terminates here
+                    // like everywhere else, but the step rule is not re-derived for a garbage radius that happens to land
+                    // inside (1.001 r+, r_sat) -- the one place where that precision mode is not exact by construction.
+                    if (K::hconst && !K::far) hs = WGSL_RULE ? clampPos<R>(N::fma_(y.r, R(0.15), hs_bias), R(0.05), R(1.0)) : R(P.h0);
+                }
+                // Fixed-step methods run the step for every lane, finished rays with h = 0 on their frozen state (nothing to
+                // select back afterwards): in budget accounting that IS the definition; with natural termination the lanes
+                // would idle under predication anyway, and keeping the step out of a divergent region lets ptxas feed its
+                // constants from uniform registers. The adaptive stepper does the same per attempt (adaptive_step_warp).
                 if (done) hs = R(0);
                 if (METHOD == 1) { step_rk4<R, 1, DEBUG>(hc, y, hs); rhs_evals += (BUDGET || !done) ? 4u : 0u; }
                 else {
-                    if constexpr (MIXED && FAR) step_symplectic_mixed<DEBUG, WGSL_RULE>(hc, hcf, y, hs, (float)hs_bias, (float)P.h0, done);
-                    else step_symplectic<R, 1, DEBUG>(hc, y, hs);
+                    if constexpr (MIXED && K::far) step_symplectic_mixed<DEBUG>(hc, hcf, y, hs, done ? 0.0f : P.f32_hconst);
+                    else step_symplectic<R, 1, DEBUG, K::polar>(hc, y, hs);
                     rhs_evals += (BUDGET || !done) ? 3u : 0u;
                 }
             }
@@ -384,20 +423,36 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
                 }
             }
         };
+        // The implicit-midpoint march is specialised per 8-step chunk (one warp vote per chunk, like the early exit, so
+        // the step loops themselves stay free of warp-synchronising instructions). Every instruction of the loop body is
+        // an issue slot -- FP64 instructions take two -- and the kernel is bound by exactly that (profiles/),
+        // so what a zone does not need is compiled out of its loop rather than predicated off:
+        //   zone 0  generic: step rule + exact radius tests; with the polar clamp iff the tile holds a polar-risk ray
+        //   zone 1  r_hconst < r < r_escape_guard for every live ray: h = h_const, no polar clamp
+        //   zone 2  (GVT_PRECISION_MIXED) additionally r > r_far and p_r > 0: f32 predictors
+        const bool polar_tile = METHOD != 2 || __any_sync(0xffffffffu, polar_ray);
         for (uint32_t it0 = 0; it0 < P.max_steps; it0 += CHUNK) {
             if (!BUDGET) { if (__all_sync(0xffffffffu, done)) break; }
             const uint32_t it1 = min(it0 + CHUNK, P.max_steps);
-            // GVT_PRECISION_MIXED: the warp takes the f32-predictor stepper for this chunk iff every live ray is on its
-            // way out (p_r > 0) beyond r_far, a chunk's worth of steps clear of r_switch, and away from the polar axis.
-            // Voted once per chunk, like the early exit, so the step loops stay free of warp-synchronising instructions.
-            bool far_chunk = false;
-            if (MIXED) far_chunk = __all_sync(0xffffffffu, done || (y.r > R(P.r_far) && y.pr > R(0) && N::abs_(y.th - half_pi) < R(1.45)));
-            if (MIXED && far_chunk) {
+            uint32_t zone = 0u;
+            if (METHOD == 2 && !polar_tile) {
+                const bool z1 = y.r > R(P.r_hconst) && y.r < R(P.r_escape_guard);
+                const uint32_t lane_zone = done ? 2u : (!z1 ? 0u : ((MIXED && y.r > R(P.r_far) && y.pr > R(0)) ? 2u : 1u));
+                zone = __reduce_min_sync(0xffffffffu, lane_zone);
+                if (!MIXED) zone = min(zone, 1u);
+            }
+            if (MIXED && zone == 2u) {
 #pragma unroll(kUnrollFar)
-                for (uint32_t it = it0; it < it1; it++) march_step(FarStep<true>{});
+                for (uint32_t it = it0; it < it1; it++) march_step(StepKind<true, true, false>{});
+            } else if (METHOD == 2 && zone >= 1u) {
+#pragma unroll(MIXED ? kUnrollNearMixed : kUnrollSymp)
+                for (uint32_t it = it0; it < it1; it++) march_step(StepKind<false, true, false>{});
+            } else if (METHOD == 2 && !polar_tile) {
+#pragma unroll(MIXED ? kUnrollNearMixed : kUnrollSymp)
+                for (uint32_t it = it0; it < it1; it++) march_step(StepKind<false, false, false>{});
             } else {
-#pragma unroll(METHOD == 0 ? 1 : (MIXED ? kUnrollNearMixed : kUnrollNear))
-                for (uint32_t it = it0; it < it1; it++) march_step(FarStep<false>{});
+#pragma unroll(METHOD == 1 ? kUnrollNear : 1)
+                for (uint32_t it = it0; it < it1; it++) march_step(StepKind<false, false, true>{});
             }
         }
         if (by_radius) term = (y.r < r_term) ? 1u : 2u;   // Horizon is tested first (mod.rs:257-263)
