@@ -719,6 +719,8 @@ static void fill_taa(const GvtCamera* cam, uint32_t W, uint32_t H, TaaParams& T)
     T.width = W; T.height = H; T.row0 = 0; T.row1 = H; T.host_out = nullptr; T.n_peer = 0;
     T.stripe = StripeMap{0u, 0u, 1u, 0u}; T.n_stripes = 0;
     T.mode = 0; T.blend = 0.75f; T.moving = 0;
+    memcpy(T.m_inv_proj, cam->inv_proj, 64); memcpy(T.m_inv_view, cam->inv_view, 64); memcpy(T.m_prev_vp, cam->prev_view_proj, 64);
+    memcpy(T.cam_pos, cam->position, 16);
 }
 
 static size_t format_bytes(uint32_t f) { return f == GVT_FORMAT_RGBA32F ? 16 : (f == GVT_FORMAT_RGBA16F ? 8 : 4); }
@@ -797,6 +799,8 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
     const bool interleave = (rp->flags & GVT_FLAG_ROW_INTERLEAVE) != 0 && r->world > 1;
     if (interleave && (!(rp->flags & GVT_FLAG_PEER_STORE) || (rp->flags & GVT_FLAG_NO_GATHER)))
         return fail(GVT_ERR_INVALID, "GVT_FLAG_ROW_INTERLEAVE needs the GVT_FLAG_PEER_STORE gather");
+    if (interleave && (rp->flags & GVT_FLAG_TAA_PRECISE))
+        return fail(GVT_ERR_UNSUPPORTED, "GVT_FLAG_TAA_PRECISE (the validation build of the resolve) runs on row blocks only");
     StripeMap sm = {0u, 0u, (uint32_t)r->world, (uint32_t)r->rank};
     uint32_t n_my = 0, n_own = row1 - row0;
     if (interleave) {
@@ -888,7 +892,8 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
         }
         T.host_out = host_alias;
         if (peer_store) { for (uint32_t q = 0; q < n_peer; q++) T.peer_out[q] = peer_targets[q]; T.n_peer = n_peer; }
-        CK(launch_taa(T, r->sm_count, r->stream));
+        if (rp->flags & GVT_FLAG_TAA_PRECISE) CK(launch_taa_precise(T, r->stream));
+        else CK(launch_taa(T, r->sm_count, r->stream));
         launches++;
     }
     CK(cudaEventRecord(r->ev[3], r->stream));
@@ -1018,7 +1023,9 @@ extern "C" int32_t gvt_render_fragment_glsl(gvt_renderer* r, const GvtGlslUnifor
 // rendering/bloom.ts:446-632 on the finished frame
 extern "C" int32_t gvt_render_bloom(gvt_renderer* r, const GvtBloomConfig* cfg, uint32_t output_format, void* host_out, double* ms) {
     if (!r || !cfg) return fail(GVT_ERR_INVALID, "null argument");
-    if (cfg->struct_size != sizeof(GvtBloomConfig)) return fail(GVT_ERR_INVALID, "GvtBloomConfig.struct_size = %u", cfg->struct_size);
+    if (cfg->struct_size < offsetof(GvtBloomConfig, precise) || cfg->struct_size > sizeof(GvtBloomConfig))
+        return fail(GVT_ERR_INVALID, "GvtBloomConfig.struct_size = %u", cfg->struct_size);
+    const bool bloom_precise = cfg->struct_size >= sizeof(GvtBloomConfig) && cfg->precise != 0;
     if (!r->frame || r->width == 0) return fail(GVT_ERR_INVALID, "no frame rendered yet");
     if (output_format != GVT_FORMAT_RGBA32F && output_format != GVT_FORMAT_RGBA16F && output_format != GVT_FORMAT_RGBA8_UNORM)
         return fail(GVT_ERR_INVALID, "bloom output is display-referred: RGBA32F, RGBA16F or RGBA8_UNORM");
@@ -1042,7 +1049,7 @@ extern "C" int32_t gvt_render_bloom(gvt_renderer* r, const GvtBloomConfig* cfg, 
     int launches = 0;
     CK(cudaEventRecord(r->ev[0], r->stream));
     CK(launch_bloom(r->frame, W, H, r->bloom_half, r->bloom_q1, r->bloom_q2, r->display, cfg->threshold, cfg->intensity,
-                    (int)cfg->blur_passes, cfg->enabled ? 1 : 0, r->sm_count, r->stream, &launches));
+                    (int)cfg->blur_passes, cfg->enabled ? 1 : 0, r->sm_count, r->stream, &launches, bloom_precise));
     CK(cudaEventRecord(r->ev[1], r->stream));
     if (host_out) {
         const size_t n_px = (size_t)W * H;
@@ -1116,6 +1123,36 @@ extern "C" int32_t gvt_trace_states(gvt_renderer* r, const GvtCamera* cam, const
     if (rgba64) CK(cudaMemcpyAsync(rgba64, r->d_rgba, n * 4 * sizeof(double), cudaMemcpyDeviceToHost, r->stream));
     CK(cudaStreamSynchronize(r->stream));
     return GVT_OK;
+}
+
+static int32_t taa_host_frames(gvt_renderer* r, TaaParams& T, uint32_t width, uint32_t height, const float* cur, const float* hist,
+                               float* out, int32_t precise, double* ms_out) {
+    CK(cudaSetDevice(r->device));
+    const size_t bytes = (size_t)width * height * sizeof(float4);
+    DevBuf b_cur, b_hist, b_out;
+    CK(b_cur.alloc(bytes)); CK(b_hist.alloc(bytes)); CK(b_out.alloc(bytes));
+    float4 *d_cur = b_cur.as<float4>(), *d_hist = b_hist.as<float4>(), *d_out = b_out.as<float4>();
+    CK(cudaMemcpyAsync(d_cur, cur, bytes, cudaMemcpyHostToDevice, r->stream));
+    CK(cudaMemcpyAsync(d_hist, hist, bytes, cudaMemcpyHostToDevice, r->stream));
+    T.cur = d_cur; T.hist = d_hist; T.out = d_out;
+    CK(cudaEventRecord(r->ev[0], r->stream));
+    if (precise) CK(launch_taa_precise(T, r->stream)); else CK(launch_taa(T, r->sm_count, r->stream));
+    CK(cudaEventRecord(r->ev[1], r->stream));
+    CK(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, r->stream));
+    CK(cudaStreamSynchronize(r->stream));
+    if (ms_out) { float t = 0.f; cudaEventElapsedTime(&t, r->ev[0], r->ev[1]); *ms_out = t; }
+    return GVT_OK;
+}
+
+extern "C" int32_t gvt_taa_resolve_ex(gvt_renderer* r, const GvtCamera* cam, uint32_t width, uint32_t height, const float* cur,
+                                      const float* hist, float* out, uint32_t webgl, float blend, int32_t camera_moving,
+                                      int32_t precise, double* ms_out) {
+    if (!r || (!cam && !webgl) || !cur || !hist || !out || width == 0 || height == 0) return fail(GVT_ERR_INVALID, "bad argument");
+    TaaParams T;
+    if (cam) fill_taa(cam, width, height, T);
+    else { memset(&T, 0, sizeof(T)); T.width = width; T.height = height; T.row1 = height; T.stripe = StripeMap{0u, 0u, 1u, 0u}; }
+    if (webgl) { T.mode = 1; T.blend = blend; T.moving = camera_moving ? 1u : 0u; }
+    return taa_host_frames(r, T, width, height, cur, hist, out, precise, ms_out);
 }
 
 extern "C" int32_t gvt_taa_resolve(gvt_renderer* r, const GvtCamera* cam, uint32_t width, uint32_t height, const float* cur,

@@ -26,20 +26,30 @@ __device__ __forceinline__ float4 fetch(const Tex16& t, int x, int y) {
 }
 __device__ __forceinline__ float4 fetch(const Tex32& t, int x, int y) { return __ldg(t.p + (size_t)y * t.w + x); }
 
+// PRECISE = true is the validation build: every operation an explicitly rounded IEEE f32 operation (no FMA contraction,
+// IEEE division, libm powf) in the order the GLSL text evaluates them, so that the pass can be tested to 1e-6 against
+// the numpy restatement of bloom.glsl.ts and the production build's FMA / MUFU shortcuts become a measured difference.
+template <bool PRECISE> __device__ __forceinline__ float mul_(float a, float b) { return PRECISE ? __fmul_rn(a, b) : a * b; }
+template <bool PRECISE> __device__ __forceinline__ float add_(float a, float b) { return PRECISE ? __fadd_rn(a, b) : a + b; }
+template <bool PRECISE> __device__ __forceinline__ float sub_(float a, float b) { return PRECISE ? __fadd_rn(a, -b) : a - b; }
+template <bool PRECISE> __device__ __forceinline__ float div_(float a, float b) { return PRECISE ? __fdiv_rn(a, b) : a / b; }
+// a + (b - a) t
+template <bool PRECISE> __device__ __forceinline__ float lerp_(float a, float b, float t) { return add_<PRECISE>(a, mul_<PRECISE>(sub_<PRECISE>(b, a), t)); }
+
 // texture(sampler, uv) with LINEAR min/mag filter and CLAMP_TO_EDGE
-template <class T> __device__ __forceinline__ float4 sample_linear(const T& t, float u, float v) {
-    const float x = u * (float)t.w - 0.5f, y = v * (float)t.h - 0.5f;
+template <bool PRECISE, class T> __device__ __forceinline__ float4 sample_linear(const T& t, float u, float v) {
+    const float x = sub_<PRECISE>(mul_<PRECISE>(u, (float)t.w), 0.5f), y = sub_<PRECISE>(mul_<PRECISE>(v, (float)t.h), 0.5f);
     const float xf = floorf(x), yf = floorf(y);
-    const float fx = x - xf, fy = y - yf;
+    const float fx = sub_<PRECISE>(x, xf), fy = sub_<PRECISE>(y, yf);
     const int xi = (int)xf, yi = (int)yf;
     const int x0 = min(max(xi, 0), t.w - 1), x1 = min(max(xi + 1, 0), t.w - 1);
     const int y0 = min(max(yi, 0), t.h - 1), y1 = min(max(yi + 1, 0), t.h - 1);
     const float4 a = fetch(t, x0, y0), b = fetch(t, x1, y0), c = fetch(t, x0, y1), d = fetch(t, x1, y1);
     float4 o;
-    { const float tp = a.x + (b.x - a.x) * fx, bt = c.x + (d.x - c.x) * fx; o.x = tp + (bt - tp) * fy; }
-    { const float tp = a.y + (b.y - a.y) * fx, bt = c.y + (d.y - c.y) * fx; o.y = tp + (bt - tp) * fy; }
-    { const float tp = a.z + (b.z - a.z) * fx, bt = c.z + (d.z - c.z) * fx; o.z = tp + (bt - tp) * fy; }
-    { const float tp = a.w + (b.w - a.w) * fx, bt = c.w + (d.w - c.w) * fx; o.w = tp + (bt - tp) * fy; }
+    o.x = lerp_<PRECISE>(lerp_<PRECISE>(a.x, b.x, fx), lerp_<PRECISE>(c.x, d.x, fx), fy);
+    o.y = lerp_<PRECISE>(lerp_<PRECISE>(a.y, b.y, fx), lerp_<PRECISE>(c.y, d.y, fx), fy);
+    o.z = lerp_<PRECISE>(lerp_<PRECISE>(a.z, b.z, fx), lerp_<PRECISE>(c.z, d.z, fx), fy);
+    o.w = lerp_<PRECISE>(lerp_<PRECISE>(a.w, b.w, fx), lerp_<PRECISE>(c.w, d.w, fx), fy);
     return o;
 }
 __device__ __forceinline__ uint2 pack_half4(float4 v) {
@@ -48,46 +58,57 @@ __device__ __forceinline__ uint2 pack_half4(float4 v) {
     o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
     return o;
 }
+// texel-centre coordinate (i + 0.5) / n
+template <bool PRECISE> __device__ __forceinline__ float centre_(int i, int n) { return div_<PRECISE>(add_<PRECISE>((float)i, 0.5f), (float)n); }
 
+template <bool PRECISE>
 __global__ void k_bloom_bright(Tex32 scene, uint2* __restrict__ dst, int dw, int dh, float threshold) {
     const int n = dw * dh;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int x = i % dw, y = i / dw;
-        const float4 c = sample_linear(scene, ((float)x + 0.5f) / (float)dw, ((float)y + 0.5f) / (float)dh);
-        const float lum = c.x * 0.299f + c.y * 0.587f + c.z * 0.114f;
+        const float4 c = sample_linear<PRECISE>(scene, centre_<PRECISE>(x, dw), centre_<PRECISE>(y, dh));
+        const float lum = add_<PRECISE>(add_<PRECISE>(mul_<PRECISE>(c.x, 0.299f), mul_<PRECISE>(c.y, 0.587f)), mul_<PRECISE>(c.z, 0.114f));
         dst[i] = pack_half4(lum > threshold ? c : make_float4(0.f, 0.f, 0.f, 0.f));
     }
 }
 
+template <bool PRECISE>
 __global__ void k_bloom_blur(Tex16 src, uint2* __restrict__ dst, int dw, int dh, float dirx, float diry) {
     const float wgt[5] = {0.227027f, 0.1945946f, 0.1216216f, 0.054054f, 0.016216f};
     const int n = dw * dh;
-    const float tx = 1.0f / (float)dw, ty = 1.0f / (float)dh;   // texelSize = 1 / u_resolution (the blur target's size)
+    const float tx = div_<PRECISE>(1.0f, (float)dw), ty = div_<PRECISE>(1.0f, (float)dh);   // texelSize = 1 / u_resolution (the blur target's size)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int x = i % dw, y = i / dw;
-        const float u = ((float)x + 0.5f) / (float)dw, v = ((float)y + 0.5f) / (float)dh;
-        float4 c = sample_linear(src, u, v);
-        float r = c.x * wgt[0], g = c.y * wgt[0], b = c.z * wgt[0];
+        const float u = centre_<PRECISE>(x, dw), v = centre_<PRECISE>(y, dh);
+        float4 c = sample_linear<PRECISE>(src, u, v);
+        float r = mul_<PRECISE>(c.x, wgt[0]), g = mul_<PRECISE>(c.y, wgt[0]), b = mul_<PRECISE>(c.z, wgt[0]);
 #pragma unroll
         for (int k = 1; k < 5; k++) {
-            const float ox = dirx * tx * (float)k, oy = diry * ty * (float)k;
-            c = sample_linear(src, u + ox, v + oy);
-            r += c.x * wgt[k]; g += c.y * wgt[k]; b += c.z * wgt[k];
-            c = sample_linear(src, u - ox, v - oy);
-            r += c.x * wgt[k]; g += c.y * wgt[k]; b += c.z * wgt[k];
+            const float ox = mul_<PRECISE>(mul_<PRECISE>(dirx, tx), (float)k), oy = mul_<PRECISE>(mul_<PRECISE>(diry, ty), (float)k);
+            c = sample_linear<PRECISE>(src, add_<PRECISE>(u, ox), add_<PRECISE>(v, oy));
+            r = add_<PRECISE>(r, mul_<PRECISE>(c.x, wgt[k])); g = add_<PRECISE>(g, mul_<PRECISE>(c.y, wgt[k])); b = add_<PRECISE>(b, mul_<PRECISE>(c.z, wgt[k]));
+            c = sample_linear<PRECISE>(src, sub_<PRECISE>(u, ox), sub_<PRECISE>(v, oy));
+            r = add_<PRECISE>(r, mul_<PRECISE>(c.x, wgt[k])); g = add_<PRECISE>(g, mul_<PRECISE>(c.y, wgt[k])); b = add_<PRECISE>(b, mul_<PRECISE>(c.z, wgt[k]));
         }
         dst[i] = pack_half4(make_float4(r, g, b, 1.0f));
     }
 }
 
 // bloom.glsl.ts:106-124. The combine pass is one read + one write of the frame; IEEE division and libm powf (three of
-// each per pixel, with their slow-path branches) made it issue-bound at 2.5 TB/s, so the final pass uses MUFU
-// rcp / lg2 / ex2 like the GLSL it restates (~1e-6 on a display-referred value that is quantised to 8 bits next).
-__device__ __forceinline__ float aces_gamma_f(float x) {
+// each per pixel, with their slow-path branches) made it issue-bound at 2.5 TB/s, so the production pass uses MUFU
+// rcp / lg2 / ex2 like the GLSL it restates (~1e-6 on a display-referred value that is quantised to 8 bits next);
+// the PRECISE build keeps IEEE division and powf.
+template <bool PRECISE> __device__ __forceinline__ float aces_gamma_f(float x) {
+    if (PRECISE) {
+        const float num = __fmul_rn(x, __fadd_rn(__fmul_rn(2.51f, x), 0.03f));
+        const float den = __fadd_rn(__fmul_rn(x, __fadd_rn(__fmul_rn(2.43f, x), 0.59f)), 0.14f);
+        return powf(fminf(fmaxf(__fdiv_rn(num, den), 0.0f), 1.0f), 0.4545f);
+    }
     const float t = fminf(fmaxf(__fdividef(x * (2.51f * x + 0.03f), x * (2.43f * x + 0.59f) + 0.14f), 0.0f), 1.0f);
     return t > 0.0f ? exp2f(0.4545f * __log2f(t)) : 0.0f;
 }
 
+template <bool PRECISE>
 __global__ void k_bloom_combine(Tex32 scene, Tex16 bloom, float4* __restrict__ dst, float intensity, int use_bloom) {
     // one thread per pixel, rows on blockIdx.y (no 64-bit division in the index arithmetic)
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -96,11 +117,37 @@ __global__ void k_bloom_combine(Tex32 scene, Tex16 bloom, float4* __restrict__ d
         const float4 s = __ldg(scene.p + i);                      // the scene is sampled at its own texel centres
         float r = s.x, g = s.y, b = s.z;
         if (use_bloom) {
-            const float4 bl = sample_linear(bloom, ((float)x + 0.5f) / (float)scene.w, ((float)y + 0.5f) / (float)scene.h);
-            r = r + bl.x * intensity; g = g + bl.y * intensity; b = b + bl.z * intensity;
+            const float4 bl = sample_linear<PRECISE>(bloom, centre_<PRECISE>(x, scene.w), centre_<PRECISE>(y, scene.h));
+            r = add_<PRECISE>(r, mul_<PRECISE>(bl.x, intensity)); g = add_<PRECISE>(g, mul_<PRECISE>(bl.y, intensity));
+            b = add_<PRECISE>(b, mul_<PRECISE>(bl.z, intensity));
         }
-        dst[i] = make_float4(aces_gamma_f(r), aces_gamma_f(g), aces_gamma_f(b), 1.0f);
+        dst[i] = make_float4(aces_gamma_f<PRECISE>(r), aces_gamma_f<PRECISE>(g), aces_gamma_f<PRECISE>(b), 1.0f);
     }
+}
+
+template <bool PRECISE>
+cudaError_t launch_bloom_t(const float4* frame, int W, int H, uint2* half_tex, uint2* q1, uint2* q2, float4* display,
+                           float threshold, float intensity, int blur_passes, int enabled, int sm_count, cudaStream_t stream,
+                           int* launches) {
+    const int hw = max(1, W / 2), hh = max(1, H / 2), bw = max(1, W / 4), bh = max(1, H / 4);
+    const Tex32 scene{frame, W, H};
+    const int grid = sm_count * 8;
+    Tex16 result{q2, bw, bh};
+    if (enabled) {
+        k_bloom_bright<PRECISE><<<grid, 256, 0, stream>>>(scene, half_tex, hw, hh, threshold);
+        (*launches)++;
+        Tex16 src{half_tex, hw, hh};
+        for (int i = 0; i < blur_passes; i++) {
+            k_bloom_blur<PRECISE><<<grid, 256, 0, stream>>>(src, q1, bw, bh, 1.0f, 0.0f);
+            k_bloom_blur<PRECISE><<<grid, 256, 0, stream>>>(Tex16{q1, bw, bh}, q2, bw, bh, 0.0f, 1.0f);
+            (*launches) += 2;
+            src = Tex16{q2, bw, bh};
+        }
+        result = src;   // blurPasses = 0: the bright texture itself is combined (bloom.ts:517-546)
+    }
+    k_bloom_combine<PRECISE><<<dim3((unsigned)((W + 255) / 256), (unsigned)min(H, 65535)), 256, 0, stream>>>(scene, result, display, intensity, enabled);
+    (*launches)++;
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -108,26 +155,9 @@ __global__ void k_bloom_combine(Tex32 scene, Tex16 bloom, float4* __restrict__ d
 // scratch: half = (W/2)*(H/2) uint2, q1 / q2 = (W/4)*(H/4) uint2 each. `display` receives the final frame.
 cudaError_t launch_bloom(const float4* frame, int W, int H, uint2* half_tex, uint2* q1, uint2* q2, float4* display,
                          float threshold, float intensity, int blur_passes, int enabled, int sm_count, cudaStream_t stream,
-                         int* launches) {
-    const int hw = max(1, W / 2), hh = max(1, H / 2), bw = max(1, W / 4), bh = max(1, H / 4);
-    const Tex32 scene{frame, W, H};
-    const int grid = sm_count * 8;
-    Tex16 result{q2, bw, bh};
-    if (enabled) {
-        k_bloom_bright<<<grid, 256, 0, stream>>>(scene, half_tex, hw, hh, threshold);
-        (*launches)++;
-        Tex16 src{half_tex, hw, hh};
-        for (int i = 0; i < blur_passes; i++) {
-            k_bloom_blur<<<grid, 256, 0, stream>>>(src, q1, bw, bh, 1.0f, 0.0f);
-            k_bloom_blur<<<grid, 256, 0, stream>>>(Tex16{q1, bw, bh}, q2, bw, bh, 0.0f, 1.0f);
-            (*launches) += 2;
-            src = Tex16{q2, bw, bh};
-        }
-        result = src;   // blurPasses = 0: the bright texture itself is combined (bloom.ts:517-546)
-    }
-    k_bloom_combine<<<dim3((unsigned)((W + 255) / 256), (unsigned)min(H, 65535)), 256, 0, stream>>>(scene, result, display, intensity, enabled);
-    (*launches)++;
-    return cudaGetLastError();
+                         int* launches, bool precise) {
+    return precise ? launch_bloom_t<true>(frame, W, H, half_tex, q1, q2, display, threshold, intensity, blur_passes, enabled, sm_count, stream, launches)
+                   : launch_bloom_t<false>(frame, W, H, half_tex, q1, q2, display, threshold, intensity, blur_passes, enabled, sm_count, stream, launches);
 }
 
 }  // namespace gvt

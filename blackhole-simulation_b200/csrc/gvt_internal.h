@@ -103,6 +103,8 @@ struct TaaParams {
     uint32_t unit_rows;    // rows per warp work unit (chosen by launch_taa)
     StripeMap stripe;      // s != 0: resolve this rank's n_stripes stripes (rows [(t world + rank) s, +s)) instead of [row0, row1)
     uint32_t n_stripes;
+    // k_taa_resolve_precise only: the raw uniforms (types/webgpu.ts:67-116), column-major
+    float m_inv_proj[16], m_inv_view[16], m_prev_vp[16], cam_pos[4];
 };
 
 // k_fragment_glsl (gvt_fragment.cu): the production WebGL2 fragment shader
@@ -125,10 +127,11 @@ cudaError_t launch_trace(const FrameParams& p, int method, int precision, bool b
                          cudaStream_t stream);
 cudaError_t launch_integrate_rays(const RayBatchParams& p, cudaStream_t stream);
 cudaError_t launch_taa(const TaaParams& p, int sm_count, cudaStream_t stream);
+cudaError_t launch_taa_precise(const TaaParams& p, cudaStream_t stream);   // IEEE build, one thread per pixel (row blocks only)
 cudaError_t launch_fragment_glsl(const GlslParams& p, int precision, int sm_count, cudaStream_t stream);
 cudaError_t launch_bloom(const float4* frame, int W, int H, uint2* half_tex, uint2* q1, uint2* q2, float4* display,
                          float threshold, float intensity, int blur_passes, int enabled, int sm_count, cudaStream_t stream,
-                         int* launches);
+                         int* launches, bool precise = false);
 cudaError_t launch_fragment_glsl_fast(const GlslParams& p, int sm_count, cudaStream_t stream);   // f32, MUFU maths
 cudaError_t launch_f32_to_f16(const float4* src, void* dst, size_t n_px, cudaStream_t stream);
 cudaError_t launch_tonemap_rgba8(const float4* src, void* dst, size_t n_px, int aces, cudaStream_t stream);

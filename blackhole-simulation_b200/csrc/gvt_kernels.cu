@@ -893,6 +893,119 @@ cudaError_t launch_taa(const TaaParams& p_in, int sm_count, cudaStream_t stream)
     return cudaGetLastError();
 }
 
+// --------------------------------------------------------------------------------------------------
+// The PRECISE build of the resolve: one thread per pixel, every operation an explicitly rounded IEEE f32 operation
+// (__fadd_rn / __fmul_rn / __fdiv_rn / __fsqrt_rn: never contracted into FMAs, never approximated) in the order the
+// shader text evaluates them -- ataa.wgsl.ts:28-83 with the UNFOLDED reprojection chain of :54-69 (inv_proj, normalise,
+// inv_view, + 12 d, prev_view_proj as three mat4 x vec4 products), reprojection.glsl.ts:70-115 for MODE 1. It exists so
+// that the resolve's SEMANTICS can be tested to 1e-6 against the numpy restatement (tests/test_gpu_taa.py), and so that
+// what the production kernel's MUFU.SQRT / MUFU.RCP / MUFU.RSQ, host-folded matrices and shuffle-order sums cost in
+// accuracy is a measured number (fast vs precise) instead of an argument. ~4x slower than k_taa_resolve; never on the
+// frame path unless GVT_FLAG_TAA_PRECISE asks for it.
+// --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ycocg_rn(float r, float g, float b, float& y, float& co, float& cg) {   // ataa.wgsl.ts:11-16
+    y = __fadd_rn(__fadd_rn(__fmul_rn(0.25f, r), __fmul_rn(0.5f, g)), __fmul_rn(0.25f, b));
+    co = __fadd_rn(__fmul_rn(0.5f, r), -__fmul_rn(0.5f, b));
+    cg = __fadd_rn(__fadd_rn(__fmul_rn(-0.25f, r), __fmul_rn(0.5f, g)), -__fmul_rn(0.25f, b));
+}
+// column-major mat4 x vec4, terms summed in column order (((m0 v0 + m1 v1) + m2 v2) + m3 v3)
+__device__ __forceinline__ void mat_vec_rn(const float* m, const float v[4], float out[4]) {
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+        out[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[r], v[0]), __fmul_rn(m[4 + r], v[1])), __fmul_rn(m[8 + r], v[2])),
+                           __fmul_rn(m[12 + r], v[3]));
+}
+template <int MODE>
+__global__ void __launch_bounds__(256) k_taa_resolve_precise(const __grid_constant__ TaaParams P) {
+    const int W = (int)P.width, H = (int)P.height;
+    const int x = (int)(blockIdx.x * 32u + (threadIdx.x & 31u));
+    const int y = (int)P.row0 + (int)(blockIdx.y * 8u + (threadIdx.x >> 5));
+    if (x >= W || y >= (int)P.row1) return;
+    float m1[3] = {0.f, 0.f, 0.f}, m2[3] = {0.f, 0.f, 0.f}, c0[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+        for (int dx = -1; dx <= 1; dx++) {                                          // ataa.wgsl.ts:36-48, clamp :43
+            const float4 p = P.cur[(size_t)min(max(y + dy, 0), H - 1) * W + min(max(x + dx, 0), W - 1)];
+            float s[3];
+            ycocg_rn(p.x, p.y, p.z, s[0], s[1], s[2]);
+#pragma unroll
+            for (int i = 0; i < 3; i++) { m1[i] = __fadd_rn(m1[i], s[i]); m2[i] = __fadd_rn(m2[i], __fmul_rn(s[i], s[i])); }
+            if (dy == 0 && dx == 0) { c0[0] = s[0]; c0[1] = s[1]; c0[2] = s[2]; }
+        }
+    const float nsig = (MODE == 1) ? 1.5f : 2.0f;
+    float lo[3], hi[3], sd0 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float mean = __fdiv_rn(m1[i], 9.0f);
+        const float sd = __fsqrt_rn(fmaxf(__fadd_rn(__fdiv_rn(m2[i], 9.0f), -__fmul_rn(mean, mean)), 0.0f));
+        if (i == 0) sd0 = sd;
+        lo[i] = __fadd_rn(mean, -__fmul_rn(nsig, sd)); hi[i] = __fadd_rn(mean, __fmul_rn(nsig, sd));
+    }
+    float hr, hg, hb, alpha;
+    if (MODE == 1) {
+        const float4 h = P.hist[(size_t)y * W + x];                                 // same texel (reprojection.glsl.ts:93-110)
+        hr = h.x; hg = h.y; hb = h.z;
+        const float wv = __fadd_rn(1.0f, -fminf(fmaxf(__fmul_rn(sd0, 4.0f), 0.0f), 0.55f));
+        alpha = P.moving ? 0.0f : __fmul_rn(P.blend, wv);
+    } else {
+        // ataa.wgsl.ts:54-69
+        const float u = __fdiv_rn(__fadd_rn((float)x, 0.5f), (float)W), v = __fdiv_rn(__fadd_rn((float)y, 0.5f), (float)H);
+        const float clip[4] = {__fadd_rn(__fmul_rn(u, 2.0f), -1.0f), -__fadd_rn(__fmul_rn(v, 2.0f), -1.0f), 1.0f, 1.0f};
+        float vt[4];
+        mat_vec_rn(P.m_inv_proj, clip, vt);
+        float vd[3] = {__fdiv_rn(vt[0], vt[3]), __fdiv_rn(vt[1], vt[3]), __fdiv_rn(vt[2], vt[3])};
+        const float n = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(vd[0], vd[0]), __fmul_rn(vd[1], vd[1])), __fmul_rn(vd[2], vd[2])));
+        const float d4[4] = {__fdiv_rn(vd[0], n), __fdiv_rn(vd[1], n), __fdiv_rn(vd[2], n), 0.0f};
+        float wd[4];
+        mat_vec_rn(P.m_inv_view, d4, wd);
+        const float wp[4] = {__fadd_rn(P.cam_pos[0], __fmul_rn(wd[0], 12.0f)), __fadd_rn(P.cam_pos[1], __fmul_rn(wd[1], 12.0f)),
+                             __fadd_rn(P.cam_pos[2], __fmul_rn(wd[2], 12.0f)), 1.0f};
+        float pc[4];
+        mat_vec_rn(P.m_prev_vp, wp, pc);
+        const float pu = __fadd_rn(__fmul_rn(__fdiv_rn(pc[0], pc[3]), 0.5f), 0.5f);
+        const float pv = __fadd_rn(__fmul_rn(__fdiv_rn(pc[1], pc[3]), -0.5f), 0.5f);
+        // textureSampleLevel + linear sampler, clamp-to-edge (ataa.wgsl.ts:72)
+        const float fx_ = fminf(fmaxf(__fadd_rn(__fmul_rn(pu, (float)W), -0.5f), 0.0f), (float)(W - 1));
+        const float fy_ = fminf(fmaxf(__fadd_rn(__fmul_rn(pv, (float)H), -0.5f), 0.0f), (float)(H - 1));
+        const int x0 = (int)floorf(fx_), y0 = (int)floorf(fy_);
+        const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+        const float fx = __fadd_rn(fx_, -(float)x0), fy = __fadd_rn(fy_, -(float)y0);
+        const float4 t00 = P.hist[(size_t)y0 * W + x0], t10 = P.hist[(size_t)y0 * W + x1];
+        const float4 t01 = P.hist[(size_t)y1 * W + x0], t11 = P.hist[(size_t)y1 * W + x1];
+        auto bil = [&](float a00, float a10, float a01, float a11) {
+            const float top = __fadd_rn(a00, __fmul_rn(__fadd_rn(a10, -a00), fx));
+            const float bot = __fadd_rn(a01, __fmul_rn(__fadd_rn(a11, -a01), fx));
+            return __fadd_rn(top, __fmul_rn(__fadd_rn(bot, -top), fy));
+        };
+        hr = bil(t00.x, t10.x, t01.x, t11.x); hg = bil(t00.y, t10.y, t01.y, t11.y); hb = bil(t00.z, t10.z, t01.z, t11.z);
+        alpha = 0.92f;                                                                // ataa.wgsl.ts:77
+    }
+    float hy, hco, hcg;
+    ycocg_rn(hr, hg, hb, hy, hco, hcg);
+    hy = fminf(fmaxf(hy, lo[0]), hi[0]); hco = fminf(fmaxf(hco, lo[1]), hi[1]); hcg = fminf(fmaxf(hcg, lo[2]), hi[2]);
+    // mix(center, history, alpha) = center (1 - alpha) + history alpha
+    const float ia = (MODE == 1) ? __fadd_rn(1.0f, -alpha) : 0.08f;                   // float32(1 - 0.92) = 0.08f
+    const float ry = __fadd_rn(__fmul_rn(c0[0], ia), __fmul_rn(hy, alpha));
+    const float ro = __fadd_rn(__fmul_rn(c0[1], ia), __fmul_rn(hco, alpha));
+    const float rg = __fadd_rn(__fmul_rn(c0[2], ia), __fmul_rn(hcg, alpha));
+    // YCoCgToRGB, ataa.wgsl.ts:18-26
+    const float4 px_out = make_float4(__fadd_rn(__fadd_rn(ry, ro), -rg), __fadd_rn(ry, rg), __fadd_rn(__fadd_rn(ry, -ro), -rg), 1.0f);
+    const size_t o = (size_t)y * W + x;
+    P.out[o] = px_out;
+    if (P.host_out) P.host_out[o] = px_out;
+    for (uint32_t q = 0; q < P.n_peer; q++) P.peer_out[q][o] = px_out;
+}
+
+cudaError_t launch_taa_precise(const TaaParams& p, cudaStream_t stream) {
+    const int rows = (int)p.row1 - (int)p.row0;
+    if (rows <= 0 || p.stripe.s != 0u) return rows <= 0 ? cudaSuccess : cudaErrorNotSupported;
+    const dim3 grid((p.width + 31u) / 32u, ((unsigned)rows + 7u) / 8u);
+    if (p.mode == 1u) k_taa_resolve_precise<1><<<grid, 256, 0, stream>>>(p);
+    else k_taa_resolve_precise<0><<<grid, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
 // RGBA32F -> RGBA16F (reprojection.ts:120-140 / webgpu/renderer.ts:161-180 texture format)
 __global__ void k_f32_to_f16(const float4* __restrict__ src, uint2* __restrict__ dst, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {

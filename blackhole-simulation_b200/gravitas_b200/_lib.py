@@ -22,6 +22,7 @@ STEP_CONSTANT, STEP_WGSL = 0, 1
 FLAG_JITTER, FLAG_BUDGET, FLAG_TAA, FLAG_NO_GATHER, FLAG_D2H_OWN_ROWS, FLAG_PEER_STORE, FLAG_TAA_WEBGL = 1, 2, 8, 16, 32, 64, 128
 FLAG_ROW_INTERLEAVE = 256
 FLAG_DEBUG_COUNTS = 512
+FLAG_TAA_PRECISE = 1024
 
 
 class GravitasError(RuntimeError):
@@ -64,7 +65,7 @@ class GvtGlslUniforms(C.Structure):  # chunks/common.ts:9-38 uniforms + shader-m
 
 class GvtBloomConfig(C.Structure):  # rendering/bloom.ts:22-39
     _fields_ = [("struct_size", C.c_uint32), ("enabled", C.c_uint32), ("intensity", C.c_float), ("threshold", C.c_float),
-                ("blur_passes", C.c_uint32)]
+                ("blur_passes", C.c_uint32), ("precise", C.c_uint32)]
 
 
 class GvtDeviceConfig(C.Structure):
@@ -137,6 +138,7 @@ SIGNATURES = {
                                 _u32, _u32, _u32, _u32, _pd, _pu32, _pu32, _pd, _pd]),
     "gvt_taa_resolve": (_i32, [_vp, C.POINTER(GvtCamera), _u32, _u32, _pf, _pf, _pf]),
     "gvt_taa_resolve_webgl": (_i32, [_vp, _u32, _u32, _pf, _pf, C.c_float, _i32, _pf]),
+    "gvt_taa_resolve_ex": (_i32, [_vp, C.POINTER(GvtCamera), _u32, _u32, _pf, _pf, _pf, _u32, C.c_float, _i32, _i32, C.POINTER(C.c_double)]),
     "gvt_render_reset_history": (_i32, [_vp]),
     "gvt_render_set_noise_textures": (_i32, [_vp, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), _u32]),
     "gvt_render_fragment_glsl": (_i32, [_vp, C.POINTER(GvtGlslUniforms), _u32, _u32, _u32, C.c_float, _u32, _vp,

@@ -231,34 +231,42 @@ class KerrRenderer:
                                      drift.ctypes.data_as(pd), rgba.ctypes.data_as(pd)))
         return dict(xp=xp, term=term, steps=steps, drift=drift, rgba=rgba)
 
-    def taa_resolve(self, camera, cur, hist):
+    def taa_resolve(self, camera, cur, hist, precise=False):
+        """ataa.wgsl.ts on host frames. precise=True: the validation build (IEEE f32 operations in shader order)."""
         cam = camera if isinstance(camera, GvtCamera) else pack_camera(camera)
         cur = np.ascontiguousarray(cur, np.float32)
         hist = np.ascontiguousarray(hist, np.float32)
         H, W = cur.shape[:2]
         out = np.zeros_like(cur)
         pf = C.POINTER(C.c_float)
-        check(lib().gvt_taa_resolve(self._h, C.byref(cam), W, H, cur.ctypes.data_as(pf), hist.ctypes.data_as(pf),
-                                    out.ctypes.data_as(pf)))
+        ms = C.c_double(0.0)
+        check(lib().gvt_taa_resolve_ex(self._h, C.byref(cam), W, H, cur.ctypes.data_as(pf), hist.ctypes.data_as(pf),
+                                       out.ctypes.data_as(pf), 0, 0.0, 0, 1 if precise else 0, C.byref(ms)))
+        self.last_taa_ms = ms.value
         return out
 
-    def taa_resolve_webgl(self, cur, hist, blend=0.75, camera_moving=False):
+    def taa_resolve_webgl(self, cur, hist, blend=0.75, camera_moving=False, precise=False):
         """ReprojectionManager.resolve (rendering/reprojection.ts:195-272) semantics on host frames."""
         cur = np.ascontiguousarray(cur, np.float32)
         hist = np.ascontiguousarray(hist, np.float32)
         H, W = cur.shape[:2]
         out = np.zeros_like(cur)
         pf = C.POINTER(C.c_float)
-        check(lib().gvt_taa_resolve_webgl(self._h, W, H, cur.ctypes.data_as(pf), hist.ctypes.data_as(pf), float(blend),
-                                          1 if camera_moving else 0, out.ctypes.data_as(pf)))
+        ms = C.c_double(0.0)
+        check(lib().gvt_taa_resolve_ex(self._h, None, W, H, cur.ctypes.data_as(pf), hist.ctypes.data_as(pf),
+                                       out.ctypes.data_as(pf), 1, float(blend), 1 if camera_moving else 0,
+                                       1 if precise else 0, C.byref(ms)))
+        self.last_taa_ms = ms.value
         return out
 
-    def bloom(self, enabled=True, intensity=0.5, threshold=0.8, blur_passes=2, fmt=_lib.FORMAT_RGBA32F, readback=True):
+    def bloom(self, enabled=True, intensity=0.5, threshold=0.8, blur_passes=2, fmt=_lib.FORMAT_RGBA32F, readback=True,
+              precise=False):
         """BloomManager.applyBloomToTexture / drawTextureToScreen (rendering/bloom.ts:446-632) on the finished frame:
-        returns the display-referred frame (ACES + gamma applied) in ``fmt``."""
+        returns the display-referred frame (ACES + gamma applied) in ``fmt``. precise=True: the validation build."""
         cfg = _lib.GvtBloomConfig()
         cfg.struct_size = C.sizeof(cfg)
         cfg.enabled, cfg.intensity, cfg.threshold, cfg.blur_passes = 1 if enabled else 0, intensity, threshold, blur_passes
+        cfg.precise = 1 if precise else 0
         out = np.zeros((self.height, self.width, 4), np.dtype(_lib.FORMAT_DTYPE[fmt])) if readback else None
         ms = C.c_double()
         check(lib().gvt_render_bloom(self._h, C.byref(cfg), fmt, out.ctypes.data_as(C.c_void_p) if readback else None, C.byref(ms)))

@@ -100,6 +100,9 @@ enum {
                                        TAA it is 16 rows traced with a one-row halo. The peer stores need no blocks. */
     GVT_FLAG_DEBUG_COUNTS = 1u << 9, /* gvt_render_fragment_glsl: also record per-pixel march steps and horizon flags for
                                        gvt_render_fragment_glsl_debug (8 B per pixel of extra stores; off by default) */
+    GVT_FLAG_TAA_PRECISE = 1u << 10, /* with GVT_FLAG_TAA: run the validation build of the resolve (every operation an IEEE
+                                       round-to-nearest f32 operation in shader order, unfolded reprojection) instead of
+                                       the production kernel (MUFU sqrt/rcp/rsq, host-folded matrices). Row blocks only. */
     GVT_FLAG_D2H_OWN_ROWS = 1u << 5 /* multi-GPU: copy only this rank's row block into host_rgba (at its place in the
                                        full-size buffer). With one host frame shared by all ranks (POSIX shm registered
                                        through gvt_host_register) the ranks assemble the frame in parallel, one
@@ -306,6 +309,12 @@ int32_t gvt_taa_resolve(gvt_renderer* r, const GvtCamera* cam, uint32_t width, u
 /* The WebGL2 variant (reprojection.glsl.ts:70-115) on caller-provided frames. */
 int32_t gvt_taa_resolve_webgl(gvt_renderer* r, uint32_t width, uint32_t height, const float* cur, const float* hist,
                               float blend, int32_t camera_moving, float* out);
+/* Both variants with two more knobs: precise != 0 runs the validation build (GVT_FLAG_TAA_PRECISE: IEEE f32 operations
+ * in shader order; tested to 1e-6 against the numpy restatement of the shader text), ms_out (may be NULL) receives the
+ * kernel's device time. webgl != 0: reprojection.glsl.ts (cam may be NULL), else ataa.wgsl.ts. */
+int32_t gvt_taa_resolve_ex(gvt_renderer* r, const GvtCamera* cam, uint32_t width, uint32_t height, const float* cur,
+                           const float* hist, float* out, uint32_t webgl, float blend, int32_t camera_moving,
+                           int32_t precise, double* ms_out);
 int32_t gvt_render_reset_history(gvt_renderer* r);
 
 /* ---- Seam B, WebGL2 pipeline: WebGLRenderer.render(params, mouse) (src/rendering/webgl/renderer.ts:173-420) ----
@@ -333,6 +342,9 @@ typedef struct GvtBloomConfig {
     float intensity;       /* 0.5 */
     float threshold;       /* 0.8 */
     uint32_t blur_passes;  /* 2 */
+    uint32_t precise;      /* validation build: IEEE f32 operations in GLSL order, libm powf (tested to 1e-6 against the numpy
+                              restatement of bloom.glsl.ts); 0 = production build (FMA contraction, MUFU rcp/lg2/ex2).
+                              Read only when struct_size covers it. */
 } GvtBloomConfig;
 int32_t gvt_render_bloom(gvt_renderer* r, const GvtBloomConfig* cfg, uint32_t output_format, void* host_out, double* ms);
 /* Parity hook: per-pixel step count and horizon flag of the last gvt_render_fragment_glsl frame rendered with

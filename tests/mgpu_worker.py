@@ -214,6 +214,34 @@ assert np.array_equal(pg.a[mine], b[mine]), f"rank {rank}: own interleaved rows 
 assert np.all(pg.a[others] == -1.0)                       # nothing but this rank's rows was touched
 assert multi.last_stats.d2h_bytes == len(mine) * W * 16 + 64
 dist.barrier()
+
+# BASELINE configs[3] at its stated size through the ranks: 7680x4320, <= 1024 adaptive RKF45 steps, natural termination,
+# row-interleaved shards over the fused peer-store gather -- bit-identical to the one-GPU frame, same step census.
+# And the headline frame (4K x 512) in both precision modes the bench reports, row blocks + ncclAllGather.
+import time
+for (W, H, kw, flags, what) in (
+        (7680, 4320, dict(method=_lib.METHOD_RKF45, max_steps=1024, step_rule=_lib.STEP_CONSTANT), _lib.FLAG_PEER_STORE | _lib.FLAG_ROW_INTERLEAVE,
+         "config 4 (8K, <=1024 RKF45), row-interleaved + peer stores"),
+        (3840, 2160, dict(method=_lib.METHOD_SYMPLECTIC, max_steps=512, step_rule=_lib.STEP_WGSL), 0, "config 3 (4K x 512, f64), row blocks + ncclAllGather"),
+        (3840, 2160, dict(method=_lib.METHOD_SYMPLECTIC, max_steps=512, step_rule=_lib.STEP_WGSL, precision=_lib.PRECISION_MIXED), _lib.FLAG_PEER_STORE,
+         "config 3 (4K x 512, mixed), row blocks + peer stores")):
+    multi.resize(W, H); single.resize(W, H)
+    if flags & _lib.FLAG_PEER_STORE:
+        multi.connect_peers(dist)
+    cam, _ = camera.default_camera(W, H)
+    phys = R.pack_physics(1.0, spin, W, H)
+    multi.params = R.RenderParams(flags=flags, **kw)
+    single.params = R.RenderParams(**kw)
+    a = np.array(multi.render(cam, phys))
+    ms_multi = multi.last_stats.total_ms
+    b = np.array(single.render(cam, phys))
+    assert np.array_equal(a, b), f"rank {rank}: {what}: frame differs from the single-GPU frame"
+    t = torch.tensor([float(multi.last_stats.steps_committed)]); dist.all_reduce(t)
+    assert int(t[0]) == int(single.last_stats.steps_committed), what
+    if rank == 0:
+        print(f"[mgpu] {what}: {world}-rank frame bit-identical to 1 GPU ({W}x{H}, {int(t[0])} steps; {ms_multi:.1f} ms vs "
+              f"{single.last_stats.total_ms:.1f} ms on one GPU)", flush=True)
+dist.barrier()
 multi.cleanup(); single.cleanup()
 dist.destroy_process_group()
 print(f"rank {rank} ok")

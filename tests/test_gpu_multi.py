@@ -18,6 +18,11 @@ def test_row_block_shard_allgather_bitwise(built):
     world = 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29671", os.path.join(ROOT, "tests", "mgpu_worker.py")]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
+    # keep the evidence: the driver's own GPU-test box has one GPU and skips this test, so the log of a `gpurun --gpus 2`
+    # run is what shows the multi-GPU bit-identity (copied to profiles/ by hand)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "test_gpu_multi_2gpu.log"), "w") as f:
+        f.write(f"$ {' '.join(cmd)}\nreturn code {p.returncode}\n--- stdout ---\n{p.stdout}\n--- stderr (tail) ---\n{p.stderr[-4000:]}\n")
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-5000:]
-    assert p.stdout.count(" ok") == world
+    assert p.stdout.count(" ok") == world and p.stdout.count("[mgpu]") == 3
