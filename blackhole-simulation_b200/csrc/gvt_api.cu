@@ -819,7 +819,24 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
     } else {
         P.x0 = 0; P.xs = 1; P.y0 = ty0; P.y1 = ty1; P.ys = 1; P.nx = W; P.ny = ty1 - ty0; P.stripe = sm;
     }
-    if (taa && r->history_valid) std::swap(r->frame, r->hist);  // last finished frame becomes the history
+    // ---- everything that can be refused is refused HERE, before any state changes or anything is enqueued: a rank that
+    //      bailed out later would leave its ping-pong parity flipped against its peers and them blocked in a collective ----
+    const bool own_early = (rp->flags & GVT_FLAG_D2H_OWN_ROWS) != 0 && r->world > 1;
+    if (host_rgba && own_early && interleave && rp->output_format != GVT_FORMAT_RGBA32F)
+        return fail(GVT_ERR_UNSUPPORTED, "interleaved own-row delivery is RGBA32F only");
+    if ((rp->flags & GVT_FLAG_PEER_STORE) != 0 && r->world > 1 && !(rp->flags & GVT_FLAG_NO_GATHER)) {
+        if (!r->d_sink) return fail(GVT_ERR_INVALID, "no barrier buffer");
+        for (int p = 0; p < r->world; p++)
+            if (p != r->rank && (p >= GVT_MAX_PEERS || !r->peer_open[p]))
+                return fail(GVT_ERR_INVALID, "GVT_FLAG_PEER_STORE: frames of rank %d not imported (gvt_render_import_peer_frames)", p);
+    }
+    // A CUDA / NCCL failure after this point is a broken device or communicator, not a caller error; the guard still
+    // drains the stream and puts the ping-pong buffers back so that this renderer's own state stays consistent.
+    struct LateGuard {
+        gvt_renderer* r; bool swapped = false, armed = true;
+        ~LateGuard() { if (armed) { cudaStreamSynchronize(r->stream); if (swapped) std::swap(r->frame, r->hist); } }
+    } late{r};
+    if (taa && r->history_valid) { std::swap(r->frame, r->hist); late.swapped = true; }  // last finished frame becomes the history
     float4* trace_out = taa ? r->cur : r->frame;
     if (glsl) G.frame = trace_out; else P.frame = trace_out;
     uint32_t launches = 0;
@@ -846,8 +863,7 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
         const int idx = (r->frame == r->buf[0]) ? 0 : 1;
         for (int p = 0; p < r->world; p++) {
             if (p == r->rank) continue;
-            if (p >= GVT_MAX_PEERS || !r->peer_open[p]) return fail(GVT_ERR_INVALID, "GVT_FLAG_PEER_STORE: frames of rank %d not imported (gvt_render_import_peer_frames)", p);
-            peer_targets[n_peer++] = r->peer[p][idx];
+            peer_targets[n_peer++] = r->peer[p][idx];          // imported: checked before the swap
         }
         if (!taa && glsl) { for (uint32_t q = 0; q < n_peer; q++) G.peer_frame[q] = peer_targets[q]; G.n_peer = n_peer; }
         else if (!taa) { for (uint32_t q = 0; q < n_peer; q++) P.peer_frame[q] = peer_targets[q]; P.n_peer = n_peer; }
@@ -899,7 +915,6 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
     CK(cudaEventRecord(r->ev[3], r->stream));
     if (peer_store) {
         // all ranks' stores must have landed before anyone reads its frame: a 1-element all-reduce is the barrier
-        if (!r->d_sink) return fail(GVT_ERR_INVALID, "no barrier buffer");
         int nrc = g_nccl.AllReduce(r->d_sink, r->d_sink, 1, kNcclFloat32, kNcclSum, r->comm, r->stream);
         if (nrc != 0) return fail(GVT_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(nrc));
     } else if (r->world > 1 && !(rp->flags & GVT_FLAG_NO_GATHER)) {
@@ -914,8 +929,7 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
     if (host_rgba && host_alias) {
         d2h += (size_t)n_own * W * sizeof(float4);   // delivered by the kernel's own stores
     } else if (host_rgba && own && interleave) {
-        if (rp->output_format != GVT_FORMAT_RGBA32F) return fail(GVT_ERR_UNSUPPORTED, "interleaved own-row delivery is RGBA32F only");
-        const size_t row_bytes = (size_t)W * sizeof(float4);
+        const size_t row_bytes = (size_t)W * sizeof(float4);                // (RGBA32F only: checked before the swap)
         if (sm.s == 1u) {   // every world-th row: one strided copy
             const size_t pitch = row_bytes * (size_t)r->world;
             if (n_own)
@@ -961,6 +975,7 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
         if (qrc != 0 || aerr != 0)
             return fail(GVT_ERR_NCCL, "NCCL asynchronous error: %s", g_nccl.GetErrorString(qrc != 0 ? qrc : aerr));
     }
+    late.armed = false;
     if (taa) r->history_valid = true;
     if (stats) {
         memset(stats, 0, sizeof(*stats));

@@ -597,18 +597,20 @@ static cudaError_t launch_impl(const GlslParams& p, int precision, int sm_count,
 #else
     auto kern = precision == 1 ? k_fragment_glsl<float> : k_fragment_glsl<double>;
 #endif
-    // the shared-memory opt-in and the occupancy query are per kernel, not per frame (they cost ~10 us each on the host)
-    static int resident[2] = {0, 0};
+    // the shared-memory opt-in and the occupancy query are per kernel AND per device, not per frame (~10 us each on the host)
+    static PerDeviceInt resident[2];
     const int ki = precision == 1 ? 1 : 0;
-    if (!resident[ki]) {
+    int* cached = resident[ki].slot();
+    int per_sm = cached ? *cached : 0;
+    if (!per_sm) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int n = 1;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, GVT_FRAG_THREADS, smem);
         if (e != cudaSuccess) return e;
-        resident[ki] = n > 0 ? n : 1;
+        per_sm = n > 0 ? n : 1;
+        if (cached) *cached = per_sm;
     }
-    const int per_sm = resident[ki];
     const uint32_t n_rows = p.stripe.s ? p.n_lattice_rows : (p.y1 - p.y0 + p.ys - 1u) / p.ys;
     const uint32_t tiles = ((p.width + 7u) / 8u) * ((n_rows + 3u) / 4u);
     const uint32_t wpc = GVT_FRAG_THREADS / 32;

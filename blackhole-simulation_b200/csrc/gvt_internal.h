@@ -122,6 +122,19 @@ struct GlslParams {
     uint32_t* dbg_steps; uint32_t* dbg_hit;   // parity hooks (full-frame arrays) or null
 };
 
+// Function attributes (the dynamic shared-memory opt-in) and occupancy are per DEVICE: a process may hold renderers on
+// several GPUs (GvtDeviceConfig.device), so per-kernel launch state is cached per device ordinal, never in a bare static.
+// Benign race between threads: both compute the same value.
+constexpr int kMaxDevices = 64;
+struct PerDeviceInt {
+    int v[kMaxDevices] = {};
+    int* slot() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) return nullptr;
+        return &v[d];
+    }
+};
+
 // launchers (gvt_kernels.cu)
 cudaError_t launch_trace(const FrameParams& p, int method, int precision, bool budget, bool debug, int sm_count,
                          cudaStream_t stream);

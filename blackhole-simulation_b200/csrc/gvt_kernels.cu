@@ -546,6 +546,8 @@ cudaError_t launch_trace(const FrameParams& p_in, int method, int precision, boo
                                       : launch_trace_t<RT, 0, false, false, GVT_MAXT_RKF>(p, sm_count, stream);           \
         if (method == 3) return debug ? launch_trace_t<RT, 3, false, true, MT>(p, sm_count, stream)              \
                                       : launch_trace_t<RT, 3, false, false, MT>(p, sm_count, stream);            \
+        if (method == 1 && budget) return debug ? launch_trace_t<RT, 1, true, true, MT>(p, sm_count, stream)    \
+                                                : launch_trace_t<RT, 1, true, false, MT>(p, sm_count, stream);  \
         if (method == 1) return debug ? launch_trace_t<RT, 1, false, true, MT>(p, sm_count, stream)              \
                                       : launch_trace_t<RT, 1, false, false, MT>(p, sm_count, stream);            \
         if (budget) return debug ? launch_trace_t<RT, 2, true, true, MT>(p, sm_count, stream)                    \
@@ -861,10 +863,13 @@ cudaError_t launch_taa(const TaaParams& p_in, int sm_count, cudaStream_t stream)
     const bool striped = p.stripe.s != 0u;
     if (striped ? p.n_stripes == 0u : rows <= 0) return cudaSuccess;
     const int wpb = 8;
-    static int resident[2] = {0, 0};   // CTAs per SM of each instantiation (occupancy query, once)
+    static PerDeviceInt resident_cache[2];   // CTAs per SM of each instantiation, per device (occupancy query, once)
     const int m = p.mode == 1u ? 1 : 0;
     // rings per CTA: 8 warps x TAA_DEPTH x 32 lanes x (16 B current + NT x 16 B taps + 8 B fractions)
     const size_t smem = (size_t)8 * TAA_DEPTH * 32 * (16 + (m ? 1 : 4) * 16 + 8);
+    int* cached = resident_cache[m].slot();
+    int resident[2] = {0, 0};
+    resident[m] = cached ? *cached : 0;
     if (!resident[m]) {
         int n = 0;
         cudaError_t e = m ? cudaFuncSetAttribute(k_taa_resolve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
@@ -874,6 +879,7 @@ cudaError_t launch_taa(const TaaParams& p_in, int sm_count, cudaStream_t stream)
               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_taa_resolve<0>, wpb * 32, smem);
         if (e != cudaSuccess) return e;
         resident[m] = n > 0 ? n : 1;
+        if (cached) *cached = resident[m];
     }
     // Rows per strip unit: every warp walks k = ceil(units / resident warps) units of (R + 2) loaded rows; pick the R
     // that minimises k (R + 2), i.e. no partial last wave and as little halo as the frame allows.

@@ -60,7 +60,11 @@ class PinnedBuffer:
         check(lib().gvt_host_alloc(nbytes, C.byref(self.ptr)))
 
     def array(self, dtype, shape):
+        """Zero-copy view of the page-locked buffer. The view keeps this PinnedBuffer alive (its base object holds a
+        reference), so a view held by the caller never outlives the memory it points into; the NEXT frame rendered into
+        the same buffer overwrites it, as a canvas would -- copy (np.array(view)) to keep a frame."""
         buf = (C.c_uint8 * self.nbytes).from_address(self.ptr.value)
+        buf._owner = self
         return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
     def free(self):
@@ -68,7 +72,11 @@ class PinnedBuffer:
             lib().gvt_host_free(self.ptr)
             self.ptr = C.c_void_p()
 
-    __del__ = free
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:      # interpreter shutdown: the module globals may already be gone
+            pass
 
 
 class SharedFrame:
@@ -292,4 +300,8 @@ class KerrRenderer:
             lib().gvt_render_destroy(self._h)
             self._h = C.c_void_p()
 
-    __del__ = cleanup
+    def __del__(self):
+        try:
+            self.cleanup()
+        except Exception:      # interpreter shutdown: the module globals may already be gone
+            pass

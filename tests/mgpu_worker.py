@@ -236,8 +236,8 @@ for (W, H, kw, flags, what) in (
     ms_multi = multi.last_stats.total_ms
     b = np.array(single.render(cam, phys))
     assert np.array_equal(a, b), f"rank {rank}: {what}: frame differs from the single-GPU frame"
-    t = torch.tensor([float(multi.last_stats.steps_committed)]); dist.all_reduce(t)
-    assert int(t[0]) == int(single.last_stats.steps_committed), what
+    t = torch.tensor([float(multi.last_stats.steps_committed)], dtype=torch.float64); dist.all_reduce(t)   # ~6e9: beyond float32
+    assert int(t[0]) == int(single.last_stats.steps_committed), (what, int(t[0]), int(single.last_stats.steps_committed))
     if rank == 0:
         print(f"[mgpu] {what}: {world}-rank frame bit-identical to 1 GPU ({W}x{H}, {int(t[0])} steps; {ms_multi:.1f} ms vs "
               f"{single.last_stats.total_ms:.1f} ms on one GPU)", flush=True)
