@@ -32,20 +32,23 @@ SPIN = 0.9990000128746033   # 0.999 as the f32 the PhysicsParams uniform carries
 SPEC_W, SPEC_H, TMAX = 256, 32, 1e7          # 128 KB RGBA32F spectral LUT: shared-memory resident
 # Algorithmic flop per geodesic step, SURVEY.md §8(d) (CSE'd count; add=mul=div=sqrt=1, FMA=2, sincos/pow = 0):
 FLOP_PER_STEP = {"symplectic": 330.0, "rk4": 440.0, "rkf45": 900.0}
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_trace_tile<double,...> launch on the full 4K x 512 frame, from
-# the committed ncu --set full capture (profiles/r01_k_trace_tile_f64_budget_4k512.txt). Reported only at N = 1.
-NCU_DRAM_BYTES_PER_LAUNCH_4K = 2654720 + 75954688   # 78.6 MB: < the 132.7 MB frame (L2 write-back in flight)
+# Profile-derived figures (DRAM traffic per launch, executed instruction mix, pipe activity) are READ from the committed,
+# machine-readable ncu export of the dominant kernel -- never pasted -- and only reported when the export was captured on
+# the build that is running (gvt_build_info() source hash); otherwise they are null and marked stale.
+PROFILE_EXPORT = os.path.join(ROOT, "profiles", "r02_k_trace_tile_f64_budget_4k512.json")
+PROFILE_EXPORT_MIXED = os.path.join(ROOT, "profiles", "r02_k_trace_tile_mixed_budget_4k512.json")
 METRIC = "geodesic steps/s at 3840x2160x512, a=0.999; % of FP32 roofline"
 
 
-def workload_config(n_gpus, peer_store=False):
+def workload_config(n_gpus, peer_store=False, interleave=False):
     return {
         "workload": "config 3: Kerr a*=0.999 (Kerr-Schild), 3840x2160, 512 fixed implicit-midpoint steps/pixel "
                     "(step rule compute.wgsl.ts:213), f64, thin-disk g-factor + Planckian redshift LUT 256x32, "
                     "camera r0=30 polar 97deg azimuth pi fov 60deg; budget accounting (W*H*512 steps/frame)",
         "width": W, "height": H, "steps_per_pixel": STEPS, "spin": SPIN, "integrator": "implicit-midpoint",
-        "precision": "f64", "shard": (f"row-block x{n_gpus} + " + ("NVLink peer stores fused into the trace kernel"
-                                                         if peer_store else "1 ncclAllGather")) if n_gpus > 1 else "single GPU",
+        "precision": "f64", "shard": ((f"rows dealt round-robin to {n_gpus} ranks + " if interleave else f"row-block x{n_gpus} + ") +
+                                      ("NVLink peer stores fused into the trace kernel" if peer_store else "1 ncclAllGather"))
+        if n_gpus > 1 else "single GPU",
         "l2": "inputs are ~131 KB (LUT + camera block), compute-bound and L2-insensitive; each frame writes a "
               "132.7 MB RGBA32F frame (> 126 MB L2), so no explicit L2 flush between iterations",
     }
@@ -130,29 +133,62 @@ def allreduce_sum(dist, x):
     return float(t[0])
 
 
+def load_profile_export(path, build_info):
+    """The committed ncu export of a kernel, or None if absent / captured on another build of the library."""
+    try:
+        with open(path) as f:
+            ex = json.load(f)
+    except (OSError, ValueError):
+        return None, "no committed ncu export"
+    if ex.get("build_info") != build_info:
+        return None, f"committed ncu export is stale (captured on '{ex.get('build_info')}', running '{build_info}')"
+    return ex, None
+
+
 def cpu_sample(target_seconds=15.0, threads=None):
-    """Time the oracle (C++ restatement of gravitas-core integrate(), all host threads) on a strided lattice of
-    the SAME 4K frame, sized to ~target_seconds of CPU work."""
+    """Time the oracle (C++ restatement of gravitas-core integrate(), built -O3 -march=native on this host, contraction
+    off) on a strided lattice of the SAME 4K frame, sized to ~target_seconds of CPU work. threads=None: all host threads."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
     from gravitas_b200 import camera
-    if threads:
-        O.lib().orc_set_num_threads(threads)
-    cores = O.lib().orc_num_threads()
     spec = O.spectrum_lut(SPEC_W, SPEC_H, TMAX)
     td = O.disk_lut(MASS, SPIN)
     opts = O.Options.default(method=O.METHOD_SYMPLECTIC, step_rule=1, max_steps=STEPS)
     rp, keep = O.make_render_params(W, H, MASS, SPIN, opts, spectrum=spec, spec_w=SPEC_W, spec_h=SPEC_H, tdisk=td)
     cam, _ = camera.default_camera(W, H)
-    probe = O.render(cam, rp, x0=5, xs=32, y0=3, ys=32, want=())            # 1/1024 of the frame
+    probe = O.render(cam, rp, x0=5, xs=32, y0=3, ys=32, want=(), native=True, threads=threads)   # 1/1024 of the frame
+    cores = threads or O.lib(True).orc_num_threads()
     rate = probe["total_steps"] / max(probe["seconds"], 1e-9)
     frac = min(1.0, target_seconds * rate / (W * H * STEPS * 0.96))
     stride = max(1, int(round((1.0 / frac) ** 0.5)))
-    res = O.render(cam, rp, x0=stride // 2, xs=stride, y0=stride // 2, ys=stride, want=())
+    res = O.render(cam, rp, x0=stride // 2, xs=stride, y0=stride // 2, ys=stride, want=(), native=True, threads=threads)
+    frame_factor = W * H / res["n"]          # sampled rays -> whole frame
     return {"value": res["total_steps"] / res["seconds"], "unit": "steps/s", "cores": cores, "kind": "port",
             "sample": f"every {stride}th pixel in x and y of the same 3840x2160x512 frame ({res['n']} rays, "
-                      f"{res['total_steps']} accepted steps, {res['seconds']:.2f} s); natural termination",
-            "seconds": res["seconds"], "steps": res["total_steps"]}
+                      f"{res['total_steps']} accepted steps, {res['seconds']:.2f} s on {cores} thread(s)); natural termination; "
+                      f"g++ -O3 -march=native -ffp-contract=off",
+            "seconds": res["seconds"], "steps": res["total_steps"], "frame_factor": frame_factor,
+            "frame_ms_extrapolated": 1e3 * res["seconds"] * frame_factor}
+
+
+def cpu_config1():
+    """BASELINE configs[0], the reference's own CPU-runnable case, in full: Schwarzschild a = 0, 256 x 256 camera rays, 128
+    adaptive RKF45 steps, Boyer-Lindquist (gravitas-wasm/src/lib.rs:444-452 options), all host threads."""
+    import numpy as np
+    import oracle as O
+    from gravitas_b200 import camera
+    Wx = Hx = 256
+    cam, _ = camera.default_camera(Wx, Hx)
+    opts = O.Options.default(max_steps=128)
+    rp_o, keep = O.make_render_params(Wx, Hx, 1.0, 0.0, opts, coords=0)
+    rays = np.array([O.camera_ray(cam, rp_o, x, y) for y in range(Hx) for x in range(Wx)])
+    O.integrate(1.0, 0.0, 0, opts, rays[:4096], native=True)           # warm the thread pool / caches
+    t0 = time.perf_counter()
+    ref = O.integrate(1.0, 0.0, 0, opts, rays, native=True)
+    dt = time.perf_counter() - t0
+    steps = float(ref["steps"].sum())
+    return {"workload": "config 1: Schwarzschild a=0, 256x256 rays, 128 adaptive RKF45 steps, Boyer-Lindquist", "ms": 1e3 * dt,
+            "steps_per_s": steps / dt, "rhs_evals_per_s": float(ref["rhs"].sum()) / dt, "cores": O.lib(True).orc_num_threads()}
 
 
 def run_reference(args):
@@ -170,9 +206,15 @@ def run_reference(args):
         tot_steps += last["steps"]; tot_s += last["seconds"]
     v = tot_steps / tot_s
     cb = {"value": v, "unit": "steps/s", "cores": last["cores"], "kind": "port", "sample": last["sample"]}
+    # a bench "step" is one 4K frame; each timed sample covered 1/frame_factor of it, so the per-frame time is the
+    # sample time x frame_factor (rays are sampled on a uniform lattice of the same frame)
+    frame_ms = 1e3 * (tot_s / args.steps) * last["frame_factor"]
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": frame_ms,
+        "ms_per_step_note": f"whole-frame time extrapolated from the timed sample: sample seconds x {last['frame_factor']:.1f} "
+                            f"(= 3840*2160 / sampled rays); the sample itself took {1e3 * tot_s / args.steps:.0f} ms per bench step",
+        "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
         "cpu_baseline": cb, "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -285,6 +327,10 @@ def run_own(args):
             print(f"[bench] rank {rank}: peer-store unavailable ({ex}); using ncclAllGather", file=sys.stderr)
         if allreduce_sum(dist, ok) == world:
             peer = _lib.FLAG_PEER_STORE
+            if args.shard == "interleaved":
+                # rows dealt round-robin: the zones of the march (near the hole / saturated step rule / polar tiles) cost
+                # differently per step, and a contiguous row block holds an uneven share of them
+                peer |= _lib.FLAG_ROW_INTERLEAVE
 
     def params(flags=0, **kw):
         r.params = R.RenderParams(method=_lib.METHOD_SYMPLECTIC, precision=_lib.PRECISION_F64, max_steps=STEPS,
@@ -329,6 +375,25 @@ def run_own(args):
     r.render(cam, phys, readback=False)
     f_ms, _, f_stats = timed_frames(r, cam, phys, max(2, args.steps // 3), dist, readback=False)
     f_steps = allreduce_sum(dist, float(sum(s.steps_executed for s in f_stats)))
+    # GVT_PRECISION_MIXED: f64 state and corrector, f32 predictors beyond 35 M (every pixel of this frame within 1e-6 of the
+    # all-f64 oracle: tests/test_gpu_parity.py::test_headline_frame_every_pixel). Same frame, same accounting.
+    r.params = R.RenderParams(method=_lib.METHOD_SYMPLECTIC, precision=_lib.PRECISION_MIXED, max_steps=STEPS,
+                              step_rule=_lib.STEP_WGSL, flags=_lib.FLAG_BUDGET | peer)
+    r.render(cam, phys, readback=False)
+    m_ms, _, m_stats = timed_frames(r, cam, phys, max(2, args.steps // 3), dist, readback=False)
+    m_steps = allreduce_sum(dist, float(sum(s.steps_executed for s in m_stats)))
+    m_trace_ms = sum(s.trace_ms for s in m_stats) / len(m_stats)
+    # N > 1: the exchange north_star names -- one ncclAllGather after the trace kernel -- beside the default fused gather
+    ag = None
+    if world > 1 and peer:
+        r.params = R.RenderParams(method=_lib.METHOD_SYMPLECTIC, precision=_lib.PRECISION_F64, max_steps=STEPS,
+                                  step_rule=_lib.STEP_WGSL, flags=_lib.FLAG_BUDGET)
+        r.render(cam, phys, readback=False)
+        a_ms, _, a_stats = timed_frames(r, cam, phys, max(2, args.steps // 2), dist, readback=False)
+        a_steps = allreduce_sum(dist, float(sum(s.steps_executed for s in a_stats)))
+        ag = {"steps_per_s": a_steps / (a_ms * 1e-3), "ms_per_frame": a_ms / len(a_stats),
+              "all_gather_ms": sum(s.gather_ms for s in a_stats) / len(a_stats),
+              "trace_kernel_ms_rank0": sum(s.trace_ms for s in a_stats) / len(a_stats)}
 
     # ---- beside the headline (one GPU only): the two other kernels of the path, a few frames each ----
     side = {}
@@ -339,8 +404,15 @@ def run_own(args):
             side = {"side_kernels_error": repr(ex)}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_sample(15.0)
-        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        full = cpu_sample(15.0)
+        cpu = {k: full[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu["frame_ms_extrapolated"] = full["frame_ms_extrapolated"]
+        one = cpu_sample(5.0, threads=1)                      # the single-thread figure beside the all-core one
+        cpu["single_thread"] = {"value": one["value"], "unit": "steps/s", "sample": one["sample"]}
+        cpu["config1"] = cpu_config1()                        # the reference's own CPU-runnable case, in full
+    build_info = _lib.lib().gvt_build_info().decode()
+    prof, prof_note = load_profile_export(PROFILE_EXPORT, build_info)
+    prof_m, _ = load_profile_export(PROFILE_EXPORT_MIXED, build_info)
 
     if rank == 0:
         fl = FLOP_PER_STEP["symplectic"]
@@ -352,17 +424,28 @@ def run_own(args):
             "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ev_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world, bool(peer)), "e2e": e2e, "gpu_launches": int(launches),
+            "config": workload_config(world, bool(peer), bool(peer & _lib.FLAG_ROW_INTERLEAVE)), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {
                 "bound": "fp64", "kernel": "k_trace_tile<double,symplectic,budget>", "achieved": ach, "peak": peak64,
                 "unit": "TFLOP/s", "frac": ach / peak64,
-                "traffic": NCU_DRAM_BYTES_PER_LAUNCH_4K if world == 1 else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch on the full frame, read from the committed ncu
+                # export of THIS build (null when the export is absent or stale, never a pasted constant)
+                "traffic": (prof["dram_bytes_per_launch"] if (prof and world == 1) else None),
+                "traffic_note": prof_note if world == 1 else "per-rank launches cover a row block; the export is of the 1-GPU launch",
+                # the 330 flop/step above is SURVEY's algorithmic (CSE'd) count; what the kernel EXECUTES per step comes from
+                # the SASS mix of the same export (DFMA = 2, DMUL = DADD = 1), scaled by the live kernel time
+                "executed_flop_per_step": prof["executed_fp64_flop_per_step"] if prof else None,
+                "executed_flop_frac": (steps_per_launch * prof["executed_fp64_flop_per_step"] / (trace_ms * 1e-3) * 1e-12 / peak64)
+                                      if (prof and world == 1) else None,
+                "fp64_pipe_instructions_per_step": prof["fp64_pipe_instructions_per_step"] if prof else None,
+                "pipe_active": (prof["fp64_pipe_active_pct"] / 100.0) if prof else None,
+                "profile_export": os.path.relpath(PROFILE_EXPORT, ROOT) if prof else None, "build_info": build_info,
                 "peak_source": "in-run DFMA micro-benchmark (gvt_measure_fma_peak; MEASURED_PEAKS.json has no "
                                "FP32/FP64 entry). The path is FMA-pipe bound, not HBM or tensor: ~0 B read and 16 B "
                                "written per pixel per 512 steps",
                 "flop_per_step": fl, "steps_per_launch": int(steps_per_launch), "kernel_ms": trace_ms,
                 "frac_of_fp32_peak": ach / peak32, "fp32_peak_tflops": peak32, "fp64_peak_tflops": peak64,
-                "hbm_bytes_per_launch": int(16 * (stats[0].rows_end - stats[0].rows_begin) * W),
+                "hbm_bytes_per_launch": int(16 * steps_per_launch // STEPS),   # one float4 store per pixel this rank produced
             },
             "cpu_baseline": cpu,
             "clocks": clocks,
@@ -373,7 +456,20 @@ def run_own(args):
                                         "census_rank0": {"horizon": int(s0.n_horizon), "escape": int(s0.n_escape),
                                                          "max_steps": int(s0.n_maxsteps), "disk_opaque": int(s0.n_disk)}},
                 "f32_budget": {"steps_per_s": f_steps / (f_ms * 1e-3), "ms_per_frame": f_ms / len(f_stats),
-                               "frac_of_fp32_peak": (f_steps / (f_ms * 1e-3)) * fl * 1e-12 / peak32 / world},
+                               "frac_of_fp32_peak": (f_steps / (f_ms * 1e-3)) * fl * 1e-12 / peak32 / world,
+                               "note": "f32 arithmetic throughout: fast, but NOT within the 1e-6 tolerance of the f64 oracle "
+                                       "(15 % of lit pixels outside it on this frame); reported as an accuracy / speed reference only"},
+                "mixed_precision": {
+                    "what": "GVT_PRECISION_MIXED: f64 state + f64 corrector of the implicit midpoint, f32 predictors (MUFU sin/cos) on "
+                            "the outbound leg beyond 35 M; every pixel of this frame within 1e-6 relative of the all-f64 oracle "
+                            "(tests/test_gpu_parity.py::test_headline_frame_every_pixel)",
+                    "steps_per_s": m_steps / (m_ms * 1e-3), "ms_per_frame": m_ms / len(m_stats), "trace_kernel_ms": m_trace_ms,
+                    "frac_of_fp32_peak": (m_steps / (m_ms * 1e-3)) * fl * 1e-12 / peak32 / world,
+                    "speedup_vs_f64": (ev_ms / args.steps) / (m_ms / len(m_stats)),
+                    "executed_fp64_flop_per_step": prof_m["executed_fp64_flop_per_step"] if prof_m else None,
+                    "executed_fp32_flop_per_step": prof_m["executed_fp32_flop_per_step"] if prof_m else None,
+                    "dram_bytes_per_launch": prof_m["dram_bytes_per_launch"] if (prof_m and world == 1) else None},
+                "allgather": ag,
                 **side,
             },
         }
@@ -599,6 +695,10 @@ def main():
     ap.add_argument("--no-peer-store", action="store_true",
                     help="N > 1: use the ncclAllGather after the trace kernel instead of the default fused gather (NVLink "
                          "peer stores from the trace kernel + 4-byte all-reduce barriers)")
+    ap.add_argument("--shard", default="blocks", choices=["blocks", "interleaved"],
+                    help="N > 1 with the fused gather: contiguous row blocks (default: budget accounting is balanced, measured "
+                         "6.24 ms/frame on 8 GPUs) or rows dealt round-robin (6.29 ms; the better choice under natural "
+                         "termination: 6.42 vs 7.12 ms)")
     ap.add_argument("--workload", default="config3", choices=["config1", "config2", "config3", "config4", "config5", "glsl", "webgl"],
                     help="config3 = the headline (default). The others print an 'extra_workload' JSON line for BASELINE "
                          "configs[0] (Schwarzschild 256x256x128 RKF45: GPU batch integrate + the CPU port), configs[1] "

@@ -37,6 +37,21 @@ static int32_t fail(int32_t code, const char* fmt, ...) {
 
 extern "C" const char* gvt_last_error(void) { return g_err.c_str(); }
 extern "C" int32_t gvt_abi_version(void) { return GVT_ABI_VERSION; }
+#ifndef GVT_SRC_HASH
+#define GVT_SRC_HASH "unknown"
+#endif
+#ifndef GVT_MAXT_F64
+#define GVT_MAXT_F64 512
+#endif
+#ifndef GVT_MAXT_F32
+#define GVT_MAXT_F32 512
+#endif
+#define GVT_STR2(x) #x
+#define GVT_STR(x) GVT_STR2(x)
+extern "C" const char* gvt_build_info(void) {
+    return "src=" GVT_SRC_HASH " maxt_f64=" GVT_STR(GVT_MAXT_F64) " maxt_f32=" GVT_STR(GVT_MAXT_F32);
+}
+
 extern "C" int32_t gvt_device_count(int32_t* out) {
     if (!out) return fail(GVT_ERR_INVALID, "null out");
     int n = 0;
@@ -440,6 +455,8 @@ struct gvt_renderer {
     bool peer_open[GVT_MAX_PEERS] = {};
     void* half_frame = nullptr; // RGBA16F staging
     bool history_valid = false;
+    float4* last_peer_target = nullptr;   // the buffer the peers filled on the previous GVT_FLAG_PEER_STORE frame
+    uint32_t rows_override[2] = {0u, 0u};  // gvt_render_rows
     FrameBlock* d_block = nullptr; FrameBlock* h_block = nullptr;   // device / pinned host
     Counters* d_counters = nullptr; Counters* h_counters = nullptr;
     float4* d_spectrum = nullptr; uint32_t spec_w = 0, spec_h = 0;
@@ -596,6 +613,7 @@ extern "C" int32_t gvt_render_resize(gvt_renderer* r, uint32_t width, uint32_t h
     CK(cudaMalloc(&r->frame, bytes));
     CK(cudaMalloc(&r->hist, bytes));
     r->buf[0] = r->frame; r->buf[1] = r->hist;
+    r->last_peer_target = nullptr;
     CK(cudaMemsetAsync(r->cur, 0, bytes, r->stream));
     CK(cudaMemsetAsync(r->frame, 0, bytes, r->stream));
     CK(cudaMemsetAsync(r->hist, 0, bytes, r->stream));  // WebGPU textures start zeroed: so does the history
@@ -789,8 +807,11 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
     }
     const bool taa = (rp->flags & GVT_FLAG_TAA) != 0;
     const bool budget = !glsl && (rp->flags & GVT_FLAG_BUDGET) != 0 && (rp->method == GVT_METHOD_RK4 || rp->method == GVT_METHOD_SYMPLECTIC);
-    const uint32_t row0 = std::min(H, (uint32_t)r->rank * r->rows_per_rank);
-    const uint32_t row1 = std::min(H, row0 + r->rows_per_rank);
+    uint32_t row0 = std::min(H, (uint32_t)r->rank * r->rows_per_rank);
+    uint32_t row1 = std::min(H, row0 + r->rows_per_rank);
+    if (r->rows_override[1] > r->rows_override[0]) {   // gvt_render_rows: one row block of the frame on a single renderer
+        row0 = std::min(H, r->rows_override[0]); row1 = std::min(H, r->rows_override[1]);
+    }
     // TAA needs a one-pixel halo of the current frame: trace one redundant row above and below the block
     const uint32_t ty0 = (taa && row0 > 0) ? row0 - 1 : row0, ty1 = (taa && row1 < H) ? row1 + 1 : row1;
     // GVT_FLAG_ROW_INTERLEAVE (peer stores only: nothing needs contiguous blocks): stripes dealt round-robin to the ranks.
@@ -836,7 +857,11 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
         gvt_renderer* r; bool swapped = false, armed = true;
         ~LateGuard() { if (armed) { cudaStreamSynchronize(r->stream); if (swapped) std::swap(r->frame, r->hist); } }
     } late{r};
-    if (taa && r->history_valid) { std::swap(r->frame, r->hist); late.swapped = true; }  // last finished frame becomes the history
+    const bool peer_req = (rp->flags & GVT_FLAG_PEER_STORE) != 0 && r->world > 1 && !(rp->flags & GVT_FLAG_NO_GATHER);
+    // The last finished frame becomes the history (TAA), and under the fused gather the two frame buffers ping-pong on
+    // every frame, TAA or not: peers then never write into the buffer a rank may still be reading (TAA history taps, the
+    // D2H copy of the previous frame), which is what lets ONE barrier per frame close the exchange (see below).
+    if ((taa && r->history_valid) || (peer_req && !taa)) { std::swap(r->frame, r->hist); late.swapped = true; }
     float4* trace_out = taa ? r->cur : r->frame;
     if (glsl) G.frame = trace_out; else P.frame = trace_out;
     uint32_t launches = 0;
@@ -877,12 +902,16 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
         h2d += sizeof(GvtGlslUniforms);   // travels in the kernel parameter block
     }
     CK(cudaMemsetAsync(r->d_counters, 0, sizeof(Counters), r->stream));
-    if (peer_store) {
-        // peers are about to write into this rank's frame: everything this rank still had queued on the previous
-        // frame (TAA history reads, D2H copy) is ahead of this barrier in stream order on every rank
+    if (peer_store && r->frame == r->last_peer_target) {
+        // Peers are about to write into the SAME buffer they filled last frame (no ping-pong happened: first TAA frame
+        // after a history reset): everything this rank still had queued on that buffer (D2H copy) must be done first --
+        // it is ahead of this barrier in stream order on every rank. When the buffers alternated, the closing barrier of
+        // the previous frame already orders those reads before any peer's next write to that buffer, and this one is
+        // skipped: one 4-byte all-reduce per frame instead of two.
         int nrc = g_nccl.AllReduce(r->d_sink, r->d_sink, 1, kNcclFloat32, kNcclSum, r->comm, r->stream);
         if (nrc != 0) return fail(GVT_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(nrc));
     }
+    if (peer_store) r->last_peer_target = r->frame;
     CK(cudaEventRecord(r->ev[1], r->stream));
     if (glsl) {
         if (interleave ? lattice_rows > 0 : G.y1 > G.y0) {
@@ -998,6 +1027,19 @@ extern "C" int32_t gvt_render_frame(gvt_renderer* r, const GvtCamera* cam, const
                                     const GvtRenderParams* rp, void* host_rgba, GvtFrameStats* stats) {
     if (!r || !cam || !phys || !rp) return fail(GVT_ERR_INVALID, "null argument");
     return render_impl(r, cam, phys, rp, nullptr, 0, host_rgba, stats);
+}
+
+// One row block [row0, row1) of the frame on a single-GPU renderer: what one rank of an N-GPU run traces, for tiled
+// rendering by a host that schedules the blocks itself and for measuring a rank's share of a frame on one device.
+extern "C" int32_t gvt_render_rows(gvt_renderer* r, const GvtCamera* cam, const GvtPhysicsParams* phys, const GvtRenderParams* rp,
+                                   uint32_t row0, uint32_t row1, void* host_rgba, GvtFrameStats* stats) {
+    if (!r || !cam || !phys || !rp) return fail(GVT_ERR_INVALID, "null argument");
+    if (r->world != 1) return fail(GVT_ERR_UNSUPPORTED, "gvt_render_rows is for single-GPU renderers (ranks already own a row block)");
+    if (row1 <= row0 || (rp->flags & (GVT_FLAG_TAA | GVT_FLAG_ROW_INTERLEAVE))) return fail(GVT_ERR_INVALID, "bad row block / flags");
+    r->rows_override[0] = row0; r->rows_override[1] = row1;
+    const int32_t rc = render_impl(r, cam, phys, rp, nullptr, 0, host_rgba, stats);
+    r->rows_override[0] = r->rows_override[1] = 0u;
+    return rc;
 }
 
 // webgl-utils.ts:259-303: createNoiseTexture / createBlueNoiseTexture (256x256 RGBA8). Only .r is ever sampled

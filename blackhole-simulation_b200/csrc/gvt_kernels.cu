@@ -197,11 +197,23 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
         s_term[wid][0] = s_term[wid][1] = s_term[wid][2] = s_term[wid][3] = 0u;
     }
 
+    // Work distribution. Natural termination: one global atomic queue of warp-tiles (rows differ widely in cost). Budget
+    // accounting: every tile costs the same, so each CTA owns an equal contiguous share of the tiles and hands them to its
+    // warps through a shared-memory counter -- all SMs then finish together, where the global queue ends with half a
+    // tile-time of stragglers on the SMs that happened to draw the last tiles (0.17 ms of a 6 ms launch at 1/8 frame:
+    // the difference between 0.972 and 0.99 kernel-side scaling efficiency at 8 GPUs; scripts/partial_frame_scaling.py).
+    __shared__ uint32_t s_next_tile;
+    const uint32_t cta_first = BUDGET ? (uint32_t)(((unsigned long long)n_tiles * blockIdx.x) / gridDim.x) : 0u;
+    const uint32_t cta_end = BUDGET ? (uint32_t)(((unsigned long long)n_tiles * (blockIdx.x + 1u)) / gridDim.x) : n_tiles;
+    if (BUDGET) {
+        if (threadIdx.x == 0) s_next_tile = cta_first;
+        __syncthreads();
+    }
     for (;;) {
         uint32_t tile = 0;
-        if (lane == 0) tile = atomicAdd(&P.counters->tile_counter, 1u);
+        if (lane == 0) tile = BUDGET ? atomicAdd(&s_next_tile, 1u) : atomicAdd(&P.counters->tile_counter, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= n_tiles) break;
+        if (tile >= cta_end) break;
         const uint32_t ti = tile % tiles_x, tj = tile / tiles_x;
         const uint32_t li = ti * TILE_W + lx, lj = tj * TILE_H + ly;  // lattice coordinates
         bool valid = (li < P.nx) && (lj < P.ny);
@@ -506,14 +518,23 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
     }
     // a CTA must not exit while its bulk copy is still in flight
     if (P.lut_in_smem && !lut_ready) mbar_wait(&bars[1], 0);
-    if (lane == 0) {
-        atomicAdd(&P.counters->steps_committed, s_acc[wid][0]);
-        atomicAdd(&P.counters->steps_executed, s_acc[wid][1]);
-        atomicAdd(&P.counters->rhs_evals, s_acc[wid][2]);
-        if (s_term[wid][0]) atomicAdd(&P.counters->n_horizon, (unsigned long long)s_term[wid][0]);
-        if (s_term[wid][1]) atomicAdd(&P.counters->n_escape, (unsigned long long)s_term[wid][1]);
-        if (s_term[wid][2]) atomicAdd(&P.counters->n_maxsteps, (unsigned long long)s_term[wid][2]);
-        if (s_term[wid][3]) atomicAdd(&P.counters->n_disk, (unsigned long long)s_term[wid][3]);
+    // census: one set of global atomics per CTA (2368 warps hitting the same seven addresses at the end of a launch
+    // serialise in L2 for tens of microseconds, which shows at 1/8-frame launches)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long a0 = 0, a1 = 0, a2 = 0;
+        uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+        for (uint32_t w = 0; w < blockDim.x / 32u; w++) {
+            a0 += s_acc[w][0]; a1 += s_acc[w][1]; a2 += s_acc[w][2];
+            t0 += s_term[w][0]; t1 += s_term[w][1]; t2 += s_term[w][2]; t3 += s_term[w][3];
+        }
+        atomicAdd(&P.counters->steps_committed, a0);
+        atomicAdd(&P.counters->steps_executed, a1);
+        atomicAdd(&P.counters->rhs_evals, a2);
+        if (t0) atomicAdd(&P.counters->n_horizon, (unsigned long long)t0);
+        if (t1) atomicAdd(&P.counters->n_escape, (unsigned long long)t1);
+        if (t2) atomicAdd(&P.counters->n_maxsteps, (unsigned long long)t2);
+        if (t3) atomicAdd(&P.counters->n_disk, (unsigned long long)t3);
     }
 }
 

@@ -89,6 +89,7 @@ _pd, _pf, _pu32, _pu64 = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(
 # every symbol include/gravitas_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "gvt_last_error": (C.c_char_p, []),
+    "gvt_build_info": (C.c_char_p, []),
     "gvt_abi_version": (_i32, []),
     "gvt_device_count": (_i32, [C.POINTER(_i32)]),
     "gvt_engine_create": (_i32, [_d, _d, C.POINTER(_vp)]),
@@ -131,6 +132,8 @@ SIGNATURES = {
     "gvt_render_init_luts": (_i32, [_vp, _d, _d, _u32, _u32, _d]),
     "gvt_render_set_luts": (_i32, [_vp, _pf, _u32, _u32, _pf, _u32, _d, _d]),
     "gvt_render_resize": (_i32, [_vp, _u32, _u32]),
+    "gvt_render_rows": (_i32, [_vp, C.POINTER(GvtCamera), C.POINTER(GvtPhysicsParams), C.POINTER(GvtRenderParams), _u32, _u32, _vp,
+                        C.POINTER(GvtFrameStats)]),
     "gvt_render_frame": (_i32, [_vp, C.POINTER(GvtCamera), C.POINTER(GvtPhysicsParams), C.POINTER(GvtRenderParams), _vp,
                                 C.POINTER(GvtFrameStats)]),
     "gvt_render_read_frame": (_i32, [_vp, _u32, _vp]),

@@ -216,6 +216,15 @@ class KerrRenderer:
             return None
         return buf.array(np.dtype(_lib.FORMAT_DTYPE[self.params.c.output_format]), (H, W, 4))
 
+    def render_rows(self, camera, physics, row0, row1):
+        """One row block of the frame (what one rank of an N-GPU run traces); the frame stays in device memory."""
+        cam = camera if isinstance(camera, GvtCamera) else pack_camera(camera)
+        st = GvtFrameStats()
+        check(lib().gvt_render_rows(self._h, C.byref(cam), C.byref(physics), C.byref(self.params.c), row0, row1, None, C.byref(st)))
+        self.width, self.height = int(physics.resolution[0]), int(physics.resolution[1])
+        self.last_stats = _stats(st)
+        return self.last_stats
+
     def read_frame(self, fmt=_lib.FORMAT_RGBA32F):
         out = np.zeros((self.height, self.width, 4), np.dtype(_lib.FORMAT_DTYPE[fmt]))
         check(lib().gvt_render_read_frame(self._h, fmt, out.ctypes.data_as(C.c_void_p)))

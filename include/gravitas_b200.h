@@ -217,6 +217,11 @@ typedef struct GvtFrameStats {
 const char* gvt_last_error(void);
 int32_t gvt_abi_version(void);
 int32_t gvt_device_count(int32_t* out);
+/* Identifies this build of the library: a hash of the kernel / API sources it was compiled from plus the launch
+ * geometry of the trace kernel, e.g. "src=3f9a12c4e07b maxt_f64=512 maxt_f32=512". bench.py compares it with the
+ * hash recorded in the committed ncu exports so that profile-derived figures (DRAM traffic, executed instruction mix)
+ * are never reported for a kernel they were not measured on. Returns a pointer to a static string. */
+const char* gvt_build_info(void);
 
 /* ---- Seam A: PhysicsEngine (gravitas-wasm/src/lib.rs) -------------------------------------------------- */
 typedef struct gvt_engine gvt_engine;
@@ -296,6 +301,11 @@ int32_t gvt_render_resize(gvt_renderer* r, uint32_t width, uint32_t height);    
  * host_rgba (width*height*4 f32 or f16) when it is non-NULL, else it stays in device memory. */
 int32_t gvt_render_frame(gvt_renderer* r, const GvtCamera* cam, const GvtPhysicsParams* phys,
                          const GvtRenderParams* params, void* host_rgba, GvtFrameStats* stats);
+/* The row block [row0, row1) of the same frame on a single-GPU renderer (what one rank of an N-GPU run traces): for hosts
+ * that tile a frame themselves, and for measuring a rank's share of a frame on one device. The rest of the frame buffer is
+ * left as it was; host_rgba (may be NULL) receives the WHOLE frame buffer. No TAA / interleave flags. */
+int32_t gvt_render_rows(gvt_renderer* r, const GvtCamera* cam, const GvtPhysicsParams* phys, const GvtRenderParams* params,
+                        uint32_t row0, uint32_t row1, void* host_rgba, GvtFrameStats* stats);
 int32_t gvt_render_read_frame(gvt_renderer* r, uint32_t format, void* host_rgba);
 /* Parity hook: per-pixel final state (x,p)[8] f64, termination, accepted steps, max|H|, f64 RGBA over the pixel
  * lattice x = x0 + i*xs, y = y0 + j*ys (y < y1). Any output may be NULL. */

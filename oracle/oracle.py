@@ -50,11 +50,43 @@ def build(force=False):
     return so
 
 
-def lib():
-    global _LIB
+def build_native():
+    """-O3 -march=native build for the TIMING legs (bench.py cpu_baseline / --impl reference). Host-specific: rebuilt when the
+    CPU model differs from the one it was built on (the repo snapshot travels to the GPU box; this directory does not)."""
+    d = os.path.join(_HERE, "_native")
+    so, stamp = os.path.join(d, "liboracle_native.so"), os.path.join(d, "host.stamp")
+    try:
+        with open("/proc/cpuinfo") as f:
+            host = next((l.split(":", 1)[1].strip() for l in f if l.startswith("model name")), "unknown")
+    except OSError:
+        host = "unknown"
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "gravitas_oracle.hpp", "glsl_fragment_oracle.hpp", "Makefile")]
+    fresh = os.path.exists(so) and os.path.exists(stamp) and open(stamp).read() == host and \
+        all(os.path.getmtime(s) <= os.path.getmtime(so) for s in srcs)
+    if not fresh:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "native"])
+        with open(stamp, "w") as f:
+            f.write(host)
+    return so
+
+
+_NATIVE = None
+
+
+def lib(native=False):
+    """native=True: the -O3 -march=native build (timing only; same source, same symbols)."""
+    global _LIB, _NATIVE
+    if native:
+        if _NATIVE is None:
+            _NATIVE = _bind(C.CDLL(build_native()))
+        return _NATIVE
     if _LIB is None:
-        _LIB = C.CDLL(build())
-        L = _LIB
+        _LIB = _bind(C.CDLL(build()))
+    return _LIB
+
+
+def _bind(L):
+    if True:
         d, i, u32, u64 = C.c_double, C.c_int, C.c_uint32, C.c_uint64
         pd, pf = C.POINTER(C.c_double), C.POINTER(C.c_float)
         for name, res, args in [
@@ -82,7 +114,7 @@ def lib():
         ]:
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-    return _LIB
+    return L
 
 
 def _pd(a):
@@ -149,7 +181,7 @@ def step_rk4(m, a, coords, xp, h):
     return xp
 
 
-def integrate(m, a, coords, opts, xp):
+def integrate(m, a, coords, opts, xp, native=False, threads=None):
     """geodesic::integrate over rays xp[n,8] -> dict of arrays."""
     xp = np.ascontiguousarray(np.atleast_2d(xp), dtype=np.float64)
     n = xp.shape[0]
@@ -161,7 +193,9 @@ def integrate(m, a, coords, opts, xp):
     rej = np.zeros(n, np.uint64)
     rhs_ = np.zeros(n, np.uint64)
     u32p, u64p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
-    lib().orc_integrate(m, a, coords, C.byref(opts), n, _pd(xp), _pd(out), term.ctypes.data_as(u32p),
+    L = lib(native)
+    L.orc_set_num_threads(int(threads) if threads else 0)
+    L.orc_integrate(m, a, coords, C.byref(opts), n, _pd(xp), _pd(out), term.ctypes.data_as(u32p),
                         steps.ctypes.data_as(u64p), _pd(drift), att.ctypes.data_as(u64p), rej.ctypes.data_as(u64p),
                         rhs_.ctypes.data_as(u64p))
     return dict(xp=out, term=term, steps=steps, drift=drift, attempts=att, rejects=rej, rhs=rhs_)
@@ -209,8 +243,10 @@ def camera_ray(cam88, rp, px, py):
     return out
 
 
-def render(cam88, rp, x0=0, xs=1, y0=0, y1=None, ys=1, want=("rgba", "xp", "term", "steps", "drift", "crossings")):
-    """Composite RGBA oracle over the lattice x = x0 + i*xs, y = y0 + j*ys (< y1)."""
+def render(cam88, rp, x0=0, xs=1, y0=0, y1=None, ys=1, want=("rgba", "xp", "term", "steps", "drift", "crossings"), native=False,
+           threads=None):
+    """Composite RGBA oracle over the lattice x = x0 + i*xs, y = y0 + j*ys (< y1). native=True: the -O3 -march=native
+    build (timing legs only); threads: worker threads for this call (default: all hardware threads)."""
     cam88 = np.ascontiguousarray(cam88, dtype=np.float32)
     if y1 is None:
         y1 = rp.height
@@ -226,7 +262,9 @@ def render(cam88, rp, x0=0, xs=1, y0=0, y1=None, ys=1, want=("rgba", "xp", "term
     drift = np.zeros((ny, nx)) if "drift" in want else None
     cross = np.zeros((ny, nx), np.uint32) if "crossings" in want else None
     ts, tr = C.c_uint64(0), C.c_uint64(0)
-    secs = lib().orc_render(
+    L = lib(native)
+    L.orc_set_num_threads(int(threads) if threads else 0)
+    secs = L.orc_render(
         _pf(cam88), C.byref(rp), x0, xs, y0, y1, ys,
         _pd(rgba) if rgba is not None else None, _pd(xp) if xp is not None else None,
         term.ctypes.data_as(u32p) if term is not None else None,

@@ -6,7 +6,10 @@ import subprocess
 import sys
 from collections import Counter
 
+import json
 rep, out, steps_per_launch = sys.argv[1], sys.argv[2], float(sys.argv[3])
+json_out = sys.argv[4] if len(sys.argv) > 4 else None      # machine-readable export (bench.py reads roofline.traffic from it)
+build_info = sys.argv[5] if len(sys.argv) > 5 else ""      # gvt_build_info() of the library the capture ran on
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
@@ -64,4 +67,33 @@ lines += ["", f"FP64-pipe instructions/step: {fp64:.1f}   FP32 arithmetic instru
 tma = [r[ix["Source"]].strip() for r in data if re.search(r"UBLKCP|UTMALDG|SYNCS", r[ix["Source"]])]
 lines += ["", "## TMA / mbarrier SASS present in the kernel:"] + sorted(set(tma))[:12]
 open(out, "w").write("\n".join(lines) + "\n")
+if json_out:
+    def num(k):
+        try:
+            return float(M[k][0].replace(",", ""))
+        except (KeyError, ValueError):
+            return None
+    unit_scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    def nbytes(k):
+        v = num(k)
+        return None if v is None else v * unit_scale.get(M[k][1], 1.0)
+    mix = {k: v / ws for k, v in c.most_common(40)}
+    exported = {
+        "kernel": M["Kernel Name"][0].strip(), "build_info": build_info, "source_report": rep.split("/")[-1],
+        "grid": int(num("launch__grid_size")), "block": int(num("launch__block_size")), "registers": int(num("launch__registers_per_thread")),
+        "steps_per_launch": steps_per_launch, "time_ms_under_ncu": num("gpu__time_duration.sum"),
+        "dram_bytes_read": nbytes("dram__bytes_read.sum"), "dram_bytes_write": nbytes("dram__bytes_write.sum"),
+        "fp64_pipe_active_pct": num("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+        "fma_pipe_active_pct": num("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+        "alu_pipe_active_pct": num("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+        "xu_pipe_active_pct": num("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+        "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+        "warp_instructions_per_step": tot / ws, "sass_mix_per_step": mix,
+        "fp64_pipe_instructions_per_step": fp64,
+        # executed flops per geodesic step: FMA = 2, MUL = ADD = 1 (compares and MUFU not counted)
+        "executed_fp64_flop_per_step": 2 * mix.get("DFMA", 0.0) + mix.get("DMUL", 0.0) + mix.get("DADD", 0.0),
+        "executed_fp32_flop_per_step": 2 * mix.get("FFMA", 0.0) + mix.get("FMUL", 0.0) + mix.get("FADD", 0.0),
+    }
+    exported["dram_bytes_per_launch"] = (exported["dram_bytes_read"] or 0) + (exported["dram_bytes_write"] or 0)
+    json.dump(exported, open(json_out, "w"), indent=1)
 print("\n".join(lines[:60]))
