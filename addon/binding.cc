@@ -2,9 +2,12 @@
 // Exposes the two seams of the reference to TypeScript:
 //   class PhysicsEngine  — same method names as the wasm-bindgen class (physics-engine/gravitas-wasm/src/lib.rs:42-465)
 //   class KerrRenderer   — init/resize/renderFrame for the src/rendering renderer API (rendering/webgpu/renderer.ts:82-411)
-// Build (on a machine with node): node-gyp rebuild (addon/binding.gyp). Not load-tested in the build image (no node);
-// syntax-checked against addon/stub/node_api.h by tests/test_abi_host.py.
+// Build (on a machine with node): node-gyp rebuild (addon/binding.gyp). Not load-tested in the build image (no node, no
+// node headers); type-checked against addon/stub/node_api.h -- a verbatim subset of Node's node_api.h / js_native_api.h
+// declarations -- by tests/test_abi_host.py. Runtime: a Node-API host with a DOM, i.e. an Electron / NW.js renderer (and
+// its workers, nodeIntegrationInWorker), see INTEGRATION.md 4.
 #include <node_api.h>
+#include <stdint.h>
 #include <string.h>
 #include "gravitas_b200.h"
 
@@ -22,6 +25,38 @@ template <class T> T* Self(napi_env env, napi_callback_info info, size_t* argc, 
     napi_unwrap(env, self, &p);
     return static_cast<T*>(p);
 }
+// What a JS PhysicsEngine wraps: the native engine plus the view it writes its SAB block into. The view is held by a
+// strong reference so that the memory outlives every tick_sab (the engine keeps a raw pointer into it).
+struct EngineBox {
+    gvt_engine* e = nullptr;
+    napi_ref sab_ref = nullptr;      // Float32Array (over a SharedArrayBuffer or ArrayBuffer) passed to attach_sab
+    uint32_t sab_byte_offset = 0;    // its byteOffset inside that buffer: what get_sab_ptr() returns (wasm: offset into memory.buffer)
+    bool attached = false;
+};
+gvt_engine* Eng(napi_env env, napi_callback_info info, size_t* argc, napi_value* argv, EngineBox** box_out = nullptr) {
+    EngineBox* b = Self<EngineBox>(env, info, argc, argv);
+    if (box_out) *box_out = b;
+    return b ? b->e : nullptr;
+}
+// A caller-provided byte range: an ArrayBuffer, or any TypedArray / DataView-less view (also over a SharedArrayBuffer, which
+// napi_get_arraybuffer_info rejects on most Node versions while napi_get_typedarray_info accepts views of it).
+bool ByteRange(napi_env env, napi_value v, void** data, size_t* bytes, napi_typedarray_type* type_out = nullptr) {
+    bool is_ta = false;
+    if (napi_is_typedarray(env, v, &is_ta) == napi_ok && is_ta) {
+        napi_typedarray_type t; size_t n = 0; napi_value ab; size_t off = 0;
+        if (napi_get_typedarray_info(env, v, &t, &n, data, &ab, &off) != napi_ok) return false;
+        static const size_t elem[] = {1, 1, 1, 2, 2, 4, 4, 4, 8, 8, 8};
+        *bytes = n * ((size_t)t < sizeof(elem) / sizeof(elem[0]) ? elem[t] : 1);
+        if (type_out) *type_out = t;
+        return true;
+    }
+    bool is_ab = false;
+    if (napi_is_arraybuffer(env, v, &is_ab) == napi_ok && is_ab) {
+        if (type_out) *type_out = napi_uint8_array;
+        return napi_get_arraybuffer_info(env, v, data, bytes) == napi_ok;
+    }
+    return false;
+}
 napi_value F32Array(napi_env env, size_t n, float** data) {
     napi_value ab, out; void* p;
     if (napi_create_arraybuffer(env, n * 4, &p, &ab) != napi_ok) return nullptr;
@@ -34,35 +69,74 @@ napi_value F32Array(napi_env env, size_t n, float** data) {
 napi_value EngineNew(napi_env env, napi_callback_info info) {                    // lib.rs:59
     size_t argc = 2; napi_value argv[2], self;
     NAPI_OK(napi_get_cb_info(env, info, &argc, argv, &self, nullptr));
-    gvt_engine* e = nullptr;
-    GVT(gvt_engine_create(Num(env, argv[0]), Num(env, argv[1]), &e));
-    NAPI_OK(napi_wrap(env, self, e, [](napi_env, void* d, void*) { gvt_engine_destroy(static_cast<gvt_engine*>(d)); }, nullptr, nullptr));
+    EngineBox* box = new EngineBox();
+    if (gvt_engine_create(Num(env, argv[0]), Num(env, argv[1]), &box->e) != GVT_OK) {
+        delete box;
+        napi_throw_error(env, nullptr, gvt_last_error());
+        return nullptr;
+    }
+    NAPI_OK(napi_wrap(env, self, box, [](napi_env fenv, void* d, void*) {
+        EngineBox* b = static_cast<EngineBox*>(d);
+        if (b->sab_ref) napi_delete_reference(fenv, b->sab_ref);
+        gvt_engine_destroy(b->e);
+        delete b;
+    }, nullptr, nullptr));
     return self;
 }
 napi_value UpdateParams(napi_env env, napi_callback_info info) {                 // lib.rs:78
     size_t argc = 2; napi_value argv[2];
-    gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
+    gvt_engine* e = Eng(env, info, &argc, argv);
     GVT(gvt_engine_update_params(e, Num(env, argv[0]), Num(env, argv[1])));
     return Undefined(env);
 }
 napi_value TickSab(napi_env env, napi_callback_info info) {                      // lib.rs:308
     size_t argc = 1; napi_value argv[1];
-    gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
+    gvt_engine* e = Eng(env, info, &argc, argv);
     GVT(gvt_engine_tick_sab(e, Num(env, argv[0])));
     return Undefined(env);
 }
-napi_value AttachSab(napi_env env, napi_callback_info info) {                    // lib.rs:74 (SharedArrayBuffer in)
-    size_t argc = 1; napi_value argv[1];
-    gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
-    void* data = nullptr; size_t len = 0;
-    NAPI_OK(napi_get_arraybuffer_info(env, argv[0], &data, &len));
-    if (len < GVT_SAB_INTERNAL_F32 * 4) { napi_throw_range_error(env, nullptr, "SAB smaller than 2048 f32"); return nullptr; }
-    GVT(gvt_engine_attach_sab(e, static_cast<float*>(data)));
+// attach_sab(view: Float32Array)            lib.rs:74 -- the engine then writes its SAB block into the caller's memory in place.
+// `view` is a Float32Array of >= 2048 elements over a SharedArrayBuffer (the worker's SAB, or the module "memory" of
+// addon/ts/index.ts) or an ArrayBuffer; a bare ArrayBuffer is accepted too. The engine holds a strong reference to it.
+napi_value AttachSab(napi_env env, napi_callback_info info) {
+    size_t argc = 1; napi_value argv[1]; EngineBox* box = nullptr;
+    gvt_engine* e = Eng(env, info, &argc, argv, &box);
+    if (!e || argc < 1) { napi_throw_error(env, nullptr, "attach_sab(view)"); return nullptr; }
+    void* data = nullptr; size_t bytes = 0; napi_typedarray_type t = napi_uint8_array;
+    if (!ByteRange(env, argv[0], &data, &bytes, &t)) {
+        napi_throw_error(env, nullptr, "attach_sab: pass a Float32Array view of the (Shared)ArrayBuffer");
+        return nullptr;
+    }
+    bool is_ta = false; napi_is_typedarray(env, argv[0], &is_ta);
+    if (is_ta && t != napi_float32_array) { napi_throw_error(env, nullptr, "attach_sab: Float32Array expected"); return nullptr; }
+    if (bytes < (size_t)GVT_SAB_INTERNAL_F32 * 4 || ((uintptr_t)data & 3u)) { napi_throw_range_error(env, nullptr, "SAB view smaller than 2048 f32 or misaligned"); return nullptr; }
+    size_t byte_offset = 0;
+    if (is_ta) { napi_typedarray_type tt; size_t n; void* d; napi_value ab; napi_get_typedarray_info(env, argv[0], &tt, &n, &d, &ab, &byte_offset); }
+    napi_ref ref = nullptr;
+    NAPI_OK(napi_create_reference(env, argv[0], 1, &ref));
+    if (gvt_engine_attach_sab(e, static_cast<float*>(data)) != GVT_OK) {
+        napi_delete_reference(env, ref);
+        napi_throw_error(env, nullptr, gvt_last_error());
+        return nullptr;
+    }
+    if (box->sab_ref) napi_delete_reference(env, box->sab_ref);     // re-attach: release the previous view
+    box->sab_ref = ref; box->sab_byte_offset = (uint32_t)byte_offset; box->attached = true;
     return Undefined(env);
 }
-napi_value GetSab(napi_env env, napi_callback_info info) {                       // get_sab_ptr, lib.rs:116 -> a copy-free view is not
-    size_t argc = 0;                                                             // possible over N-API without an external buffer;
-    gvt_engine* e = Self<gvt_engine>(env, info, &argc, nullptr);                 // hosts should use attach_sab. This returns a snapshot.
+// get_sab_ptr()                              lib.rs:116 -- the wasm build returns the byte offset of the engine's 2048-f32 block inside
+// `memory.buffer`; physics.worker.ts:153-163 and physics-bridge.ts:107 divide it by 4 and index a Float32Array over that
+// buffer. Here it is the byteOffset of the attached view inside ITS buffer -- addon/ts/index.ts attaches every engine to a
+// region of the one SharedArrayBuffer its init() hands out as `memory.buffer`, so the unchanged worker reads live values.
+napi_value GetSabPtr(napi_env env, napi_callback_info info) {
+    size_t argc = 0; EngineBox* box = nullptr;
+    gvt_engine* e = Eng(env, info, &argc, nullptr, &box);
+    if (!e || !box->attached) { napi_throw_error(env, nullptr, "get_sab_ptr: no SAB view attached (addon/ts/index.ts attaches one per engine)"); return nullptr; }
+    napi_value v; napi_create_uint32(env, box->sab_byte_offset, &v);
+    return v;
+}
+napi_value GetSab(napi_env env, napi_callback_info info) {                       // a snapshot copy of the engine-owned block (debugging aid)
+    size_t argc = 0;
+    gvt_engine* e = Eng(env, info, &argc, nullptr);
     const float* p = nullptr; float* out = nullptr;
     GVT(gvt_engine_get_sab_ptr(e, &p));
     napi_value arr = F32Array(env, GVT_SAB_INTERNAL_F32, &out);
@@ -71,13 +145,13 @@ napi_value GetSab(napi_env env, napi_callback_info info) {                      
 }
 napi_value SetCameraState(napi_env env, napi_callback_info info) {               // lib.rs:120
     size_t argc = 6; napi_value argv[6];
-    gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
+    gvt_engine* e = Eng(env, info, &argc, argv);
     GVT(gvt_engine_set_camera_state(e, Num(env, argv[0]), Num(env, argv[1]), Num(env, argv[2]), 0, 0, 0));
     return Undefined(env);
 }
 napi_value SetAutoSpin(napi_env env, napi_callback_info info) {                  // lib.rs:124
     size_t argc = 1; napi_value argv[1]; bool b = false;
-    gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
+    gvt_engine* e = Eng(env, info, &argc, argv);
     napi_get_value_bool(env, argv[0], &b);
     GVT(gvt_engine_set_auto_spin(e, b ? 1 : 0));
     return Undefined(env);
@@ -85,7 +159,7 @@ napi_value SetAutoSpin(napi_env env, napi_callback_info info) {                 
 #define ENGINE_GETTER(NAME, CALL)                                          \
     napi_value NAME(napi_env env, napi_callback_info info) {                \
         size_t argc = 2; napi_value argv[2];                                \
-        gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);           \
+        gvt_engine* e = Eng(env, info, &argc, argv);           \
         double out = 0;                                                     \
         GVT(CALL);                                                          \
         napi_value v; napi_create_double(env, out, &v); return v;           \
@@ -99,7 +173,7 @@ ENGINE_GETTER(ComputeShadowRadius, gvt_engine_compute_shadow_radius(e, &out))   
 ENGINE_GETTER(ComputeDiskFlux, gvt_engine_compute_disk_flux(e, Num(env, argv[0]), &out))            // lib.rs:199
 napi_value ShadowCurve(napi_env env, napi_callback_info info) {                  // lib.rs:161
     size_t argc = 2; napi_value argv[2];
-    gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
+    gvt_engine* e = Eng(env, info, &argc, argv);
     const double theta = Num(env, argv[0]);
     const uint32_t n_points = (uint32_t)Num(env, argv[1]);
     uint32_t n = 0;
@@ -111,7 +185,7 @@ napi_value ShadowCurve(napi_env env, napi_callback_info info) {                 
 }
 napi_value ShadowShift(napi_env env, napi_callback_info info) {                  // lib.rs:179
     size_t argc = 1; napi_value argv[1];
-    gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
+    gvt_engine* e = Eng(env, info, &argc, argv);
     float* out = nullptr;
     napi_value arr = F32Array(env, 2, &out);
     if (arr) GVT(gvt_engine_compute_shadow_shift(e, Num(env, argv[0]), out));
@@ -124,7 +198,7 @@ ENGINE_GETTER(ComputeFrameDragOmega, gvt_engine_compute_frame_drag_omega(e, Num(
 ENGINE_GETTER(ComputeFlammHeight, gvt_engine_compute_flamm_height(e, Num(env, argv[0]), &out))                       // lib.rs:296
 napi_value ComputeProperDistance(napi_env env, napi_callback_info info) {                                           // lib.rs:302
     size_t argc = 3; napi_value argv[3];
-    gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
+    gvt_engine* e = Eng(env, info, &argc, argv);
     double out = 0;
     GVT(gvt_engine_compute_proper_distance(e, Num(env, argv[0]), Num(env, argv[1]), (uint32_t)Num(env, argv[2]), &out));
     napi_value v; napi_create_double(env, out, &v); return v;
@@ -132,7 +206,7 @@ napi_value ComputeProperDistance(napi_env env, napi_callback_info info) {       
 typedef int32_t (*FieldFn)(gvt_engine*, double, double, uint32_t, uint32_t, float*);
 template <FieldFn FN> napi_value Field(napi_env env, napi_callback_info info) {   // (rMin, rMax, n1, n2) -> Float32Array(3 n1 n2)
     size_t argc = 4; napi_value argv[4];
-    gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
+    gvt_engine* e = Eng(env, info, &argc, argv);
     const uint32_t n1 = (uint32_t)Num(env, argv[2]), n2 = (uint32_t)Num(env, argv[3]);
     float* out = nullptr;
     napi_value arr = F32Array(env, (size_t)3 * n1 * n2, &out);
@@ -141,7 +215,7 @@ template <FieldFn FN> napi_value Field(napi_env env, napi_callback_info info) { 
 }
 napi_value ErgosphereMesh(napi_env env, napi_callback_info info) {                                                  // lib.rs:153
     size_t argc = 2; napi_value argv[2];
-    gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
+    gvt_engine* e = Eng(env, info, &argc, argv);
     const uint32_t n1 = (uint32_t)Num(env, argv[0]), n2 = (uint32_t)Num(env, argv[1]);
     float* out = nullptr;
     napi_value arr = F32Array(env, (size_t)3 * n1 * n2, &out);
@@ -150,7 +224,7 @@ napi_value ErgosphereMesh(napi_env env, napi_callback_info info) {              
 }
 napi_value DiskLut(napi_env env, napi_callback_info info) {                      // lib.rs:107
     size_t argc = 0;
-    gvt_engine* e = Self<gvt_engine>(env, info, &argc, nullptr);
+    gvt_engine* e = Eng(env, info, &argc, nullptr);
     float* out = nullptr;
     napi_value arr = F32Array(env, 512, &out);
     if (arr) GVT(gvt_engine_generate_disk_lut(e, out));
@@ -158,7 +232,7 @@ napi_value DiskLut(napi_env env, napi_callback_info info) {                     
 }
 napi_value DiskLutPtr(napi_env env, napi_callback_info info) {                   // lib.rs:112: a copy of the engine-owned LUT
     size_t argc = 0;
-    gvt_engine* e = Self<gvt_engine>(env, info, &argc, nullptr);
+    gvt_engine* e = Eng(env, info, &argc, nullptr);
     const float* p = nullptr; uint32_t n = 0;
     GVT(gvt_engine_get_disk_lut_ptr(e, &p, &n));
     float* out = nullptr;
@@ -168,7 +242,7 @@ napi_value DiskLutPtr(napi_env env, napi_callback_info info) {                  
 }
 napi_value SpectrumLut(napi_env env, napi_callback_info info) {                  // lib.rs:128
     size_t argc = 3; napi_value argv[3];
-    gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
+    gvt_engine* e = Eng(env, info, &argc, argv);
     const uint32_t w = (uint32_t)Num(env, argv[0]), h = (uint32_t)Num(env, argv[1]);
     float* out = nullptr;
     napi_value arr = F32Array(env, (size_t)w * h * 4, &out);
@@ -177,7 +251,7 @@ napi_value SpectrumLut(napi_env env, napi_callback_info info) {                 
 }
 napi_value IntegrateRay(napi_env env, napi_callback_info info) {                 // lib.rs:422
     size_t argc = 4; napi_value argv[4];
-    gvt_engine* e = Self<gvt_engine>(env, info, &argc, argv);
+    gvt_engine* e = Eng(env, info, &argc, argv);
     uint32_t n = 0; napi_get_array_length(env, argv[0], &n);
     if (n < 8) return argv[0];                                                   // lib.rs:429-431: returned unchanged
     double in8[8], out8[8]; bool ks = false;
@@ -192,7 +266,7 @@ napi_value IntegrateRay(napi_env env, napi_callback_info info) {                
 }
 napi_value SabLayout(napi_env env, napi_callback_info info) {                    // lib.rs:411
     size_t argc = 0;
-    gvt_engine* e = Self<gvt_engine>(env, info, &argc, nullptr);
+    gvt_engine* e = Eng(env, info, &argc, nullptr);
     uint32_t l[5];
     GVT(gvt_engine_get_sab_layout(e, l));
     void* data; napi_value ab, out;
@@ -235,12 +309,12 @@ uint32_t OptU32(napi_env env, napi_value obj, const char* key, uint32_t dflt) {
 napi_value RenderFrame(napi_env env, napi_callback_info info) {
     size_t argc = 4; napi_value argv[4];
     gvt_renderer* r = Self<gvt_renderer>(env, info, &argc, argv);
-    napi_typedarray_type t; size_t n; void *cam, *phys, *out; napi_value ab; size_t off, outlen;
-    NAPI_OK(napi_get_typedarray_info(env, argv[0], &t, &n, &cam, &ab, &off));
-    if (t != napi_float32_array || n < 88) { napi_throw_range_error(env, nullptr, "camera: Float32Array(88) expected"); return nullptr; }
-    NAPI_OK(napi_get_typedarray_info(env, argv[1], &t, &n, &phys, &ab, &off));
-    if (n < 8) { napi_throw_range_error(env, nullptr, "physics: 32 bytes expected"); return nullptr; }
-    NAPI_OK(napi_get_arraybuffer_info(env, argv[3], &out, &outlen));
+    napi_typedarray_type t; void *cam, *phys, *out; size_t nbytes, outlen;
+    if (!r || argc < 4) { napi_throw_error(env, nullptr, "renderFrame(camera, physics, options, out)"); return nullptr; }
+    if (!ByteRange(env, argv[0], &cam, &nbytes, &t) || t != napi_float32_array || nbytes < sizeof(GvtCamera)) { napi_throw_range_error(env, nullptr, "camera: Float32Array(88) expected"); return nullptr; }
+    // PhysicsParams is 6 f32 + 2 u32 (types/webgpu.ts:42-64): any 32-bit view of >= 32 bytes
+    if (!ByteRange(env, argv[1], &phys, &nbytes, &t) || (t != napi_float32_array && t != napi_uint32_array && t != napi_int32_array) || nbytes < sizeof(GvtPhysicsParams)) { napi_throw_range_error(env, nullptr, "physics: 32-bit typed array of 32 bytes expected"); return nullptr; }
+    if (!ByteRange(env, argv[3], &out, &outlen)) { napi_throw_error(env, nullptr, "out: ArrayBuffer or typed array expected"); return nullptr; }
     GvtRenderParams p; gvt_render_params_default(&p);
     p.max_steps = OptU32(env, argv[2], "maxSteps", p.max_steps);
     p.method = OptU32(env, argv[2], "method", p.method);
@@ -265,10 +339,10 @@ napi_value RenderFrame(napi_env env, napi_callback_info info) {
 napi_value SetNoiseTextures(napi_env env, napi_callback_info info) {
     size_t argc = 2; napi_value argv[2];
     gvt_renderer* r = Self<gvt_renderer>(env, info, &argc, argv);
-    napi_typedarray_type t; size_t n0, n1; void *a, *b; napi_value ab; size_t off;
-    NAPI_OK(napi_get_typedarray_info(env, argv[0], &t, &n0, &a, &ab, &off));
-    NAPI_OK(napi_get_typedarray_info(env, argv[1], &t, &n1, &b, &ab, &off));
-    if (n0 < 262144 || n1 < 262144) { napi_throw_range_error(env, nullptr, "Uint8Array(256*256*4) expected"); return nullptr; }
+    napi_typedarray_type t0, t1; size_t n0 = 0, n1 = 0; void *a, *b;
+    if (!r || !ByteRange(env, argv[0], &a, &n0, &t0) || !ByteRange(env, argv[1], &b, &n1, &t1) ||
+        (t0 != napi_uint8_array && t0 != napi_uint8_clamped_array) || (t1 != napi_uint8_array && t1 != napi_uint8_clamped_array) ||
+        n0 < 262144 || n1 < 262144) { napi_throw_range_error(env, nullptr, "Uint8Array(256*256*4) expected"); return nullptr; }
     GVT(gvt_render_set_noise_textures(r, static_cast<const uint8_t*>(a), static_cast<const uint8_t*>(b), 256));
     return Undefined(env);
 }
@@ -278,10 +352,10 @@ napi_value SetNoiseTextures(napi_env env, napi_callback_info info) {
 napi_value RenderFragment(napi_env env, napi_callback_info info) {
     size_t argc = 3; napi_value argv[3];
     gvt_renderer* r = Self<gvt_renderer>(env, info, &argc, argv);
-    napi_typedarray_type t; size_t n; void *u, *out; napi_value ab; size_t off, outlen;
-    NAPI_OK(napi_get_typedarray_info(env, argv[0], &t, &n, &u, &ab, &off));
-    if (n * 4 < sizeof(GvtGlslUniforms)) { napi_throw_range_error(env, nullptr, "uniforms: 155 words expected"); return nullptr; }
-    NAPI_OK(napi_get_arraybuffer_info(env, argv[2], &out, &outlen));
+    napi_typedarray_type t; size_t nbytes; void *u, *out; size_t outlen;
+    if (!r || !ByteRange(env, argv[0], &u, &nbytes, &t) || (t != napi_float32_array && t != napi_uint32_array && t != napi_int32_array) ||
+        nbytes < sizeof(GvtGlslUniforms)) { napi_throw_range_error(env, nullptr, "uniforms: 155 32-bit words expected"); return nullptr; }
+    if (!ByteRange(env, argv[2], &out, &outlen)) { napi_throw_error(env, nullptr, "out: ArrayBuffer or typed array expected"); return nullptr; }
     const uint32_t precision = OptU32(env, argv[1], "precision", GVT_PRECISION_F32_FAST);
     const uint32_t flags = OptU32(env, argv[1], "flags", 0), format = OptU32(env, argv[1], "format", GVT_FORMAT_RGBA32F);
     const uint32_t moving = OptU32(env, argv[1], "cameraMoving", 0);
@@ -310,11 +384,20 @@ napi_value Bloom(napi_env env, napi_callback_info info) {
     bool has = false; napi_value v;
     if (napi_has_named_property(env, argv[0], "intensity", &has) == napi_ok && has) { napi_get_named_property(env, argv[0], "intensity", &v); cfg.intensity = (float)Num(env, v); }
     if (napi_has_named_property(env, argv[0], "threshold", &has) == napi_ok && has) { napi_get_named_property(env, argv[0], "threshold", &v); cfg.threshold = (float)Num(env, v); }
+    cfg.precise = OptU32(env, argv[0], "precise", 0);
     void* out; size_t outlen;
-    NAPI_OK(napi_get_arraybuffer_info(env, argv[1], &out, &outlen));
+    if (!r || !ByteRange(env, argv[1], &out, &outlen)) { napi_throw_error(env, nullptr, "bloom(options, out: ArrayBuffer | typed array)"); return nullptr; }
+    const uint32_t format = OptU32(env, argv[0], "format", GVT_FORMAT_RGBA8_UNORM);
     double ms = 0;
-    if (outlen == 0) out = nullptr;
-    GVT(gvt_render_bloom(r, &cfg, OptU32(env, argv[0], "format", GVT_FORMAT_RGBA8_UNORM), out, &ms));
+    if (outlen == 0) out = nullptr;                                               // result stays on the device
+    else {
+        // the library writes width*height pixels of `format`: the caller's buffer must hold them (it knows the frame size)
+        uint32_t w = 0, h = 0;
+        GVT(gvt_render_get_size(r, &w, &h));
+        const size_t need = (size_t)w * h * (format == GVT_FORMAT_RGBA32F ? 16 : format == GVT_FORMAT_RGBA16F ? 8 : 4);
+        if (outlen < need) { napi_throw_range_error(env, nullptr, "bloom: output buffer smaller than width*height*bytes-per-pixel"); return nullptr; }
+    }
+    GVT(gvt_render_bloom(r, &cfg, format, out, &ms));
     napi_value o; napi_create_double(env, ms, &o);
     return o;
 }
@@ -324,7 +407,8 @@ napi_value Bloom(napi_env env, napi_callback_info info) {
 NAPI_MODULE_INIT() {
     const napi_property_descriptor engine[] = {
         {"update_params", 0, UpdateParams, 0, 0, 0, napi_default, 0}, {"tick_sab", 0, TickSab, 0, 0, 0, napi_default, 0},
-        {"attach_sab", 0, AttachSab, 0, 0, 0, napi_default, 0}, {"get_sab", 0, GetSab, 0, 0, 0, napi_default, 0},
+        {"attach_sab", 0, AttachSab, 0, 0, 0, napi_default, 0}, {"get_sab_ptr", 0, GetSabPtr, 0, 0, 0, napi_default, 0},
+        {"get_sab", 0, GetSab, 0, 0, 0, napi_default, 0},
         {"get_sab_layout", 0, SabLayout, 0, 0, 0, napi_default, 0},
         {"set_camera_state", 0, SetCameraState, 0, 0, 0, napi_default, 0}, {"set_auto_spin", 0, SetAutoSpin, 0, 0, 0, napi_default, 0},
         {"compute_horizon", 0, ComputeHorizon, 0, 0, 0, napi_default, 0}, {"compute_isco", 0, ComputeIsco, 0, 0, 0, napi_default, 0},

@@ -1,7 +1,9 @@
-/* MINIMAL N-API DECLARATIONS FOR SYNTAX CHECKING ONLY.
+/* MINIMAL N-API DECLARATIONS FOR TYPE CHECKING ONLY.
  * This image has neither node nor its headers; this file declares just the Node-API (stable C ABI, nodejs.org/api/n-api)
- * types and functions addon/binding.cc uses, so that `g++ -fsyntax-only` can check the shim here. A real build uses
- * node's own <node_api.h> (node-gyp / cmake-js put it on the include path) and never sees this file. */
+ * types and functions addon/binding.cc uses -- with the parameter lists of Node's own js_native_api.h / node_api.h
+ * (Node-API version 8) -- so that `g++ -fsyntax-only` can check the shim here. It proves the C++ type-checks against
+ * those signatures, not that it loads: a real build uses node's own <node_api.h> (node-gyp / cmake-js put it on the
+ * include path) and never sees this file. */
 #ifndef GVT_NODE_API_STUB_H
 #define GVT_NODE_API_STUB_H
 #include <stddef.h>
@@ -17,7 +19,7 @@ typedef enum { napi_ok = 0, napi_invalid_arg, napi_object_expected, napi_generic
 typedef enum { napi_default = 0 } napi_property_attributes;
 typedef enum {
     napi_int8_array, napi_uint8_array, napi_uint8_clamped_array, napi_int16_array, napi_uint16_array, napi_int32_array,
-    napi_uint32_array, napi_float32_array, napi_float64_array
+    napi_uint32_array, napi_float32_array, napi_float64_array, napi_bigint64_array, napi_biguint64_array
 } napi_typedarray_type;
 typedef napi_value (*napi_callback)(napi_env env, napi_callback_info info);
 typedef void (*napi_finalize)(napi_env env, void* finalize_data, void* finalize_hint);
@@ -46,6 +48,11 @@ napi_status napi_get_arraybuffer_info(napi_env, napi_value arraybuffer, void** d
 napi_status napi_create_typedarray(napi_env, napi_typedarray_type, size_t length, napi_value arraybuffer, size_t byte_offset, napi_value* result);
 napi_status napi_get_typedarray_info(napi_env, napi_value typedarray, napi_typedarray_type* type, size_t* length, void** data, napi_value* arraybuffer, size_t* byte_offset);
 napi_status napi_define_class(napi_env, const char* utf8name, size_t length, napi_callback constructor, void* data, size_t property_count, const napi_property_descriptor* properties, napi_value* result);
+napi_status napi_is_typedarray(napi_env, napi_value value, bool* result);
+napi_status napi_is_arraybuffer(napi_env, napi_value value, bool* result);
+napi_status napi_create_reference(napi_env, napi_value value, uint32_t initial_refcount, napi_ref* result);
+napi_status napi_delete_reference(napi_env, napi_ref ref);
+napi_status napi_get_reference_value(napi_env, napi_ref ref, napi_value* result);
 napi_status napi_throw_error(napi_env, const char* code, const char* msg);
 napi_status napi_throw_range_error(napi_env, const char* code, const char* msg);
 #define NAPI_MODULE_INIT() extern "C" napi_value napi_register_module_v1(napi_env env, napi_value exports)

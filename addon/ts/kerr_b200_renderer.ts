@@ -1,5 +1,8 @@
 // Drop-in for src/rendering/webgpu/renderer.ts (WebGPURenderer): same public methods, render() fills a frame buffer
 // through the addon and blits it. Callers (components/canvas/WebGPUCanvas.tsx:73-194) are unchanged.
+// RUNTIME: this file needs BOTH a DOM (the canvas it blits to) and Node-API (the addon, via ./index): an Electron / NW.js
+// renderer process with nodeIntegration. In a stock browser the frames would have to come from a render server instead
+// (INTEGRATION.md 4); that transport is not part of this repository.
 import { KerrRenderer } from "./index";
 import { CameraUniforms, PhysicsParams, writeCameraUniforms, writePhysicsParams } from "@/types/webgpu";
 

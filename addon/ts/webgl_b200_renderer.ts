@@ -1,6 +1,7 @@
 // Drop-in for src/rendering/webgl/renderer.ts (WebGLRenderer): same public surface (init / resize / render(params,
 // mouse) / cleanup / error / onMetricsUpdate); render() runs the production fragment shader as one CUDA kernel through
 // the addon and blits the tone-mapped frame. Callers (components/canvas/WebGLCanvas.tsx) are unchanged.
+// RUNTIME: needs a DOM and Node-API together (Electron / NW.js renderer with nodeIntegration), like kerr_b200_renderer.ts.
 import { KerrRenderer } from "./index";
 import type { SimulationParams } from "@/types/simulation";
 import { DEFAULT_FEATURES, getMaxRaySteps } from "@/types/features";

@@ -621,6 +621,12 @@ extern "C" int32_t gvt_render_resize(gvt_renderer* r, uint32_t width, uint32_t h
     return GVT_OK;
 }
 
+extern "C" int32_t gvt_render_get_size(gvt_renderer* r, uint32_t* width, uint32_t* height) {
+    if (!r || !width || !height) return fail(GVT_ERR_INVALID, "null argument");
+    *width = r->width; *height = r->height;
+    return GVT_OK;
+}
+
 extern "C" int32_t gvt_render_reset_history(gvt_renderer* r) {
     if (!r) return fail(GVT_ERR_INVALID, "null renderer");
     if (r->hist) CK(cudaMemsetAsync(r->hist, 0, (size_t)r->width * r->padded_height * sizeof(float4), r->stream));

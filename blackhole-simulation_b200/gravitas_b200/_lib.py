@@ -137,6 +137,7 @@ SIGNATURES = {
     "gvt_render_frame": (_i32, [_vp, C.POINTER(GvtCamera), C.POINTER(GvtPhysicsParams), C.POINTER(GvtRenderParams), _vp,
                                 C.POINTER(GvtFrameStats)]),
     "gvt_render_read_frame": (_i32, [_vp, _u32, _vp]),
+    "gvt_render_get_size": (_i32, [_vp, C.POINTER(_u32), C.POINTER(_u32)]),
     "gvt_trace_states": (_i32, [_vp, C.POINTER(GvtCamera), C.POINTER(GvtPhysicsParams), C.POINTER(GvtRenderParams), _u32,
                                 _u32, _u32, _u32, _u32, _pd, _pu32, _pu32, _pd, _pd]),
     "gvt_taa_resolve": (_i32, [_vp, C.POINTER(GvtCamera), _u32, _u32, _pf, _pf, _pf]),

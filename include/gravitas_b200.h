@@ -326,6 +326,8 @@ int32_t gvt_taa_resolve_ex(gvt_renderer* r, const GvtCamera* cam, uint32_t width
                            const float* hist, float* out, uint32_t webgl, float blend, int32_t camera_moving,
                            int32_t precise, double* ms_out);
 int32_t gvt_render_reset_history(gvt_renderer* r);
+/* Size of the frame buffers (0 x 0 before the first resize / frame): what a binding needs to validate caller buffers. */
+int32_t gvt_render_get_size(gvt_renderer* r, uint32_t* width, uint32_t* height);
 
 /* ---- Seam B, WebGL2 pipeline: WebGLRenderer.render(params, mouse) (src/rendering/webgl/renderer.ts:173-420) ----
  * The two 256x256 RGBA8 noise textures the reference fills with Math.random() at init (webgl-utils.ts:259-303);

@@ -181,8 +181,9 @@ def test_product_does_not_reference_the_oracle():
 
 
 def test_napi_shim_compiles_against_the_header():
-    """addon/binding.cc (the N-API shim of INTEGRATION.md) is syntax-checked against include/gravitas_b200.h and a
-    minimal declaration-only node_api.h (node itself is not in this image, so it cannot be load-tested here)."""
+    """addon/binding.cc (the N-API shim of INTEGRATION.md) is type-checked against include/gravitas_b200.h and a
+    declaration-only subset of Node's node_api.h written out in addon/stub/ (node and its headers are not in this image):
+    this proves the C++ is well-formed against those signatures, nothing about loading under node."""
     import shutil
     import subprocess
     gxx = shutil.which("g++")
@@ -195,7 +196,7 @@ def test_napi_shim_compiles_against_the_header():
     src = open(os.path.join(ROOT, "addon", "binding.cc")).read()
     for name in ("tick_sab", "attach_sab", "update_params", "set_camera_state", "set_auto_spin", "compute_horizon",
                  "compute_isco", "compute_photon_sphere", "compute_dilation", "generate_disk_lut",
-                 "generate_spectrum_lut", "integrate_ray_relativistic", "get_sab_layout"):
+                 "generate_spectrum_lut", "integrate_ray_relativistic", "get_sab_layout", "get_sab_ptr"):
         assert f'"{name}"' in src, f"PhysicsEngine.{name} (gravitas-wasm/src/lib.rs) missing from the shim"
 
 
@@ -276,3 +277,64 @@ def test_spacetime_visualisation_helpers(built):
         assert abs(np.linalg.norm(mesh[4, 0]) - 2.0 * m) < 1e-5 * m and abs(abs(mesh[0, 0, 1]) - e.compute_horizon()) < 1e-5 * m
     with pytest.raises(built.GravitasError):
         e1.generate_curvature_field(2.0, 10.0, 1, 5)          # the reference divides by (n - 1)
+
+
+def test_unchanged_worker_sequence_against_the_module_contract(built):
+    """Replays src/workers/physics.worker.ts:60-68,111-176 VERBATIM against the module shape of addon/ts/index.ts (its
+    Python twin gravitas_b200/wasm_module.py): `init()` -> `.memory.buffer`, `new PhysicsEngine`, `tick_sab`, seqlock +1,
+    `get_sab_ptr() / 4` -> `wasmF32.subarray(...)` copies of the CAMERA and PHYSICS blocks into the app's SAB, seqlock +1.
+    The copied values must be the ones an engine writing straight into an attached SAB produces, the pointer a non-zero
+    byte offset inside memory.buffer, and two engines must not share a region."""
+    from gravitas_b200 import wasm_module as M
+    OFF = built.OFFSETS
+    # --- worker INIT (physics.worker.ts:38-68)
+    sab = np.zeros(2 * 1024 * 1024 // 4, np.float32)                     # data.sab: SharedArrayBuffer(2 MiB), physics-bridge.ts:60
+    sab_seq = sab.view(np.int32)                                         # sabSequenceView = new Int32Array(sab)
+    wasm_module = M.init()                                               # await wasmModuleWrap.default()
+    engine = M.PhysicsEngine(1.0, 0.9)                                   # new PhysicsEngine(mass, spin)
+    wasm_memory = wasm_module.memory                                     # (self as any).wasmMemory = wasmModule.memory
+    # --- a reference engine that writes an attached SAB directly (lib.rs:74): the ground truth for the copied blocks
+    direct = built.PhysicsEngine(1.0, 0.9)
+    direct_sab = np.zeros(4096, np.float32)
+    direct.attach_sab(direct_sab)
+    for e in (engine, direct):
+        e.set_camera_state(0.0, -3.7, 29.8, 0.0, 0.0, 0.0)
+        e.set_auto_spin(True)
+    ptr0 = engine.get_sab_ptr()
+    assert isinstance(ptr0, int) and ptr0 > 0 and ptr0 % 4 == 0 and ptr0 + 2048 * 4 <= wasm_memory.buffer.nbytes
+    for k in range(5):
+        # --- calculate() (physics.worker.ts:111-176)
+        wasm_f32 = wasm_memory.buffer.view(np.float32)                   # wasmF32 = new Float32Array(memory.buffer)
+        engine.tick_sab(0.016)                                           # engine.tick_sab(clampedDt)
+        direct.tick_sab(0.016)
+        sab_seq[OFF["TELEMETRY"]] += 1                                   # Atomics.add(sabSequenceView, OFFSETS.TELEMETRY, 1)
+        start = engine.get_sab_ptr() // 4                                # wasmSABPtr / 4
+        sab[OFF["CAMERA"]:OFF["PHYSICS"]] = wasm_f32[start + OFF["CAMERA"]:start + OFF["PHYSICS"]]
+        sab[OFF["PHYSICS"]:OFF["TELEMETRY"]] = wasm_f32[start + OFF["PHYSICS"]:start + OFF["TELEMETRY"]]
+        sab_seq[OFF["TELEMETRY"]] += 1
+        assert sab_seq[OFF["TELEMETRY"]] == 2 * (k + 1)                  # an int32 counter, +2 per tick (SURVEY 8b)
+        assert np.array_equal(sab[OFF["CAMERA"]:OFF["TELEMETRY"]], direct_sab[OFF["CAMERA"]:OFF["TELEMETRY"]])
+        assert sab[OFF["PHYSICS"]] == np.float32(engine.compute_horizon()) and np.any(sab[OFF["CAMERA"]:OFF["CAMERA"] + 3] != 0)
+    # --- physics-bridge.ts:105-125 fallback views: inputs written through memory.buffer at ptr + CONTROL*4 reach the engine
+    ctrl = wasm_memory.buffer[ptr0 + OFF["CONTROL"] * 4: ptr0 + OFF["CONTROL"] * 4 + 64].view(np.float32)
+    ctrl[1] = 0.25; ctrl[4] = 0.016
+    cam_before = wasm_memory.buffer.view(np.float32)[ptr0 // 4 + OFF["CAMERA"]: ptr0 // 4 + OFF["CAMERA"] + 3].copy()
+    engine.tick_sab(0.0)                                                 # dt from CONTROL[4] (lib.rs:317-328)
+    assert ctrl[1] == 0.0                                                # consumed and zeroed by the engine
+    assert np.any(wasm_memory.buffer.view(np.float32)[ptr0 // 4 + OFF["CAMERA"]: ptr0 // 4 + OFF["CAMERA"] + 3] != cam_before)
+    other = M.PhysicsEngine(1.0, 0.5)
+    assert other.get_sab_ptr() != ptr0 and abs(other.get_sab_ptr() - ptr0) >= 2048 * 4
+    assert M.init().memory is wasm_memory                                # one memory object per module, like a wasm instance
+
+
+def test_addon_sources_honour_the_memory_contract():
+    """Static checks of the shim sources (node is absent here): index.ts allocates one SharedArrayBuffer, attaches a region
+    per engine and never hands out an unrelated buffer; binding.cc exports get_sab_ptr, holds a reference on the attached
+    view, and validates every caller buffer it writes into."""
+    ts = open(os.path.join(ROOT, "addon", "ts", "index.ts")).read()
+    cc = open(os.path.join(ROOT, "addon", "binding.cc")).read()
+    assert ts.count("new SharedArrayBuffer(") == 1 and "this.attach_sab(region)" in ts and "return { memory }" in ts
+    assert '"get_sab_ptr"' in cc and "napi_create_reference" in cc and "napi_delete_reference" in cc
+    assert "gvt_render_get_size" in cc and cc.count("output buffer") + cc.count("out: ArrayBuffer") >= 3
+    for name in ("attach_sab", "get_sab_ptr", "tick_sab"):
+        assert name in ts
