@@ -926,8 +926,18 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
             launches++;
         }
     } else if (P.ny > 0) {
+        const char* tl = getenv("GVT_TIMELINE_DUMP");          // diagnostics: per-warp start / end / tile count of this launch
+        DevBuf tl_buf;
+        const size_t tl_n = (size_t)r->sm_count * 32 * 3;
+        if (tl && *tl) { CK(tl_buf.alloc(tl_n * 8)); CK(cudaMemsetAsync(tl_buf.as<char>(), 0, tl_n * 8, r->stream)); P.timeline = tl_buf.as<unsigned long long>(); }
         CK(launch_trace(P, rp->method, rp->precision, budget, false, r->sm_count, r->stream));
         launches++;
+        if (P.timeline) {
+            std::vector<unsigned long long> h(tl_n);
+            CK(cudaMemcpyAsync(h.data(), P.timeline, tl_n * 8, cudaMemcpyDeviceToHost, r->stream));
+            CK(cudaStreamSynchronize(r->stream));
+            if (FILE* f = fopen(tl, "wb")) { fwrite(h.data(), 8, tl_n, f); fclose(f); }
+        }
     }
     CK(cudaEventRecord(r->ev[2], r->stream));
     if (taa && (interleave ? n_my > 0 : row1 > row0)) {

@@ -61,6 +61,7 @@ struct FrameParams {
     uint32_t width, height;                                   // full frame
     uint32_t x0, xs, y0, y1, ys;                              // pixel lattice traced by this launch
     uint32_t nx, ny;                                          // lattice extent
+    uint32_t tile_w_log2, _pad_tile;                          // warp tile = 2^tile_w_log2 x (32 >> tile_w_log2) pixels: 3 (8x4), 4 (16x2), 5 (32x1)
     uint32_t max_steps, renorm_interval, step_rule;
     uint32_t tdisk_n, spec_w, spec_h, lut_in_smem;
     const FrameBlock* block;                                  // global copy of the TMA-staged block
@@ -72,6 +73,7 @@ struct FrameParams {
     uint32_t n_peer, _pad_peer;
     StripeMap stripe;                                         // s != 0: lattice rows map to frame rows through stripe_row()
     Counters* counters;
+    unsigned long long* timeline;                             // diagnostics (GVT_TIMELINE_DUMP): per warp {globaltimer at start, at end, tiles}, or null
     // parity-hook outputs (DEBUG instantiations only), dense over the lattice
     double* dbg_xp; uint32_t* dbg_term; uint32_t* dbg_steps; double* dbg_drift; double* dbg_rgba;
 };

@@ -113,7 +113,6 @@ __device__ __forceinline__ void sample_spectrum(const float4* lut, uint32_t W, u
 #define GVT_UNROLL_FAR 1           // unroll of the f32-predictor step loop
 #endif
 constexpr int kUnrollSymp = GVT_UNROLL_SYMP, kUnrollNear = GVT_UNROLL_NEAR, kUnrollNearMixed = GVT_UNROLL_NEAR_MIXED, kUnrollFar = GVT_UNROLL_FAR;
-constexpr int TILE_W = 8, TILE_H = 4;
 
 // Compile-time flavour of one march step (the step loop is instantiated once per flavour a kernel needs and the warp
 // picks one per 8-step chunk): FAR = f32 predictors (GVT_PRECISION_MIXED), HCONST = the step rule has saturated and
@@ -174,8 +173,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
     const float4* lut = P.lut_in_smem ? lut_s : P.spectrum;
 
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t lx = lane & (TILE_W - 1), ly = lane / TILE_W;
-    const uint32_t tiles_x = (P.nx + TILE_W - 1) / TILE_W, tiles_y = (P.ny + TILE_H - 1) / TILE_H;
+    // One warp = one tile of 32 pixels: 8x4 (compute.wgsl.ts:147 uses 8x8 groups), or 16x2 / 32x1 when the launch's row
+    // count is not a multiple of 4 -- a rank's 270-row block of a 2160-row frame would otherwise end in a half-empty
+    // tile row (0.7 % of the launch).
+    const uint32_t tw_log2 = P.tile_w_log2, TW = 1u << tw_log2, TH = 32u >> tw_log2;
+    const uint32_t lx = lane & (TW - 1u), ly = lane >> tw_log2;
+    const uint32_t tiles_x = (P.nx + TW - 1u) >> tw_log2, tiles_y = (P.ny + TH - 1u) / TH;
     const uint32_t n_tiles = tiles_x * tiles_y;
 
     HoleRay<R> hc;
@@ -197,25 +200,27 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
         s_term[wid][0] = s_term[wid][1] = s_term[wid][2] = s_term[wid][3] = 0u;
     }
 
+    unsigned long long t_warp_start = 0; uint32_t n_my_tiles = 0;
+    if (P.timeline) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_warp_start));
     // Work distribution. Natural termination: one global atomic queue of warp-tiles (rows differ widely in cost). Budget
-    // accounting: every tile costs the same, so each CTA owns an equal contiguous share of the tiles and hands them to its
-    // warps through a shared-memory counter -- all SMs then finish together, where the global queue ends with half a
-    // tile-time of stragglers on the SMs that happened to draw the last tiles (0.17 ms of a 6 ms launch at 1/8 frame:
-    // the difference between 0.972 and 0.99 kernel-side scaling efficiency at 8 GPUs; scripts/partial_frame_scaling.py).
+    // accounting: every tile costs nearly the same, so each CTA owns an equal share of the tiles -- dealt round-robin
+    // (tile = CTA + k * grid), because the zones of the march do make tiles near the hole and on the polar columns a few
+    // per cent dearer and a contiguous share would concentrate them -- and hands them to its warps through a
+    // shared-memory counter. All SMs then finish together, where the global queue ends with the SMs that drew the last
+    // tiles still busy (per-warp timelines: scripts/timeline_probe.py).
     __shared__ uint32_t s_next_tile;
-    const uint32_t cta_first = BUDGET ? (uint32_t)(((unsigned long long)n_tiles * blockIdx.x) / gridDim.x) : 0u;
-    const uint32_t cta_end = BUDGET ? (uint32_t)(((unsigned long long)n_tiles * (blockIdx.x + 1u)) / gridDim.x) : n_tiles;
     if (BUDGET) {
-        if (threadIdx.x == 0) s_next_tile = cta_first;
+        if (threadIdx.x == 0) s_next_tile = 0u;
         __syncthreads();
     }
     for (;;) {
         uint32_t tile = 0;
-        if (lane == 0) tile = BUDGET ? atomicAdd(&s_next_tile, 1u) : atomicAdd(&P.counters->tile_counter, 1u);
+        if (lane == 0) tile = BUDGET ? blockIdx.x + atomicAdd(&s_next_tile, 1u) * gridDim.x : atomicAdd(&P.counters->tile_counter, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= cta_end) break;
+        if (tile >= n_tiles) break;
+        n_my_tiles++;
         const uint32_t ti = tile % tiles_x, tj = tile / tiles_x;
-        const uint32_t li = ti * TILE_W + lx, lj = tj * TILE_H + ly;  // lattice coordinates
+        const uint32_t li = ti * TW + lx, lj = tj * TH + ly;  // lattice coordinates
         bool valid = (li < P.nx) && (lj < P.ny);
         const uint32_t px = P.x0 + min(li, P.nx - 1) * P.xs;
         uint32_t py = P.y0 + min(lj, P.ny - 1) * P.ys;
@@ -516,6 +521,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
             }
         }
     }
+    if (P.timeline && lane == 0) {
+        unsigned long long t_end;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
+        unsigned long long* o = P.timeline + 3ull * (blockIdx.x * (blockDim.x >> 5) + wid);
+        o[0] = t_warp_start; o[1] = t_end; o[2] = n_my_tiles;
+    }
     // a CTA must not exit while its bulk copy is still in flight
     if (P.lut_in_smem && !lut_ready) mbar_wait(&bars[1], 0);
     // census: one set of global atomics per CTA (2368 warps hitting the same seven addresses at the end of a launch
@@ -547,7 +558,8 @@ static cudaError_t launch_trace_t(const FrameParams& p, int sm_count, cudaStream
     if (p.lut_in_smem) smem += (size_t)p.spec_w * p.spec_h * sizeof(float4);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const uint32_t tiles = ((p.nx + TILE_W - 1) / TILE_W) * ((p.ny + TILE_H - 1) / TILE_H);
+    const uint32_t tw = 1u << p.tile_w_log2, th = 32u >> p.tile_w_log2;
+    const uint32_t tiles = ((p.nx + tw - 1) / tw) * ((p.ny + th - 1) / th);
     const uint32_t warps_per_cta = MAXT / 32;
     uint32_t ctas = (tiles + warps_per_cta - 1) / warps_per_cta;
     if (ctas > (uint32_t)sm_count) ctas = (uint32_t)sm_count;  // persistent: one CTA per SM
@@ -559,6 +571,8 @@ static cudaError_t launch_trace_t(const FrameParams& p, int sm_count, cudaStream
 cudaError_t launch_trace(const FrameParams& p_in, int method, int precision, bool budget, bool debug, int sm_count,
                          cudaStream_t stream) {
     FrameParams p = p_in;
+    // the squarest warp tile that wastes no lanes on the launch's last tile row
+    p.tile_w_log2 = (p.ny % 4u != 0u && p.ny % 2u == 0u && p.nx % 16u == 0u) ? 4u : 3u;
     const TrigTable tt = GVT_TRIG_TABLE_INIT;
     p.trig = tt;
 #define GVT_DISPATCH(RT, MT)                                                                                   \
