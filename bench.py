@@ -262,6 +262,23 @@ def side_kernels(r, local, camera, R, _lib):
     side["taa_resolve"] = {"kernel": "k_taa_resolve<0>", "ms": t, "bound": "hbm", "algorithmic_bytes": taa_bytes,
                            "achieved_gbs": taa_bytes / (t * 1e-3) * 1e-9, "peak_gbs": hbm_gbs, "peak_source": hbm_src,
                            "frac": taa_bytes / (t * 1e-3) * 1e-9 / hbm_gbs}
+    # the same resolve on the RGBA16F-native frame chain (the reference's texture format): 8 B current + 8 B history + 8 B store
+    r.set_frame_format(_lib.FORMAT_RGBA16F)
+    try:
+        prev, taa16 = None, []
+        for k in range(6):
+            c5, vp = camera.default_camera(W, H, azimuth=math.pi + 0.005 * k, prev_view_proj=prev)
+            r.render(c5, R.pack_physics(MASS, SPIN, W, H, frame_index=k), readback=False)
+            prev = vp
+            if k >= 2:
+                taa16.append(r.last_stats.taa_ms)
+        t16 = sorted(taa16)[len(taa16) // 2]
+        b16 = 24 * W * H
+        side["taa_resolve_rgba16f"] = {"kernel": "k_taa_resolve<0, F16>", "ms": t16, "bound": "hbm", "algorithmic_bytes": b16,
+                                       "achieved_gbs": b16 / (t16 * 1e-3) * 1e-9, "peak_gbs": hbm_gbs, "frac": b16 / (t16 * 1e-3) * 1e-9 / hbm_gbs,
+                                       "pixels_per_s": W * H / (t16 * 1e-3)}
+    finally:
+        r.set_frame_format(_lib.FORMAT_RGBA32F)
     # the whole WebGL2 fragment shader (k_fragment_glsl, MUFU build), ultra-quality preset, + bloom / final pass
     from gravitas_b200 import webgl
     wr = webgl.WebGLRenderer(device=local, noise_seed=11)

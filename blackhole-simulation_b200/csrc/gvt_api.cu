@@ -457,6 +457,11 @@ struct gvt_renderer {
     bool history_valid = false;
     float4* last_peer_target = nullptr;   // the buffer the peers filled on the previous GVT_FLAG_PEER_STORE frame
     uint32_t rows_override[2] = {0u, 0u};  // gvt_render_rows
+    bool frame_f16 = false;               // cur / frame / hist hold RGBA16F (gvt_render_set_frame_format)
+    size_t px_bytes() const { return frame_f16 ? 8 : 16; }
+    uint32_t storage_format() const { return frame_f16 ? GVT_FORMAT_RGBA16F : GVT_FORMAT_RGBA32F; }
+    // byte address of pixel `px` in one of the frame-chain buffers
+    char* at(float4* base, size_t px) const { return reinterpret_cast<char*>(base) + px * px_bytes(); }
     FrameBlock* d_block = nullptr; FrameBlock* h_block = nullptr;   // device / pinned host
     Counters* d_counters = nullptr; Counters* h_counters = nullptr;
     float4* d_spectrum = nullptr; uint32_t spec_w = 0, spec_h = 0;
@@ -608,7 +613,7 @@ extern "C" int32_t gvt_render_resize(gvt_renderer* r, uint32_t width, uint32_t h
     r->width = width; r->height = height;
     r->rows_per_rank = (height + r->world - 1) / r->world;
     r->padded_height = r->rows_per_rank * r->world;  // all-gather needs equal blocks
-    const size_t bytes = (size_t)width * r->padded_height * sizeof(float4);
+    const size_t bytes = (size_t)width * r->padded_height * r->px_bytes();
     CK(cudaMalloc(&r->cur, bytes));
     CK(cudaMalloc(&r->frame, bytes));
     CK(cudaMalloc(&r->hist, bytes));
@@ -621,6 +626,19 @@ extern "C" int32_t gvt_render_resize(gvt_renderer* r, uint32_t width, uint32_t h
     return GVT_OK;
 }
 
+// The format of the frame chain (cur / frame / hist): RGBA32F (default, the parity format) or RGBA16F, the reference's own
+// texture format (rendering/reprojection.ts:120-140, webgpu/renderer.ts:161-180). Re-allocates the buffers, clears the history.
+extern "C" int32_t gvt_render_set_frame_format(gvt_renderer* r, uint32_t format) {
+    if (!r || (format != GVT_FORMAT_RGBA32F && format != GVT_FORMAT_RGBA16F)) return fail(GVT_ERR_INVALID, "frame format: RGBA32F or RGBA16F");
+    const bool f16 = format == GVT_FORMAT_RGBA16F;
+    if (f16 == r->frame_f16) return GVT_OK;
+    r->frame_f16 = f16;
+    if (!r->cur) return GVT_OK;
+    const uint32_t w = r->width, h = r->height;
+    r->width = r->height = 0;                     // force gvt_render_resize to re-allocate
+    return gvt_render_resize(r, w, h);
+}
+
 extern "C" int32_t gvt_render_get_size(gvt_renderer* r, uint32_t* width, uint32_t* height) {
     if (!r || !width || !height) return fail(GVT_ERR_INVALID, "null argument");
     *width = r->width; *height = r->height;
@@ -629,7 +647,7 @@ extern "C" int32_t gvt_render_get_size(gvt_renderer* r, uint32_t* width, uint32_
 
 extern "C" int32_t gvt_render_reset_history(gvt_renderer* r) {
     if (!r) return fail(GVT_ERR_INVALID, "null renderer");
-    if (r->hist) CK(cudaMemsetAsync(r->hist, 0, (size_t)r->width * r->padded_height * sizeof(float4), r->stream));
+    if (r->hist) CK(cudaMemsetAsync(r->hist, 0, (size_t)r->width * r->padded_height * r->px_bytes(), r->stream));
     r->history_valid = false;
     return GVT_OK;
 }
@@ -748,13 +766,15 @@ static void fill_taa(const GvtCamera* cam, uint32_t W, uint32_t H, TaaParams& T)
 }
 
 static size_t format_bytes(uint32_t f) { return f == GVT_FORMAT_RGBA32F ? 16 : (f == GVT_FORMAT_RGBA16F ? 8 : 4); }
-// converts pixels [px0, px0 + npx) of the finished frame into the staging buffer in `format` (not RGBA32F)
+// converts pixels [px0, px0 + npx) of the finished frame into the staging buffer in `format` (!= the storage format)
 static int32_t convert_frame(gvt_renderer* r, uint32_t format, size_t px0, size_t npx) {
     const size_t n_px = (size_t)r->width * r->height;
-    if (!r->half_frame) CK(cudaMalloc(&r->half_frame, n_px * 8));
+    if (!r->half_frame) CK(cudaMalloc(&r->half_frame, n_px * 16));
     char* dst = static_cast<char*>(r->half_frame) + px0 * format_bytes(format);
-    if (format == GVT_FORMAT_RGBA16F) CK(launch_f32_to_f16(r->frame + px0, dst, npx, r->stream));
-    else CK(launch_tonemap_rgba8(r->frame + px0, dst, npx, format == GVT_FORMAT_RGBA8_ACES ? 1 : (format == GVT_FORMAT_RGBA8_UNORM ? 2 : 0), r->stream));
+    const float4* src = reinterpret_cast<const float4*>(r->at(r->frame, px0));
+    if (format == GVT_FORMAT_RGBA16F) CK(launch_f32_to_f16(src, dst, npx, r->stream));                    // storage is RGBA32F here
+    else if (format == GVT_FORMAT_RGBA32F) CK(launch_f16_to_f32(src, reinterpret_cast<float4*>(dst), npx, r->stream));   // storage is RGBA16F
+    else CK(launch_tonemap_rgba8(src, dst, npx, format == GVT_FORMAT_RGBA8_ACES ? 1 : (format == GVT_FORMAT_RGBA8_UNORM ? 2 : 0), r->stream, r->frame_f16));
     return GVT_OK;
 }
 
@@ -762,12 +782,12 @@ extern "C" int32_t gvt_render_read_frame(gvt_renderer* r, uint32_t format, void*
     if (!r || !host_rgba || !r->frame || format > GVT_FORMAT_RGBA8_UNORM) return fail(GVT_ERR_INVALID, "bad argument / no frame");
     CK(cudaSetDevice(r->device));
     const size_t n_px = (size_t)r->width * r->height;
-    if (format != GVT_FORMAT_RGBA32F) {
+    if (format != r->storage_format()) {
         int32_t rc = convert_frame(r, format, 0, n_px);
         if (rc != GVT_OK) return rc;
         CK(cudaMemcpyAsync(host_rgba, r->half_frame, n_px * format_bytes(format), cudaMemcpyDeviceToHost, r->stream));
     } else {
-        CK(cudaMemcpyAsync(host_rgba, r->frame, n_px * sizeof(float4), cudaMemcpyDeviceToHost, r->stream));
+        CK(cudaMemcpyAsync(host_rgba, r->frame, n_px * r->px_bytes(), cudaMemcpyDeviceToHost, r->stream));
     }
     CK(cudaStreamSynchronize(r->stream));
     return GVT_OK;
@@ -849,8 +869,8 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
     // ---- everything that can be refused is refused HERE, before any state changes or anything is enqueued: a rank that
     //      bailed out later would leave its ping-pong parity flipped against its peers and them blocked in a collective ----
     const bool own_early = (rp->flags & GVT_FLAG_D2H_OWN_ROWS) != 0 && r->world > 1;
-    if (host_rgba && own_early && interleave && rp->output_format != GVT_FORMAT_RGBA32F)
-        return fail(GVT_ERR_UNSUPPORTED, "interleaved own-row delivery is RGBA32F only");
+    if (host_rgba && own_early && interleave && rp->output_format != r->storage_format())
+        return fail(GVT_ERR_UNSUPPORTED, "interleaved own-row delivery needs output_format == the frame chain's format");
     if ((rp->flags & GVT_FLAG_PEER_STORE) != 0 && r->world > 1 && !(rp->flags & GVT_FLAG_NO_GATHER)) {
         if (!r->d_sink) return fail(GVT_ERR_INVALID, "no barrier buffer");
         for (int p = 0; p < r->world; p++)
@@ -869,7 +889,7 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
     // D2H copy of the previous frame), which is what lets ONE barrier per frame close the exchange (see below).
     if ((taa && r->history_valid) || (peer_req && !taa)) { std::swap(r->frame, r->hist); late.swapped = true; }
     float4* trace_out = taa ? r->cur : r->frame;
-    if (glsl) G.frame = trace_out; else P.frame = trace_out;
+    if (glsl) { G.frame = trace_out; G.frame_f16 = r->frame_f16 ? 1u : 0u; } else { P.frame = trace_out; P.frame_f16 = r->frame_f16 ? 1u : 0u; }
     uint32_t launches = 0;
     uint64_t h2d = 0, d2h = 0;
     // Host frame delivery. If the caller's buffer is page-locked (gvt_host_alloc / gvt_host_register) and this rank
@@ -878,7 +898,7 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
     // copy follows. Otherwise the finished frame is copied after the last kernel.
     const bool own = (rp->flags & GVT_FLAG_D2H_OWN_ROWS) != 0 && r->world > 1;
     float4* host_alias = nullptr;
-    if (host_rgba && rp->output_format == GVT_FORMAT_RGBA32F && (r->world == 1 || own)) {
+    if (host_rgba && rp->output_format == r->storage_format() && (r->world == 1 || own)) {
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, host_rgba) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
             host_alias = static_cast<float4*>(at.devicePointer);
@@ -944,7 +964,7 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
         TaaParams T;
         if (cam) fill_taa(cam, W, H, T);
         else { memset(&T, 0, sizeof(T)); T.width = W; T.height = H; }
-        T.cur = r->cur; T.hist = r->hist; T.out = r->frame;
+        T.cur = r->cur; T.hist = r->hist; T.out = r->frame; T.frame_f16 = r->frame_f16 ? 1u : 0u;
         T.row0 = row0; T.row1 = row1;
         T.stripe = sm; T.n_stripes = n_my;
         if (rp->flags & GVT_FLAG_TAA_WEBGL) {
@@ -963,7 +983,7 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
         int nrc = g_nccl.AllReduce(r->d_sink, r->d_sink, 1, kNcclFloat32, kNcclSum, r->comm, r->stream);
         if (nrc != 0) return fail(GVT_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(nrc));
     } else if (r->world > 1 && !(rp->flags & GVT_FLAG_NO_GATHER)) {
-        const size_t count = (size_t)r->rows_per_rank * W * 4;  // floats per rank block
+        const size_t count = (size_t)r->rows_per_rank * W * r->px_bytes() / 4;  // 4-byte words per rank block
         int nrc = g_nccl.AllGather(reinterpret_cast<const float*>(r->frame) + (size_t)r->rank * count, r->frame, count,
                                    kNcclFloat32, r->comm, r->stream);
         if (nrc != 0) return fail(GVT_ERR_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString(nrc));
@@ -972,9 +992,9 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
     CK(cudaMemcpyAsync(r->h_counters, r->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, r->stream));
     d2h += sizeof(Counters);
     if (host_rgba && host_alias) {
-        d2h += (size_t)n_own * W * sizeof(float4);   // delivered by the kernel's own stores
+        d2h += (size_t)n_own * W * r->px_bytes();   // delivered by the kernel's own stores
     } else if (host_rgba && own && interleave) {
-        const size_t row_bytes = (size_t)W * sizeof(float4);                // (RGBA32F only: checked before the swap)
+        const size_t row_bytes = (size_t)W * r->px_bytes();                 // (storage format only: checked before the swap)
         if (sm.s == 1u) {   // every world-th row: one strided copy
             const size_t pitch = row_bytes * (size_t)r->world;
             if (n_own)
@@ -994,7 +1014,7 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
         const size_t n_px = (size_t)W * H;
         // which pixels go back: the whole frame, or only this rank's row block at its place in the host frame
         const size_t px0 = own ? (size_t)row0 * W : 0, npx = own ? (size_t)(row1 - row0) * W : n_px;
-        if (rp->output_format != GVT_FORMAT_RGBA32F) {
+        if (rp->output_format != r->storage_format()) {
             const size_t bpp = format_bytes(rp->output_format);
             if (npx) {
                 int32_t crc = convert_frame(r, rp->output_format, px0, npx);
@@ -1006,9 +1026,9 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
             d2h += npx * bpp;
         } else {
             if (npx)
-                CK(cudaMemcpyAsync(static_cast<char*>(host_rgba) + px0 * sizeof(float4), r->frame + px0, npx * sizeof(float4),
+                CK(cudaMemcpyAsync(static_cast<char*>(host_rgba) + px0 * r->px_bytes(), r->at(r->frame, px0), npx * r->px_bytes(),
                                    cudaMemcpyDeviceToHost, r->stream));
-            d2h += npx * sizeof(float4);
+            d2h += npx * r->px_bytes();
         }
     }
     CK(cudaEventRecord(r->ev[5], r->stream));
@@ -1122,14 +1142,14 @@ extern "C" int32_t gvt_render_bloom(gvt_renderer* r, const GvtBloomConfig* cfg, 
     int launches = 0;
     CK(cudaEventRecord(r->ev[0], r->stream));
     CK(launch_bloom(r->frame, W, H, r->bloom_half, r->bloom_q1, r->bloom_q2, r->display, cfg->threshold, cfg->intensity,
-                    (int)cfg->blur_passes, cfg->enabled ? 1 : 0, r->sm_count, r->stream, &launches, bloom_precise));
+                    (int)cfg->blur_passes, cfg->enabled ? 1 : 0, r->sm_count, r->stream, &launches, bloom_precise, r->frame_f16));
     CK(cudaEventRecord(r->ev[1], r->stream));
     if (host_out) {
         const size_t n_px = (size_t)W * H;
         if (output_format == GVT_FORMAT_RGBA32F) {
             CK(cudaMemcpyAsync(host_out, r->display, n_px * sizeof(float4), cudaMemcpyDeviceToHost, r->stream));
         } else {
-            if (!r->half_frame) CK(cudaMalloc(&r->half_frame, n_px * 8));
+            if (!r->half_frame) CK(cudaMalloc(&r->half_frame, n_px * 16));
             if (output_format == GVT_FORMAT_RGBA16F) CK(launch_f32_to_f16(r->display, r->half_frame, n_px, r->stream));
             else CK(launch_tonemap_rgba8(r->display, r->half_frame, n_px, 2, r->stream));
             CK(cudaMemcpyAsync(host_out, r->half_frame, n_px * format_bytes(output_format), cudaMemcpyDeviceToHost, r->stream));
@@ -1198,10 +1218,10 @@ extern "C" int32_t gvt_trace_states(gvt_renderer* r, const GvtCamera* cam, const
     return GVT_OK;
 }
 
-static int32_t taa_host_frames(gvt_renderer* r, TaaParams& T, uint32_t width, uint32_t height, const float* cur, const float* hist,
-                               float* out, int32_t precise, double* ms_out) {
+static int32_t taa_host_frames(gvt_renderer* r, TaaParams& T, uint32_t width, uint32_t height, const void* cur, const void* hist,
+                               void* out, int32_t precise, double* ms_out) {
     CK(cudaSetDevice(r->device));
-    const size_t bytes = (size_t)width * height * sizeof(float4);
+    const size_t bytes = (size_t)width * height * (T.frame_f16 ? 8 : 16);
     DevBuf b_cur, b_hist, b_out;
     CK(b_cur.alloc(bytes)); CK(b_hist.alloc(bytes)); CK(b_out.alloc(bytes));
     float4 *d_cur = b_cur.as<float4>(), *d_hist = b_hist.as<float4>(), *d_out = b_out.as<float4>();
@@ -1217,14 +1237,16 @@ static int32_t taa_host_frames(gvt_renderer* r, TaaParams& T, uint32_t width, ui
     return GVT_OK;
 }
 
-extern "C" int32_t gvt_taa_resolve_ex(gvt_renderer* r, const GvtCamera* cam, uint32_t width, uint32_t height, const float* cur,
-                                      const float* hist, float* out, uint32_t webgl, float blend, int32_t camera_moving,
-                                      int32_t precise, double* ms_out) {
+extern "C" int32_t gvt_taa_resolve_ex(gvt_renderer* r, const GvtCamera* cam, uint32_t width, uint32_t height, const void* cur,
+                                      const void* hist, void* out, uint32_t frame_format, uint32_t webgl, float blend,
+                                      int32_t camera_moving, int32_t precise, double* ms_out) {
     if (!r || (!cam && !webgl) || !cur || !hist || !out || width == 0 || height == 0) return fail(GVT_ERR_INVALID, "bad argument");
+    if (frame_format != GVT_FORMAT_RGBA32F && frame_format != GVT_FORMAT_RGBA16F) return fail(GVT_ERR_INVALID, "frame_format: RGBA32F or RGBA16F");
     TaaParams T;
     if (cam) fill_taa(cam, width, height, T);
     else { memset(&T, 0, sizeof(T)); T.width = width; T.height = height; T.row1 = height; T.stripe = StripeMap{0u, 0u, 1u, 0u}; }
     if (webgl) { T.mode = 1; T.blend = blend; T.moving = camera_moving ? 1u : 0u; }
+    T.frame_f16 = frame_format == GVT_FORMAT_RGBA16F ? 1u : 0u;
     return taa_host_frames(r, T, width, height, cur, hist, out, precise, ms_out);
 }
 

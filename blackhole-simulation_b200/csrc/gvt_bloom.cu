@@ -61,8 +61,9 @@ __device__ __forceinline__ uint2 pack_half4(float4 v) {
 // texel-centre coordinate (i + 0.5) / n
 template <bool PRECISE> __device__ __forceinline__ float centre_(int i, int n) { return div_<PRECISE>(add_<PRECISE>((float)i, 0.5f), (float)n); }
 
-template <bool PRECISE>
-__global__ void k_bloom_bright(Tex32 scene, uint2* __restrict__ dst, int dw, int dh, float threshold) {
+// ST = Tex32 (RGBA32F frame chain) or Tex16 (RGBA16F frame chain: the reference's own scene texture format)
+template <bool PRECISE, class ST>
+__global__ void k_bloom_bright(ST scene, uint2* __restrict__ dst, int dw, int dh, float threshold) {
     const int n = dw * dh;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int x = i % dw, y = i / dw;
@@ -108,13 +109,13 @@ template <bool PRECISE> __device__ __forceinline__ float aces_gamma_f(float x) {
     return t > 0.0f ? exp2f(0.4545f * __log2f(t)) : 0.0f;
 }
 
-template <bool PRECISE>
-__global__ void k_bloom_combine(Tex32 scene, Tex16 bloom, float4* __restrict__ dst, float intensity, int use_bloom) {
+template <bool PRECISE, class ST>
+__global__ void k_bloom_combine(ST scene, Tex16 bloom, float4* __restrict__ dst, float intensity, int use_bloom) {
     // one thread per pixel, rows on blockIdx.y (no 64-bit division in the index arithmetic)
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     for (int y = blockIdx.y; y < scene.h && x < scene.w; y += gridDim.y) {
         const size_t i = (size_t)y * scene.w + x;
-        const float4 s = __ldg(scene.p + i);                      // the scene is sampled at its own texel centres
+        const float4 s = fetch(scene, x, y);                      // the scene is sampled at its own texel centres
         float r = s.x, g = s.y, b = s.z;
         if (use_bloom) {
             const float4 bl = sample_linear<PRECISE>(bloom, centre_<PRECISE>(x, scene.w), centre_<PRECISE>(y, scene.h));
@@ -125,16 +126,15 @@ __global__ void k_bloom_combine(Tex32 scene, Tex16 bloom, float4* __restrict__ d
     }
 }
 
-template <bool PRECISE>
-cudaError_t launch_bloom_t(const float4* frame, int W, int H, uint2* half_tex, uint2* q1, uint2* q2, float4* display,
+template <bool PRECISE, class ST>
+cudaError_t launch_bloom_t(const ST scene, int W, int H, uint2* half_tex, uint2* q1, uint2* q2, float4* display,
                            float threshold, float intensity, int blur_passes, int enabled, int sm_count, cudaStream_t stream,
                            int* launches) {
     const int hw = max(1, W / 2), hh = max(1, H / 2), bw = max(1, W / 4), bh = max(1, H / 4);
-    const Tex32 scene{frame, W, H};
     const int grid = sm_count * 8;
     Tex16 result{q2, bw, bh};
     if (enabled) {
-        k_bloom_bright<PRECISE><<<grid, 256, 0, stream>>>(scene, half_tex, hw, hh, threshold);
+        k_bloom_bright<PRECISE, ST><<<grid, 256, 0, stream>>>(scene, half_tex, hw, hh, threshold);
         (*launches)++;
         Tex16 src{half_tex, hw, hh};
         for (int i = 0; i < blur_passes; i++) {
@@ -145,7 +145,7 @@ cudaError_t launch_bloom_t(const float4* frame, int W, int H, uint2* half_tex, u
         }
         result = src;   // blurPasses = 0: the bright texture itself is combined (bloom.ts:517-546)
     }
-    k_bloom_combine<PRECISE><<<dim3((unsigned)((W + 255) / 256), (unsigned)min(H, 65535)), 256, 0, stream>>>(scene, result, display, intensity, enabled);
+    k_bloom_combine<PRECISE, ST><<<dim3((unsigned)((W + 255) / 256), (unsigned)min(H, 65535)), 256, 0, stream>>>(scene, result, display, intensity, enabled);
     (*launches)++;
     return cudaGetLastError();
 }
@@ -155,9 +155,15 @@ cudaError_t launch_bloom_t(const float4* frame, int W, int H, uint2* half_tex, u
 // scratch: half = (W/2)*(H/2) uint2, q1 / q2 = (W/4)*(H/4) uint2 each. `display` receives the final frame.
 cudaError_t launch_bloom(const float4* frame, int W, int H, uint2* half_tex, uint2* q1, uint2* q2, float4* display,
                          float threshold, float intensity, int blur_passes, int enabled, int sm_count, cudaStream_t stream,
-                         int* launches, bool precise) {
-    return precise ? launch_bloom_t<true>(frame, W, H, half_tex, q1, q2, display, threshold, intensity, blur_passes, enabled, sm_count, stream, launches)
-                   : launch_bloom_t<false>(frame, W, H, half_tex, q1, q2, display, threshold, intensity, blur_passes, enabled, sm_count, stream, launches);
+                         int* launches, bool precise, bool scene_f16) {
+#define GVT_BLOOM_ARGS W, H, half_tex, q1, q2, display, threshold, intensity, blur_passes, enabled, sm_count, stream, launches
+    if (scene_f16) {
+        const Tex16 scene{reinterpret_cast<const uint2*>(frame), W, H};
+        return precise ? launch_bloom_t<true, Tex16>(scene, GVT_BLOOM_ARGS) : launch_bloom_t<false, Tex16>(scene, GVT_BLOOM_ARGS);
+    }
+    const Tex32 scene{frame, W, H};
+    return precise ? launch_bloom_t<true, Tex32>(scene, GVT_BLOOM_ARGS) : launch_bloom_t<false, Tex32>(scene, GVT_BLOOM_ARGS);
+#undef GVT_BLOOM_ARGS
 }
 
 }  // namespace gvt

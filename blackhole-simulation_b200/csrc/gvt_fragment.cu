@@ -21,6 +21,7 @@
 // launch_fragment_glsl_fast, float only, where the same source maps onto MUFU (rcp/rsq/sqrt/ex2/lg2/sin/cos) the
 // way a GLSL compiler maps the shader: no slow-path branches, a third of the instructions.
 #include "gvt_internal.h"
+#include <cuda_fp16.h>
 
 namespace gvt {
 #ifdef GVT_FRAGMENT_FAST
@@ -32,6 +33,17 @@ namespace fragment_precise {
 namespace {
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// frame targets are RGBA32F or RGBA16F (the reference's texture format, reprojection.ts:120-140)
+__device__ __forceinline__ void frag_store_px(float4* base, size_t idx, const float4& v, bool f16) {
+    if (f16) {
+        const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(base)[idx] = o;
+    } else {
+        base[idx] = v;
+    }
+}
 
 template <class R> struct GM;
 template <> struct GM<float> {
@@ -568,10 +580,11 @@ __global__ void __launch_bounds__(GVT_FRAG_THREADS, GVT_FRAG_MINB) k_fragment_gl
             // NaN guard: GLSL leaves a NaN fragment undefined; here it becomes black instead of poisoning TAA / bloom
             if (!(px_out.x == px_out.x) || !(px_out.y == px_out.y) || !(px_out.z == px_out.z)) px_out = make_float4(0.f, 0.f, 0.f, 1.0f);
             const size_t o = (size_t)py * P.width + px;
-            if (P.frame) P.frame[o] = px_out;
-            if (P.host_frame) P.host_frame[o] = px_out;
+            const bool f16 = P.frame_f16 != 0u;
+            if (P.frame) frag_store_px(P.frame, o, px_out, f16);
+            if (P.host_frame) frag_store_px(P.host_frame, o, px_out, f16);
 #pragma unroll 1
-            for (uint32_t q = 0; q < P.n_peer; q++) P.peer_frame[q][o] = px_out;
+            for (uint32_t q = 0; q < P.n_peer; q++) frag_store_px(P.peer_frame[q], o, px_out, f16);
             if (P.dbg_steps) P.dbg_steps[o] = steps;
             if (P.dbg_hit) P.dbg_hit[o] = hitHorizon ? 1u : 0u;
         }

@@ -70,7 +70,7 @@ struct FrameParams {
     float4* host_frame;                                       // device alias of a page-locked HOST frame (or null): the
                                                               // epilogue stores the pixel there too, so no D2H copy follows
     float4* peer_frame[8];                                    // GVT_FLAG_PEER_STORE: the same frame on every other rank
-    uint32_t n_peer, _pad_peer;
+    uint32_t n_peer, frame_f16;                               // frame_f16 != 0: frame / host_frame / peer_frame hold RGBA16F (8 B per pixel)
     StripeMap stripe;                                         // s != 0: lattice rows map to frame rows through stripe_row()
     Counters* counters;
     unsigned long long* timeline;                             // diagnostics (GVT_TIMELINE_DUMP): per warp {globaltimer at start, at end, tiles}, or null
@@ -102,6 +102,7 @@ struct TaaParams {
     float4* host_out;      // device alias of a page-locked host frame, or null
     float4* peer_out[8];   // GVT_FLAG_PEER_STORE targets
     uint32_t n_peer;
+    uint32_t frame_f16;    // cur / hist / out (and host_out, peer_out) are RGBA16F: 8 B per pixel, f32 arithmetic
     uint32_t unit_rows;    // rows per warp work unit (chosen by launch_taa)
     StripeMap stripe;      // s != 0: resolve this rank's n_stripes stripes (rows [(t world + rank) s, +s)) instead of [row0, row1)
     uint32_t n_stripes;
@@ -120,6 +121,7 @@ struct GlslParams {
     const uint8_t* blue_r;        // 256*256 red channel of u_blueNoiseTex (one tap per pixel, stays in global)
     float4* frame; float4* host_frame; float4* peer_frame[8];
     uint32_t n_peer;
+    uint32_t frame_f16;           // the three frame targets hold RGBA16F
     Counters* counters;
     uint32_t* dbg_steps; uint32_t* dbg_hit;   // parity hooks (full-frame arrays) or null
 };
@@ -146,10 +148,11 @@ cudaError_t launch_taa_precise(const TaaParams& p, cudaStream_t stream);   // IE
 cudaError_t launch_fragment_glsl(const GlslParams& p, int precision, int sm_count, cudaStream_t stream);
 cudaError_t launch_bloom(const float4* frame, int W, int H, uint2* half_tex, uint2* q1, uint2* q2, float4* display,
                          float threshold, float intensity, int blur_passes, int enabled, int sm_count, cudaStream_t stream,
-                         int* launches, bool precise = false);
+                         int* launches, bool precise = false, bool scene_f16 = false);
 cudaError_t launch_fragment_glsl_fast(const GlslParams& p, int sm_count, cudaStream_t stream);   // f32, MUFU maths
 cudaError_t launch_f32_to_f16(const float4* src, void* dst, size_t n_px, cudaStream_t stream);
-cudaError_t launch_tonemap_rgba8(const float4* src, void* dst, size_t n_px, int aces, cudaStream_t stream);
+cudaError_t launch_f16_to_f32(const void* src, float4* dst, size_t n_px, cudaStream_t stream);
+cudaError_t launch_tonemap_rgba8(const float4* src, void* dst, size_t n_px, int aces, cudaStream_t stream, bool src_f16 = false);
 cudaError_t launch_fma_peak(int precision, int sm_count, unsigned long long iters, float* sink, cudaStream_t stream,
                             double* flops_out);
 

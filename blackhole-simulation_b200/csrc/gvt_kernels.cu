@@ -51,6 +51,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // --------------------------------------------------------------------------------------------------
+// Frame-buffer pixel formats. The frame chain (cur / frame / hist) is RGBA32F -- the parity format -- or RGBA16F, the
+// reference's own texture format (rendering/reprojection.ts:120-140, webgpu/renderer.ts:161-180): half the HBM bytes of
+// the TAA and bloom passes, no conversion pass for hosts that want RGBA16F.
+// --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint2 pack_half4(const float4& v) {
+    const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+    return o;
+}
+__device__ __forceinline__ float4 unpack_half4(const uint2& v) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void store_px(float4* base, size_t idx, const float4& v, bool f16) {
+    if (f16) reinterpret_cast<uint2*>(base)[idx] = pack_half4(v);
+    else base[idx] = v;
+}
+__device__ __forceinline__ float4 load_px(const float4* base, size_t idx, bool f16) {
+    return f16 ? unpack_half4(reinterpret_cast<const uint2*>(base)[idx]) : base[idx];
+}
+
+// --------------------------------------------------------------------------------------------------
 // LUT sampling (the two joints the reference never wired in f64; the sampling rule is specified in DESIGN.md)
 // --------------------------------------------------------------------------------------------------
 template <class R>
@@ -481,10 +504,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
             // NaN guard (failure detection): a ray that went non-finite must not poison the TAA history
             float4 px_out = make_float4((float)col[0], (float)col[1], (float)col[2], 1.0f);
             if (!(px_out.x == px_out.x) || !(px_out.y == px_out.y) || !(px_out.z == px_out.z)) px_out = make_float4(0.f, 0.f, 0.f, 1.0f);
-            if (P.frame) P.frame[(size_t)py * P.width + px] = px_out;
-            if (P.host_frame) P.host_frame[(size_t)py * P.width + px] = px_out;   // posted PCIe write, off the critical path
+            const size_t o = (size_t)py * P.width + px;
+            const bool f16 = P.frame_f16 != 0u;
+            if (P.frame) store_px(P.frame, o, px_out, f16);
+            if (P.host_frame) store_px(P.host_frame, o, px_out, f16);             // posted PCIe write, off the critical path
             for (uint32_t q = 0; q < P.n_peer; q++)                               // fused gather: NVLink peer stores
-                P.peer_frame[q][(size_t)py * P.width + px] = px_out;
+                store_px(P.peer_frame[q], o, px_out, f16);
             if (DEBUG) {
                 const size_t k = (size_t)lj * P.nx + li;
                 if (P.dbg_xp && METHOD == 3) {
@@ -737,22 +762,31 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 
-template <int MODE>
+// 8-B flavour of the per-lane asynchronous copy, for RGBA16F frames (cp.async.cg is 16-B only)
+__device__ __forceinline__ void cp_async8_s(uint32_t dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ uint2 lds64u(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+// F16: cur / hist / out are RGBA16F (8 B per pixel); the arithmetic stays f32.
+template <int MODE, bool F16>
 __global__ void __launch_bounds__(256, GVT_TAA_MINB) k_taa_resolve(const __grid_constant__ TaaParams P) {
     constexpr int NT = (MODE == 1) ? 1 : 4;                        // history taps per pixel
+    constexpr uint32_t ES = F16 ? 8u : 16u;                        // bytes per pixel of the frame chain
+    constexpr uint32_t LS = 32u * ES;                              // one ring row: 32 lanes
+    auto cp_px = [](uint32_t dst, const void* src) { if (F16) cp_async8_s(dst, src); else cp_async16_s(dst, src); };
+    auto ld_px = [](uint32_t a) { return F16 ? unpack_half4(lds64u(a)) : lds128(a); };
     // per-warp, per-lane rings: every lane reads back only what it copied itself, so no warp-level synchronisation
     extern __shared__ __align__(16) unsigned char taa_smem[];     // dynamic: TAA_DEPTH = 3 already exceeds the 48 KB static limit
-    typedef float4 (*RingCur)[TAA_DEPTH][32];
-    typedef float4 (*RingTap)[TAA_DEPTH][NT][32];
-    typedef float2 (*RingFrac)[TAA_DEPTH][32];
-    RingCur ring_cur = reinterpret_cast<RingCur>(taa_smem);
-    RingTap ring_tap = reinterpret_cast<RingTap>(taa_smem + sizeof(float4) * 8 * TAA_DEPTH * 32);
-    RingFrac ring_frac = reinterpret_cast<RingFrac>(taa_smem + sizeof(float4) * 8 * TAA_DEPTH * 32 * (1 + NT));
     // this lane's ring entries, as shared-space byte addresses fixed for the whole kernel: slot s of the current-frame
-    // ring is at my_cur + s * 512, tap t of slot s at my_tap + (s * NT + t) * 512, the fractions at my_frac + s * 256
-    const uint32_t my_cur = smem_u32(&ring_cur[threadIdx.x >> 5][0][threadIdx.x & 31]);
-    const uint32_t my_tap = smem_u32(&ring_tap[threadIdx.x >> 5][0][0][threadIdx.x & 31]);
-    const uint32_t my_frac = smem_u32(&ring_frac[threadIdx.x >> 5][0][threadIdx.x & 31]);
+    // ring is at my_cur + s * LS, tap t of slot s at my_tap + (s * NT + t) * LS, the fractions at my_frac + s * 256
+    const uint32_t smem0 = smem_u32(taa_smem), w_ = threadIdx.x >> 5, l_ = threadIdx.x & 31;
+    const uint32_t my_cur = smem0 + (w_ * TAA_DEPTH * 32u + l_) * ES;
+    const uint32_t my_tap = smem0 + 8u * TAA_DEPTH * LS + (w_ * TAA_DEPTH * NT * 32u + l_) * ES;
+    const uint32_t my_frac = smem0 + 8u * TAA_DEPTH * LS * (1u + NT) + (w_ * TAA_DEPTH * 32u + l_) * 8u;
     const int W = (int)P.width, H = (int)P.height;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int strips_x = (W + TAA_STRIP_W - 1) / TAA_STRIP_W;
@@ -776,7 +810,8 @@ __global__ void __launch_bounds__(256, GVT_TAA_MINB) k_taa_resolve(const __grid_
         const int y_end = min(y_begin + TAA_ROWS, striped ? H : (int)P.row1);
         const int n_rows = y_end - y_begin;
         if (n_rows <= 0) continue;
-        const float4* col = P.cur + xc;
+        const char* col = reinterpret_cast<const char*>(P.cur) + (size_t)xc * ES;
+        const char* hist_b = reinterpret_cast<const char*>(P.hist);
 
         // column-only part of the reprojection (MODE 0)
         const float cx = fmaf((float)x + 0.5f, 2.0f / (float)W, -1.0f);
@@ -791,14 +826,14 @@ __global__ void __launch_bounds__(256, GVT_TAA_MINB) k_taa_resolve(const __grid_
         // taps (+ bilinear fractions) of row y_begin + j.
         auto issue = [&](int k) {
             const uint32_t slot = (uint32_t)k % TAA_DEPTH;
-            if (k <= n_rows + 1) cp_async16_s(my_cur + slot * 512u, col + (size_t)min(max(y_begin - 1 + k, 0), H - 1) * W);
+            if (k <= n_rows + 1) cp_px(my_cur + slot * LS, col + (size_t)min(max(y_begin - 1 + k, 0), H - 1) * W * ES);
             const int j = k - 2;
             if (j >= 0 && j < n_rows) {
                 const int y = y_begin + j;
-                const uint32_t tap = my_tap + slot * (NT * 512u);
+                const uint32_t tap = my_tap + slot * (NT * LS);
                 if (MODE == 1) {
                     // WebGL2 resolve: history at the same texel (reprojection.glsl.ts:93-110)
-                    cp_async16_s(tap, P.hist + (size_t)y * W + xc);
+                    cp_px(tap, hist_b + ((size_t)y * W + xc) * ES);
                 } else {
                     // reprojection at depth 12 through prev_view_proj (ataa.wgsl.ts:54-69), factored form (header)
                     const float cy = -fmaf((float)y + 0.5f, 2.0f / (float)H, -1.0f);
@@ -816,10 +851,10 @@ __global__ void __launch_bounds__(256, GVT_TAA_MINB) k_taa_resolve(const __grid_
                     const float hxf = floorf(hx), hyf = floorf(hy);
                     const int x0 = (int)hxf, y0 = (int)hyf;
                     // one 64-bit address, the other three taps by small element offsets (0 or 1 column, 0 or W rows)
-                    const float4* t00 = P.hist + ((size_t)y0 * W + x0);
-                    const int dx = (x0 + 1 < W) ? 1 : 0, dy = (y0 + 1 < H) ? W : 0;
-                    cp_async16_s(tap, t00); cp_async16_s(tap + 512u, t00 + dx);
-                    cp_async16_s(tap + 1024u, t00 + dy); cp_async16_s(tap + 1536u, t00 + dy + dx);
+                    const char* t00 = hist_b + ((size_t)y0 * W + x0) * ES;
+                    const size_t dx = (x0 + 1 < W) ? ES : 0, dy = (y0 + 1 < H) ? (size_t)W * ES : 0;
+                    cp_px(tap, t00); cp_px(tap + LS, t00 + dx);
+                    cp_px(tap + 2u * LS, t00 + dy); cp_px(tap + 3u * LS, t00 + dy + dx);
                     sts64(my_frac + slot * 256u, hx - hxf, hy - hyf);
                 }
             }
@@ -830,17 +865,17 @@ __global__ void __launch_bounds__(256, GVT_TAA_MINB) k_taa_resolve(const __grid_
         // rolling window of per-pixel YCoCg moments for rows y-1, y, y+1
         YCC2 a, b, c;
         cp_async_wait<TAA_DEPTH - 1>();
-        a = moments_of(lds128(my_cur));
+        a = moments_of(ld_px(my_cur));
         issue(TAA_DEPTH);
         cp_async_wait<TAA_DEPTH - 1>();
-        b = moments_of(lds128(my_cur + (1u % TAA_DEPTH) * 512u));
+        b = moments_of(ld_px(my_cur + (1u % TAA_DEPTH) * LS));
         issue(TAA_DEPTH + 1);
 #pragma unroll taa_unroll
         for (int y = y_begin; y < y_end; y++) {
             const int k = y - y_begin + 2;
             const uint32_t slot = (uint32_t)k % TAA_DEPTH;
             cp_async_wait<TAA_DEPTH - 1>();
-            c = moments_of(lds128(my_cur + slot * 512u));
+            c = moments_of(ld_px(my_cur + slot * LS));
             // vertical sums (this lane's column), then horizontal 3-tap by shuffles
             const float m1y = sum3(a.y + b.y + c.y), m1o = sum3(a.co + b.co + c.co), m1g = sum3(a.cg + b.cg + c.cg);
             const float m2y = sum3(a.yy + b.yy + c.yy), m2o = sum3(a.coco + b.coco + c.coco);
@@ -856,13 +891,13 @@ __global__ void __launch_bounds__(256, GVT_TAA_MINB) k_taa_resolve(const __grid_
                     lo[i] = fmaf(-nsig, sd, mean[i]); hi[i] = fmaf(nsig, sd, mean[i]);
                 }
                 float hr, hg, hb, fb_;
-                const uint32_t tap = my_tap + slot * (NT * 512u);
-                const float4 h00 = lds128(tap);
+                const uint32_t tap = my_tap + slot * (NT * LS);
+                const float4 h00 = ld_px(tap);
                 if (MODE == 1) {
                     hr = h00.x; hg = h00.y; hb = h00.z;
                     fb_ = fb_gl * (1.0f - fminf(fmaxf(sd_y * 4.0f, 0.0f), 0.55f));   // variance-guided weight
                 } else {
-                    const float4 h10 = lds128(tap + 512u), h01 = lds128(tap + 1024u), h11 = lds128(tap + 1536u);
+                    const float4 h10 = ld_px(tap + LS), h01 = ld_px(tap + 2u * LS), h11 = ld_px(tap + 3u * LS);
                     const float2 fr = lds64(my_frac + slot * 256u);
                     const float tr = fmaf(h10.x - h00.x, fr.x, h00.x), br = fmaf(h11.x - h01.x, fr.x, h01.x);
                     const float tg = fmaf(h10.y - h00.y, fr.x, h00.y), bg = fmaf(h11.y - h01.y, fr.x, h01.y);
@@ -879,10 +914,10 @@ __global__ void __launch_bounds__(256, GVT_TAA_MINB) k_taa_resolve(const __grid_
                 // YCoCgToRGB, ataa.wgsl.ts:18-26
                 const float4 px_out = make_float4(ry + ro - rg, ry + rg, ry - ro - rg, 1.0f);
                 const size_t o = (size_t)y * W + x;
-                P.out[o] = px_out;
-                if (P.host_out) P.host_out[o] = px_out;
+                store_px(P.out, o, px_out, F16);
+                if (P.host_out) store_px(P.host_out, o, px_out, F16);
 #pragma unroll 1
-                for (uint32_t q = 0; q < P.n_peer; q++) P.peer_out[q][o] = px_out;
+                for (uint32_t q = 0; q < P.n_peer; q++) store_px(P.peer_out[q], o, px_out, F16);
             }
             a = b; b = c;
             issue(k + TAA_DEPTH);   // refills the slot this iteration has just finished reading
@@ -898,27 +933,26 @@ cudaError_t launch_taa(const TaaParams& p_in, int sm_count, cudaStream_t stream)
     const bool striped = p.stripe.s != 0u;
     if (striped ? p.n_stripes == 0u : rows <= 0) return cudaSuccess;
     const int wpb = 8;
-    static PerDeviceInt resident_cache[2];   // CTAs per SM of each instantiation, per device (occupancy query, once)
-    const int m = p.mode == 1u ? 1 : 0;
-    // rings per CTA: 8 warps x TAA_DEPTH x 32 lanes x (16 B current + NT x 16 B taps + 8 B fractions)
-    const size_t smem = (size_t)8 * TAA_DEPTH * 32 * (16 + (m ? 1 : 4) * 16 + 8);
-    int* cached = resident_cache[m].slot();
-    int resident[2] = {0, 0};
-    resident[m] = cached ? *cached : 0;
-    if (!resident[m]) {
+    static PerDeviceInt resident_cache[4];   // CTAs per SM of each instantiation, per device (occupancy query, once)
+    const int m = p.mode == 1u ? 1 : 0, f = p.frame_f16 ? 1 : 0;
+    // rings per CTA: 8 warps x TAA_DEPTH x 32 lanes x (ES B current + NT x ES B taps + 8 B fractions)
+    const size_t es = f ? 8 : 16;
+    const size_t smem = (size_t)8 * TAA_DEPTH * 32 * (es + (m ? 1 : 4) * es + 8);
+    void (*kern)(TaaParams) = m ? (f ? k_taa_resolve<1, true> : k_taa_resolve<1, false>) : (f ? k_taa_resolve<0, true> : k_taa_resolve<0, false>);
+    int* cached = resident_cache[2 * m + f].slot();
+    int resident = cached ? *cached : 0;
+    if (!resident) {
         int n = 0;
-        cudaError_t e = m ? cudaFuncSetAttribute(k_taa_resolve<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                          : cudaFuncSetAttribute(k_taa_resolve<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = m ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_taa_resolve<1>, wpb * 32, smem)
-              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_taa_resolve<0>, wpb * 32, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, wpb * 32, smem);
         if (e != cudaSuccess) return e;
-        resident[m] = n > 0 ? n : 1;
-        if (cached) *cached = resident[m];
+        resident = n > 0 ? n : 1;
+        if (cached) *cached = resident;
     }
     // Rows per strip unit: every warp walks k = ceil(units / resident warps) units of (R + 2) loaded rows; pick the R
     // that minimises k (R + 2), i.e. no partial last wave and as little halo as the frame allows.
-    const int max_warps = max(sm_count, 1) * resident[m] * wpb;
+    const int max_warps = max(sm_count, 1) * resident * wpb;
     int best_r = 16;
     long best_cost = -1;
     for (int R = 4; R <= 64; R++) {
@@ -928,9 +962,8 @@ cudaError_t launch_taa(const TaaParams& p_in, int sm_count, cudaStream_t stream)
     }
     p.unit_rows = (uint32_t)best_r;
     const int n_work = striped ? strips_x * (int)p.n_stripes : strips_x * ((rows + best_r - 1) / best_r);
-    const int blocks = min((n_work + wpb - 1) / wpb, max(sm_count, 1) * resident[m]);
-    if (m) k_taa_resolve<1><<<blocks, wpb * 32, smem, stream>>>(p);
-    else k_taa_resolve<0><<<blocks, wpb * 32, smem, stream>>>(p);
+    const int blocks = min((n_work + wpb - 1) / wpb, max(sm_count, 1) * resident);
+    kern<<<blocks, wpb * 32, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -962,12 +995,13 @@ __global__ void __launch_bounds__(256) k_taa_resolve_precise(const __grid_consta
     const int x = (int)(blockIdx.x * 32u + (threadIdx.x & 31u));
     const int y = (int)P.row0 + (int)(blockIdx.y * 8u + (threadIdx.x >> 5));
     if (x >= W || y >= (int)P.row1) return;
+    const bool f16 = P.frame_f16 != 0u;              // RGBA16F frames: texels widen exactly, the result is rounded once on store
     float m1[3] = {0.f, 0.f, 0.f}, m2[3] = {0.f, 0.f, 0.f}, c0[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int dy = -1; dy <= 1; dy++)
 #pragma unroll
         for (int dx = -1; dx <= 1; dx++) {                                          // ataa.wgsl.ts:36-48, clamp :43
-            const float4 p = P.cur[(size_t)min(max(y + dy, 0), H - 1) * W + min(max(x + dx, 0), W - 1)];
+            const float4 p = load_px(P.cur, (size_t)min(max(y + dy, 0), H - 1) * W + min(max(x + dx, 0), W - 1), f16);
             float s[3];
             ycocg_rn(p.x, p.y, p.z, s[0], s[1], s[2]);
 #pragma unroll
@@ -985,7 +1019,7 @@ __global__ void __launch_bounds__(256) k_taa_resolve_precise(const __grid_consta
     }
     float hr, hg, hb, alpha;
     if (MODE == 1) {
-        const float4 h = P.hist[(size_t)y * W + x];                                 // same texel (reprojection.glsl.ts:93-110)
+        const float4 h = load_px(P.hist, (size_t)y * W + x, f16);                   // same texel (reprojection.glsl.ts:93-110)
         hr = h.x; hg = h.y; hb = h.z;
         const float wv = __fadd_rn(1.0f, -fminf(fmaxf(__fmul_rn(sd0, 4.0f), 0.0f), 0.55f));
         alpha = P.moving ? 0.0f : __fmul_rn(P.blend, wv);
@@ -1012,8 +1046,8 @@ __global__ void __launch_bounds__(256) k_taa_resolve_precise(const __grid_consta
         const int x0 = (int)floorf(fx_), y0 = (int)floorf(fy_);
         const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
         const float fx = __fadd_rn(fx_, -(float)x0), fy = __fadd_rn(fy_, -(float)y0);
-        const float4 t00 = P.hist[(size_t)y0 * W + x0], t10 = P.hist[(size_t)y0 * W + x1];
-        const float4 t01 = P.hist[(size_t)y1 * W + x0], t11 = P.hist[(size_t)y1 * W + x1];
+        const float4 t00 = load_px(P.hist, (size_t)y0 * W + x0, f16), t10 = load_px(P.hist, (size_t)y0 * W + x1, f16);
+        const float4 t01 = load_px(P.hist, (size_t)y1 * W + x0, f16), t11 = load_px(P.hist, (size_t)y1 * W + x1, f16);
         auto bil = [&](float a00, float a10, float a01, float a11) {
             const float top = __fadd_rn(a00, __fmul_rn(__fadd_rn(a10, -a00), fx));
             const float bot = __fadd_rn(a01, __fmul_rn(__fadd_rn(a11, -a01), fx));
@@ -1033,9 +1067,9 @@ __global__ void __launch_bounds__(256) k_taa_resolve_precise(const __grid_consta
     // YCoCgToRGB, ataa.wgsl.ts:18-26
     const float4 px_out = make_float4(__fadd_rn(__fadd_rn(ry, ro), -rg), __fadd_rn(ry, rg), __fadd_rn(__fadd_rn(ry, -ro), -rg), 1.0f);
     const size_t o = (size_t)y * W + x;
-    P.out[o] = px_out;
-    if (P.host_out) P.host_out[o] = px_out;
-    for (uint32_t q = 0; q < P.n_peer; q++) P.peer_out[q][o] = px_out;
+    store_px(P.out, o, px_out, f16);
+    if (P.host_out) store_px(P.host_out, o, px_out, f16);
+    for (uint32_t q = 0; q < P.n_peer; q++) store_px(P.peer_out[q], o, px_out, f16);
 }
 
 cudaError_t launch_taa_precise(const TaaParams& p, cudaStream_t stream) {
@@ -1063,15 +1097,24 @@ cudaError_t launch_f32_to_f16(const float4* src, void* dst, size_t n_px, cudaStr
     return cudaGetLastError();
 }
 
+// RGBA16F frame chain -> RGBA32F hosts
+__global__ void k_f16_to_f32(const uint2* __restrict__ src, float4* __restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = unpack_half4(src[i]);
+}
+cudaError_t launch_f16_to_f32(const void* src, float4* dst, size_t n_px, cudaStream_t stream) {
+    k_f16_to_f32<<<148 * 8, 256, 0, stream>>>(reinterpret_cast<const uint2*>(src), dst, n_px);
+    return cudaGetLastError();
+}
+
 // Display-ready 8-bit output: Reinhard (webgpu/renderer.ts:45-47) or ACES + gamma (bloom.glsl.ts:106-124, no bloom).
 __device__ __forceinline__ float aces_gamma(float c) {
     const float t = fminf(fmaxf((c * (2.51f * c + 0.03f)) / (c * (2.43f * c + 0.59f) + 0.14f), 0.0f), 1.0f);
     return powf(t, 0.4545f);
 }
 __device__ __forceinline__ uint32_t unorm8(float v) { return (uint32_t)__float2int_rn(fminf(fmaxf(v, 0.0f), 1.0f) * 255.0f); }
-__global__ void k_tonemap_rgba8(const float4* __restrict__ src, uint32_t* __restrict__ dst, size_t n, int aces) {
+__global__ void k_tonemap_rgba8(const float4* __restrict__ src, uint32_t* __restrict__ dst, size_t n, int aces, bool src_f16) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float4 v = src[i];
+        const float4 v = load_px(src, i, src_f16);
         float r, g, b;
         if (aces == 1) { r = aces_gamma(v.x); g = aces_gamma(v.y); b = aces_gamma(v.z); }
         else if (aces == 2) { r = v.x; g = v.y; b = v.z; }   // already display-referred: quantise only
@@ -1079,8 +1122,8 @@ __global__ void k_tonemap_rgba8(const float4* __restrict__ src, uint32_t* __rest
         dst[i] = unorm8(r) | (unorm8(g) << 8) | (unorm8(b) << 16) | (unorm8(v.w) << 24);
     }
 }
-cudaError_t launch_tonemap_rgba8(const float4* src, void* dst, size_t n_px, int aces, cudaStream_t stream) {
-    k_tonemap_rgba8<<<148 * 8, 256, 0, stream>>>(src, reinterpret_cast<uint32_t*>(dst), n_px, aces);
+cudaError_t launch_tonemap_rgba8(const float4* src, void* dst, size_t n_px, int aces, cudaStream_t stream, bool src_f16) {
+    k_tonemap_rgba8<<<148 * 8, 256, 0, stream>>>(src, reinterpret_cast<uint32_t*>(dst), n_px, aces, src_f16);
     return cudaGetLastError();
 }
 

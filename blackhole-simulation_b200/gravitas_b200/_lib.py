@@ -142,7 +142,8 @@ SIGNATURES = {
                                 _u32, _u32, _u32, _u32, _pd, _pu32, _pu32, _pd, _pd]),
     "gvt_taa_resolve": (_i32, [_vp, C.POINTER(GvtCamera), _u32, _u32, _pf, _pf, _pf]),
     "gvt_taa_resolve_webgl": (_i32, [_vp, _u32, _u32, _pf, _pf, C.c_float, _i32, _pf]),
-    "gvt_taa_resolve_ex": (_i32, [_vp, C.POINTER(GvtCamera), _u32, _u32, _pf, _pf, _pf, _u32, C.c_float, _i32, _i32, C.POINTER(C.c_double)]),
+    "gvt_taa_resolve_ex": (_i32, [_vp, C.POINTER(GvtCamera), _u32, _u32, _vp, _vp, _vp, _u32, _u32, C.c_float, _i32, _i32, C.POINTER(C.c_double)]),
+    "gvt_render_set_frame_format": (_i32, [_vp, _u32]),
     "gvt_render_reset_history": (_i32, [_vp]),
     "gvt_render_set_noise_textures": (_i32, [_vp, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), _u32]),
     "gvt_render_fragment_glsl": (_i32, [_vp, C.POINTER(GvtGlslUniforms), _u32, _u32, _u32, C.c_float, _u32, _vp,

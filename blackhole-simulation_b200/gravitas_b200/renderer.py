@@ -248,33 +248,35 @@ class KerrRenderer:
                                      drift.ctypes.data_as(pd), rgba.ctypes.data_as(pd)))
         return dict(xp=xp, term=term, steps=steps, drift=drift, rgba=rgba)
 
-    def taa_resolve(self, camera, cur, hist, precise=False):
-        """ataa.wgsl.ts on host frames. precise=True: the validation build (IEEE f32 operations in shader order)."""
-        cam = camera if isinstance(camera, GvtCamera) else pack_camera(camera)
-        cur = np.ascontiguousarray(cur, np.float32)
-        hist = np.ascontiguousarray(hist, np.float32)
+    def _taa(self, cam, cur, hist, webgl, blend, moving, precise):
+        """Host-frame entry of both resolves; float16 inputs run the RGBA16F flavour of the kernels (8 B per pixel)."""
+        cur = np.ascontiguousarray(cur)
+        f16 = cur.dtype == np.float16
+        dt = np.float16 if f16 else np.float32
+        cur = np.ascontiguousarray(cur, dt)
+        hist = np.ascontiguousarray(hist, dt)
         H, W = cur.shape[:2]
         out = np.zeros_like(cur)
-        pf = C.POINTER(C.c_float)
         ms = C.c_double(0.0)
-        check(lib().gvt_taa_resolve_ex(self._h, C.byref(cam), W, H, cur.ctypes.data_as(pf), hist.ctypes.data_as(pf),
-                                       out.ctypes.data_as(pf), 0, 0.0, 0, 1 if precise else 0, C.byref(ms)))
+        check(lib().gvt_taa_resolve_ex(self._h, C.byref(cam) if cam is not None else None, W, H, cur.ctypes.data_as(C.c_void_p),
+                                       hist.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                                       _lib.FORMAT_RGBA16F if f16 else _lib.FORMAT_RGBA32F, 1 if webgl else 0, float(blend),
+                                       1 if moving else 0, 1 if precise else 0, C.byref(ms)))
         self.last_taa_ms = ms.value
         return out
 
+    def taa_resolve(self, camera, cur, hist, precise=False):
+        """ataa.wgsl.ts on host frames (float32, or float16 = RGBA16F textures). precise=True: the validation build."""
+        cam = camera if isinstance(camera, GvtCamera) else pack_camera(camera)
+        return self._taa(cam, cur, hist, False, 0.0, False, precise)
+
     def taa_resolve_webgl(self, cur, hist, blend=0.75, camera_moving=False, precise=False):
         """ReprojectionManager.resolve (rendering/reprojection.ts:195-272) semantics on host frames."""
-        cur = np.ascontiguousarray(cur, np.float32)
-        hist = np.ascontiguousarray(hist, np.float32)
-        H, W = cur.shape[:2]
-        out = np.zeros_like(cur)
-        pf = C.POINTER(C.c_float)
-        ms = C.c_double(0.0)
-        check(lib().gvt_taa_resolve_ex(self._h, None, W, H, cur.ctypes.data_as(pf), hist.ctypes.data_as(pf),
-                                       out.ctypes.data_as(pf), 1, float(blend), 1 if camera_moving else 0,
-                                       1 if precise else 0, C.byref(ms)))
-        self.last_taa_ms = ms.value
-        return out
+        return self._taa(None, cur, hist, True, blend, camera_moving, precise)
+
+    def set_frame_format(self, fmt):
+        """RGBA32F (default, parity format) or RGBA16F (the reference's texture format) for cur / frame / hist."""
+        check(lib().gvt_render_set_frame_format(self._h, fmt))
 
     def bloom(self, enabled=True, intensity=0.5, threshold=0.8, blur_passes=2, fmt=_lib.FORMAT_RGBA32F, readback=True,
               precise=False):

@@ -322,10 +322,16 @@ int32_t gvt_taa_resolve_webgl(gvt_renderer* r, uint32_t width, uint32_t height, 
 /* Both variants with two more knobs: precise != 0 runs the validation build (GVT_FLAG_TAA_PRECISE: IEEE f32 operations
  * in shader order; tested to 1e-6 against the numpy restatement of the shader text), ms_out (may be NULL) receives the
  * kernel's device time. webgl != 0: reprojection.glsl.ts (cam may be NULL), else ataa.wgsl.ts. */
-int32_t gvt_taa_resolve_ex(gvt_renderer* r, const GvtCamera* cam, uint32_t width, uint32_t height, const float* cur,
-                           const float* hist, float* out, uint32_t webgl, float blend, int32_t camera_moving,
-                           int32_t precise, double* ms_out);
+int32_t gvt_taa_resolve_ex(gvt_renderer* r, const GvtCamera* cam, uint32_t width, uint32_t height, const void* cur,
+                           const void* hist, void* out, uint32_t frame_format /* GVT_FORMAT_RGBA32F | RGBA16F: the three buffers */,
+                           uint32_t webgl, float blend, int32_t camera_moving, int32_t precise, double* ms_out);
 int32_t gvt_render_reset_history(gvt_renderer* r);
+/* Format of the frame chain (trace output, finished frame, TAA history): GVT_FORMAT_RGBA32F (default; the parity format) or
+ * GVT_FORMAT_RGBA16F, the reference's own texture format (rendering/reprojection.ts:120-140, webgpu/renderer.ts:161-180):
+ * the producing kernels store half4, the TAA resolve and the bloom passes read / write 8 B per pixel (f32 arithmetic), and
+ * an RGBA16F host frame is delivered without a conversion pass. Re-allocates the buffers and clears the history; with
+ * peer stores, re-import the peers' frames afterwards. */
+int32_t gvt_render_set_frame_format(gvt_renderer* r, uint32_t format);
 /* Size of the frame buffers (0 x 0 before the first resize / frame): what a binding needs to validate caller buffers. */
 int32_t gvt_render_get_size(gvt_renderer* r, uint32_t* width, uint32_t* height);
 

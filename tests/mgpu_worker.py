@@ -242,6 +242,30 @@ for (W, H, kw, flags, what) in (
         print(f"[mgpu] {what}: {world}-rank frame bit-identical to 1 GPU ({W}x{H}, {int(t[0])} steps; {ms_multi:.1f} ms vs "
               f"{single.last_stats.total_ms:.1f} ms on one GPU)", flush=True)
 dist.barrier()
+
+# the RGBA16F-native frame chain across ranks: half4 peer stores / half-sized all-gather, TAA history in f16 on every rank
+for flags_extra, name in ((0, "ncclAllGather"), (_lib.FLAG_PEER_STORE, "peer stores")):
+    W, H, steps = 256, 144, 96
+    for rr in (multi, single):
+        rr.set_frame_format(_lib.FORMAT_RGBA16F)
+        rr.resize(W, H); rr.reset_history()
+    if flags_extra:
+        multi.connect_peers(dist)
+    prev = None
+    for k in range(3):
+        cam, vp = camera.default_camera(W, H, azimuth=math.pi + 0.005 * k, prev_view_proj=prev)
+        phys = R.pack_physics(1.0, spin, W, H, frame_index=k)
+        fl = _lib.FLAG_TAA | _lib.FLAG_JITTER
+        multi.params = R.RenderParams(max_steps=steps, flags=fl | flags_extra, output_format=_lib.FORMAT_RGBA16F)
+        single.params = R.RenderParams(max_steps=steps, flags=fl, output_format=_lib.FORMAT_RGBA16F)
+        a = np.array(multi.render(cam, phys)); b = np.array(single.render(cam, phys))
+        assert a.dtype == np.float16 and np.array_equal(a.view(np.uint16), b.view(np.uint16)), f"rank {rank}: RGBA16F chain differs ({name}, k={k})"
+        prev = vp
+    if rank == 0:
+        print(f"[mgpu] RGBA16F frame chain + TAA, {name}: {world}-rank frames bit-identical to 1 GPU", flush=True)
+for rr in (multi, single):
+    rr.set_frame_format(_lib.FORMAT_RGBA32F)
+dist.barrier()
 multi.cleanup(); single.cleanup()
 dist.destroy_process_group()
 print(f"rank {rank} ok")

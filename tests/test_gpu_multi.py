@@ -25,4 +25,4 @@ def test_row_block_shard_allgather_bitwise(built):
     with open(os.path.join(ROOT, "gpurun_out", "test_gpu_multi_2gpu.log"), "w") as f:
         f.write(f"$ {' '.join(cmd)}\nreturn code {p.returncode}\n--- stdout ---\n{p.stdout}\n--- stderr (tail) ---\n{p.stderr[:8000]}\n...\n{p.stderr[-4000:]}\n")
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-5000:]
-    assert p.stdout.count(" ok") == world and p.stdout.count("[mgpu]") == 3
+    assert p.stdout.count(" ok") == world and p.stdout.count("[mgpu]") == 5
