@@ -299,6 +299,12 @@ napi_value Resize(napi_env env, napi_callback_info info) {                      
     GVT(gvt_render_resize(r, (uint32_t)Num(env, argv[0]), (uint32_t)Num(env, argv[1])));
     return Undefined(env);
 }
+napi_value SetFrameFormat(napi_env env, napi_callback_info info) {               // (format: 0 = RGBA32F, 1 = RGBA16F)  reprojection.ts:120-140
+    size_t argc = 1; napi_value argv[1];
+    gvt_renderer* r = Self<gvt_renderer>(env, info, &argc, argv);
+    GVT(gvt_render_set_frame_format(r, (uint32_t)Num(env, argv[0])));
+    return Undefined(env);
+}
 uint32_t OptU32(napi_env env, napi_value obj, const char* key, uint32_t dflt) {
     bool has = false; napi_value v;
     if (napi_has_named_property(env, obj, key, &has) != napi_ok || !has) return dflt;
@@ -428,6 +434,7 @@ NAPI_MODULE_INIT() {
         {"integrate_ray_relativistic", 0, IntegrateRay, 0, 0, 0, napi_default, 0}};
     const napi_property_descriptor renderer[] = {
         {"initLuts", 0, InitLuts, 0, 0, 0, napi_default, 0}, {"resize", 0, Resize, 0, 0, 0, napi_default, 0},
+        {"setFrameFormat", 0, SetFrameFormat, 0, 0, 0, napi_default, 0},
         {"renderFrame", 0, RenderFrame, 0, 0, 0, napi_default, 0},
         {"setNoiseTextures", 0, SetNoiseTextures, 0, 0, 0, napi_default, 0}, {"renderFragment", 0, RenderFragment, 0, 0, 0, napi_default, 0},
         {"bloom", 0, Bloom, 0, 0, 0, napi_default, 0}};

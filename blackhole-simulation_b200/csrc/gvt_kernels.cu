@@ -390,7 +390,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
         // too large for that (it spills when unrolled).
         constexpr uint32_t CHUNK = 8;
         // One march step, in the flavour `kind` (StepKind).
-        auto march_step = [&](auto kind) {
+        bool parked = false;               // HCONST chunks: this ray left the chunk's radius window and waits for the replay below
+        uint32_t park_it = 0;
+        auto march_step = [&](auto kind, uint32_t it) {
             using K = decltype(kind);
             const R th0 = y.th, r_prev = y.r;
             R hs = R(0);
@@ -401,22 +403,21 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
                 adaptive_step_warp<R, 1>(hc, y, h, R(P.tol), !done, rhs_evals);
             } else {
                 // Hot path of the radius tests (f64): ONE unsigned range test on the high word of r says "strictly inside
-                // (lo, escape_r)", lo = 1.001 r+ or, in HCONST chunks, the radius where the step rule saturates. Only a
-                // ray outside that window -- at a boundary, or a numerically blown-up one that broke the chunk's travel
-                // bound -- takes the exact tests and the generic step rule, so termination and step size are exact for
-                // every ray in every f64 zone. (Measured alternatives: no test at all is 0.9 % faster and gets the step
-                // count of ~10 blown-up rays per 4K frame wrong; parking such rays and replaying them after the chunk is
-                // exact too, and 1 % slower than these predicated instructions.)
+                // (lo, escape_r)", lo = 1.001 r+ or, in HCONST chunks, the radius where the step rule saturates.
                 bool inside;
                 if (sizeof(R) == 8) inside = ((uint32_t)hiword(y.r) - P.alive_lo[K::hconst ? 1 : 0]) < P.alive_span[K::hconst ? 1 : 0];
                 else inside = K::hconst ? (y.r > R(P.r_sat) && y.r < escape_r) : false;
-                hs = K::hconst ? R(P.h_const) : (WGSL_RULE ? clampPos<R>(N::fma_(y.r, R(0.15), hs_bias), R(0.05), R(1.0)) : R(P.h0));
-                if (!inside && !done) {
-                    if (lt_pos(y.r, r_term) || gt_pos(y.r, escape_r)) { done = true; by_radius = true; }
-                    // f32-predictor (FAR) chunks hold rays on their way out beyond r_far; one that blew up terminates here
-                    // like everywhere else, but the step rule is not re-derived for a garbage radius that happens to land
-                    // inside (1.001 r+, r_sat) -- the one place where that precision mode is not exact by construction.
-                    if (K::hconst && !K::far) hs = WGSL_RULE ? clampPos<R>(N::fma_(y.r, R(0.15), hs_bias), R(0.05), R(1.0)) : R(P.h0);
+                if (K::hconst) {
+                    // A live ray outside the window broke the chunk's travel bound -- only a numerically blown-up one can.
+                    // It is PARKED (frozen like a finished ray, three predicated instructions) and the generic loop replays
+                    // it from this very step once the chunk is over, so termination and step size stay exact for every ray
+                    // in every zone. (ptxas would predicate the exact tests and the generic step rule into this loop
+                    // otherwise -- ~17 issue slots per step for something that happens to ~10 rays per 4K frame.)
+                    if (!inside && !done) { done = true; parked = true; park_it = it; }
+                    hs = R(P.h_const);
+                } else {
+                    if (!inside && !done && (lt_pos(y.r, r_term) || gt_pos(y.r, escape_r))) { done = true; by_radius = true; }
+                    hs = WGSL_RULE ? clampPos<R>(N::fma_(y.r, R(0.15), hs_bias), R(0.05), R(1.0)) : R(P.h0);
                 }
                 // Fixed-step methods run the step for every lane, finished rays with h = 0 on their frozen state (nothing to
                 // select back afterwards): in budget accounting that IS the definition; with natural termination the lanes
@@ -483,16 +484,34 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
             }
             if (MIXED && zone == 2u) {
 #pragma unroll(kUnrollFar)
-                for (uint32_t it = it0; it < it1; it++) march_step(StepKind<true, true, false>{});
+                for (uint32_t it = it0; it < it1; it++) march_step(StepKind<true, true, false>{}, it);
             } else if (METHOD == 2 && zone >= 1u) {
 #pragma unroll(MIXED ? kUnrollNearMixed : kUnrollSymp)
-                for (uint32_t it = it0; it < it1; it++) march_step(StepKind<false, true, false>{});
+                for (uint32_t it = it0; it < it1; it++) march_step(StepKind<false, true, false>{}, it);
             } else if (METHOD == 2 && !polar_tile) {
 #pragma unroll(MIXED ? kUnrollNearMixed : kUnrollSymp)
-                for (uint32_t it = it0; it < it1; it++) march_step(StepKind<false, false, false>{});
+                for (uint32_t it = it0; it < it1; it++) march_step(StepKind<false, false, false>{}, it);
             } else {
 #pragma unroll(METHOD == 1 ? kUnrollNear : 1)
-                for (uint32_t it = it0; it < it1; it++) march_step(StepKind<false, false, true>{});
+                for (uint32_t it = it0; it < it1; it++) march_step(StepKind<false, false, true>{}, it);
+            }
+            // Replay of parked rays (see HCONST above): the generic step, everyone else frozen, each parked ray from the
+            // step it was parked at. Rare enough that its cost is the one vote per chunk.
+            if (METHOD == 2 && zone >= 1u && __any_sync(0xffffffffu, parked)) {
+                const bool mine = parked, done_saved = done;
+                const uint32_t rhs_saved = rhs_evals;
+                bool fin = false;                                  // a replayed ray's own "done"
+                const uint32_t first = __reduce_min_sync(0xffffffffu, mine ? park_it : it1);
+#pragma unroll 1
+                for (uint32_t it = first; it < it1; it++) {
+                    const bool act = mine && it >= park_it && !fin;
+                    done = !act;
+                    march_step(StepKind<false, false, true>{}, it);
+                    if (act) fin = done;
+                }
+                done = mine ? fin : done_saved;
+                if (BUDGET) rhs_evals = rhs_saved;                 // budget accounting counted these steps in the zone loop already
+                parked = false;
             }
         }
         if (by_radius) term = (y.r < r_term) ? 1u : 2u;   // Horizon is tested first (mod.rs:257-263)
