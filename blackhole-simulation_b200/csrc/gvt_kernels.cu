@@ -141,8 +141,8 @@ constexpr int kUnrollSymp = GVT_UNROLL_SYMP, kUnrollNear = GVT_UNROLL_NEAR, kUnr
 // picks one per 8-step chunk): FAR = f32 predictors (GVT_PRECISION_MIXED), HCONST = the step rule has saturated and
 // neither termination radius is within reach, so h is a constant and the radius tests are dropped, POLAR = the ray
 // may come within reach of the polar clamp (kerr.rs:417,448,494) and the RHS carries it.
-template <bool FAR, bool HCONST, bool POLAR> struct StepKind {
-    static constexpr bool far = FAR, hconst = HCONST, polar = POLAR;
+template <bool FAR, bool HCONST, bool POLAR, bool ROT = false> struct StepKind {
+    static constexpr bool far = FAR, hconst = HCONST, polar = POLAR, rot = ROT;   // ROT: shifted angles by rotation (trig_rot)
 };
 // A ray whose conserved L_z = p_phi satisfies L^2 > kPolarSafe (Q + a^2 + L^2) cannot approach the axis: the polar
 // potential Theta = Q + a^2 cos^2 - L^2 cot^2 >= 0 gives sin^2(theta) >= L^2 / (Q + a^2 + L^2) > 1e-4 along the whole
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
         // ---- camera -> (x, p): compute.wgsl.ts:159-187 ----
         Ray<R> y;
         Vec3<R> wdir;          // world-space ray direction (the Cartesian march of METHOD 3 starts from it)
-        bool polar_ray = true;
+        bool polar_ray = true, rot_ray = false;
         {
             const R ndcx = N::fma_(N::fma_(R((double)px), R(fb->inv_width), R(fb->jx)), R(2), R(-1));
             const R ndcy = N::fma_(N::fma_(R((double)py), R(fb->inv_height), R(fb->jy)), R(2), R(-1));
@@ -291,6 +291,13 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
             const R ct2 = ct * ct;
             const R Q = N::fma_(y.pth, y.pth, ct2 * N::fma_(hc.pph2, N::rcp(R(fb->safe_st) * R(fb->safe_st)), -hc.a2));
             polar_ray = !(hc.pph2 > R(kPolarSafe) * (Q + hc.a2 + hc.pph2));
+            // zone 2 of the f64 kernel needs |(h/2) p_theta / Sigma| <= 1/16 beyond r_far - travel; p_theta^2 <= Q + a^2.
+            // It is also closed to rays on which the reference scheme itself goes unstable out there: near its polar turning
+            // point the theta-oscillator has stiffness k = 3 (Q + a^2 + L^2)^2 / (L^2 Sigma^2), and the two-iteration
+            // midpoint blows up for h^2 k >~ 4 -- those rays end as garbage in the oracle too, and only the generic
+            // arithmetic reproduces the oracle's garbage step for step (P.rot_stab carries h^2 / r_min^4 with a 4x margin).
+            const R qal = Q + hc.a2 + hc.pph2;
+            rot_ray = (Q + hc.a2) <= R(P.rot_q_max) && hc.pph2 >= R(P.rot_stab) * qal * qal;
         }
 
         // The spectral-LUT copy was issued before ray generation; by now it has had a tile's worth of set-up time to
@@ -413,6 +420,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
                     // it from this very step once the chunk is over, so termination and step size stay exact for every ray
                     // in every zone. (ptxas would predicate the exact tests and the generic step rule into this loop
                     // otherwise -- ~17 issue slots per step for something that happens to ~10 rays per 4K frame.)
+                    // (the rotated-trigonometry zone also parks a ray whose p_theta has left the range its |d theta| <= 1/16
+                    // bound was derived from: a ray that blew up elsewhere and wandered in)
+                    if (K::rot && sizeof(R) == 8) inside = inside && (((uint32_t)hiword(y.pth) & 0x7fffffffu) < P.rot_pth_hi);
                     if (!inside && !done) { done = true; parked = true; park_it = it; }
                     hs = R(P.h_const);
                 } else {
@@ -427,6 +437,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
                 if (METHOD == 1) { step_rk4<R, 1, DEBUG>(hc, y, hs); rhs_evals += (BUDGET || !done) ? 4u : 0u; }
                 else {
                     if constexpr (MIXED && K::far) step_symplectic_mixed<DEBUG>(hc, hcf, y, hs, done ? 0.0f : P.f32_hconst);
+                    else if constexpr (K::rot && sizeof(R) == 8) step_symplectic_rot<DEBUG>(hc, y, hs);
                     else step_symplectic<R, 1, DEBUG, K::polar>(hc, y, hs);
                     rhs_evals += (BUDGET || !done) ? 3u : 0u;
                 }
@@ -472,19 +483,24 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
         //   zone 1  r_hconst < r < r_escape_guard for every live ray: h = h_const, no polar clamp
         //   zone 2  (GVT_PRECISION_MIXED) additionally r > r_far and p_r > 0: f32 predictors
         const bool polar_tile = METHOD != 2 || __any_sync(0xffffffffu, polar_ray);
+        const bool rot_tile = !MIXED && sizeof(R) == 8 && __all_sync(0xffffffffu, rot_ray);
         for (uint32_t it0 = 0; it0 < P.max_steps; it0 += CHUNK) {
             if (!BUDGET) { if (__all_sync(0xffffffffu, done)) break; }
             const uint32_t it1 = min(it0 + CHUNK, P.max_steps);
             uint32_t zone = 0u;
             if (METHOD == 2 && !polar_tile) {
                 const bool z1 = y.r > R(P.r_hconst) && y.r < R(P.r_escape_guard);
-                const uint32_t lane_zone = done ? 2u : (!z1 ? 0u : ((MIXED && y.r > R(P.r_far) && y.pr > R(0)) ? 2u : 1u));
+                // zone 2: f32 predictors for rays on their way out (MIXED), rotated trigonometry for any ray that far (f64)
+                const uint32_t lane_zone = done ? 2u : (!z1 ? 0u : ((y.r > R(P.r_far) && (!MIXED || y.pr > R(0))) ? 2u : 1u));
                 zone = __reduce_min_sync(0xffffffffu, lane_zone);
-                if (!MIXED) zone = min(zone, 1u);
+                if (!MIXED && !rot_tile) zone = min(zone, 1u);
             }
             if (MIXED && zone == 2u) {
 #pragma unroll(kUnrollFar)
                 for (uint32_t it = it0; it < it1; it++) march_step(StepKind<true, true, false>{}, it);
+            } else if (METHOD == 2 && !MIXED && zone == 2u) {
+#pragma unroll(kUnrollSymp)
+                for (uint32_t it = it0; it < it1; it++) march_step(StepKind<false, true, false, true>{}, it);
             } else if (METHOD == 2 && zone >= 1u) {
 #pragma unroll(MIXED ? kUnrollNearMixed : kUnrollSymp)
                 for (uint32_t it = it0; it < it1; it++) march_step(StepKind<false, true, false>{}, it);
