@@ -712,10 +712,10 @@ def main():
     ap.add_argument("--no-peer-store", action="store_true",
                     help="N > 1: use the ncclAllGather after the trace kernel instead of the default fused gather (NVLink "
                          "peer stores from the trace kernel + 4-byte all-reduce barriers)")
-    ap.add_argument("--shard", default="blocks", choices=["blocks", "interleaved"],
-                    help="N > 1 with the fused gather: contiguous row blocks (default: budget accounting is balanced, measured "
-                         "6.24 ms/frame on 8 GPUs) or rows dealt round-robin (6.29 ms; the better choice under natural "
-                         "termination: 6.42 vs 7.12 ms)")
+    ap.add_argument("--shard", default="interleaved", choices=["blocks", "interleaved"],
+                    help="N > 1 with the fused gather: rows dealt round-robin to the ranks (default: the zones of the march make "
+                         "rows near the hole dearer even under budget accounting; measured on 8 GPUs 6.01 ms/frame, natural "
+                         "termination 5.92 ms) or contiguous row blocks (6.12 / 6.22 ms)")
     ap.add_argument("--workload", default="config3", choices=["config1", "config2", "config3", "config4", "config5", "glsl", "webgl"],
                     help="config3 = the headline (default). The others print an 'extra_workload' JSON line for BASELINE "
                          "configs[0] (Schwarzschild 256x256x128 RKF45: GPU batch integrate + the CPU port), configs[1] "
