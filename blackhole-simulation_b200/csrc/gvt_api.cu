@@ -725,11 +725,16 @@ static int32_t build_frame(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
         const char* e = getenv("GVT_MIXED_RSWITCH");   // tuning experiments only
         const double r_switch = (e && atof(e) > 0.0 ? atof(e) : 35.0) * bh.mass;
         P.r_far = std::max(r_switch + travel, P.r_hconst);
-        {   // |(h/2) p_theta / Sigma| <= 1/16 with Sigma >= (r_far - travel)^2 and p_theta^2 <= Q + a^2
+        {   // |h p_theta / Sigma| <= 1/16 (the whole step's move in theta: the chained rotation of step_symplectic_rot; the
+            // predictor shifts are half of it) with Sigma >= (r_far - travel)^2 and p_theta^2 <= Q + a^2
             const double rmin = P.r_far - travel, hc = std::max(std::fabs(P.h_const), 1e-300);
-            const double pth_max = rmin * rmin / (8.0 * hc);
+            const double pth_max = rmin * rmin / (16.0 * hc);
             P.rot_q_max = pth_max * pth_max;
-            P.rot_stab = 3.0 * hc * hc / (rmin * rmin * rmin * rmin);      // 4x the h^2 k = 4 estimate (3/4 h^2 / r_min^4)
+            // 32x the h^2 k = 4 estimate (3/4 h^2 / r_min^4). Measured on the headline frame: with trig_full every step a 4x margin
+            // reproduced the oracle's census on all 8.3 M pixels; the chained rotation (rounding a few ulp looser) needs 16x for
+            // the last marginal ray, a pixel column next to the image of the spin axis.
+            P.rot_stab = 24.0 * hc * hc / (rmin * rmin * rmin * rmin);
+            if (const char* m = getenv("GVT_ROT_STAB_MULT")) if (atof(m) > 0.0) P.rot_stab *= atof(m);   // tuning experiments only
             if (getenv("GVT_NO_ROT")) P.rot_q_max = -1.0;                    // diagnostics: f64 zone 2 closed
             { uint64_t b; const double pm = pth_max; memcpy(&b, &pm, 8); P.rot_pth_hi = (uint32_t)(b >> 32); }   // |p_theta| < ~pth_max
         }

@@ -531,15 +531,17 @@ __device__ __forceinline__ void step_symplectic(const HoleRay<R>& c, Ray<R>& y, 
     if (WITH_T) y.t = N::fma_(d.dt, h, y.t);
 }
 
-// The implicit-midpoint step with ONE full trigonometric evaluation (at the step's own theta) and the two shifted angles
-// by rotation (trig_rot). Callers guarantee |(h/2) p_theta / Sigma| <= 1/16 for the whole chunk and a ray off the polar
-// axis (k_trace_tile's zone 2 of the f64 kernel); f64 only.
+// The implicit-midpoint step with NO full trigonometric evaluation: (s0, c0) = (sin, cos) of the step's own theta come in
+// from the caller, the two predictor-shifted angles are rotations of them (trig_rot), and so is the pair of the NEW theta
+// the step hands back -- theta moves by h p_theta / Sigma, as small as the shifts. The caller anchors (s0, c0) with one
+// trig_full per 8-step chunk, so rounding of the chained rotations (~1 ulp each) never accumulates beyond a chunk.
+// Callers guarantee |h p_theta / Sigma| <= 1/16 for the whole chunk and a ray off the polar axis (k_trace_tile's zone 2
+// of the f64 kernel); f64 only. theta itself is updated exactly as in step_symplectic.
 template <bool WITH_T, class RS>
-__device__ __forceinline__ void step_symplectic_rot(const HoleRay<RS>& c, Ray<RS>& y, RS h) {
+__device__ __forceinline__ void step_symplectic_rot(const HoleRay<RS>& c, Ray<RS>& y, RS h, double& s0, double& c0) {
     using N = Num<RS>;
     const RS hh = RS(0.5) * h;
-    double s0, c0, s1, c1;
-    trig_full(*c.trig, (double)y.th, s0, c0);
+    double s1, c1;
     DerivU<RS> d = rhs_ks_u<RS, false, false, false>(c, y.r, RS(s0), RS(s0 * c0), y.pr, y.pth);
     RS f = hh * d.isig;
     RS mr = N::fma_(d.dr, f, y.r), mpr = N::fma_(d.dpr, f, y.pr), mpth = N::fma_(d.dpth, f, y.pth);
@@ -555,6 +557,8 @@ __device__ __forceinline__ void step_symplectic_rot(const HoleRay<RS>& c, Ray<RS
     y.pr = N::fma_(d.dpr, f, y.pr);
     y.pth = N::fma_(d.dpth, f, y.pth);
     if (WITH_T) { y.ph = N::fma_(d.dph, f, y.ph); y.t = N::fma_(d.dt, h, y.t); }
+    trig_rot(*c.trig, s0, c0, (double)(d.dth * f), s1, c1);
+    s0 = s1; c0 = c1;
 }
 
 // GVT_PRECISION_MIXED: the same implicit-midpoint step with its two fixed-point (predictor) evaluations in f32 and the

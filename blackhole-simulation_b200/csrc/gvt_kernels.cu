@@ -223,8 +223,18 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
         s_term[wid][0] = s_term[wid][1] = s_term[wid][2] = s_term[wid][3] = 0u;
     }
 
-    unsigned long long t_warp_start = 0; uint32_t n_my_tiles = 0;
-    if (P.timeline) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_warp_start));
+    // Nothing that is only needed before or after a tile's march may stay in registers across it: the step loops sit at the
+    // 128-register cap, and every extra live value there evicts FP64 constants from the uniform registers (measured on the
+    // SASS: +21 LDC per step for one more live loop bound). So the tile number is parked in shared memory and the pixel
+    // coordinates are recomputed from it in the epilogue (`locate`), and the timeline diagnostics live there too.
+    __shared__ uint32_t s_tile[MAXT / 32];
+    __shared__ unsigned long long s_tstart[MAXT / 32];
+    __shared__ uint32_t s_ntiles[MAXT / 32];
+    if (P.timeline && lane == 0) {
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+        s_tstart[wid] = t0; s_ntiles[wid] = 0u;
+    }
     // Work distribution. Natural termination: one global atomic queue of warp-tiles (rows differ widely in cost). Budget
     // accounting: every tile costs nearly the same, so each CTA owns an equal share of the tiles -- dealt round-robin
     // (tile = CTA + k * grid), because the zones of the march do make tiles near the hole and on the polar columns a few
@@ -241,17 +251,24 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
         if (lane == 0) tile = BUDGET ? blockIdx.x + atomicAdd(&s_next_tile, 1u) * gridDim.x : atomicAdd(&P.counters->tile_counter, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= n_tiles) break;
-        n_my_tiles++;
-        const uint32_t ti = tile % tiles_x, tj = tile / tiles_x;
-        const uint32_t li = ti * TW + lx, lj = tj * TH + ly;  // lattice coordinates
-        bool valid = (li < P.nx) && (lj < P.ny);
-        const uint32_t px = P.x0 + min(li, P.nx - 1) * P.xs;
-        uint32_t py = P.y0 + min(lj, P.ny - 1) * P.ys;
-        if (P.stripe.s) {   // GVT_FLAG_ROW_INTERLEAVE: this rank's stripes (+ TAA halo rows); rows off the frame are skipped
-            uint32_t row;
-            valid = stripe_row(P.stripe, min(lj, P.ny - 1), P.height, row) && valid;
-            py = min(row, P.height - 1);
-        }
+        if (P.timeline && lane == 0) s_ntiles[wid]++;
+        // tile -> this lane's pixel: here for ray generation and AGAIN in the epilogue, from the tile number parked in shared memory
+        auto locate = [&](uint32_t tl, uint32_t& li, uint32_t& lj, uint32_t& px, uint32_t& py) -> bool {
+            const uint32_t ti = tl % tiles_x, tj = tl / tiles_x;
+            li = ti * TW + lx; lj = tj * TH + ly;  // lattice coordinates
+            bool ok = (li < P.nx) && (lj < P.ny);
+            px = P.x0 + min(li, P.nx - 1) * P.xs;
+            py = P.y0 + min(lj, P.ny - 1) * P.ys;
+            if (P.stripe.s) {   // GVT_FLAG_ROW_INTERLEAVE: this rank's stripes (+ TAA halo rows); rows off the frame are skipped
+                uint32_t row;
+                ok = stripe_row(P.stripe, min(lj, P.ny - 1), P.height, row) && ok;
+                py = min(row, P.height - 1);
+            }
+            return ok;
+        };
+        if (lane == 0) s_tile[wid] = tile;
+        uint32_t px, py;
+        { uint32_t li_, lj_; (void)locate(tile, li_, lj_, px, py); }
 
         // ---- camera -> (x, p): compute.wgsl.ts:159-187 ----
         Ray<R> y;
@@ -399,6 +416,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
         // One march step, in the flavour `kind` (StepKind).
         bool parked = false;               // HCONST chunks: this ray left the chunk's radius window and waits for the replay below
         uint32_t park_it = 0;
+        double rot_s = 0.0, rot_c = 0.0;   // zone 2 of the f64 kernel: (sin, cos)(theta), anchored per chunk and chained by rotation
         auto march_step = [&](auto kind, uint32_t it) {
             using K = decltype(kind);
             const R th0 = y.th, r_prev = y.r;
@@ -437,7 +455,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
                 if (METHOD == 1) { step_rk4<R, 1, DEBUG>(hc, y, hs); rhs_evals += (BUDGET || !done) ? 4u : 0u; }
                 else {
                     if constexpr (MIXED && K::far) step_symplectic_mixed<DEBUG>(hc, hcf, y, hs, done ? 0.0f : P.f32_hconst);
-                    else if constexpr (K::rot && sizeof(R) == 8) step_symplectic_rot<DEBUG>(hc, y, hs);
+                    else if constexpr (K::rot && sizeof(R) == 8) step_symplectic_rot<DEBUG>(hc, y, hs, rot_s, rot_c);
                     else step_symplectic<R, 1, DEBUG, K::polar>(hc, y, hs);
                     rhs_evals += (BUDGET || !done) ? 3u : 0u;
                 }
@@ -499,6 +517,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
 #pragma unroll(kUnrollFar)
                 for (uint32_t it = it0; it < it1; it++) march_step(StepKind<true, true, false>{}, it);
             } else if (METHOD == 2 && !MIXED && zone == 2u) {
+                if constexpr (sizeof(R) == 8) trig_full(P.trig, (double)y.th, rot_s, rot_c);
 #pragma unroll(kUnrollSymp)
                 for (uint32_t it = it0; it < it1; it++) march_step(StepKind<false, true, false, true>{}, it);
             } else if (METHOD == 2 && zone >= 1u) {
@@ -535,6 +554,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
         }   // METHOD != 3
 
         // ---- epilogue: coalesced float4 store + census ----
+        __syncwarp();
+        uint32_t li, lj;
+        const bool valid = locate(*reinterpret_cast<volatile uint32_t*>(&s_tile[wid]), li, lj, px, py);
         if (valid) {
             // NaN guard (failure detection): a ray that went non-finite must not poison the TAA history
             float4 px_out = make_float4((float)col[0], (float)col[1], (float)col[2], 1.0f);
@@ -585,7 +607,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
         unsigned long long t_end;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
         unsigned long long* o = P.timeline + 3ull * (blockIdx.x * (blockDim.x >> 5) + wid);
-        o[0] = t_warp_start; o[1] = t_end; o[2] = n_my_tiles;
+        o[0] = s_tstart[wid]; o[1] = t_end; o[2] = s_ntiles[wid];
     }
     // a CTA must not exit while its bulk copy is still in flight
     if (P.lut_in_smem && !lut_ready) mbar_wait(&bars[1], 0);

@@ -80,7 +80,10 @@ def test_bench_own_arm_json_contract():
     e = d["e2e"]
     assert e["value"] > 5e10 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] >= 3840 * 2160 * 16
     r = d["roofline"]
-    assert 0.5 < r["frac"] < 1.0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
+    assert 0.5 < r["frac"] < 1.0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    # traffic is read from the committed ncu export of THIS build (keyed by the kernel-source hash); a build newer than the
+    # last capture must say so instead of reporting a stale number
+    assert (r["traffic"] is not None and r["traffic"] > 0) or (r["traffic"] is None and r["traffic_note"])
     assert d["clocks"]["sm_mhz"] > 0 and isinstance(d["clocks"]["reasons"], list)
     x = d["extra"]
     assert "side_kernels_error" not in x and 0.2 < x["taa_resolve"]["frac"] < 1.0 and x["webgl_fragment_shader"]["ms"] > 0
