@@ -727,7 +727,10 @@ static int32_t build_frame(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
         P.r_far = std::max(r_switch + travel, P.r_hconst);
         {   // |h p_theta / Sigma| <= 1/16 (the whole step's move in theta: the chained rotation of step_symplectic_rot; the
             // predictor shifts are half of it) with Sigma >= (r_far - travel)^2 and p_theta^2 <= Q + a^2
-            const double rmin = P.r_far - travel, hc = std::max(std::fabs(P.h_const), 1e-300);
+            // The zone also drops the equatorial-crossing test, so it opens only where a chunk cannot reach the disk's outer
+            // edge (compute.wgsl.ts:216-218 shades crossings inside r_out only).
+            P.r_rot = std::max(P.r_far, rp->disk_r_out + travel + 1e-3);
+            const double rmin = P.r_rot - travel, hc = std::max(std::fabs(P.h_const), 1e-300);
             const double pth_max = rmin * rmin / (16.0 * hc);
             P.rot_q_max = pth_max * pth_max;
             // 32x the h^2 k = 4 estimate (3/4 h^2 / r_min^4). Measured on the headline frame: with trig_full every step a 4x margin

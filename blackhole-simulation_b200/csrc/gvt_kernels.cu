@@ -141,8 +141,9 @@ constexpr int kUnrollSymp = GVT_UNROLL_SYMP, kUnrollNear = GVT_UNROLL_NEAR, kUnr
 // picks one per 8-step chunk): FAR = f32 predictors (GVT_PRECISION_MIXED), HCONST = the step rule has saturated and
 // neither termination radius is within reach, so h is a constant and the radius tests are dropped, POLAR = the ray
 // may come within reach of the polar clamp (kerr.rs:417,448,494) and the RHS carries it.
-template <bool FAR, bool HCONST, bool POLAR, bool ROT = false> struct StepKind {
+template <bool FAR, bool HCONST, bool POLAR, bool ROT = false, bool NODISK = false> struct StepKind {
     static constexpr bool far = FAR, hconst = HCONST, polar = POLAR, rot = ROT;   // ROT: shifted angles by rotation (trig_rot)
+    static constexpr bool nodisk = NODISK;   // the whole chunk stays beyond the disk's outer edge: no equatorial-crossing test
 };
 // A ray whose conserved L_z = p_phi satisfies L^2 > kPolarSafe (Q + a^2 + L^2) cannot approach the axis: the polar
 // potential Theta = Q + a^2 cos^2 - L^2 cot^2 >= 0 gives sin^2(theta) >= L^2 / (Q + a^2 + L^2) > 1e-4 along the whole
@@ -467,9 +468,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
                 if (DEBUG) max_drift = N::max_(max_drift, N::abs_(hamiltonian_of<R, 1>(hc, y.r, y.th, y.pr, y.pth)));
                 // ---- thin-disk crossing (compute.wgsl.ts:216-254 with a18 + a19 + a20):
                 //      (th0 - pi/2)(th1 - pi/2) <= 0  <=>  the sides differ or the ray sits exactly on the plane
-                const int side = equator_side(y.th);
-                const bool crossed = (side != side_prev) || (side == 0);
-                side_prev = side;
+                // (a chunk that provably stays beyond the disk's outer edge compiles the whole block out: K::nodisk)
+                const int side = K::nodisk ? 0 : equator_side(y.th);
+                const bool crossed = !K::nodisk && ((side != side_prev) || (side == 0));
+                if (!K::nodisk) side_prev = side;
                 if (crossed) {
                     const R dth = y.th - th0;
                     const R f = (dth == R(0)) ? R(0) : (half_pi - th0) * N::rcp(dth);
@@ -509,7 +511,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
             if (METHOD == 2 && !polar_tile) {
                 const bool z1 = y.r > R(P.r_hconst) && y.r < R(P.r_escape_guard);
                 // zone 2: f32 predictors for rays on their way out (MIXED), rotated trigonometry for any ray that far (f64)
-                const uint32_t lane_zone = done ? 2u : (!z1 ? 0u : ((y.r > R(P.r_far) && (!MIXED || y.pr > R(0))) ? 2u : 1u));
+                const uint32_t lane_zone = done ? 2u : (!z1 ? 0u : ((y.r > R(MIXED ? P.r_far : P.r_rot) && (!MIXED || y.pr > R(0))) ? 2u : 1u));
                 zone = __reduce_min_sync(0xffffffffu, lane_zone);
                 if (!MIXED && !rot_tile) zone = min(zone, 1u);
             }
@@ -519,7 +521,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
             } else if (METHOD == 2 && !MIXED && zone == 2u) {
                 if constexpr (sizeof(R) == 8) trig_full(P.trig, (double)y.th, rot_s, rot_c);
 #pragma unroll(kUnrollSymp)
-                for (uint32_t it = it0; it < it1; it++) march_step(StepKind<false, true, false, true>{}, it);
+                for (uint32_t it = it0; it < it1; it++) march_step(StepKind<false, true, false, true, true>{}, it);
+                side_prev = equator_side(y.th);        // the invariant the crossing test of the other zones relies on
             } else if (METHOD == 2 && zone >= 1u) {
 #pragma unroll(MIXED ? kUnrollNearMixed : kUnrollSymp)
                 for (uint32_t it = it0; it < it1; it++) march_step(StepKind<false, true, false>{}, it);
