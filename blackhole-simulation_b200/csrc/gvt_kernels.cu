@@ -502,6 +502,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
         //   zone 0  generic: step rule + exact radius tests; with the polar clamp iff the tile holds a polar-risk ray
         //   zone 1  r_hconst < r < r_escape_guard for every live ray: h = h_const, no polar clamp
         //   zone 2  (GVT_PRECISION_MIXED) additionally r > r_far and p_r > 0: f32 predictors
+        //   zone 3  additionally beyond the disk's outer edge (r > r_rot): no crossing test; f64 rot tiles: rotated trigonometry
         const bool polar_tile = METHOD != 2 || __any_sync(0xffffffffu, polar_ray);
         const bool rot_tile = !MIXED && sizeof(R) == 8 && __all_sync(0xffffffffu, rot_ray);
         for (uint32_t it0 = 0; it0 < P.max_steps; it0 += CHUNK) {
@@ -510,19 +511,30 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
             uint32_t zone = 0u;
             if (METHOD == 2 && !polar_tile) {
                 const bool z1 = y.r > R(P.r_hconst) && y.r < R(P.r_escape_guard);
-                // zone 2: f32 predictors for rays on their way out (MIXED), rotated trigonometry for any ray that far (f64)
-                const uint32_t lane_zone = done ? 2u : (!z1 ? 0u : ((y.r > R(MIXED ? P.r_far : P.r_rot) && (!MIXED || y.pr > R(0))) ? 2u : 1u));
+                // zone 2: f32 predictors for rays on their way out (MIXED only). zone 3: beyond the disk's outer edge by a
+                // chunk's travel -- no equatorial-crossing test; f64: with rotated trigonometry (rot tiles only), MIXED: with
+                // the f32 predictors (outbound rays), f32: the saturated-step loop without the disk block
+                const bool out = !MIXED || y.pr > R(0);
+                const uint32_t lane_zone = done ? 3u : (!z1 ? 0u : ((y.r > R(P.r_rot) && out) ? 3u : ((MIXED && y.r > R(P.r_far) && out) ? 2u : 1u)));
                 zone = __reduce_min_sync(0xffffffffu, lane_zone);
-                if (!MIXED && !rot_tile) zone = min(zone, 1u);
+                if (!MIXED && sizeof(R) == 8 && !rot_tile) zone = min(zone, 1u);
             }
-            if (MIXED && zone == 2u) {
+            if (MIXED && zone == 3u) {
+#pragma unroll(kUnrollFar)
+                for (uint32_t it = it0; it < it1; it++) march_step(StepKind<true, true, false, false, true>{}, it);
+                side_prev = equator_side(y.th);        // the invariant the crossing test of the other zones relies on
+            } else if (MIXED && zone == 2u) {
 #pragma unroll(kUnrollFar)
                 for (uint32_t it = it0; it < it1; it++) march_step(StepKind<true, true, false>{}, it);
-            } else if (METHOD == 2 && !MIXED && zone == 2u) {
+            } else if (METHOD == 2 && !MIXED && sizeof(R) == 8 && zone == 3u) {
                 if constexpr (sizeof(R) == 8) trig_full(P.trig, (double)y.th, rot_s, rot_c);
 #pragma unroll(kUnrollSymp)
                 for (uint32_t it = it0; it < it1; it++) march_step(StepKind<false, true, false, true, true>{}, it);
-                side_prev = equator_side(y.th);        // the invariant the crossing test of the other zones relies on
+                side_prev = equator_side(y.th);
+            } else if (METHOD == 2 && sizeof(R) == 4 && zone == 3u) {
+#pragma unroll(kUnrollSymp)
+                for (uint32_t it = it0; it < it1; it++) march_step(StepKind<false, true, false, false, true>{}, it);
+                side_prev = equator_side(y.th);
             } else if (METHOD == 2 && zone >= 1u) {
 #pragma unroll(MIXED ? kUnrollNearMixed : kUnrollSymp)
                 for (uint32_t it = it0; it < it1; it++) march_step(StepKind<false, true, false>{}, it);
