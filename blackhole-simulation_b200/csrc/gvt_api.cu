@@ -725,21 +725,20 @@ static int32_t build_frame(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
         const char* e = getenv("GVT_MIXED_RSWITCH");   // tuning experiments only
         const double r_switch = (e && atof(e) > 0.0 ? atof(e) : 35.0) * bh.mass;
         P.r_far = std::max(r_switch + travel, P.r_hconst);
-        {   // |h p_theta / Sigma| <= 1/16 (the whole step's move in theta: the chained rotation of step_symplectic_rot; the
-            // predictor shifts are half of it) with Sigma >= (r_far - travel)^2 and p_theta^2 <= Q + a^2
-            // The zone also drops the equatorial-crossing test, so it opens only where a chunk cannot reach the disk's outer
-            // edge (compute.wgsl.ts:216-218 shades crossings inside r_out only).
+        {   // f64 zone 3: rotated trigonometry (step_symplectic_rot) and no equatorial-crossing test. It opens where a chunk
+            // cannot reach the disk's outer edge (compute.wgsl.ts:216-218 shades crossings inside r_out only) and, per ray,
+            // where a whole step turns theta by at most 2^-8: r > travel + sqrt(256 h B), B^2 = Q + a^2 (k_trace_tile).
             P.r_rot = std::max(P.r_far, rp->disk_r_out + travel + 1e-3);
             const double rmin = P.r_rot - travel, hc = std::max(std::fabs(P.h_const), 1e-300);
-            const double pth_max = rmin * rmin / (16.0 * hc);
-            P.rot_q_max = pth_max * pth_max;
+            P.rot_travel = travel; P.rot_k = 256.0 * hc;
+            P.f32_rot_travel = (float)travel; P.f32_rot_inv_k = (float)(1.0 / P.rot_k);
+            P.rot_q_max = 1e300;
             // 32x the h^2 k = 4 estimate (3/4 h^2 / r_min^4). Measured on the headline frame: with trig_full every step a 4x margin
             // reproduced the oracle's census on all 8.3 M pixels; the chained rotation (rounding a few ulp looser) needs 16x for
             // the last marginal ray, a pixel column next to the image of the spin axis.
             P.rot_stab = 24.0 * hc * hc / (rmin * rmin * rmin * rmin);
             if (const char* m = getenv("GVT_ROT_STAB_MULT")) if (atof(m) > 0.0) P.rot_stab *= atof(m);   // tuning experiments only
-            if (getenv("GVT_NO_ROT")) P.rot_q_max = -1.0;                    // diagnostics: f64 zone 2 closed
-            { uint64_t b; const double pm = pth_max; memcpy(&b, &pm, 8); P.rot_pth_hi = (uint32_t)(b >> 32); }   // |p_theta| < ~pth_max
+            if (getenv("GVT_NO_ROT")) P.rot_q_max = -1.0;                    // diagnostics: f64 zone 3 closed
         }
         P.f32_M = (float)bh.mass; P.f32_a = (float)bh.a(); P.f32_a2 = (float)(bh.a() * bh.a()); P.f32_twoM = (float)(2.0 * bh.mass); P.f32_hconst = (float)P.h_const;
     }

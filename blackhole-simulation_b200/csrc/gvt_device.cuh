@@ -180,6 +180,16 @@ __device__ __forceinline__ void trig_rot(const TrigTable& T, double s0, double c
     s = fma(c0, sd, s0 * cd);
     c = fma(-s0, sd, c0 * cd);
 }
+// The same for |d| <= 2^-8: two series terms less each (first neglected: d^7/7! and d^6/6!, < 5e-18 relative), 10 FP64
+// instructions. What the far zone of the f64 kernel uses for all three rotations of a step.
+__device__ __forceinline__ void trig_rot_small(const TrigTable& T, double s0, double c0, double d, double& s, double& c) {
+    const double* K = T.d;
+    const double z = d * d;
+    const double sd = fma(d * z, fma(K[5], z, K[4]), d);
+    const double cd = fma(z, fma(z, K[10], -0.5), 1.0);
+    s = fma(c0, sd, s0 * cd);
+    c = fma(-s0, sd, c0 * cd);
+}
 __device__ __forceinline__ void trig_pair(const TrigTable& T, float x, float& a, float& sc) {
     const float* K = T.f;
     const float kf_m = fmaf(x, K[0], K[1]);
@@ -535,8 +545,8 @@ __device__ __forceinline__ void step_symplectic(const HoleRay<R>& c, Ray<R>& y, 
 // from the caller, the two predictor-shifted angles are rotations of them (trig_rot), and so is the pair of the NEW theta
 // the step hands back -- theta moves by h p_theta / Sigma, as small as the shifts. The caller anchors (s0, c0) with one
 // trig_full per 8-step chunk, so rounding of the chained rotations (~1 ulp each) never accumulates beyond a chunk.
-// Callers guarantee |h p_theta / Sigma| <= 1/16 for the whole chunk and a ray off the polar axis (k_trace_tile's zone 2
-// of the f64 kernel); f64 only. theta itself is updated exactly as in step_symplectic.
+// Callers guarantee |h p_theta / Sigma| <= 2^-8 for the whole chunk (trig_rot_small) and a ray off the polar axis
+// (k_trace_tile's zone 3 of the f64 kernel); f64 only. theta itself is updated exactly as in step_symplectic.
 template <bool WITH_T, class RS>
 __device__ __forceinline__ void step_symplectic_rot(const HoleRay<RS>& c, Ray<RS>& y, RS h, double& s0, double& c0) {
     using N = Num<RS>;
@@ -545,11 +555,11 @@ __device__ __forceinline__ void step_symplectic_rot(const HoleRay<RS>& c, Ray<RS
     DerivU<RS> d = rhs_ks_u<RS, false, false, false>(c, y.r, RS(s0), RS(s0 * c0), y.pr, y.pth);
     RS f = hh * d.isig;
     RS mr = N::fma_(d.dr, f, y.r), mpr = N::fma_(d.dpr, f, y.pr), mpth = N::fma_(d.dpth, f, y.pth);
-    trig_rot(*c.trig, s0, c0, (double)(d.dth * f), s1, c1);
+    trig_rot_small(*c.trig, s0, c0, (double)(d.dth * f), s1, c1);
     d = rhs_ks_u<RS, false, false, false>(c, mr, RS(s1), RS(s1 * c1), mpr, mpth);
     f = hh * d.isig;
     mr = N::fma_(d.dr, f, y.r); mpr = N::fma_(d.dpr, f, y.pr); mpth = N::fma_(d.dpth, f, y.pth);
-    trig_rot(*c.trig, s0, c0, (double)(d.dth * f), s1, c1);
+    trig_rot_small(*c.trig, s0, c0, (double)(d.dth * f), s1, c1);
     d = rhs_ks_u<RS, WITH_T, WITH_T, false>(c, mr, RS(s1), RS(s1 * c1), mpr, mpth);
     f = h * d.isig;
     y.r = N::fma_(d.dr, f, y.r);
@@ -557,7 +567,7 @@ __device__ __forceinline__ void step_symplectic_rot(const HoleRay<RS>& c, Ray<RS
     y.pr = N::fma_(d.dpr, f, y.pr);
     y.pth = N::fma_(d.dpth, f, y.pth);
     if (WITH_T) { y.ph = N::fma_(d.dph, f, y.ph); y.t = N::fma_(d.dt, h, y.t); }
-    trig_rot(*c.trig, s0, c0, (double)(d.dth * f), s1, c1);
+    trig_rot_small(*c.trig, s0, c0, (double)(d.dth * f), s1, c1);
     s0 = s1; c0 = c1;
 }
 

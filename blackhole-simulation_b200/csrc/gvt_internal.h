@@ -53,12 +53,13 @@ struct FrameParams {
     double h_const;                                           //   horizon cannot be reached within one chunk
     double r_escape_guard;                                    // below it the escape radius cannot be reached within one chunk
     double r_sat;                                             // where the step rule saturates (r+ + 1/0.15; r_term for the constant rule)
-    uint32_t rot_pth_hi, _pad_rot;                            // high word of the largest |p_theta| the rotated zone accepts
+    double rot_travel, rot_k;                                 // f64 zone 3: a ray enters beyond travel + sqrt(rot_k B), B^2 = Q + a^2; rot_k = 256 h
+    float f32_rot_travel, f32_rot_inv_k;
     uint32_t alive_lo[2], alive_span[2];                      // hot-path "alive" window on the high word of r: [0] (r_term, escape_r),
                                                               //   [1] (r_sat, escape_r): inside iff (hi(r) - lo) < span (unsigned)
     double r_far;                                             // zone 2 of GVT_PRECISION_MIXED (f32 predictors) beyond this radius
     double r_rot;                                             // zone 2 of the f64 kernel (rotated trigonometry, no disk test): beyond r_far AND the disk's outer edge
-    double rot_q_max;                                         // f64 zone 2 is open to rays with Q + a^2 <= this (|d theta| <= 1/16 per stage)
+    double rot_q_max;                                         // f64 zone 3 is open to rays with Q + a^2 <= this (a switch: huge, or < 0 = closed)
     double rot_stab;                                          //   and L^2 >= rot_stab (Q + a^2 + L^2)^2 (stable polar turning point out there)
     float f32_M, f32_a, f32_a2, f32_twoM, f32_hconst;         // the predictors' hole constants and (float)h_const
     double tdisk_rin, tdisk_scale;                            // (n-1)/(rout-rin)

@@ -275,6 +275,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
         Ray<R> y;
         Vec3<R> wdir;          // world-space ray direction (the Cartesian march of METHOD 3 starts from it)
         bool polar_ray = true, rot_ray = false;
+        float rot_rsmall = 0.0f;   // f64 zone 3 (rotated trigonometry) opens to this ray beyond this radius
         {
             const R ndcx = N::fma_(N::fma_(R((double)px), R(fb->inv_width), R(fb->jx)), R(2), R(-1));
             const R ndcy = N::fma_(N::fma_(R((double)py), R(fb->inv_height), R(fb->jy)), R(2), R(-1));
@@ -316,6 +317,13 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
             // arithmetic reproduces the oracle's garbage step for step (P.rot_stab carries h^2 / r_min^4 with a 4x margin).
             const R qal = Q + hc.a2 + hc.pph2;
             rot_ray = (Q + hc.a2) <= R(P.rot_q_max) && hc.pph2 >= R(P.rot_stab) * qal * qal;
+            // ... and only from the radius on where a whole step turns theta by at most 2^-8 (trig_rot_small):
+            // |h p_theta / Sigma| <= h B / r_min^2 with B^2 = Q + a^2 >= p_theta^2 (Carter) and r_min = r - travel, i.e.
+            // r > travel + sqrt(256 h B). One float per ray, rounded up.
+            if (!MIXED && sizeof(R) == 8 && METHOD == 2) {
+                const double B = sqrt_nr(fmax((double)(Q + hc.a2), 0.0));
+                rot_rsmall = __double2float_ru(P.rot_travel + sqrt_nr(P.rot_k * B));
+            }
         }
 
         // The spectral-LUT copy was issued before ray generation; by now it has had a tile's worth of set-up time to
@@ -417,7 +425,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
         // One march step, in the flavour `kind` (StepKind).
         bool parked = false;               // HCONST chunks: this ray left the chunk's radius window and waits for the replay below
         uint32_t park_it = 0;
-        double rot_s = 0.0, rot_c = 0.0;   // zone 2 of the f64 kernel: (sin, cos)(theta), anchored per chunk and chained by rotation
+        double rot_s = 0.0, rot_c = 0.0;   // zone 3 of the f64 kernel: (sin, cos)(theta), anchored per chunk and chained by rotation
+        uint32_t rot_pth_hi = 0u;          //   and the chunk's bound on the high word of |p_theta| (beyond it the ray is parked)
         auto march_step = [&](auto kind, uint32_t it) {
             using K = decltype(kind);
             const R th0 = y.th, r_prev = y.r;
@@ -441,7 +450,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
                     // otherwise -- ~17 issue slots per step for something that happens to ~10 rays per 4K frame.)
                     // (the rotated-trigonometry zone also parks a ray whose p_theta has left the range its |d theta| <= 1/16
                     // bound was derived from: a ray that blew up elsewhere and wandered in)
-                    if (K::rot && sizeof(R) == 8) inside = inside && (((uint32_t)hiword(y.pth) & 0x7fffffffu) < P.rot_pth_hi);
+                    if (K::rot && sizeof(R) == 8) inside = inside && (((uint32_t)hiword(y.pth) & 0x7fffffffu) < rot_pth_hi);
                     if (!inside && !done) { done = true; parked = true; park_it = it; }
                     hs = R(P.h_const);
                 } else {
@@ -515,7 +524,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
                 // chunk's travel -- no equatorial-crossing test; f64: with rotated trigonometry (rot tiles only), MIXED: with
                 // the f32 predictors (outbound rays), f32: the saturated-step loop without the disk block
                 const bool out = !MIXED || y.pr > R(0);
-                const uint32_t lane_zone = done ? 3u : (!z1 ? 0u : ((y.r > R(P.r_rot) && out) ? 3u : ((MIXED && y.r > R(P.r_far) && out) ? 2u : 1u)));
+                const bool far3 = y.r > R(P.r_rot) && out && (MIXED || sizeof(R) == 4 || __double2float_rd((double)y.r) > rot_rsmall);
+                const uint32_t lane_zone = done ? 3u : (!z1 ? 0u : (far3 ? 3u : ((MIXED && y.r > R(P.r_far) && out) ? 2u : 1u)));
                 zone = __reduce_min_sync(0xffffffffu, lane_zone);
                 if (!MIXED && sizeof(R) == 8 && !rot_tile) zone = min(zone, 1u);
             }
@@ -527,7 +537,13 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
 #pragma unroll(kUnrollFar)
                 for (uint32_t it = it0; it < it1; it++) march_step(StepKind<true, true, false>{}, it);
             } else if (METHOD == 2 && !MIXED && sizeof(R) == 8 && zone == 3u) {
-                if constexpr (sizeof(R) == 8) trig_full(P.trig, (double)y.th, rot_s, rot_c);
+                if constexpr (sizeof(R) == 8) {
+                    trig_full(P.trig, (double)y.th, rot_s, rot_c);
+                    // the |p_theta| the ray's radius gate was derived from, B = (r_small - travel)^2 / (256 h): a ray beyond it
+                    // blew up elsewhere and wandered in -- it is parked and replayed by the generic loop
+                    const float t = rot_rsmall - P.f32_rot_travel;
+                    rot_pth_hi = (uint32_t)__double2hiint((double)(t * t * P.f32_rot_inv_k * 1.001f)) + 1u;
+                }
 #pragma unroll(kUnrollSymp)
                 for (uint32_t it = it0; it < it1; it++) march_step(StepKind<false, true, false, true, true>{}, it);
                 side_prev = equator_side(y.th);
