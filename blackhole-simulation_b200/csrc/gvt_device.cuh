@@ -431,14 +431,15 @@ __device__ __forceinline__ Deriv<R> rhs_at(const HoleRay<R>& c, R r, R th, R pr,
 
 // The quadratic of invariants/renormalization.rs:13-45 and H of invariants/mod.rs:25-37 share the metric
 // evaluation; `want` selects what to produce.
-template <class R, int COORDS>
+// KNOWN_SIN: `th` carries sin(theta) itself (the rotated zone of the f64 kernel has it at hand), no evaluation here.
+template <class R, int COORDS, bool KNOWN_SIN = false>
 __device__ __forceinline__ void null_quadratic(const HoleRay<R>& c, R r, R th, R pth, R& A, R& B, R& C) {
     using N = Num<R>;
     const R r2 = r * r;
     const R delta = N::fma_(-c.twoM, r, r2 + c.a2);
     if (COORDS == 1) {
-        R a, sc;
-        trig_pair(*c.trig, th, a, sc);
+        R a = th, sc;
+        if (!KNOWN_SIN) trig_pair(*c.trig, th, a, sc);
         const R sin2 = floorAt<R>(a * a, R(1e-12));
         const R cos2 = R(1) - sin2;
         const R sigma = N::fma_(c.a2, cos2, r2);
@@ -469,11 +470,11 @@ __device__ __forceinline__ void null_quadratic(const HoleRay<R>& c, R r, R th, R
 }
 
 // invariants/renormalization.rs:13-45
-template <class R, int COORDS>
+template <class R, int COORDS, bool KNOWN_SIN = false>
 __device__ __forceinline__ R renormalize_pr(const HoleRay<R>& c, R r, R th, R pr, R pth) {
     using N = Num<R>;
     R A, B, C;
-    null_quadratic<R, COORDS>(c, r, th, pth, A, B, C);
+    null_quadratic<R, COORDS, KNOWN_SIN>(c, r, th, pth, A, B, C);
     if (N::abs_(A) > R(1e-12)) {
         const R disc = N::fma_(B, B, R(-4) * A * C);
         if (disc >= R(0)) {

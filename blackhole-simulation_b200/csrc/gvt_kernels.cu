@@ -471,7 +471,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
                 }
             }
             if (!done) {
-                if (renorm_in == 0u) { y.pr = renormalize_pr<R, 1>(hc, y.r, y.th, y.pr, y.pth); renorm_in = P.renorm_interval; }
+                if (renorm_in == 0u) {
+                    // (the rotated zone holds sin(theta) of the new state already: no trigonometric evaluation here either)
+                    if constexpr (K::rot && sizeof(R) == 8) y.pr = renormalize_pr<R, 1, true>(hc, y.r, R(rot_s), y.pr, y.pth);
+                    else y.pr = renormalize_pr<R, 1>(hc, y.r, y.th, y.pr, y.pth);
+                    renorm_in = P.renorm_interval;
+                }
                 renorm_in--;
                 steps++;
                 if (DEBUG) max_drift = N::max_(max_drift, N::abs_(hamiltonian_of<R, 1>(hc, y.r, y.th, y.pr, y.pth)));
