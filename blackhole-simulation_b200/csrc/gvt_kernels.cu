@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
             if (!done) {
                 if (renorm_in == 0u) {
                     // (the rotated zone holds sin(theta) of the new state already: no trigonometric evaluation here either)
-                    if constexpr (K::rot && sizeof(R) == 8) y.pr = renormalize_pr<R, 1, true>(hc, y.r, R(rot_s), y.pr, y.pth);
+                    if constexpr (K::rot && sizeof(R) == 8) y.pr = renormalize_pr_far<R>(hc, y.r, R(rot_s), y.pr, y.pth);
                     else y.pr = renormalize_pr<R, 1>(hc, y.r, y.th, y.pr, y.pth);
                     renorm_in = P.renorm_interval;
                 }
