@@ -63,7 +63,7 @@ def setup(renderer, oracle, luts, W, H, **kw):
     # the oracle has f64 and f32 only: GVT_PRECISION_MIXED (3) is compared against the all-f64 scheme it must reproduce
     rp, keep = oracle.make_render_params(W, H, 1.0, spin, opts, precision=precision if precision in (0, 1) else 0,
                                          frame_index=frame_index, jitter=1 if flags & 1 else 0, spectrum=spec,
-                                         spec_w=SPEC_W, spec_h=SPEC_H, tdisk=td)
+                                         spec_w=SPEC_W, spec_h=SPEC_H, tdisk=td, disk_r_out=kw.get("disk_r_out", 50.0))
     return cam, phys, rp, keep
 
 
@@ -170,6 +170,29 @@ def test_other_spins_and_cameras(renderer, oracle, luts, spin, polar, azimuth):
     cam, phys, rp, keep = setup(renderer, oracle, luts, 64, 36, spin=spin, max_steps=256,
                                 cam=dict(polar_deg=polar, azimuth=azimuth))
     compare(renderer, oracle, cam, phys, rp, allow_unstable=2e-2)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(cam=dict(r0=100.0, polar_deg=80.0), max_steps=512),                       # inbound through zone 3 -> 1 -> 0 and out again
+    dict(cam=dict(r0=200.0, polar_deg=120.0, azimuth=2.5), spin=-0.7, max_steps=640),
+    dict(cam=dict(r0=75.0, polar_deg=90.5), max_steps=400),                          # camera next to the disk plane, just outside the disk
+    dict(cam=dict(r0=66.0, polar_deg=60.0), max_steps=300),                          # starts a few M beyond zone 3's inner edge
+    dict(disk_r_out=20.0, max_steps=384),                                            # small disk: zone 3 opens at r_far instead of r_out + travel
+    dict(escape_radius=80.0, max_steps=256),                                         # escape radius next to the zone's inner edge
+    dict(cam=dict(r0=150.0, polar_deg=97.0), method=1, max_steps=256),               # RK4 never takes the specialised zones
+    dict(cam=dict(r0=120.0, polar_deg=70.0), flags=2, max_steps=320),                # budget accounting from afar
+], ids=lambda kw: "-".join(f"{k}={v}" for k, v in kw.items() if k != "cam") + "-r0=" + str(kw.get("cam", {}).get("r0", 30.0)))
+def test_far_cameras_and_zone3_edges(renderer, oracle, luts, kw):
+    """Zone 3 of the f64 kernel (beyond the disk's outer edge: no equatorial-crossing test, chained rotated trigonometry,
+    Sigma-free renormalisation) entered from OUTSIDE: cameras at 66-200 M whose rays come in through it, hand over to the inner
+    zones (side-of-the-plane invariant, parked-ray replay) and leave through it again; its radius gates next to the disk's
+    and the escape radius' edges. Whole small frames against the oracle: RGBA at the north_star tolerance, identical step
+    counts and terminations, final states to 1e-8."""
+    cam, phys, rp, keep = setup(renderer, oracle, luts, 64, 36, **dict(kw))
+    ref, got = compare(renderer, oracle, cam, phys, rp)
+    frame = np.array(renderer.render(cam, phys))
+    assert np.array_equal(frame, got["rgba"].astype(np.float32))                   # production instantiation == parity hook
+    assert (ref["rgba"][..., :3].sum(-1) > 0).sum() > 0                            # the disk is in view
 
 
 def test_jitter_and_ragged_lattice(renderer, oracle, luts):
