@@ -311,7 +311,37 @@ uint32_t OptU32(napi_env env, napi_value obj, const char* key, uint32_t dflt) {
     napi_get_named_property(env, obj, key, &v);
     return (uint32_t)Num(env, v);
 }
-// renderFrame(cameraF32x88, physF32x8, {maxSteps, method, precision, taa, jitter, f16}, outArrayBuffer) -> stats   renderer.ts:280
+// A frame target in DEVICE memory: importExternalFd(fd, bytes, device = 0, dedicated = false) maps memory
+// the presenter exported from its graphics API (VK_KHR_external_memory_fd / GL_EXT_memory_object_fd) and returns an opaque
+// value that renderFrame / renderFragment / bloom accept in place of the output ArrayBuffer: the frame never crosses host
+// memory. The mapping is released when the value is collected.
+struct ExternalTarget { gvt_external_buffer* h; void* ptr; uint64_t bytes; };
+napi_value ImportExternalFd(napi_env env, napi_callback_info info) {
+    size_t argc = 4; napi_value argv[4];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    if (argc < 2) { napi_throw_error(env, nullptr, "importExternalFd(fd, bytes, device = 0, dedicated = false)"); return nullptr; }
+    bool dedicated = false;
+    if (argc > 3) napi_get_value_bool(env, argv[3], &dedicated);
+    ExternalTarget* t = new ExternalTarget{nullptr, nullptr, (uint64_t)Num(env, argv[1])};
+    if (gvt_external_import_fd(argc > 2 ? (int32_t)Num(env, argv[2]) : 0, (int32_t)Num(env, argv[0]), t->bytes, dedicated ? 1 : 0, &t->h, &t->ptr) != GVT_OK) {
+        delete t; napi_throw_error(env, nullptr, gvt_last_error()); return nullptr;
+    }
+    napi_value out;
+    NAPI_OK(napi_create_external(env, t, [](napi_env, void* d, void*) { ExternalTarget* x = static_cast<ExternalTarget*>(d); gvt_external_release(x->h); delete x; }, nullptr, &out));
+    return out;
+}
+// the output argument of the frame calls: an ArrayBuffer / typed array (host memory) or an imported external target
+bool OutRange(napi_env env, napi_value v, void** data, size_t* bytes) {
+    napi_valuetype vt;
+    if (napi_typeof(env, v, &vt) == napi_ok && vt == napi_external) {
+        void* p = nullptr;
+        if (napi_get_value_external(env, v, &p) != napi_ok || !p) return false;
+        *data = static_cast<ExternalTarget*>(p)->ptr; *bytes = (size_t)static_cast<ExternalTarget*>(p)->bytes;
+        return true;
+    }
+    return ByteRange(env, v, data, bytes);
+}
+// renderFrame(cameraF32x88, physF32x8, {maxSteps, method, precision, taa, jitter, f16}, outArrayBuffer | externalTarget) -> stats   renderer.ts:280
 napi_value RenderFrame(napi_env env, napi_callback_info info) {
     size_t argc = 4; napi_value argv[4];
     gvt_renderer* r = Self<gvt_renderer>(env, info, &argc, argv);
@@ -320,7 +350,7 @@ napi_value RenderFrame(napi_env env, napi_callback_info info) {
     if (!ByteRange(env, argv[0], &cam, &nbytes, &t) || t != napi_float32_array || nbytes < sizeof(GvtCamera)) { napi_throw_range_error(env, nullptr, "camera: Float32Array(88) expected"); return nullptr; }
     // PhysicsParams is 6 f32 + 2 u32 (types/webgpu.ts:42-64): any 32-bit view of >= 32 bytes
     if (!ByteRange(env, argv[1], &phys, &nbytes, &t) || (t != napi_float32_array && t != napi_uint32_array && t != napi_int32_array) || nbytes < sizeof(GvtPhysicsParams)) { napi_throw_range_error(env, nullptr, "physics: 32-bit typed array of 32 bytes expected"); return nullptr; }
-    if (!ByteRange(env, argv[3], &out, &outlen)) { napi_throw_error(env, nullptr, "out: ArrayBuffer or typed array expected"); return nullptr; }
+    if (!OutRange(env, argv[3], &out, &outlen)) { napi_throw_error(env, nullptr, "out: ArrayBuffer, typed array or external target expected"); return nullptr; }
     GvtRenderParams p; gvt_render_params_default(&p);
     p.max_steps = OptU32(env, argv[2], "maxSteps", p.max_steps);
     p.method = OptU32(env, argv[2], "method", p.method);
@@ -361,7 +391,7 @@ napi_value RenderFragment(napi_env env, napi_callback_info info) {
     napi_typedarray_type t; size_t nbytes; void *u, *out; size_t outlen;
     if (!r || !ByteRange(env, argv[0], &u, &nbytes, &t) || (t != napi_float32_array && t != napi_uint32_array && t != napi_int32_array) ||
         nbytes < sizeof(GvtGlslUniforms)) { napi_throw_range_error(env, nullptr, "uniforms: 155 32-bit words expected"); return nullptr; }
-    if (!ByteRange(env, argv[2], &out, &outlen)) { napi_throw_error(env, nullptr, "out: ArrayBuffer or typed array expected"); return nullptr; }
+    if (!OutRange(env, argv[2], &out, &outlen)) { napi_throw_error(env, nullptr, "out: ArrayBuffer, typed array or external target expected"); return nullptr; }
     const uint32_t precision = OptU32(env, argv[1], "precision", GVT_PRECISION_F32_FAST);
     const uint32_t flags = OptU32(env, argv[1], "flags", 0), format = OptU32(env, argv[1], "format", GVT_FORMAT_RGBA32F);
     const uint32_t moving = OptU32(env, argv[1], "cameraMoving", 0);
@@ -392,7 +422,7 @@ napi_value Bloom(napi_env env, napi_callback_info info) {
     if (napi_has_named_property(env, argv[0], "threshold", &has) == napi_ok && has) { napi_get_named_property(env, argv[0], "threshold", &v); cfg.threshold = (float)Num(env, v); }
     cfg.precise = OptU32(env, argv[0], "precise", 0);
     void* out; size_t outlen;
-    if (!r || !ByteRange(env, argv[1], &out, &outlen)) { napi_throw_error(env, nullptr, "bloom(options, out: ArrayBuffer | typed array)"); return nullptr; }
+    if (!r || !OutRange(env, argv[1], &out, &outlen)) { napi_throw_error(env, nullptr, "bloom(options, out: ArrayBuffer | typed array | external target)"); return nullptr; }
     const uint32_t format = OptU32(env, argv[0], "format", GVT_FORMAT_RGBA8_UNORM);
     double ms = 0;
     if (outlen == 0) out = nullptr;                                               // result stays on the device
@@ -443,5 +473,8 @@ NAPI_MODULE_INIT() {
     NAPI_OK(napi_set_named_property(env, exports, "PhysicsEngine", cls));
     NAPI_OK(napi_define_class(env, "KerrRenderer", NAPI_AUTO_LENGTH, RendererNew, nullptr, sizeof(renderer) / sizeof(renderer[0]), renderer, &cls));
     NAPI_OK(napi_set_named_property(env, exports, "KerrRenderer", cls));
+    napi_value fn;
+    NAPI_OK(napi_create_function(env, "importExternalFd", NAPI_AUTO_LENGTH, ImportExternalFd, nullptr, &fn));
+    NAPI_OK(napi_set_named_property(env, exports, "importExternalFd", fn));
     return exports;
 }

@@ -56,6 +56,13 @@ napi_status napi_get_reference_value(napi_env, napi_ref ref, napi_value* result)
 napi_status napi_throw_error(napi_env, const char* code, const char* msg);
 napi_status napi_throw_range_error(napi_env, const char* code, const char* msg);
 #define NAPI_MODULE_INIT() extern "C" napi_value napi_register_module_v1(napi_env env, napi_value exports)
+
+/* externals (opaque native pointers held by JS values) */
+napi_status napi_create_function(napi_env env, const char* utf8name, size_t length, napi_callback cb, void* data, napi_value* result);
+napi_status napi_create_external(napi_env env, void* data, napi_finalize finalize_cb, void* finalize_hint, napi_value* result);
+napi_status napi_get_value_external(napi_env env, napi_value value, void** result);
+typedef enum { napi_undefined, napi_null, napi_boolean, napi_number, napi_string, napi_symbol, napi_object, napi_function, napi_external, napi_bigint } napi_valuetype;
+napi_status napi_typeof(napi_env env, napi_value value, napi_valuetype* result);
 #ifdef __cplusplus
 }
 #endif

@@ -800,9 +800,9 @@ extern "C" int32_t gvt_render_read_frame(gvt_renderer* r, uint32_t format, void*
     if (format != r->storage_format()) {
         int32_t rc = convert_frame(r, format, 0, n_px);
         if (rc != GVT_OK) return rc;
-        CK(cudaMemcpyAsync(host_rgba, r->half_frame, n_px * format_bytes(format), cudaMemcpyDeviceToHost, r->stream));
+        CK(cudaMemcpyAsync(host_rgba, r->half_frame, n_px * format_bytes(format), cudaMemcpyDefault, r->stream));
     } else {
-        CK(cudaMemcpyAsync(host_rgba, r->frame, n_px * r->px_bytes(), cudaMemcpyDeviceToHost, r->stream));
+        CK(cudaMemcpyAsync(host_rgba, r->frame, n_px * r->px_bytes(), cudaMemcpyDefault, r->stream));
     }
     CK(cudaStreamSynchronize(r->stream));
     return GVT_OK;
@@ -911,14 +911,23 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
     // produces every pixel it has to deliver (single GPU, or GVT_FLAG_D2H_OWN_ROWS), the producing kernel stores each
     // finished pixel straight into host memory over PCIe (132.7 MB spread over the whole kernel: ~2 GB/s) and no D2H
     // copy follows. Otherwise the finished frame is copied after the last kernel.
+    // The same holds for a frame target in DEVICE memory -- a buffer of the presenter's graphics API imported through
+    // gvt_external_import_fd (cudaImportExternalMemory), or any device allocation of the caller: the producing kernel
+    // stores into it directly and the frame never crosses host memory.
     const bool own = (rp->flags & GVT_FLAG_D2H_OWN_ROWS) != 0 && r->world > 1;
     float4* host_alias = nullptr;
-    if (host_rgba && rp->output_format == r->storage_format() && (r->world == 1 || own)) {
+    bool device_target = false;
+    if (host_rgba) {
         cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, host_rgba) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
-            host_alias = static_cast<float4*>(at.devicePointer);
-        else
-            (void)cudaGetLastError();   // pageable memory: not an error, just the copy path
+        if (cudaPointerGetAttributes(&at, host_rgba) == cudaSuccess) {
+            device_target = at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+            if (rp->output_format == r->storage_format() && (r->world == 1 || own)) {
+                if (at.type == cudaMemoryTypeHost && at.devicePointer) host_alias = static_cast<float4*>(at.devicePointer);
+                else if (device_target && at.devicePointer) host_alias = static_cast<float4*>(at.devicePointer);
+            }
+        } else {
+            (void)cudaGetLastError();   // pageable memory on an old driver: not an error, just the copy path
+        }
     }
     if (glsl) G.host_frame = taa ? nullptr : host_alias; else P.host_frame = taa ? nullptr : host_alias;
     // Fused gather: the producing kernel writes each finished pixel into the same frame on every peer.
@@ -1006,6 +1015,7 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
     CK(cudaEventRecord(r->ev[4], r->stream));
     CK(cudaMemcpyAsync(r->h_counters, r->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, r->stream));
     d2h += sizeof(Counters);
+    const uint64_t d2h_before_frame = d2h;
     if (host_rgba && host_alias) {
         d2h += (size_t)n_own * W * r->px_bytes();   // delivered by the kernel's own stores
     } else if (host_rgba && own && interleave) {
@@ -1015,13 +1025,13 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
             if (n_own)
                 CK(cudaMemcpy2DAsync(static_cast<char*>(host_rgba) + (size_t)r->rank * row_bytes, pitch,
                                      reinterpret_cast<const char*>(r->frame) + (size_t)r->rank * row_bytes, pitch, row_bytes, n_own,
-                                     cudaMemcpyDeviceToHost, r->stream));
+                                     cudaMemcpyDefault, r->stream));
         } else {            // 16-row stripes: one contiguous copy each
             for (uint32_t t = 0; t < n_my; t++) {
                 const size_t y = (size_t)(t * (uint32_t)r->world + (uint32_t)r->rank) * sm.s;
                 const size_t n = std::min<size_t>(sm.s, H - y);
                 CK(cudaMemcpyAsync(static_cast<char*>(host_rgba) + y * row_bytes, reinterpret_cast<const char*>(r->frame) + y * row_bytes,
-                                   n * row_bytes, cudaMemcpyDeviceToHost, r->stream));
+                                   n * row_bytes, cudaMemcpyDefault, r->stream));
             }
         }
         d2h += (size_t)n_own * row_bytes;
@@ -1036,16 +1046,17 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
                 if (crc != GVT_OK) return crc;
                 launches++;
                 CK(cudaMemcpyAsync(static_cast<char*>(host_rgba) + px0 * bpp, static_cast<char*>(r->half_frame) + px0 * bpp,
-                                   npx * bpp, cudaMemcpyDeviceToHost, r->stream));
+                                   npx * bpp, cudaMemcpyDefault, r->stream));
             }
             d2h += npx * bpp;
         } else {
             if (npx)
                 CK(cudaMemcpyAsync(static_cast<char*>(host_rgba) + px0 * r->px_bytes(), r->at(r->frame, px0), npx * r->px_bytes(),
-                                   cudaMemcpyDeviceToHost, r->stream));
+                                   cudaMemcpyDefault, r->stream));
             d2h += npx * r->px_bytes();
         }
     }
+    if (device_target) d2h = d2h_before_frame;   // a device-memory target: the frame stayed on the device
     CK(cudaEventRecord(r->ev[5], r->stream));
     CK(cudaStreamSynchronize(r->stream));
     if (r->comm && g_nccl.CommGetAsyncError) {
@@ -1162,12 +1173,12 @@ extern "C" int32_t gvt_render_bloom(gvt_renderer* r, const GvtBloomConfig* cfg, 
     if (host_out) {
         const size_t n_px = (size_t)W * H;
         if (output_format == GVT_FORMAT_RGBA32F) {
-            CK(cudaMemcpyAsync(host_out, r->display, n_px * sizeof(float4), cudaMemcpyDeviceToHost, r->stream));
+            CK(cudaMemcpyAsync(host_out, r->display, n_px * sizeof(float4), cudaMemcpyDefault, r->stream));
         } else {
             if (!r->half_frame) CK(cudaMalloc(&r->half_frame, n_px * 16));
             if (output_format == GVT_FORMAT_RGBA16F) CK(launch_f32_to_f16(r->display, r->half_frame, n_px, r->stream));
             else CK(launch_tonemap_rgba8(r->display, r->half_frame, n_px, 2, r->stream));
-            CK(cudaMemcpyAsync(host_out, r->half_frame, n_px * format_bytes(output_format), cudaMemcpyDeviceToHost, r->stream));
+            CK(cudaMemcpyAsync(host_out, r->half_frame, n_px * format_bytes(output_format), cudaMemcpyDefault, r->stream));
         }
     }
     CK(cudaStreamSynchronize(r->stream));
@@ -1321,6 +1332,92 @@ extern "C" int32_t gvt_host_register(void* p, size_t bytes) {
 }
 extern "C" int32_t gvt_host_unregister(void* p) {
     if (p) CK(cudaHostUnregister(p));
+    return GVT_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// External-memory hand-off: the presenter allocates the frame image / buffer in its graphics API with an
+// exportable POSIX fd (VK_KHR_external_memory_fd, GL_EXT_memory_object_fd -- or a CUDA VMM allocation exported with
+// cuMemExportToShareableHandle), this side maps it and every frame entry point accepts the mapped pointer as its target.
+// --------------------------------------------------------------------------------------------------
+struct gvt_external_buffer { cudaExternalMemory_t mem = nullptr; void* ptr = nullptr; int device = 0; };
+struct gvt_external_semaphore { cudaExternalSemaphore_t sem = nullptr; int device = 0; };
+
+extern "C" int32_t gvt_external_import_fd(int32_t device, int32_t fd, uint64_t bytes, int32_t dedicated,
+                                          gvt_external_buffer** out, void** device_ptr) {
+    if (!out || !device_ptr || fd < 0 || bytes == 0) return fail(GVT_ERR_INVALID, "bad argument");
+    int nd = 0;
+    if (cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0) return fail(GVT_ERR_NO_DEVICE, "no CUDA device");
+    if (device < 0 || device >= nd) return fail(GVT_ERR_INVALID, "device %d out of range (%d devices)", device, nd);
+    CK(cudaSetDevice(device));
+    cudaExternalMemoryHandleDesc hd;
+    memset(&hd, 0, sizeof(hd));
+    hd.type = cudaExternalMemoryHandleTypeOpaqueFd; hd.handle.fd = fd; hd.size = bytes;
+    hd.flags = dedicated ? cudaExternalMemoryDedicated : 0;
+    gvt_external_buffer* b = new (std::nothrow) gvt_external_buffer();
+    if (!b) return fail(GVT_ERR_INVALID, "out of memory");
+    b->device = device;
+    cudaError_t e = cudaImportExternalMemory(&b->mem, &hd);     // on success the driver owns the fd
+    if (e != cudaSuccess) { delete b; (void)cudaGetLastError(); return fail(GVT_ERR_CUDA, "cudaImportExternalMemory: %s", cudaGetErrorString(e)); }
+    cudaExternalMemoryBufferDesc bd;
+    memset(&bd, 0, sizeof(bd));
+    bd.offset = 0; bd.size = bytes;
+    e = cudaExternalMemoryGetMappedBuffer(&b->ptr, b->mem, &bd);
+    if (e != cudaSuccess) { cudaDestroyExternalMemory(b->mem); delete b; (void)cudaGetLastError(); return fail(GVT_ERR_CUDA, "cudaExternalMemoryGetMappedBuffer: %s", cudaGetErrorString(e)); }
+    *out = b; *device_ptr = b->ptr;
+    return GVT_OK;
+}
+extern "C" int32_t gvt_external_release(gvt_external_buffer* b) {
+    if (!b) return GVT_OK;
+    cudaSetDevice(b->device);
+    if (b->ptr) cudaFree(b->ptr);                               // the documented way to unmap a mapped external buffer
+    if (b->mem) cudaDestroyExternalMemory(b->mem);
+    delete b;
+    return GVT_OK;
+}
+extern "C" int32_t gvt_external_semaphore_import_fd(int32_t device, int32_t fd, int32_t timeline, gvt_external_semaphore** out) {
+    if (!out || fd < 0) return fail(GVT_ERR_INVALID, "bad argument");
+    int nd = 0;
+    if (cudaGetDeviceCount(&nd) != cudaSuccess || nd == 0) return fail(GVT_ERR_NO_DEVICE, "no CUDA device");
+    if (device < 0 || device >= nd) return fail(GVT_ERR_INVALID, "device %d out of range (%d devices)", device, nd);
+    CK(cudaSetDevice(device));
+    cudaExternalSemaphoreHandleDesc hd;
+    memset(&hd, 0, sizeof(hd));
+    hd.type = timeline ? cudaExternalSemaphoreHandleTypeTimelineSemaphoreFd : cudaExternalSemaphoreHandleTypeOpaqueFd;
+    hd.handle.fd = fd;
+    gvt_external_semaphore* x = new (std::nothrow) gvt_external_semaphore();
+    if (!x) return fail(GVT_ERR_INVALID, "out of memory");
+    x->device = device;
+    cudaError_t e = cudaImportExternalSemaphore(&x->sem, &hd);
+    if (e != cudaSuccess) { delete x; (void)cudaGetLastError(); return fail(GVT_ERR_CUDA, "cudaImportExternalSemaphore: %s", cudaGetErrorString(e)); }
+    *out = x;
+    return GVT_OK;
+}
+extern "C" int32_t gvt_external_semaphore_release(gvt_external_semaphore* x) {
+    if (!x) return GVT_OK;
+    cudaSetDevice(x->device);
+    if (x->sem) cudaDestroyExternalSemaphore(x->sem);
+    delete x;
+    return GVT_OK;
+}
+// Enqueued on the renderer's stream: the next frame's kernels start after the wait, a signal fires after everything
+// already enqueued (every frame entry point returns with its stream drained, so a signal right after it is immediate).
+extern "C" int32_t gvt_render_wait_external(gvt_renderer* r, gvt_external_semaphore* x, uint64_t value) {
+    if (!r || !x) return fail(GVT_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(r->device));
+    cudaExternalSemaphoreWaitParams wp;
+    memset(&wp, 0, sizeof(wp));
+    wp.params.fence.value = value;
+    CK(cudaWaitExternalSemaphoresAsync(&x->sem, &wp, 1, r->stream));
+    return GVT_OK;
+}
+extern "C" int32_t gvt_render_signal_external(gvt_renderer* r, gvt_external_semaphore* x, uint64_t value) {
+    if (!r || !x) return fail(GVT_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(r->device));
+    cudaExternalSemaphoreSignalParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.params.fence.value = value;
+    CK(cudaSignalExternalSemaphoresAsync(&x->sem, &sp, 1, r->stream));
     return GVT_OK;
 }
 

@@ -15,6 +15,6 @@ with ``GravitasError`` when no sm_100 device is present or the shared library is
 """
 from ._lib import GravitasError, lib, lib_path, OFFSETS  # noqa: F401
 from .engine import PhysicsEngine, init_hooks  # noqa: F401
-from .renderer import KerrRenderer, RenderParams, FrameStats  # noqa: F401
+from .renderer import KerrRenderer, RenderParams, FrameStats, DeviceTarget, ExternalBuffer  # noqa: F401
 from .webgl import WebGLRenderer  # noqa: F401
 from . import camera, shard, webgl  # noqa: F401

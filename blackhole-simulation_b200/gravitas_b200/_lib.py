@@ -156,6 +156,12 @@ SIGNATURES = {
     "gvt_host_free": (_i32, [_vp]),
     "gvt_host_register": (_i32, [_vp, C.c_size_t]),
     "gvt_host_unregister": (_i32, [_vp]),
+    "gvt_external_import_fd": (_i32, [_i32, _i32, C.c_uint64, _i32, C.POINTER(_vp), C.POINTER(_vp)]),
+    "gvt_external_release": (_i32, [_vp]),
+    "gvt_external_semaphore_import_fd": (_i32, [_i32, _i32, _i32, C.POINTER(_vp)]),
+    "gvt_external_semaphore_release": (_i32, [_vp]),
+    "gvt_render_wait_external": (_i32, [_vp, _vp, C.c_uint64]),
+    "gvt_render_signal_external": (_i32, [_vp, _vp, C.c_uint64]),
     "gvt_measure_fma_peak": (_i32, [_vp, _i32, _pd, _pd]),
     "gvt_device_info": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.c_char_p]),
 }

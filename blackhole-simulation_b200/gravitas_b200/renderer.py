@@ -79,6 +79,45 @@ class PinnedBuffer:
             pass
 
 
+class DeviceTarget:
+    """A frame target in DEVICE memory: a raw device pointer of the caller -- a buffer of the presenter's
+    graphics API mapped through `ExternalBuffer.import_fd`, or any device allocation. Passed as `out=` to the frame calls;
+    the producing kernel stores into it (or one device-to-device copy follows) and nothing comes back to the host."""
+
+    def __init__(self, ptr, nbytes=0):
+        self.ptr = C.c_void_p(int(ptr))
+        self.nbytes = nbytes
+
+    def array(self, dtype, shape):
+        return None                      # the frame stays on the device
+
+
+class ExternalBuffer(DeviceTarget):
+    """Memory another API exported as a POSIX fd (VK_KHR_external_memory_fd / GL_EXT_memory_object_fd / a CUDA VMM
+    allocation), mapped with cudaImportExternalMemory. On success the driver owns the fd."""
+
+    def __init__(self, handle, ptr, nbytes):
+        super().__init__(ptr, nbytes)
+        self._h = handle
+
+    @classmethod
+    def import_fd(cls, fd, nbytes, device=0, dedicated=False):
+        h, p = C.c_void_p(), C.c_void_p()
+        check(lib().gvt_external_import_fd(device, fd, nbytes, 1 if dedicated else 0, C.byref(h), C.byref(p)))
+        return cls(h, p.value, nbytes)
+
+    def release(self):
+        if self._h:
+            lib().gvt_external_release(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
 class SharedFrame:
     """One host frame buffer shared by all ranks of a box (POSIX shared memory, page-locked in every process): with
     GVT_FLAG_D2H_OWN_ROWS each rank copies its row block straight into it, so the consumer (rank 0's host) gets the
@@ -225,7 +264,10 @@ class KerrRenderer:
         self.last_stats = _stats(st)
         return self.last_stats
 
-    def read_frame(self, fmt=_lib.FORMAT_RGBA32F):
+    def read_frame(self, fmt=_lib.FORMAT_RGBA32F, out=None):
+        if out is not None:                       # a DeviceTarget (or any object with .ptr): the frame goes there
+            check(lib().gvt_render_read_frame(self._h, fmt, out.ptr))
+            return None
         out = np.zeros((self.height, self.width, 4), np.dtype(_lib.FORMAT_DTYPE[fmt]))
         check(lib().gvt_render_read_frame(self._h, fmt, out.ctypes.data_as(C.c_void_p)))
         return out
@@ -279,15 +321,19 @@ class KerrRenderer:
         check(lib().gvt_render_set_frame_format(self._h, fmt))
 
     def bloom(self, enabled=True, intensity=0.5, threshold=0.8, blur_passes=2, fmt=_lib.FORMAT_RGBA32F, readback=True,
-              precise=False):
+              precise=False, out=None):
         """BloomManager.applyBloomToTexture / drawTextureToScreen (rendering/bloom.ts:446-632) on the finished frame:
         returns the display-referred frame (ACES + gamma applied) in ``fmt``. precise=True: the validation build."""
         cfg = _lib.GvtBloomConfig()
         cfg.struct_size = C.sizeof(cfg)
         cfg.enabled, cfg.intensity, cfg.threshold, cfg.blur_passes = 1 if enabled else 0, intensity, threshold, blur_passes
         cfg.precise = 1 if precise else 0
-        out = np.zeros((self.height, self.width, 4), np.dtype(_lib.FORMAT_DTYPE[fmt])) if readback else None
         ms = C.c_double()
+        if out is not None:                       # a DeviceTarget: the display-referred frame stays on the device
+            check(lib().gvt_render_bloom(self._h, C.byref(cfg), fmt, out.ptr, C.byref(ms)))
+            self.last_bloom_ms = ms.value
+            return None
+        out = np.zeros((self.height, self.width, 4), np.dtype(_lib.FORMAT_DTYPE[fmt])) if readback else None
         check(lib().gvt_render_bloom(self._h, C.byref(cfg), fmt, out.ctypes.data_as(C.c_void_p) if readback else None, C.byref(ms)))
         self.last_bloom_ms = ms.value
         return out

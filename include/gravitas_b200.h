@@ -380,6 +380,28 @@ int32_t gvt_host_free(void* p);
 /* Page-lock caller-owned host memory (e.g. a shared-memory frame all ranks of a box write into). */
 int32_t gvt_host_register(void* p, size_t bytes);
 int32_t gvt_host_unregister(void* p);
+/* Frame targets in DEVICE memory -- the hand-off without host memory. Wherever a frame entry point takes
+ * a host buffer (gvt_render_frame, gvt_render_rows, gvt_render_fragment_glsl, gvt_render_read_frame, gvt_render_bloom) it
+ * also takes a device pointer: when the requested format is the frame chain's own (and this rank produces every pixel it
+ * delivers) the producing kernel stores each finished pixel straight into it, otherwise one device-to-device copy follows;
+ * GvtFrameStats.d2h_bytes then counts no frame bytes. The reference keeps its frames on the GPU as RGBA16F textures
+ * (src/rendering/reprojection.ts:120-140, webgpu/renderer.ts:161-180); this is the equivalent.
+ *   gvt_external_import_fd          maps memory another API exported as a POSIX fd (VK_KHR_external_memory_fd,
+ *                                   GL_EXT_memory_object_fd, or a CUDA VMM allocation: cuMemExportToShareableHandle) with
+ *                                   cudaImportExternalMemory + cudaExternalMemoryGetMappedBuffer; on success the driver owns
+ *                                   the fd. `dedicated` = the allocation is dedicated to one image (VkMemoryDedicatedAllocateInfo).
+ *   gvt_external_semaphore_import_fd  the same for a binary (timeline = 0) or timeline semaphore
+ *                                   (VK_KHR_external_semaphore_fd / GL_EXT_semaphore_fd).
+ *   gvt_render_wait_external / gvt_render_signal_external  enqueue a wait / a signal on the renderer's stream: wait before a
+ *                                   frame call (the presenter has finished sampling the target), signal after it. */
+typedef struct gvt_external_buffer gvt_external_buffer;
+typedef struct gvt_external_semaphore gvt_external_semaphore;
+int32_t gvt_external_import_fd(int32_t device, int32_t fd, uint64_t bytes, int32_t dedicated, gvt_external_buffer** out, void** device_ptr);
+int32_t gvt_external_release(gvt_external_buffer* b);
+int32_t gvt_external_semaphore_import_fd(int32_t device, int32_t fd, int32_t timeline, gvt_external_semaphore** out);
+int32_t gvt_external_semaphore_release(gvt_external_semaphore* s);
+int32_t gvt_render_wait_external(gvt_renderer* r, gvt_external_semaphore* s, uint64_t value);
+int32_t gvt_render_signal_external(gvt_renderer* r, gvt_external_semaphore* s, uint64_t value);
 /* In-run FMA-pipe micro-benchmarks (dependent-chain FFMA / DFMA, all SMs): the FP32/FP64 roofline denominators
  * MEASURED_PEAKS.json does not carry. Returns TFLOP/s (2 flop per FMA). */
 int32_t gvt_measure_fma_peak(gvt_renderer* r, int32_t precision, double* out_tflops, double* out_ms);
