@@ -64,6 +64,8 @@ export class PhysicsEngine extends NativePhysicsEngine {
 }
 
 export const KerrRenderer = addon.KerrRenderer;
+// importExternalFd(fd, bytes, device, dedicated): an opaque frame target in device memory (INTEGRATION.md 6)
+export const importExternalFd: (fd: number, bytes: number, device?: number, dedicated?: boolean) => unknown = addon.importExternalFd;
 export function init_hooks(): void {}                             // lib.rs:30-33: the wasm panic hook has no native counterpart
 
 export default async function init(): Promise<{ memory: { buffer: SharedArrayBuffer } }> {

@@ -3,7 +3,7 @@
 // RUNTIME: this file needs BOTH a DOM (the canvas it blits to) and Node-API (the addon, via ./index): an Electron / NW.js
 // renderer process with nodeIntegration. In a stock browser the frames would have to come from a render server instead
 // (INTEGRATION.md 4); that transport is not part of this repository.
-import { KerrRenderer } from "./index";
+import { KerrRenderer, importExternalFd } from "./index";
 import { CameraUniforms, PhysicsParams, writeCameraUniforms, writePhysicsParams } from "@/types/webgpu";
 
 export class KerrB200Renderer {
@@ -13,6 +13,7 @@ export class KerrB200Renderer {
   private maxSteps = 150;                                       // compute.wgsl.ts:13 default
   private width = 0;
   private height = 0;
+  private target: unknown = null;                              // imported external frame target, or null (host frame + blit)
 
   async init(canvas: HTMLCanvasElement): Promise<boolean> {     // renderer.ts:82
     this.ctx = canvas.getContext("2d");
@@ -29,11 +30,18 @@ export class KerrB200Renderer {
     this.out = new ArrayBuffer(width * height * 16);
     this.r.resize(width, height);
   }
+  /** Hand-off without host memory (INTEGRATION.md 6): `fd` is the POSIX fd of a linear RGBA32F buffer the presenter
+   *  exported from its graphics API (VK_KHR_external_memory_fd / GL_EXT_memory_object_fd). Frames are then stored into
+   *  it by the producing kernel and `render` skips the canvas blit -- the presenter samples the buffer itself. */
+  setExternalTarget(fd: number, bytes: number, device = 0): void {
+    this.target = importExternalFd(fd, bytes, device, false);
+  }
   render(camera: CameraUniforms, physics: PhysicsParams): void {             // renderer.ts:280
     const [w, h] = physics.resolution;
     if (w !== this.width || h !== this.height) this.resize(w, h);
     const cam = new Float32Array(88); writeCameraUniforms(cam, camera);      // types/webgpu.ts:89-116
     const ph = new Float32Array(8); writePhysicsParams(ph, physics);         // types/webgpu.ts:67-87
+    if (this.target) { this.r.renderFrame(cam, ph, { maxSteps: this.maxSteps, taa: 1, jitter: 1 }, this.target); return; }
     this.r.renderFrame(cam, ph, { maxSteps: this.maxSteps, taa: 1, jitter: 1 }, this.out);
     this.blit(new Float32Array(this.out), w, h);
   }
