@@ -277,3 +277,31 @@ def test_disk_flux_against_page_thorne_quadrature(built, a_star):
         assert worst_vs_bpt < 5e-6
     else:
         assert worst_vs_bpt > 0.1          # the reference's spin terms are not BPT's (see the docstring)
+
+
+def test_blackbody_lut_against_colorimetry_tables(built):
+    """generate_blackbody_lut (spectrum.rs:12-102: Planck's law x a Gaussian fit of the CIE 1931 observer, 380-780 nm at 2 nm,
+    XYZ -> linear sRGB): the chromaticity of its texels against the tabulated Planckian locus (CIE 15:2004), and the redshift
+    rule -- a texel depends on T g only, times g^4.
+    FINDING: the reference's colour-matching fit (spectrum.rs:50-63) carries the constants of Wyman, Sloan & Shirley's 2013
+    multi-lobe fit but with ONE width per lobe where that fit is piecewise (different widths left and right of each peak), so
+    its whites sit +0.03 in x and +0.01..+0.04 in y off the locus (a 6500 K black body comes out as linear RGB 1 : 0.84 : 0.60).
+    Followed as coded; the tolerance below is that bias, and the ordering along the locus is asserted exactly."""
+    eng = built.PhysicsEngine(1.0, 0.0)
+    srgb_to_xyz = np.array([[0.4124564, 0.3575761, 0.1804375], [0.2126729, 0.7151522, 0.0721750], [0.0193339, 0.1191920, 0.9503041]])
+
+    def texel(t_kelvin, g_row=19):                       # W = 4, H = 100: row 19 <-> g = 0.05 + 4.95 * 19 / 99 = 1, last column <-> T = T_max
+        lut = np.asarray(eng.generate_spectrum_lut(4, 100, t_kelvin), np.float64).reshape(100, 4, 4)
+        return lut[g_row, 3, :3]
+    xs = []
+    for t_kelvin, (x_ref, y_ref) in {2856.0: (0.4476, 0.4074), 4000.0: (0.3805, 0.3768), 6500.0: (0.3135, 0.3237),
+                                      10000.0: (0.2807, 0.2884)}.items():
+        xyz = srgb_to_xyz @ texel(t_kelvin)
+        x, y = xyz[0] / xyz.sum(), xyz[1] / xyz.sum()
+        assert 0.0 < x - x_ref < 0.045 and 0.0 < y - y_ref < 0.045, (t_kelvin, x, y)
+        xs.append(x)
+    assert xs == sorted(xs, reverse=True)                # hotter is bluer: x falls monotonically along the locus
+    # redshift: (T = 13000 K, g = 1/2) is the 6500 K spectrum dimmed by g^4. Row for g = 0.5: 0.05 + 4.95 * y / 99 = 0.5 -> y = 9
+    half = texel(13000.0, g_row=9)
+    full = texel(6500.0)
+    np.testing.assert_allclose(half, full * 0.5 ** 4, rtol=3e-6)
