@@ -700,6 +700,7 @@ static int32_t build_frame(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
 
     memset(&P, 0, sizeof(P));
     P.M = bh.mass; P.a = bh.a(); P.spin = bh.spin; P.rh = bh.horizon(); P.r_term = P.rh * 1.001;
+    P.a2 = P.a * P.a; P.twoM = 2.0 * P.M;
     P.sqrtM = std::sqrt(bh.mass);
     P.escape_r = rp->escape_radius; P.r_in = bh.isco(true); P.r_out = rp->disk_r_out;
     P.tol = rp->tolerance; P.h0 = rp->initial_step;

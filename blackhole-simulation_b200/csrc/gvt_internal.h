@@ -47,6 +47,7 @@ struct FrameParams {
     TrigTable trig;                                           // set by the launcher (GVT_TRIG_TABLE_INIT)
     double M, a, spin, rh, r_term, escape_r, r_in, r_out;   // r_term = 1.001 * r+ (geodesic/mod.rs:257)
     double sqrtM;                                             // sqrt(M) for the Keplerian frequency (redshift.rs:72)
+    double a2, twoM;                                          // a * a, 2 M: what HoleRay<double> would otherwise compute per thread
     double tol, h0;
     // Zone radii of the march (chunk-level, warp-uniform specialisations of the step loop; see k_trace_tile):
     double r_hconst;                                          // beyond it the step rule has saturated: h == h_const, and the

@@ -208,6 +208,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
     HoleRay<R> hc;
     hc.trig = &P.trig;
     hc.set_hole(R(P.M), R(P.a));
+    // f64: the derived hole constants straight from the parameter block (host-computed, the same IEEE products): a value
+    // COMPUTED in the kernel lives in vector registers, one READ from the constant bank reaches the step loops' DFMAs as a
+    // uniform-register operand -- a two-register DFMA (2 issue cycles) where a three-register one takes 3
+    if (sizeof(R) == 8) { hc.a2 = R(P.a2); hc.twoM = R(P.twoM); }
     const R r_term = R(P.r_term), escape_r = R(P.escape_r), rh = R(P.rh);
     const R half_pi = R(1.5707963267948966);
     const R hs_bias = R(-0.15) * rh;              // step rule compute.wgsl.ts:213 as one FMA: 0.15 r - 0.15 r+
@@ -305,6 +309,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
             y.pr = pr_far;
             y.pth = pth_far * r0 * r0;
             hc.set_ray(R(-1), pph_far * r0 * r0 * st * st);
+            // p_t = -1 for every camera ray (E = 1): its products with the hole constants are the constants themselves up to
+            // sign -- exact identities (scalings by 1, 2), so nothing changes numerically -- and named this way they stay
+            // constant-bank operands instead of per-thread register values (see set_hole above)
+            hc.twoM_pt = -hc.twoM; hc.twoM_pt2 = hc.twoM; hc.M_two_pt = -hc.twoM; hc.M_pt2 = hc.M;
             if (MIXED) hcf.set_ray(-1.0f, (float)hc.pph);
             // Carter constant of the ray at the camera, for the polar-safety test (kPolarSafe)
             const R ct2 = ct * ct;
