@@ -924,7 +924,10 @@ static int32_t render_impl(gvt_renderer* r, const GvtCamera* cam, const GvtPhysi
             device_target = at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
             if (rp->output_format == r->storage_format() && (r->world == 1 || own)) {
                 if (at.type == cudaMemoryTypeHost && at.devicePointer) host_alias = static_cast<float4*>(at.devicePointer);
-                else if (device_target && at.devicePointer) host_alias = static_cast<float4*>(at.devicePointer);
+                // (a target on ANOTHER device is reached by the copy below, not by this kernel's stores: peer access to it
+                // is the caller's business and is not assumed)
+                else if (device_target && at.devicePointer && (at.type == cudaMemoryTypeManaged || at.device == r->device))
+                    host_alias = static_cast<float4*>(at.devicePointer);
             }
         } else {
             (void)cudaGetLastError();   // pageable memory on an old driver: not an error, just the copy path
