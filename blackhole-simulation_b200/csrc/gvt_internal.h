@@ -59,7 +59,7 @@ struct FrameParams {
     uint32_t alive_lo[2], alive_span[2];                      // hot-path "alive" window on the high word of r: [0] (r_term, escape_r),
                                                               //   [1] (r_sat, escape_r): inside iff (hi(r) - lo) < span (unsigned)
     double r_far;                                             // zone 2 of GVT_PRECISION_MIXED (f32 predictors) beyond this radius
-    double r_rot;                                             // zone 2 of the f64 kernel (rotated trigonometry, no disk test): beyond r_far AND the disk's outer edge
+    double r_rot;                                             // zone 3 (no disk test; f64: rotated trigonometry): beyond r_far AND the disk's outer edge by a chunk's travel
     double rot_q_max;                                         // f64 zone 3 is open to rays with Q + a^2 <= this (a switch: huge, or < 0 = closed)
     double rot_stab;                                          //   and L^2 >= rot_stab (Q + a^2 + L^2)^2 (stable polar turning point out there)
     float f32_M, f32_a, f32_a2, f32_twoM, f32_hconst;         // the predictors' hole constants and (float)h_const

@@ -318,11 +318,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_trace_tile(const __grid_constant__ 
             const R ct2 = ct * ct;
             const R Q = N::fma_(y.pth, y.pth, ct2 * N::fma_(hc.pph2, N::rcp(R(fb->safe_st) * R(fb->safe_st)), -hc.a2));
             polar_ray = !(hc.pph2 > R(kPolarSafe) * (Q + hc.a2 + hc.pph2));
-            // zone 2 of the f64 kernel needs |(h/2) p_theta / Sigma| <= 1/16 beyond r_far - travel; p_theta^2 <= Q + a^2.
-            // It is also closed to rays on which the reference scheme itself goes unstable out there: near its polar turning
+            // Zone 3 of the f64 kernel (rotated trigonometry) is closed to rays on which the reference scheme itself goes unstable
+            // out there: near its polar turning
             // point the theta-oscillator has stiffness k = 3 (Q + a^2 + L^2)^2 / (L^2 Sigma^2), and the two-iteration
             // midpoint blows up for h^2 k >~ 4 -- those rays end as garbage in the oracle too, and only the generic
-            // arithmetic reproduces the oracle's garbage step for step (P.rot_stab carries h^2 / r_min^4 with a 4x margin).
+            // arithmetic reproduces the oracle's garbage step for step (P.rot_stab carries h^2 / r_min^4 with a 32x margin).
             const R qal = Q + hc.a2 + hc.pph2;
             rot_ray = (Q + hc.a2) <= R(P.rot_q_max) && hc.pph2 >= R(P.rot_stab) * qal * qal;
             // ... and only from the radius on where a whole step turns theta by at most 2^-8 (trig_rot_small):
